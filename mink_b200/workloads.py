@@ -1,0 +1,139 @@
+"""The five BASELINE.json configurations as data, plus the synthetic-input generator.
+
+Each workload names the robot, the task list, the limits and the solver settings taken from the
+reference examples (file:line cited per entry), following SURVEY.md 8(d).  The same dictionaries
+drive (a) the golden-vector generator, which instantiates the *reference's* task/limit classes,
+(b) this package's own task/limit classes, (c) bench.py.
+"""
+
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional, Tuple
+
+import numpy as np
+
+PI = float(np.pi)
+
+WORKLOADS: Dict[str, dict] = {
+    # BASELINE config 1: UR5e single instance, FrameTask + PostureTask + ConfigurationLimit
+    # (examples/arm_ur5e.py:20-28,66,74: dt = 1/500, damping 1e-3, lm_damping 1).
+    "ur5e": dict(
+        robot="ur5e", scene="universal_robots_ur5e/scene.xml", key="home",
+        frames=[dict(name="attachment_site", type="site", position_cost=1.0, orientation_cost=1.0,
+                     lm_damping=1.0)],
+        posture=dict(cost=1e-2), com=None,
+        limits=[dict(kind="configuration", gain=0.95)],
+        dt=2e-3, damping=1e-3, batch=1,
+    ),
+    # BASELINE config 2: UR5e batch 4096, same tasks, no inequality limits (pure damped LS).
+    "ur5e_dls": dict(
+        robot="ur5e", scene="universal_robots_ur5e/scene.xml", key="home",
+        frames=[dict(name="attachment_site", type="site", position_cost=1.0, orientation_cost=1.0,
+                     lm_damping=1.0)],
+        posture=dict(cost=1e-2), com=None, limits=[],
+        dt=2e-3, damping=1e-3, batch=4096,
+    ),
+    # BASELINE config 3 (headline): G1, 3 FrameTasks + PostureTask + configuration/velocity limits
+    # (examples/humanoid_g1.py:22-40,80,88: foot tasks 200/10 lm 1, pelvis 0/10, posture 1,
+    #  dt = 1/200, damping 1e-1; velocity limit pi rad/s as tests/test_velocity_limit.py:23-25).
+    "g1": dict(
+        robot="g1", scene="unitree_g1/scene.xml", key="stand",
+        frames=[dict(name="left_foot", type="site", position_cost=200.0, orientation_cost=10.0, lm_damping=1.0),
+                dict(name="right_foot", type="site", position_cost=200.0, orientation_cost=10.0, lm_damping=1.0),
+                dict(name="pelvis", type="body", position_cost=0.0, orientation_cost=10.0, lm_damping=0.0)],
+        posture=dict(cost=1.0), com=None,
+        limits=[dict(kind="configuration", gain=0.95), dict(kind="velocity", vmax=PI)],
+        dt=5e-3, damping=1e-1, batch=65536,
+    ),
+    # BASELINE config 4: Shadow Hand, 5 fingertip FrameTasks + PostureTask, joint limits
+    # (examples/hand_shadow.py:19-35,53,63: position cost 1, lm 1, posture 1e-2, dt 1/500, damping 1e-5).
+    "shadow": dict(
+        robot="shadow", scene="shadow_hand/scene_left.xml", key="grasp hard",
+        frames=[dict(name=f, type="site", position_cost=1.0, orientation_cost=0.0, lm_damping=1.0)
+                for f in ("thumb", "first", "middle", "ring", "little")],
+        posture=dict(cost=1e-2), com=None,
+        limits=[dict(kind="configuration", gain=0.95)],
+        dt=2e-3, damping=1e-5, batch=16384,
+    ),
+    # BASELINE config 5: Spot, 4 foot FrameTasks (geoms) + ComTask + CollisionAvoidanceLimit
+    # (examples/quadruped_spot.py:37-42; ComTask cost as examples/humanoid_g1.py:29).
+    "spot": dict(
+        robot="spot", scene="boston_dynamics_spot/scene.xml", key="home",
+        frames=[dict(name=f, type="geom", position_cost=1.0, orientation_cost=0.0, lm_damping=0.0)
+                for f in ("FL", "FR", "HR", "HL")],
+        posture=None, com=dict(cost=200.0),
+        limits=[dict(kind="collision", pairs=[(["FL", "FR", "HR", "HL"], ["floor"]),
+                                              (["FL", "FR", "HR", "HL"], ["FL", "FR", "HR", "HL"])],
+                     gain=0.85, minimum_distance=0.005, detection_distance=0.3, bound_relaxation=0.0)],
+        dt=2e-3, damping=1e-3, batch=32768,
+    ),
+}
+
+
+def _quat_exp(w: np.ndarray) -> np.ndarray:
+    """exp of rotation vectors [...,3] -> unit quaternions wxyz."""
+    th = np.linalg.norm(w, axis=-1, keepdims=True)
+    half = 0.5 * th
+    k = np.where(th > 1e-12, np.sin(half) / np.maximum(th, 1e-300), 0.5)
+    return np.concatenate([np.cos(half), k * w], axis=-1)
+
+
+def sample_q(fm, key_q: np.ndarray, B: int, rng: np.random.Generator) -> np.ndarray:
+    """q per SURVEY.md 8(d): scalar joints uniform in the inner 80 % of their range (unlimited:
+    +-0.8 pi), free joint = keyframe position + U(-0.2,0.2)^3 with orientation exp(N(0,0.2^2)^3)."""
+    q = np.tile(key_q, (B, 1)).astype(np.float64)
+    for n in range(fm.nnode):
+        t, a, d = int(fm.node_type[n]), int(fm.node_qadr[n]), int(fm.node_dadr[n])
+        if t == 0:
+            q[:, a:a + 3] = key_q[a:a + 3] + rng.uniform(-0.2, 0.2, size=(B, 3))
+            q[:, a + 3:a + 7] = _quat_exp(rng.normal(0.0, 0.2, size=(B, 3)))
+        elif t == 1:
+            q[:, a:a + 4] = _quat_exp(rng.normal(0.0, 0.2, size=(B, 3)))
+        else:
+            if fm.dof_limited[d]:
+                lo, hi = fm.dof_lo[d], fm.dof_hi[d]
+            else:
+                lo, hi = -PI, PI
+            q[:, a] = rng.uniform(lo + 0.1 * (hi - lo), hi - 0.1 * (hi - lo), size=B)
+    return q
+
+
+def perturb_q(fm, q: np.ndarray, sigma: float, rng: np.random.Generator) -> np.ndarray:
+    """q' = q (+) delta, delta ~ N(0, sigma^2) on the scalar (hinge/slide) dofs only."""
+    qp = q.copy()
+    for n in range(fm.nnode):
+        if int(fm.node_type[n]) >= 2:
+            a = int(fm.node_qadr[n])
+            qp[:, a] += rng.normal(0.0, sigma, size=q.shape[0])
+    return qp
+
+
+FkFn = Callable[[np.ndarray], Tuple[np.ndarray, Optional[np.ndarray]]]
+
+
+def make_inputs(fm, wl: dict, B: int, fk: FkFn, seed: int = 0, sigma: float = 0.1,
+                aligned_fraction: float = 0.01) -> dict:
+    """Synthetic batch for a workload.
+
+    `fk(q[B,nq]) -> (frame poses [B,F,7] wxyz_xyz, com [B,3] or None)` is supplied by the caller
+    (the oracle in tests/golden generation, the CUDA FK in bench.py).  A fraction of the instances
+    gets a target orientation *exactly* equal to the current one, which exercises the reference's
+    identity branch of SE3.ljacinv (mink/lie/se3.py:213).
+    """
+    rng = np.random.default_rng(seed)
+    key_q = fm.key(wl["key"])
+    q = sample_q(fm, key_q, B, rng)
+    qp = perturb_q(fm, q, sigma, rng)
+    poses_now, _ = fk(q)
+    poses_tgt, com_tgt = fk(qp)
+    targets = np.array(poses_tgt, dtype=np.float64, copy=True)
+    n_al = int(round(aligned_fraction * B))
+    if B >= 8 and n_al == 0 and aligned_fraction > 0:
+        n_al = 1
+    if n_al:
+        idx = rng.choice(B, size=n_al, replace=False)
+        targets[idx, :, :4] = poses_now[idx, :, :4]
+    out = dict(q=q, frame_targets=targets, posture_target=key_q.copy())
+    if wl.get("com") is not None:
+        out["com_target"] = np.array(com_tgt, dtype=np.float64, copy=True)
+    return out
