@@ -1,0 +1,287 @@
+// bik_build.h -- host-side lowering: BIKM model blob + task/limit descriptors -> problem image.
+// Shared by the C-ABI implementation (bik_api.cu) and the host emulation used by CPU tests.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/bik.h"
+#include "bik_layout.h"
+
+namespace bik {
+
+struct HostModel {
+  int nq = 0, nv = 0, nnode = 0, ncom = 0;
+  std::vector<int32_t> node_parent, node_type, node_qadr, node_dadr, dof_node, dof_qadr, dof_limited, com_node;
+  std::vector<double> node_pos, node_quat, node_axis, node_jpos, qpos0, dof_lo, dof_hi, com_pos, com_mass;
+};
+
+inline bool blob_section(const uint8_t* blob, size_t nbytes, const char* name, const uint8_t** data, uint32_t* dtype, uint32_t* count) {
+  const uint32_t* h = reinterpret_cast<const uint32_t*>(blob);
+  uint32_t nsec = h[3];
+  for (uint32_t s = 0; s < nsec; ++s) {
+    const uint8_t* t = blob + 48 + 32 * s;
+    if (48 + 32 * (s + 1) > nbytes) return false;
+    if (strncmp(reinterpret_cast<const char*>(t), name, 20) == 0) {
+      memcpy(dtype, t + 20, 4); memcpy(count, t + 24, 4);
+      uint32_t off; memcpy(&off, t + 28, 4);
+      size_t bytes = size_t(*count) * (*dtype == 0 ? 4 : 8);
+      if (off + bytes > nbytes) return false;
+      *data = blob + off;
+      return true;
+    }
+  }
+  return false;
+}
+
+inline bool parse_model_blob(const void* blob_, size_t nbytes, HostModel* m, std::string* err) {
+  const uint8_t* blob = static_cast<const uint8_t*>(blob_);
+  if (nbytes < 48) { *err = "blob too small"; return false; }
+  const uint32_t* h = reinterpret_cast<const uint32_t*>(blob);
+  if (h[0] != 0x4D4B4942u || h[1] != 1u || h[2] != nbytes) { *err = "not a BIKM v1 blob"; return false; }
+  const int32_t* hi = reinterpret_cast<const int32_t*>(blob + 16);
+  m->nq = hi[0]; m->nv = hi[1]; m->nnode = hi[2]; m->ncom = hi[3];
+  auto geti = [&](const char* name, std::vector<int32_t>* v, size_t expect) {
+    const uint8_t* d; uint32_t dt, cnt;
+    if (!blob_section(blob, nbytes, name, &d, &dt, &cnt) || dt != 0 || cnt != expect) { *err = std::string("bad section ") + name; return false; }
+    v->resize(cnt); if (cnt) memcpy(v->data(), d, cnt * 4); return true;
+  };
+  auto getd = [&](const char* name, std::vector<double>* v, size_t expect) {
+    const uint8_t* d; uint32_t dt, cnt;
+    if (!blob_section(blob, nbytes, name, &d, &dt, &cnt) || dt != 1 || cnt != expect) { *err = std::string("bad section ") + name; return false; }
+    v->resize(cnt); if (cnt) memcpy(v->data(), d, cnt * 8); return true;
+  };
+  size_t nn = m->nnode, nv = m->nv, nc = m->ncom;
+  return geti("node_parent", &m->node_parent, nn) && geti("node_type", &m->node_type, nn) && geti("node_qadr", &m->node_qadr, nn) &&
+         geti("node_dadr", &m->node_dadr, nn) && getd("node_pos", &m->node_pos, 3 * nn) && getd("node_quat", &m->node_quat, 4 * nn) &&
+         getd("node_axis", &m->node_axis, 3 * nn) && getd("node_jpos", &m->node_jpos, 3 * nn) && getd("qpos0", &m->qpos0, m->nq) &&
+         geti("dof_node", &m->dof_node, nv) && geti("dof_qadr", &m->dof_qadr, nv) && geti("dof_limited", &m->dof_limited, nv) &&
+         getd("dof_lo", &m->dof_lo, nv) && getd("dof_hi", &m->dof_hi, nv) && geti("com_node", &m->com_node, nc) &&
+         getd("com_pos", &m->com_pos, 3 * nc) && getd("com_mass", &m->com_mass, nc);
+}
+
+// List scheduling of the tree onto G lanes: a node may run one step after its parent.
+// Priority = height of the subtree below the node (critical path first).
+inline void lane_program(const HostModel& m, int G, std::vector<int32_t>* prog, int* nsteps) {
+  int n = m.nnode;
+  std::vector<int> height(n, 0), done_step(n, -1);
+  for (int i = n - 1; i >= 0; --i) { int p = m.node_parent[i]; if (p >= 0) height[p] = std::max(height[p], height[i] + 1); }
+  std::vector<char> done(n, 0);
+  int remaining = n, step = 0;
+  prog->clear();
+  while (remaining > 0) {
+    std::vector<int> ready;
+    for (int i = 0; i < n; ++i) if (!done[i]) { int p = m.node_parent[i]; if (p < 0 || (done[p] && done_step[p] < step)) ready.push_back(i); }
+    std::stable_sort(ready.begin(), ready.end(), [&](int a, int b) { return height[a] > height[b]; });
+    for (int g = 0; g < G; ++g) {
+      if (g < (int)ready.size()) { int i = ready[g]; prog->push_back(i); done[i] = 1; done_step[i] = step; --remaining; }
+      else prog->push_back(-1);
+    }
+    ++step;
+  }
+  *nsteps = step;
+}
+
+struct ImageBuilder {
+  std::vector<uint32_t> w;
+  int alloc(int words) { int off = (int)w.size(); w.resize(w.size() + ((words + 3) & ~3), 0u); return off; }
+  float* f(int off) { return reinterpret_cast<float*>(w.data() + off); }
+  int32_t* i(int off) { return reinterpret_cast<int32_t*>(w.data() + off); }
+};
+
+inline void put_frame(const bik_frame& fr, int32_t* node, float* lpos, float* lquat) {
+  *node = fr.node;
+  double n = sqrt(fr.quat[0] * fr.quat[0] + fr.quat[1] * fr.quat[1] + fr.quat[2] * fr.quat[2] + fr.quat[3] * fr.quat[3]);
+  if (!(n > 0)) n = 1;
+  for (int k = 0; k < 3; ++k) lpos[k] = (float)fr.pos[k];
+  for (int k = 0; k < 4; ++k) lquat[k] = (float)(fr.quat[k] / n);
+}
+
+// Returns false and sets *err on unsupported input.
+inline bool build_image(const HostModel& m, const bik_task_desc* tasks, int ntasks, const bik_limit_desc* limits, int nlimits, int G,
+                        std::vector<uint32_t>* image, std::string* err) {
+  const float INF = std::numeric_limits<float>::infinity();
+  ImageBuilder b;
+  int hoff = b.alloc(sizeof(PHeader) / 4);
+  PHeader H;
+  memset(&H, 0, sizeof H);
+  H.nq = m.nq; H.nv = m.nv; H.nnode = m.nnode; H.G = G;
+  if (m.nv > 64) { *err = "nv > 64 is not supported by the warp-per-problem solver"; return false; }
+  if (m.nnode > 32767) { *err = "too many nodes"; return false; }
+  for (int t = 0; t < ntasks; ++t) {
+    if (tasks[t].kind == BIK_TASK_FRAME) H.F++;
+    else if (tasks[t].kind == BIK_TASK_POSTURE) H.P++;
+    else if (tasks[t].kind == BIK_TASK_COM) H.C++;
+    else { *err = "unknown task kind"; return false; }
+    if (!(tasks[t].gain >= 0.0 && tasks[t].gain <= 1.0)) { *err = "`gain` must be in the range [0, 1]"; return false; }
+    if (tasks[t].lm_damping < 0.0) { *err = "`lm_damping` must be >= 0"; return false; }
+  }
+  H.K = 6 * H.F + 3 * H.C;
+
+  // nodes
+  H.off_nodes = b.alloc(NODE_WORDS * m.nnode);
+  for (int n = 0; n < m.nnode; ++n) {
+    NodeRec r; memset(&r, 0, sizeof r);
+    r.parent = m.node_parent[n]; r.type = m.node_type[n]; r.qadr = m.node_qadr[n]; r.dadr = m.node_dadr[n];
+    if (r.parent >= n) { *err = "nodes must be ordered parents first"; return false; }
+    for (int k = 0; k < 3; ++k) { r.pos[k] = (float)m.node_pos[3 * n + k]; r.axis[k] = (float)m.node_axis[3 * n + k]; r.jpos[k] = (float)m.node_jpos[3 * n + k]; }
+    for (int k = 0; k < 4; ++k) r.quat[k] = (float)m.node_quat[4 * n + k];
+    memcpy(b.w.data() + H.off_nodes + NODE_WORDS * n, &r, sizeof r);
+  }
+  H.off_qpos0 = b.alloc(m.nq);
+  for (int k = 0; k < m.nq; ++k) b.f(H.off_qpos0)[k] = (float)m.qpos0[k];
+  std::vector<int32_t> prog; int nsteps = 0;
+  lane_program(m, G, &prog, &nsteps);
+  H.nsteps = nsteps;
+  H.off_prog = b.alloc((int)prog.size());
+  if (!prog.empty()) memcpy(b.i(H.off_prog), prog.data(), prog.size() * 4);
+  H.off_dofnode = b.alloc(m.nv); H.off_dofqadr = b.alloc(m.nv); H.off_range = b.alloc(2 * m.nv);
+  for (int d = 0; d < m.nv; ++d) {
+    b.i(H.off_dofnode)[d] = m.dof_node[d]; b.i(H.off_dofqadr)[d] = m.dof_qadr[d];
+    b.f(H.off_range)[d] = m.dof_limited[d] ? (float)m.dof_lo[d] : -INF;
+    b.f(H.off_range)[m.nv + d] = m.dof_limited[d] ? (float)m.dof_hi[d] : INF;
+  }
+
+  // frame tasks + ancestor-dof column lists
+  H.off_frames = b.alloc(FRAME_WORDS * std::max(H.F, 1));
+  std::vector<int32_t> cols;
+  {
+    int fi = 0, ci = 0, row = 0;
+    for (int t = 0; t < ntasks; ++t) {
+      if (tasks[t].kind == BIK_TASK_FRAME) {
+        FrameRec r; memset(&r, 0, sizeof r);
+        put_frame(tasks[t].frame, &r.node, r.lpos, r.lquat);
+        if (r.node >= m.nnode) { *err = "frame node out of range"; return false; }
+        for (int k = 0; k < 6; ++k) { if (tasks[t].cost[k] < 0) { *err = "cost should be >= 0"; return false; } r.cost[k] = (float)tasks[t].cost[k]; }
+        r.gain = (float)tasks[t].gain; r.lm = (float)tasks[t].lm_damping; r.row0 = row;
+        r.col_off = (int)cols.size();
+        std::vector<int32_t> mine;
+        for (int n = r.node; n >= 0; n = m.node_parent[n]) {
+          int nd = m.node_type[n] == JNT_FREE ? 6 : (m.node_type[n] == JNT_BALL ? 3 : 1);
+          for (int k = nd - 1; k >= 0; --k) mine.push_back((m.node_dadr[n] + k) | (n << 16));
+        }
+        std::reverse(mine.begin(), mine.end());
+        r.ncols = (int)mine.size();
+        cols.insert(cols.end(), mine.begin(), mine.end());
+        memcpy(b.w.data() + H.off_frames + FRAME_WORDS * fi, &r, sizeof r);
+        ++fi; row += 6;
+      } else if (tasks[t].kind == BIK_TASK_COM) { ++ci; row += 3; }
+    }
+  }
+  // CoM bookkeeping (always emitted; cheap) -- mj_jacSubtreeCom(body 1) restated per node.
+  H.off_comnodes = b.alloc(COMNODE_WORDS * std::max(m.nnode, 1));
+  {
+    std::vector<double> own_m(m.nnode, 0.0), sub_m(m.nnode, 0.0), own_c(3 * (size_t)m.nnode, 0.0);
+    double total = 0, fixed[3] = {0, 0, 0};
+    for (int c = 0; c < m.ncom; ++c) {
+      int n = m.com_node[c]; double ms = m.com_mass[c]; total += ms;
+      if (n < 0) { for (int k = 0; k < 3; ++k) fixed[k] += ms * m.com_pos[3 * c + k]; continue; }
+      own_m[n] += ms; for (int k = 0; k < 3; ++k) own_c[3 * n + k] += ms * m.com_pos[3 * c + k];
+    }
+    for (int n = m.nnode - 1; n >= 0; --n) { sub_m[n] += own_m[n]; if (m.node_parent[n] >= 0) sub_m[m.node_parent[n]] += sub_m[n]; }
+    for (int n = 0; n < m.nnode; ++n) {
+      ComNodeRec r; memset(&r, 0, sizeof r);
+      r.own_m = (float)own_m[n]; r.sub_m = (float)sub_m[n];
+      for (int k = 0; k < 3; ++k) r.own_c[k] = (float)own_c[3 * n + k];
+      memcpy(b.w.data() + H.off_comnodes + COMNODE_WORDS * n, &r, sizeof r);
+    }
+    H.com_total_mass = (float)total;
+    for (int k = 0; k < 3; ++k) H.com_fixed[k] = (float)fixed[k];
+    H.com_cols_off = (int)cols.size();
+    for (int d = 0; d < m.nv; ++d) { int n = m.dof_node[d]; if (sub_m[n] > 0) cols.push_back(d | (n << 16)); }
+    H.com_ncols = (int)cols.size() - H.com_cols_off;
+    if (H.C > 0 && !(total > 0)) { *err = "ComTask needs a model with mass in the subtree of body 1"; return false; }
+  }
+  H.off_cols = b.alloc((int)std::max<size_t>(cols.size(), 1));
+  if (!cols.empty()) memcpy(b.i(H.off_cols), cols.data(), cols.size() * 4);
+
+  // posture + com task records
+  H.off_posture = b.alloc(std::max(H.P, 1) * (2 + m.nv));
+  H.off_com = b.alloc(std::max(H.C, 1) * 8);
+  {
+    int pi = 0, ci = 0, row = 0;
+    for (int t = 0; t < ntasks; ++t) {
+      if (tasks[t].kind == BIK_TASK_FRAME) { row += 6; continue; }
+      if (tasks[t].kind == BIK_TASK_POSTURE) {
+        float* p = b.f(H.off_posture) + pi * (2 + m.nv);
+        p[0] = (float)tasks[t].gain; p[1] = (float)tasks[t].lm_damping;
+        if (!tasks[t].dof_cost) { *err = "posture task needs dof_cost[nv]"; return false; }
+        for (int d = 0; d < m.nv; ++d) {
+          if (tasks[t].dof_cost[d] < 0) { *err = "cost should be >= 0"; return false; }
+          bool isfree = m.node_type[m.dof_node[d]] == JNT_FREE;
+          p[2 + d] = isfree ? 0.f : (float)tasks[t].dof_cost[d];  // e and J are zeroed on free dofs (posture_task.py:115-116,139-140)
+        }
+        ++pi;
+      } else {
+        float* p = b.f(H.off_com) + ci * 8;
+        for (int k = 0; k < 3; ++k) { if (tasks[t].cost[k] < 0) { *err = "cost must be >= 0"; return false; } p[k] = (float)tasks[t].cost[k]; }
+        p[3] = (float)tasks[t].gain; p[4] = (float)tasks[t].lm_damping;
+        reinterpret_cast<int32_t*>(p)[5] = row;
+        ++ci; row += 3;
+      }
+    }
+  }
+
+  // limits
+  int ncfg = 0;
+  for (int l = 0; l < nlimits; ++l) if (limits[l].kind == BIK_LIMIT_CONFIGURATION) ++ncfg;
+  if (ncfg > MAX_CFG_LIMITS) { *err = "at most 2 ConfigurationLimits per problem"; return false; }
+  H.ncfg = ncfg;
+  H.off_cfg = b.alloc(std::max(ncfg, 1) * (2 + 2 * m.nv));
+  H.off_vmax = b.alloc(m.nv);
+  for (int d = 0; d < m.nv; ++d) b.f(H.off_vmax)[d] = INF;
+  int ci = 0, ncoll = 0;
+  for (int l = 0; l < nlimits; ++l) {
+    const bik_limit_desc& L = limits[l];
+    if (L.kind == BIK_LIMIT_CONFIGURATION) {
+      if (!(L.gain > 0.0 && L.gain <= 1.0)) { *err = "ConfigurationLimit gain must be in the range (0, 1]"; return false; }
+      float* p = b.f(H.off_cfg) + ci * (2 + 2 * m.nv);
+      p[0] = (float)L.gain;
+      for (int d = 0; d < m.nv; ++d) { p[2 + d] = -INF; p[2 + m.nv + d] = INF; }
+      for (int k = 0; k < L.n; ++k) {
+        int d = L.dof[k];
+        if (d < 0 || d >= m.nv || m.dof_qadr[d] < 0) { *err = "ConfigurationLimit: only slide/hinge dofs are supported"; return false; }
+        p[2 + d] = (float)L.lower[k]; p[2 + m.nv + d] = (float)L.upper[k];
+      }
+      ++ci;
+    } else if (L.kind == BIK_LIMIT_VELOCITY) {
+      H.has_vel = 1;
+      for (int k = 0; k < L.n; ++k) {
+        int d = L.dof[k];
+        if (d < 0 || d >= m.nv) { *err = "VelocityLimit dof out of range"; return false; }
+        if (m.node_type[m.dof_node[d]] == JNT_FREE) { *err = "Free joint is not supported"; return false; }
+        b.f(H.off_vmax)[d] = std::min(b.f(H.off_vmax)[d], (float)L.vmax[k]);
+      }
+    } else if (L.kind == BIK_LIMIT_COLLISION) {
+      if (++ncoll > 1) { *err = "at most one CollisionAvoidanceLimit per problem"; return false; }
+      H.ngeoms = L.ngeoms; H.npairs = L.n;
+      H.coll_gain = (float)L.gain; H.coll_dmin = (float)L.minimum_distance; H.coll_ddet = (float)L.detection_distance; H.coll_relax = (float)L.bound_relaxation;
+      H.off_geoms = b.alloc(GEOM_WORDS * std::max(L.ngeoms, 1)); H.off_pairs = b.alloc(2 * std::max(L.n, 1));
+      for (int g = 0; g < L.ngeoms; ++g) {
+        GeomRec r; memset(&r, 0, sizeof r);
+        r.type = L.geoms[g].type;
+        if (r.type != BIK_GEOM_PLANE && r.type != BIK_GEOM_SPHERE && r.type != BIK_GEOM_CAPSULE) { *err = "collision geoms must be plane, sphere or capsule"; return false; }
+        put_frame(L.geoms[g].frame, &r.node, r.lpos, r.lquat);
+        for (int k = 0; k < 3; ++k) r.size[k] = (float)L.geoms[g].size[k];
+        memcpy(b.w.data() + H.off_geoms + GEOM_WORDS * g, &r, sizeof r);
+      }
+      for (int k = 0; k < 2 * L.n; ++k) {
+        if (L.pairs[k] < 0 || L.pairs[k] >= L.ngeoms) { *err = "collision pair index out of range"; return false; }
+        b.i(H.off_pairs)[k] = L.pairs[k];
+      }
+      for (int k = 0; k < L.n; ++k) if (L.geoms[L.pairs[2 * k]].type == BIK_GEOM_PLANE && L.geoms[L.pairs[2 * k + 1]].type == BIK_GEOM_PLANE) { *err = "plane-plane pair"; return false; }
+    } else { *err = "unknown limit kind"; return false; }
+  }
+  if (!H.off_geoms) { H.off_geoms = b.alloc(GEOM_WORDS); H.off_pairs = b.alloc(4); }
+  H.words = (int)b.w.size();
+  memcpy(b.w.data() + hoff, &H, sizeof H);
+  *image = b.w;
+  return true;
+}
+
+}  // namespace bik

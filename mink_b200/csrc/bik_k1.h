@@ -1,0 +1,523 @@
+// bik_k1.h -- K1: forward kinematics + task errors + task Jacobians (+ collision rows).
+//
+// Mapping: G lanes cooperate on one robot instance (G in {1,2,4,8,16,32}); a warp of W lanes
+// therefore carries IPW = W/G consecutive instances.  The tree is walked by a host-compiled lane
+// program (bik_build.h: lane_program): at step s lane g composes node prog[s][g] from its parent's
+// pose, which an earlier step left in the per-instance shared-memory state.  Jacobian columns are
+// written into a per-warp staging tile and flushed as contiguous runs, so that global stores are
+// coalesced no matter how the lanes were assigned.
+//
+// The same source is compiled for the host with W = G = 1 (tests/host_emu) -- every cross-lane
+// primitive degenerates to a no-op there.
+//
+// Reference semantics: mujoco mj_kinematics / mj_jac via mink/configuration.py:63-64,144-153;
+// FrameTask mink/tasks/frame_task.py:95-146; ComTask mink/tasks/com_task.py:71-97;
+// PostureTask.compute_error mink/tasks/posture_task.py:87-118;
+// CollisionAvoidanceLimit mink/limits/collision_avoidance_limit.py:59-72,187-210.
+#pragma once
+#include "bik_layout.h"
+#include "bik_math.h"
+
+#if defined(__CUDA_ARCH__)
+#define BIK_SYNCWARP() __syncwarp()
+#else
+#define BIK_SYNCWARP() ((void)0)
+#endif
+
+#if defined(__CUDACC__)
+#define BIK_INF_F (__int_as_float(0x7f800000))
+#else
+#define BIK_INF_F (INFINITY)
+#endif
+
+namespace bik {
+
+typedef V3<float> F3;
+typedef Q4<float> FQ;
+typedef M3<float> FM;
+
+struct PView {
+  const uint32_t* base;
+  BIK_HD const PHeader& h() const { return *reinterpret_cast<const PHeader*>(base); }
+  BIK_HD const NodeRec& node(int n) const { return *reinterpret_cast<const NodeRec*>(base + h().off_nodes + NODE_WORDS * n); }
+  BIK_HD const FrameRec& frame(int f) const { return *reinterpret_cast<const FrameRec*>(base + h().off_frames + FRAME_WORDS * f); }
+  BIK_HD const ComNodeRec& comnode(int n) const { return *reinterpret_cast<const ComNodeRec*>(base + h().off_comnodes + COMNODE_WORDS * n); }
+  BIK_HD const GeomRec& geom(int g) const { return *reinterpret_cast<const GeomRec*>(base + h().off_geoms + GEOM_WORDS * g); }
+  BIK_HD const float* f(int off) const { return reinterpret_cast<const float*>(base + off); }
+  BIK_HD const int32_t* i(int off) const { return reinterpret_cast<const int32_t*>(base + off); }
+};
+
+struct K1Args {
+  int B;
+  const float* q;        // [B][nq]
+  const float* ftgt;     // [B][F][7]
+  const float* ptgt;     // [B or 1][P][nq]
+  const float* ctgt;     // [B][C][3]
+  int pbatched;
+  float dt;
+  float* J;              // [B][K][nv]
+  float* e;              // [B][K]
+  float* ep;             // [B][P][nv]
+  float* Gc;             // [B][npairs][nv]
+  float* hc;             // [B][npairs]
+};
+
+// ---- per-warp scratch layout (floats) ------------------------------------------------------
+BIK_HD int k1_state_stride(const PHeader& h) {  // pose (7) + CoM first moment (3) per node, odd stride
+  int s = 7 * h.nnode + (h.C > 0 ? 3 * h.nnode : 0);
+  return s | 1;
+}
+BIK_HD int k1_stage_rows(const PHeader& h) { return 6; }
+BIK_HD int k1_warp_words(const PHeader& h, int ipw) {
+  int w = ipw * k1_state_stride(h) + ipw * k1_stage_rows(h) * h.nv + ipw * (h.K > 0 ? h.K : 1);
+  return (w + 3) & ~3;
+}
+
+BIK_HD FQ ld_q(const float* p) { return q4<float>(p[0], p[1], p[2], p[3]); }
+BIK_HD F3 ld_v(const float* p) { return v3<float>(p[0], p[1], p[2]); }
+
+// One node of the tree: pose of the node frame after its joint (mj_kinematics, one joint per node).
+BIK_HD void fk_node(const PView& P, int n, const float* q, float* xs) {
+  const NodeRec& r = P.node(n);
+  FQ quat;
+  F3 pos;
+  if (r.type == JNT_FREE) {
+    pos = ld_v(q + r.qadr);
+    quat = ld_q(q + r.qadr + 3);
+  } else {
+    if (r.parent >= 0) {
+      FQ pq = ld_q(xs + 7 * r.parent);
+      pos = ld_v(xs + 7 * r.parent + 4) + qrot(pq, ld_v(r.pos));
+      quat = qmul(pq, ld_q(r.quat));
+    } else {
+      pos = ld_v(r.pos);
+      quat = ld_q(r.quat);
+    }
+    const float* q0 = P.f(P.h().off_qpos0);
+    if (r.type == JNT_SLIDE) {
+      pos = pos + (q[r.qadr] - q0[r.qadr]) * qrot(quat, ld_v(r.axis));
+    } else {
+      F3 jp = ld_v(r.jpos);
+      bool off_centre = (jp.x != 0.f) || (jp.y != 0.f) || (jp.z != 0.f);
+      F3 anchor = pos;
+      if (off_centre) anchor = pos + qrot(quat, jp);
+      FQ ql;
+      if (r.type == JNT_HINGE) {
+        float s, c;
+        bik_sincos<float>(0.5f * (q[r.qadr] - q0[r.qadr]), &s, &c);
+        ql = q4<float>(c, s * r.axis[0], s * r.axis[1], s * r.axis[2]);
+      } else {
+        ql = qnormalize(ld_q(q + r.qadr));
+      }
+      quat = qmul(quat, ql);
+      if (off_centre) pos = anchor - qrot(quat, jp);
+    }
+  }
+  quat = qnormalize(quat);
+  float* o = xs + 7 * n;
+  o[0] = quat.w; o[1] = quat.x; o[2] = quat.y; o[3] = quat.z; o[4] = pos.x; o[5] = pos.y; o[6] = pos.z;
+}
+
+BIK_HD void frame_pose(int node, const float* lpos, const float* lquat, const float* xs, FQ* qf, F3* pf) {
+  if (node < 0) { *qf = ld_q(lquat); *pf = ld_v(lpos); return; }
+  FQ nq = ld_q(xs + 7 * node);
+  *qf = qnormalize(qmul(nq, ld_q(lquat)));
+  *pf = ld_v(xs + 7 * node + 4) + qrot(nq, ld_v(lpos));
+}
+
+// World-aligned point-Jacobian column of dof `d` (owned by node n) for a point p moving with a
+// descendant of n: jp = linear part, jr = angular part (mj_jac restated per column).
+BIK_HD void jac_column(const PView& P, int d, int n, const float* xs, F3 p, F3* jp, F3* jr) {
+  const NodeRec& r = P.node(n);
+  FQ nq = ld_q(xs + 7 * n);
+  F3 np = ld_v(xs + 7 * n + 4);
+  int k = d - r.dadr;
+  if (r.type == JNT_HINGE) {
+    F3 ax = qrot(nq, ld_v(r.axis));
+    F3 anchor = np + qrot(nq, ld_v(r.jpos));
+    *jr = ax; *jp = cross(ax, p - anchor);
+  } else if (r.type == JNT_SLIDE) {
+    *jr = v3<float>(0.f, 0.f, 0.f); *jp = qrot(nq, ld_v(r.axis));
+  } else if (r.type == JNT_FREE && k < 3) {
+    *jr = v3<float>(0.f, 0.f, 0.f); *jp = v3<float>(k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f);
+  } else {  // rotational dof of a free or ball joint: body-frame axis k
+    int c = (r.type == JNT_FREE) ? k - 3 : k;
+    F3 ax = qrot(nq, v3<float>(c == 0 ? 1.f : 0.f, c == 1 ? 1.f : 0.f, c == 2 ? 1.f : 0.f));
+    F3 anchor = (r.type == JNT_FREE) ? np : np + qrot(nq, ld_v(r.jpos));
+    *jr = ax; *jp = cross(ax, p - anchor);
+  }
+}
+
+// FrameTask error and the two 3x3 blocks that map world-aligned (jp, jr) columns to task-Jacobian
+// columns:  J[:,d] = [A1 jp + A2 jr ; A1 jr]   with A1 = -Ji R^T, A2 = -Mi R^T.
+BIK_HD void frame_task(FQ qf, F3 pf, const float* tgt, F3* ev, F3* ew, FM* A1, FM* A2) {
+  FQ tq = qnormalize(ld_q(tgt));
+  F3 tp = ld_v(tgt + 4);
+  // e = log(T_wb^-1 T_wt)                                (frame_task.py:119-122)
+  se3_log<float>(qmul(qconj(qf), tq), qrot_inv(qf, tp - pf), ev, ew);
+  // jlog(T_wt^-1 T_wb) = ljacinv(-log(T_tb))            (frame_task.py:145-146, lie/base.py:151-156)
+  F3 v, w;
+  se3_log<float>(qmul(qconj(tq), qf), qrot_inv(tq, pf - tp), &v, &w);
+  FM Ji, Mi;
+  se3_ljacinv_blocks<float>(v3<float>(-v.x, -v.y, -v.z), v3<float>(-w.x, -w.y, -w.z), &Ji, &Mi);
+  FM Rt = mtrans(q2mat(qf));
+  *A1 = mmul(Ji, Rt);
+  *A2 = mmul(Mi, Rt);
+  for (int i = 0; i < 9; ++i) { A1->m[i] = -A1->m[i]; A2->m[i] = -A2->m[i]; }
+}
+
+// ---- primitive geom distance (plane / sphere / capsule) ------------------------------------
+BIK_HD void seg_closest(F3 p1, F3 d1, F3 p2, F3 d2, F3* a, F3* b) {
+  F3 r = p1 - p2;
+  float A = dot(d1, d1), E = dot(d2, d2), Bq = dot(d1, d2), C = dot(d1, r), F = dot(d2, r);
+  float den = A * E - Bq * Bq, s = 0.f, t = 0.f;
+  if (den > 1e-12f) s = fminf(fmaxf((Bq * F - C * E) / den, -1.f), 1.f);
+  if (E > 1e-12f) t = (Bq * s + F) / E;
+  if (t < -1.f || t > 1.f) {
+    t = t < -1.f ? -1.f : 1.f;
+    s = (A > 1e-12f) ? fminf(fmaxf((Bq * t - C) / A, -1.f), 1.f) : 0.f;
+  }
+  *a = p1 + s * d1; *b = p2 + t * d2;
+}
+BIK_HD float geom_distance(const GeomRec& g1, const GeomRec& g2, const float* xs, float distmax, F3* on1, F3* on2) {
+  const GeomRec* A = &g1; const GeomRec* Bg = &g2;
+  bool swap = false;
+  if (g2.type == 0) { A = &g2; Bg = &g1; swap = true; }
+  FQ qa, qb; F3 pa, pb;
+  frame_pose(A->node, A->lpos, A->lquat, xs, &qa, &pa);
+  frame_pose(Bg->node, Bg->lpos, Bg->lquat, xs, &qb, &pb);
+  F3 oa, ob; float dist;
+  F3 zb = qrot(qb, v3<float>(0.f, 0.f, 1.f));
+  if (A->type == 0) {  // plane vs sphere/capsule
+    F3 n = qrot(qa, v3<float>(0.f, 0.f, 1.f));
+    F3 end = pb;
+    if (Bg->type == 3) {
+      F3 e1 = pb + Bg->size[1] * zb, e2 = pb - Bg->size[1] * zb;
+      end = dot(e1 - pa, n) <= dot(e2 - pa, n) ? e1 : e2;
+    }
+    float hgt = dot(end - pa, n);
+    dist = hgt - Bg->size[0];
+    ob = end - Bg->size[0] * n; oa = end - hgt * n;
+  } else {
+    F3 d1 = v3<float>(0.f, 0.f, 0.f), d2 = d1, a, b;
+    if (A->type == 3) d1 = A->size[1] * qrot(qa, v3<float>(0.f, 0.f, 1.f));
+    if (Bg->type == 3) d2 = Bg->size[1] * zb;
+    seg_closest(pa, d1, pb, d2, &a, &b);
+    F3 v = b - a;
+    float L = sqrtf(dot(v, v));
+    F3 nr = L > 1e-15f ? (1.f / L) * v : v3<float>(1.f, 0.f, 0.f);
+    dist = L - A->size[0] - Bg->size[0];
+    oa = a + A->size[0] * nr; ob = b - Bg->size[0] * nr;
+  }
+  if (dist >= distmax) return distmax;
+  if (swap) { *on1 = ob; *on2 = oa; } else { *on1 = oa; *on2 = ob; }
+  return dist;
+}
+
+// ---- staging flush: IPW x (R*nv) floats -> global rows [inst][row0 .. row0+R) ----------------
+template <int W>
+BIK_HD void flush_rows(const float* stage, int chunk, int nvalid, float* out, long long inst_stride, int lane) {
+  for (int li = 0; li < nvalid; ++li) {
+    float* o = out + li * inst_stride;
+    const float* s = stage + li * chunk;
+    for (int k = lane; k < chunk; k += W) o[k] = s[k];
+  }
+}
+
+// One warp tile: instances [inst0, inst0 + IPW) clipped to B.
+template <int G, int W>
+BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, float* wsm, int lane) {
+  const PHeader& h = P.h();
+  constexpr int IPW = W / G;
+  const int nv = h.nv, nq = h.nq, K = h.K;
+  const int li = lane / G, g = lane % G;
+  const int b = inst0 + li;
+  const int nvalid = (a.B - inst0) < IPW ? (a.B - inst0) : IPW;
+  const bool valid = li < nvalid;
+  const int SS = k1_state_stride(h);
+  float* state = wsm;
+  float* stage = wsm + IPW * SS;
+  float* estage = stage + IPW * 6 * nv;
+  float* xs = state + li * SS;
+  const float* qb = a.q + (long long)(valid ? b : inst0) * nq;
+
+  // ---- forward kinematics over the lane program --------------------------------------------
+  const int32_t* prog = P.i(h.off_prog);
+  for (int s = 0; s < h.nsteps; ++s) {
+    int n = prog[s * G + g];
+    if (valid && n >= 0) fk_node(P, n, qb, xs);
+    BIK_SYNCWARP();
+  }
+
+  // ---- frame tasks -------------------------------------------------------------------------
+  const int32_t* cols = P.i(h.off_cols);
+  for (int f = 0; f < h.F; ++f) {
+    const FrameRec& fr = P.frame(f);
+    for (int k = lane; k < IPW * 6 * nv; k += W) stage[k] = 0.f;
+    BIK_SYNCWARP();
+    if (valid) {
+      FQ qf; F3 pf, ev, ew; FM A1, A2;
+      frame_pose(fr.node, fr.lpos, fr.lquat, xs, &qf, &pf);
+      frame_task(qf, pf, a.ftgt + ((long long)b * h.F + f) * 7, &ev, &ew, &A1, &A2);
+      if (g == 0) {
+        float* eo = estage + li * K + fr.row0;
+        eo[0] = ev.x; eo[1] = ev.y; eo[2] = ev.z; eo[3] = ew.x; eo[4] = ew.y; eo[5] = ew.z;
+      }
+      float* st = stage + li * 6 * nv;
+      for (int c = g; c < fr.ncols; c += G) {
+        int ent = cols[fr.col_off + c], d = ent & 0xffff, n = ent >> 16;
+        F3 jp, jr;
+        jac_column(P, d, n, xs, pf, &jp, &jr);
+        F3 top = mmul(A1, jp) + mmul(A2, jr), bot = mmul(A1, jr);
+        st[d] = top.x; st[nv + d] = top.y; st[2 * nv + d] = top.z;
+        st[3 * nv + d] = bot.x; st[4 * nv + d] = bot.y; st[5 * nv + d] = bot.z;
+      }
+    }
+    BIK_SYNCWARP();
+    flush_rows<W>(stage, 6 * nv, nvalid, a.J + ((long long)inst0 * K + fr.row0) * nv, (long long)K * nv, lane);
+    BIK_SYNCWARP();
+  }
+
+  // ---- centre-of-mass tasks (mj_comPos + mj_jacSubtreeCom for body 1) -------------------------
+  if (h.C > 0) {
+    float* S = xs + 7 * h.nnode;  // first moments per node
+    if (valid && g == 0) {
+      for (int n = 0; n < h.nnode; ++n) {
+        const ComNodeRec& cn = P.comnode(n);
+        F3 m = cn.own_m * ld_v(xs + 7 * n + 4) + qrot(ld_q(xs + 7 * n), ld_v(cn.own_c));
+        S[3 * n] = m.x; S[3 * n + 1] = m.y; S[3 * n + 2] = m.z;
+      }
+      for (int n = h.nnode - 1; n >= 0; --n) {
+        int p = P.node(n).parent;
+        if (p >= 0) { S[3 * p] += S[3 * n]; S[3 * p + 1] += S[3 * n + 1]; S[3 * p + 2] += S[3 * n + 2]; }
+      }
+    }
+    BIK_SYNCWARP();
+    const float invM = 1.f / h.com_total_mass;
+    for (int c = 0; c < h.C; ++c) {
+      const float* cr = P.f(h.off_com) + 8 * c;
+      const int row0 = reinterpret_cast<const int32_t*>(cr)[5];
+      for (int k = lane; k < IPW * 3 * nv; k += W) stage[k] = 0.f;
+      BIK_SYNCWARP();
+      if (valid) {
+        if (g == 0) {
+          F3 tot = ld_v(h.com_fixed);
+          for (int n = 0; n < h.nnode; ++n) if (P.node(n).parent < 0) tot = tot + ld_v(S + 3 * n);
+          const float* tg = a.ctgt + ((long long)b * h.C + c) * 3;
+          float* eo = estage + li * K + row0;  // e = com - target (com_task.py:82)
+          eo[0] = tot.x * invM - tg[0]; eo[1] = tot.y * invM - tg[1]; eo[2] = tot.z * invM - tg[2];
+        }
+        float* st = stage + li * 3 * nv;
+        for (int ci = g; ci < h.com_ncols; ci += G) {
+          int ent = cols[h.com_cols_off + ci], d = ent & 0xffff, n = ent >> 16;
+          const NodeRec& r = P.node(n);
+          float Ms = P.comnode(n).sub_m;
+          FQ nq_ = ld_q(xs + 7 * n); F3 np = ld_v(xs + 7 * n + 4), Sn = ld_v(S + 3 * n), col;
+          int k = d - r.dadr;
+          if (r.type == JNT_SLIDE) col = (Ms * invM) * qrot(nq_, ld_v(r.axis));
+          else if (r.type == JNT_FREE && k < 3) col = v3<float>(k == 0 ? Ms * invM : 0.f, k == 1 ? Ms * invM : 0.f, k == 2 ? Ms * invM : 0.f);
+          else {
+            F3 ax, anchor;
+            if (r.type == JNT_HINGE) { ax = qrot(nq_, ld_v(r.axis)); anchor = np + qrot(nq_, ld_v(r.jpos)); }
+            else {
+              int cc = (r.type == JNT_FREE) ? k - 3 : k;
+              ax = qrot(nq_, v3<float>(cc == 0 ? 1.f : 0.f, cc == 1 ? 1.f : 0.f, cc == 2 ? 1.f : 0.f));
+              anchor = (r.type == JNT_FREE) ? np : np + qrot(nq_, ld_v(r.jpos));
+            }
+            col = invM * cross(ax, Sn - Ms * anchor);
+          }
+          st[d] = col.x; st[nv + d] = col.y; st[2 * nv + d] = col.z;
+        }
+      }
+      BIK_SYNCWARP();
+      flush_rows<W>(stage, 3 * nv, nvalid, a.J + ((long long)inst0 * K + row0) * nv, (long long)K * nv, lane);
+      BIK_SYNCWARP();
+    }
+  }
+
+  // ---- task errors out (contiguous IPW x K run) ------------------------------------------------
+  if (K > 0)
+    for (int k = lane; k < nvalid * K; k += W) a.e[(long long)inst0 * K + k] = estage[k];
+
+  // ---- posture errors: e = q* (-) q, free-joint dofs zeroed (posture_task.py:107-118) ------------
+  if (h.P > 0) {
+    const int32_t* dofnode = P.i(h.off_dofnode);
+    const int32_t* dofqadr = P.i(h.off_dofqadr);
+    for (int k = lane; k < nvalid * h.P * nv; k += W) {
+      int l2 = k / (h.P * nv), rem = k - l2 * (h.P * nv), p = rem / nv, d = rem - p * nv;
+      const float* qq = a.q + (long long)(inst0 + l2) * nq;
+      const float* tg = a.ptgt + ((long long)(a.pbatched ? (inst0 + l2) : 0) * h.P + p) * nq;
+      float val = 0.f;
+      int qa = dofqadr[d];
+      if (qa >= 0) val = tg[qa] - qq[qa];
+      else {
+        const NodeRec& r = P.node(dofnode[d]);
+        if (r.type == JNT_BALL) {
+          F3 w = quat_sub<float>(qnormalize(ld_q(tg + r.qadr)), qnormalize(ld_q(qq + r.qadr)));
+          int c = d - r.dadr;
+          val = c == 0 ? w.x : (c == 1 ? w.y : w.z);
+        }
+      }
+      a.ep[(long long)inst0 * h.P * nv + k] = val;
+    }
+  }
+
+  // ---- collision rows (collision_avoidance_limit.py:187-210), 6 pairs per staging pass -----------
+  if (h.npairs > 0) {
+    const int32_t* pairs = P.i(h.off_pairs);
+    for (int p0 = 0; p0 < h.npairs; p0 += 6) {
+      int np_ = h.npairs - p0 < 6 ? h.npairs - p0 : 6;
+      for (int k = lane; k < IPW * np_ * nv; k += W) stage[k] = 0.f;
+      BIK_SYNCWARP();
+      if (valid) {
+        for (int pi = g; pi < np_; pi += G) {
+          const GeomRec& g1 = P.geom(pairs[2 * (p0 + pi)]);
+          const GeomRec& g2 = P.geom(pairs[2 * (p0 + pi) + 1]);
+          F3 o1, o2;
+          float dist = geom_distance(g1, g2, xs, h.coll_ddet, &o1, &o2);
+          float hval = BIK_INF_F;
+          if (dist != h.coll_ddet) {
+            hval = dist > h.coll_dmin ? h.coll_gain * (dist - h.coll_dmin) / a.dt + h.coll_relax : h.coll_relax;
+            F3 nr = o2 - o1;
+            float L = sqrtf(dot(nr, nr));
+            nr = L > 1e-15f ? (1.f / L) * nr : v3<float>(1.f, 0.f, 0.f);
+            float* st = stage + (li * np_ + pi) * nv;
+            for (int side = 0; side < 2; ++side) {  // row = -n.(Jp2 - Jp1)
+              const GeomRec& gg = side ? g2 : g1;
+              F3 pt = side ? o2 : o1;
+              float sgn = side ? -1.f : 1.f;
+              for (int n = gg.node; n >= 0; n = P.node(n).parent) {
+                const NodeRec& r = P.node(n);
+                int nd = r.type == JNT_FREE ? 6 : (r.type == JNT_BALL ? 3 : 1);
+                for (int k = 0; k < nd; ++k) {
+                  F3 jp, jr;
+                  jac_column(P, r.dadr + k, n, xs, pt, &jp, &jr);
+                  st[r.dadr + k] += sgn * dot(nr, jp);
+                }
+              }
+            }
+          }
+          a.hc[(long long)b * h.npairs + p0 + pi] = hval;
+        }
+      }
+      BIK_SYNCWARP();
+      flush_rows<W>(stage, np_ * nv, nvalid, a.Gc + ((long long)inst0 * h.npairs + p0) * nv, (long long)h.npairs * nv, lane);
+      BIK_SYNCWARP();
+    }
+  }
+}
+
+// ---- FK of arbitrary frames / body-frame Jacobians (Configuration API) -------------------------
+struct FkArgs {
+  int B, nframes;
+  const float* q;
+  float* poses;   // [B][nframes][7] or null
+  float* com;     // [B][3] or null
+  float* J;       // [B][nframes][6][nv] or null
+  FrameRec frames[16];
+};
+
+template <int G, int W>
+BIK_HD void fk_warp_tile(const PView& P, const FkArgs& a, int inst0, float* wsm, int lane) {
+  const PHeader& h = P.h();
+  constexpr int IPW = W / G;
+  const int li = lane / G, g = lane % G, b = inst0 + li, nv = h.nv;
+  const int nvalid = (a.B - inst0) < IPW ? (a.B - inst0) : IPW;
+  const bool valid = li < nvalid;
+  const int SS = 7 * h.nnode | 1;
+  float* xs = wsm + li * SS;
+  const float* qb = a.q + (long long)(valid ? b : inst0) * h.nq;
+  const int32_t* prog = P.i(h.off_prog);
+  for (int s = 0; s < h.nsteps; ++s) {
+    int n = prog[s * G + g];
+    if (valid && n >= 0) fk_node(P, n, qb, xs);
+    BIK_SYNCWARP();
+  }
+  if (!valid) return;
+  for (int f = g; f < a.nframes; f += G) {
+    const FrameRec& fr = a.frames[f];
+    FQ qf; F3 pf;
+    frame_pose(fr.node, fr.lpos, fr.lquat, xs, &qf, &pf);
+    FM R = q2mat(qf);
+    if (a.poses) {
+      FQ qs = mat2quat(R);  // sign convention of SO3.from_matrix (configuration.py:182)
+      float* o = a.poses + ((long long)b * a.nframes + f) * 7;
+      o[0] = qs.w; o[1] = qs.x; o[2] = qs.y; o[3] = qs.z; o[4] = pf.x; o[5] = pf.y; o[6] = pf.z;
+    }
+    if (a.J) {  // blockdiag(R^T, R^T) [jacp; jacr]  (configuration.py:143-153)
+      float* o = a.J + ((long long)b * a.nframes + f) * 6 * nv;
+      for (int k = 0; k < 6 * nv; ++k) o[k] = 0.f;
+      FM Rt = mtrans(R);
+      for (int n = fr.node; n >= 0; n = P.node(n).parent) {
+        const NodeRec& r = P.node(n);
+        int nd = r.type == JNT_FREE ? 6 : (r.type == JNT_BALL ? 3 : 1);
+        for (int k = 0; k < nd; ++k) {
+          F3 jp, jr;
+          int d = r.dadr + k;
+          jac_column(P, d, n, xs, pf, &jp, &jr);
+          F3 top = mmul(Rt, jp), bot = mmul(Rt, jr);
+          o[d] = top.x; o[nv + d] = top.y; o[2 * nv + d] = top.z; o[3 * nv + d] = bot.x; o[4 * nv + d] = bot.y; o[5 * nv + d] = bot.z;
+        }
+      }
+    }
+  }
+  if (a.com && g == 0) {
+    F3 tot = ld_v(h.com_fixed);
+    for (int n = 0; n < h.nnode; ++n) {
+      const ComNodeRec& cn = P.comnode(n);
+      tot = tot + cn.own_m * ld_v(xs + 7 * n + 4) + qrot(ld_q(xs + 7 * n), ld_v(cn.own_c));
+    }
+    float invM = h.com_total_mass > 0.f ? 1.f / h.com_total_mass : 0.f;
+    a.com[(long long)b * 3] = tot.x * invM; a.com[(long long)b * 3 + 1] = tot.y * invM; a.com[(long long)b * 3 + 2] = tot.z * invM;
+  }
+}
+
+// ---- integrate / check_limits / box limits: one thread per instance ----------------------------
+BIK_HD void integrate_instance(const PView& P, float* q, const float* dq) {  // mj_integratePos, dt folded into dq
+  const PHeader& h = P.h();
+  for (int n = 0; n < h.nnode; ++n) {
+    const NodeRec& r = P.node(n);
+    if (r.type == JNT_FREE) {
+      for (int k = 0; k < 3; ++k) q[r.qadr + k] += dq[r.dadr + k];
+      FQ o = quat_integrate<float>(ld_q(q + r.qadr + 3), ld_v(dq + r.dadr + 3));
+      q[r.qadr + 3] = o.w; q[r.qadr + 4] = o.x; q[r.qadr + 5] = o.y; q[r.qadr + 6] = o.z;
+    } else if (r.type == JNT_BALL) {
+      FQ o = quat_integrate<float>(ld_q(q + r.qadr), ld_v(dq + r.dadr));
+      q[r.qadr] = o.w; q[r.qadr + 1] = o.x; q[r.qadr + 2] = o.y; q[r.qadr + 3] = o.z;
+    } else {
+      q[r.qadr] += dq[r.dadr];
+    }
+  }
+}
+BIK_HD int check_limits_instance(const PView& P, const float* q, float tol) {  // configuration.py:77-110
+  const PHeader& h = P.h();
+  const int32_t* dofqadr = P.i(h.off_dofqadr);
+  const float* rng = P.f(h.off_range);
+  int bad = 0;
+  for (int d = 0; d < h.nv; ++d) {
+    int qa = dofqadr[d];
+    if (qa < 0) continue;
+    float v = q[qa];
+    if (v < rng[d] - tol || v > rng[h.nv + d] + tol) bad = 1;
+    if (!(v == v)) bad |= 4;
+  }
+  return bad;
+}
+// lo <= dq <= hi from ConfigurationLimit(s) and VelocityLimit (configuration_limit.py:98-124, velocity_limit.py:99-101)
+BIK_HD void box_dof(const PView& P, int d, const float* q, float dt, float* lo, float* hi) {
+  const PHeader& h = P.h();
+  float l = -BIK_INF_F, u = BIK_INF_F;
+  int qa = P.i(h.off_dofqadr)[d];
+  if (qa >= 0) {
+    float qi = q[qa];
+    for (int c = 0; c < h.ncfg; ++c) {
+      const float* p = P.f(h.off_cfg) + c * (2 + 2 * h.nv);
+      float up = p[0] * (p[2 + h.nv + d] - qi), dn = p[0] * (qi - p[2 + d]);
+      u = fminf(u, up); l = fmaxf(l, -dn);
+    }
+  }
+  if (h.has_vel) { float vm = dt * P.f(h.off_vmax)[d]; u = fminf(u, vm); l = fmaxf(l, -vm); }
+  *lo = l; *hi = u;
+}
+
+}  // namespace bik

@@ -1,0 +1,383 @@
+// bik_k2.h -- K2: per-instance QP assembly and exact solve, one warp per problem.
+//
+//   H = damping I + sum_t (W_t J_t)^T (W_t J_t) + mu_t I,   c = sum_t -(W_t(-gain_t e_t))^T W_t J_t
+//       (reference mink/tasks/task.py:105-138, mink/solve_ik.py:13-22)
+//   min 1/2 dq^T H dq + c^T dq   s.t.  lo <= dq <= hi  [+ general rows G dq <= h]
+//       (reference mink/solve_ik.py:43-65,101 -> qpsolvers)
+//
+// Structure exploited: frame-task Jacobians only have their ancestor-dof columns
+// non-zero, so each task adds a small dense block to H; the posture task is diagonal; configuration
+// and velocity limits share their index set and collapse to one box per dof.
+//
+// Solver: block principal pivoting (Kunisch-Rendl infeasible active set with the Judice-Pires
+// single-pivot safeguard) -- every iteration guesses the active set, solves the reduced system with
+// a fresh packed Cholesky of the free block and flips every violated index at once.  It terminates
+// at the exact KKT point of the strictly convex QP, i.e. the same optimum quadprog/daqp return.
+// General rows (collision) join the same pivoting through a Schur complement on the factor.
+//
+// Lanes own rows (row i -> lane i % W); reductions over lanes use shuffles.  W = 1 on the host.
+#pragma once
+#include "bik_k1.h"
+
+namespace bik {
+
+struct K2Args {
+  int B;
+  const float* q;    // [B][nq]
+  const float* J;    // [B][K][nv]
+  const float* e;    // [B][K]
+  const float* ep;   // [B][P][nv]
+  const float* Gc;   // [B][npairs][nv]
+  const float* hc;   // [B][npairs]
+  float dt;
+  double damping;
+  float* dq;         // [B][nv]
+  int32_t* status;   // [B] or null (OR-ed into)
+  int32_t* iters;    // [B] or null: active-set iterations (diagnostics)
+  double* Hout;      // [B][nv][nv] or null  (bik_qp_objective)
+  double* cout;      // [B][nv] or null
+  float* lo_out;     // [B][nv] or null      (bik_limits_box)
+  float* hi_out;
+};
+
+enum { K2_MAX_GEN = 16 };  // general (collision) rows that may be active at once
+
+BIK_HD int tri(int i) { return (i * (i + 1)) >> 1; }
+
+// per-warp scratch, in bytes, for scalar type of size `ts`
+BIK_HD int k2_warp_bytes(const PHeader& h, int ts) {
+  int n = h.nv, np = h.npairs;
+  int words_T = 2 * tri(n) + 6 * n + (np > 0 ? (K2_MAX_GEN * n + K2_MAX_GEN * K2_MAX_GEN + 3 * K2_MAX_GEN + np) : 0);
+  int bytes = words_T * ts + 4 * (2 * n + 3 * np + 12) + 4 * ((h.K > 0 ? h.K : 1) * (n + 1));
+  return (bytes + 15) & ~15;
+}
+
+template <typename T> BIK_HD T bik_sqrt(T x);
+template <> BIK_HD float bik_sqrt<float>(float x) { return sqrtf(x); }
+template <> BIK_HD double bik_sqrt<double>(double x) { return sqrt(x); }
+
+template <int W> BIK_HD int warp_sum_i(int v) {
+#if defined(__CUDA_ARCH__)
+  for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#endif
+  return v;
+}
+template <int W> BIK_HD int warp_max_i(int v) {
+#if defined(__CUDA_ARCH__)
+  for (int o = W / 2; o > 0; o >>= 1) { int t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+#endif
+  return v;
+}
+
+template <typename T> struct K2Ws {
+  T *Hp, *Lp, *c, *lo, *hi, *x, *y, *g;
+  T *Y, *S, *lam, *rg, *hg, *sg;  // general rows: Y = L^-1 G_F^T (K2_MAX_GEN x n), S Schur, lam, rhs, h, slack
+  int *st, *idx, *gst, *gidx, *gnew;
+  float *wJ, *we;
+};
+template <typename T> BIK_HD K2Ws<T> k2_carve(const PHeader& h, void* mem) {
+  K2Ws<T> w;
+  int n = h.nv, np = h.npairs;
+  T* p = reinterpret_cast<T*>(mem);
+  w.Hp = p; p += tri(n); w.Lp = p; p += tri(n);
+  w.c = p; p += n; w.lo = p; p += n; w.hi = p; p += n; w.x = p; p += n; w.y = p; p += n; w.g = p; p += n;
+  w.Y = w.S = w.lam = w.rg = w.hg = w.sg = nullptr;
+  if (np > 0) { w.Y = p; p += K2_MAX_GEN * n; w.S = p; p += K2_MAX_GEN * K2_MAX_GEN; w.lam = p; p += K2_MAX_GEN; w.rg = p; p += K2_MAX_GEN; w.sg = p; p += K2_MAX_GEN; w.hg = p; p += np; }
+  int* ip = reinterpret_cast<int*>(p);
+  w.st = ip; ip += n; w.idx = ip; ip += n; w.gst = ip; ip += np + 4; w.gidx = ip; ip += np + 4; w.gnew = ip; ip += np + 4;
+  float* fp = reinterpret_cast<float*>(ip);
+  w.wJ = fp; fp += (h.K > 0 ? h.K : 1) * n; w.we = fp;
+  return w;
+}
+
+template <typename T> BIK_HD T Hsym(const T* Hp, int i, int j) { return i >= j ? Hp[tri(i) + j] : Hp[tri(j) + i]; }
+
+// ---- assembly ------------------------------------------------------------------------------
+template <typename T, int W>
+BIK_HD void k2_assemble(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane) {
+  const PHeader& h = P.h();
+  const int n = h.nv, K = h.K;
+  const float* Jb = a.J + (long long)b * K * n;
+  const float* eb = a.e + (long long)b * K;
+  const int32_t* cols = P.i(h.off_cols);
+  for (int k = lane; k < tri(n); k += W) w.Hp[k] = T(0);
+  // weighted rows  W J  and  W(-gain e)
+  for (int f = 0; f < h.F; ++f) {
+    const FrameRec& fr = P.frame(f);
+    for (int k = lane; k < 6 * n; k += W) { int r = k / n; w.wJ[fr.row0 * n + k] = fr.cost[r] * Jb[fr.row0 * n + k]; }
+    for (int r = lane; r < 6; r += W) w.we[fr.row0 + r] = fr.cost[r] * (-fr.gain * eb[fr.row0 + r]);
+  }
+  for (int c = 0; c < h.C; ++c) {
+    const float* cr = P.f(h.off_com) + 8 * c;
+    int row0 = reinterpret_cast<const int32_t*>(cr)[5];
+    for (int k = lane; k < 3 * n; k += W) { int r = k / n; w.wJ[row0 * n + k] = cr[r] * Jb[row0 * n + k]; }
+    for (int r = lane; r < 3; r += W) w.we[row0 + r] = cr[r] * (-cr[3] * eb[row0 + r]);
+  }
+  BIK_SYNCWARP();
+  // block contributions (W J)^T (W J), lower triangle, only over each task's non-zero columns
+  for (int t = 0; t < h.F + h.C; ++t) {
+    int row0, nr, nc, coff;
+    if (t < h.F) { const FrameRec& fr = P.frame(t); row0 = fr.row0; nr = 6; nc = fr.ncols; coff = fr.col_off; }
+    else { const float* cr = P.f(h.off_com) + 8 * (t - h.F); row0 = reinterpret_cast<const int32_t*>(cr)[5]; nr = 3; nc = h.com_ncols; coff = h.com_cols_off; }
+    for (int p = lane; p < nc * nc; p += W) {
+      int ia = p / nc, ib = p - ia * nc;
+      if (ib > ia) continue;
+      int ca = cols[coff + ia] & 0xffff, cb = cols[coff + ib] & 0xffff;
+      T s = T(0);
+      for (int r = 0; r < nr; ++r) s += T(w.wJ[(row0 + r) * n + ca]) * T(w.wJ[(row0 + r) * n + cb]);
+      w.Hp[tri(ca) + cb] += s;
+    }
+    BIK_SYNCWARP();
+  }
+  // Levenberg-Marquardt terms mu_t = lm_t ||W(-gain e)||^2 (task.py:131) -- every lane, same order
+  T mu = T(a.damping);
+  for (int f = 0; f < h.F; ++f) {
+    const FrameRec& fr = P.frame(f);
+    if (fr.lm != 0.f) { T s = T(0); for (int r = 0; r < 6; ++r) s += T(w.we[fr.row0 + r]) * T(w.we[fr.row0 + r]); mu += T(fr.lm) * s; }
+  }
+  for (int c = 0; c < h.C; ++c) {
+    const float* cr = P.f(h.off_com) + 8 * c;
+    int row0 = reinterpret_cast<const int32_t*>(cr)[5];
+    if (cr[4] != 0.f) { T s = T(0); for (int r = 0; r < 3; ++r) s += T(w.we[row0 + r]) * T(w.we[row0 + r]); mu += T(cr[4]) * s; }
+  }
+  for (int p = 0; p < h.P; ++p) {
+    const float* pr = P.f(h.off_posture) + p * (2 + n);
+    if (pr[1] != 0.f) {
+      const float* epb = a.ep + ((long long)b * h.P + p) * n;
+      T s = T(0);
+      for (int d = 0; d < n; ++d) { T v = T(pr[2 + d]) * T(pr[0]) * T(epb[d]); s += v * v; }
+      mu += T(pr[1]) * s;
+    }
+  }
+  // linear term and diagonal
+  for (int d = lane; d < n; d += W) {
+    T cd = T(0);
+    for (int r = 0; r < K; ++r) cd -= T(w.we[r]) * T(w.wJ[r * n + d]);
+    T hd = mu;
+    for (int p = 0; p < h.P; ++p) {
+      const float* pr = P.f(h.off_posture) + p * (2 + n);
+      T wgt = T(pr[2 + d]);
+      hd += wgt * wgt;                                                        // (W J)^T (W J), J = -I
+      cd -= T(pr[0]) * wgt * wgt * T(a.ep[((long long)b * h.P + p) * n + d]);  // -(W(-g e))^T W (-I)
+    }
+    w.Hp[tri(d) + d] += hd;
+    w.c[d] = cd;
+    float lo, hi;
+    box_dof(P, d, a.q + (long long)b * h.nq, a.dt, &lo, &hi);
+    w.lo[d] = T(lo); w.hi[d] = T(hi);
+  }
+  BIK_SYNCWARP();
+}
+
+// ---- packed Cholesky of the free block + solves ------------------------------------------------
+// Lp holds, on entry, the lower triangle of the nf x nf matrix to factor (compact indices).
+template <typename T, int W>
+BIK_HD int k2_cholesky(T* Lp, int nf, int lane) {
+  constexpr int SLOTS = (64 + W - 1) / W;
+  int bad = 0;
+  for (int j = 0; j < nf; ++j) {
+    T tmp[SLOTS];
+    const T* Lj = Lp + tri(j);
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      int i = lane + s * W;
+      tmp[s] = T(0);
+      if (i >= j && i < nf) {
+        T* Li = Lp + tri(i);
+        T v = Li[j];
+        for (int k = 0; k < j; ++k) v -= Li[k] * Lj[k];
+        tmp[s] = v;
+        if (i == j) { if (!(v > T(0))) { bad = 1; v = T(1e-30); } Li[j] = bik_sqrt<T>(v); }
+      }
+    }
+    BIK_SYNCWARP();
+    T inv = T(1) / Lj[j];
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      int i = lane + s * W;
+      if (i > j && i < nf) Lp[tri(i) + j] = tmp[s] * inv;
+    }
+    BIK_SYNCWARP();
+  }
+  return bad;
+}
+// y <- L^-1 y
+template <typename T, int W>
+BIK_HD void k2_forward(const T* Lp, T* y, int nf, int lane) {
+  constexpr int SLOTS = (64 + W - 1) / W;
+  for (int k = 0; k < nf; ++k) {
+    if (k % W == lane) y[k] = y[k] / Lp[tri(k) + k];
+    BIK_SYNCWARP();
+    T yk = y[k];
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) { int i = lane + s * W; if (i > k && i < nf) y[i] -= Lp[tri(i) + k] * yk; }
+  }
+  BIK_SYNCWARP();
+}
+// y <- L^-T y
+template <typename T, int W>
+BIK_HD void k2_backward(const T* Lp, T* y, int nf, int lane) {
+  constexpr int SLOTS = (64 + W - 1) / W;
+  for (int k = nf - 1; k >= 0; --k) {
+    if (k % W == lane) y[k] = y[k] / Lp[tri(k) + k];
+    BIK_SYNCWARP();
+    T xk = y[k];
+    const T* Lk = Lp + tri(k);
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) { int i = lane + s * W; if (i < k) y[i] -= Lk[i] * xk; }
+  }
+  BIK_SYNCWARP();
+}
+
+template <typename T> struct K2Tol;
+template <> struct K2Tol<double> { static BIK_HD double x() { return 1e-12; } static BIK_HD double g() { return 1e-9; } };
+template <> struct K2Tol<float> { static BIK_HD float x() { return 1e-7f; } static BIK_HD float g() { return 1e-4f; } };
+
+// Returns status bits.  On exit w.x holds dq.
+template <typename T, int W>
+BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane, int* iters_out) {
+  const PHeader& h = P.h();
+  const int n = h.nv, np = h.npairs;
+  const int MAXIT = 60, PATIENCE = 3;
+  const T tolx = K2Tol<T>::x(), tolg = K2Tol<T>::g();
+  const float* Gb = np > 0 ? a.Gc + (long long)b * np * n : nullptr;
+  for (int i = lane; i < n; i += W) w.st[i] = 0;
+  for (int r = lane; r < np; r += W) { w.gst[r] = 0; w.hg[r] = T(a.hc[(long long)b * np + r]); }
+  BIK_SYNCWARP();
+  int status = 0, best = n + np + 1, patience = PATIENCE, it = 0;
+  for (; it < MAXIT; ++it) {
+    // compact free list / active general rows (every lane writes the same values)
+    int nf = 0, ng = 0;
+    for (int i = 0; i < n; ++i) if (w.st[i] == 0) { w.idx[nf] = i; ++nf; }
+    for (int r = 0; r < np; ++r) if (w.gst[r]) { if (ng < K2_MAX_GEN) { w.gidx[ng] = r; ++ng; } }
+    BIK_SYNCWARP();
+    // x on the bounds, rhs of the reduced system, copy of H_FF
+    for (int i = lane; i < n; i += W) w.x[i] = w.st[i] == 1 ? w.lo[i] : (w.st[i] == 2 ? w.hi[i] : T(0));
+    BIK_SYNCWARP();
+    for (int i = lane; i < nf; i += W) {
+      int ii = w.idx[i];
+      T r = -w.c[ii];
+      for (int j = 0; j < n; ++j) if (w.st[j]) r -= Hsym(w.Hp, ii, j) * w.x[j];
+      w.y[i] = r;
+      T* Li = w.Lp + tri(i);
+      for (int j = 0; j <= i; ++j) Li[j] = Hsym(w.Hp, ii, w.idx[j]);
+    }
+    BIK_SYNCWARP();
+    if (k2_cholesky<T, W>(w.Lp, nf, lane)) status |= 4;
+    status = warp_max_i<W>(status);
+    if (ng == 0) {
+      k2_forward<T, W>(w.Lp, w.y, nf, lane);
+      k2_backward<T, W>(w.Lp, w.y, nf, lane);
+    } else {
+      // KKT with active general rows R:  [H_FF G_RF^T; G_RF 0][x_F; lam] = [y; h_R - G_RA x_A]
+      // Y_r = L^-1 G_rF^T,  S = Y Y^T,  lam = S^-1 (Y (L^-1 y) - rhs),  x_F = L^-T (L^-1 y - Y^T lam)
+      for (int r = 0; r < ng; ++r) {
+        const float* Gr = Gb + (long long)w.gidx[r] * n;
+        T* Yr = w.Y + r * n;
+        for (int i = lane; i < nf; i += W) Yr[i] = T(Gr[w.idx[i]]);
+        if (lane == 0) { T s = w.hg[w.gidx[r]]; for (int j = 0; j < n; ++j) if (w.st[j]) s -= T(Gr[j]) * w.x[j]; w.rg[r] = s; }
+        BIK_SYNCWARP();
+        k2_forward<T, W>(w.Lp, Yr, nf, lane);
+      }
+      k2_forward<T, W>(w.Lp, w.y, nf, lane);
+      if (lane == 0) {  // tiny dense solve, serial
+        for (int r = 0; r < ng; ++r) {
+          for (int s = 0; s <= r; ++s) { T v = T(0); for (int i = 0; i < nf; ++i) v += w.Y[r * n + i] * w.Y[s * n + i]; w.S[r * K2_MAX_GEN + s] = v; w.S[s * K2_MAX_GEN + r] = v; }
+          T v = -w.rg[r]; for (int i = 0; i < nf; ++i) v += w.Y[r * n + i] * w.y[i]; w.lam[r] = v;
+        }
+        for (int j = 0; j < ng; ++j) {  // Cholesky of S in place + solve
+          T d = w.S[j * K2_MAX_GEN + j]; for (int k = 0; k < j; ++k) d -= w.S[j * K2_MAX_GEN + k] * w.S[j * K2_MAX_GEN + k];
+          d = bik_sqrt<T>(d > T(0) ? d : T(1e-30)); w.S[j * K2_MAX_GEN + j] = d;
+          for (int i = j + 1; i < ng; ++i) { T v = w.S[i * K2_MAX_GEN + j]; for (int k = 0; k < j; ++k) v -= w.S[i * K2_MAX_GEN + k] * w.S[j * K2_MAX_GEN + k]; w.S[i * K2_MAX_GEN + j] = v / d; }
+        }
+        for (int i = 0; i < ng; ++i) { T v = w.lam[i]; for (int k = 0; k < i; ++k) v -= w.S[i * K2_MAX_GEN + k] * w.lam[k]; w.lam[i] = v / w.S[i * K2_MAX_GEN + i]; }
+        for (int i = ng - 1; i >= 0; --i) { T v = w.lam[i]; for (int k = i + 1; k < ng; ++k) v -= w.S[k * K2_MAX_GEN + i] * w.lam[k]; w.lam[i] = v / w.S[i * K2_MAX_GEN + i]; }
+      }
+      BIK_SYNCWARP();
+      for (int i = lane; i < nf; i += W) { T v = w.y[i]; for (int r = 0; r < ng; ++r) v -= w.Y[r * n + i] * w.lam[r]; w.y[i] = v; }
+      BIK_SYNCWARP();
+      k2_backward<T, W>(w.Lp, w.y, nf, lane);
+    }
+    for (int i = lane; i < nf; i += W) w.x[w.idx[i]] = w.y[i];
+    BIK_SYNCWARP();
+    // gradient on the active bounds, feasibility of free variables and of general rows.
+    // Proposed new states go to w.idx (free after the scatter above) and w.gnew.
+    int ninf = 0, last = -1;
+    for (int i = lane; i < n; i += W) {
+      int cur = w.st[i], ns = cur;
+      if (cur == 0) {
+        T xi = w.x[i];
+        if (xi < w.lo[i] - tolx * (T(1) + (w.lo[i] < 0 ? -w.lo[i] : w.lo[i]))) ns = 1;
+        else if (xi > w.hi[i] + tolx * (T(1) + (w.hi[i] < 0 ? -w.hi[i] : w.hi[i]))) ns = 2;
+      } else {
+        T gi = w.c[i];
+        for (int j = 0; j < n; ++j) gi += Hsym(w.Hp, i, j) * w.x[j];
+        for (int r = 0; r < ng; ++r) gi += T(Gb[(long long)w.gidx[r] * n + i]) * w.lam[r];
+        if (cur == 1 && gi < -tolg) ns = 0;
+        else if (cur == 2 && gi > tolg) ns = 0;
+      }
+      w.idx[i] = ns;
+      if (ns != cur) { ++ninf; last = i > last ? i : last; }
+    }
+    for (int r = lane; r < np; r += W) {
+      int cur = w.gst[r], ns = cur;
+      T hr = w.hg[r];
+      if (!(hr < T(1e30))) ns = 0;  // inactive row: h = +inf (collision_avoidance_limit.py:192-199)
+      else if (cur == 0) {
+        T sv = -hr;
+        for (int j = 0; j < n; ++j) sv += T(Gb[(long long)r * n + j]) * w.x[j];
+        if (sv > tolx * (T(1) + (hr < 0 ? -hr : hr))) ns = 1;
+      } else {
+        int k = 0;
+        while (k < ng && w.gidx[k] != r) ++k;
+        if (k < ng && w.lam[k] < -tolg) ns = 0;
+      }
+      w.gnew[r] = ns;
+      if (ns != cur) { ++ninf; last = n + r > last ? n + r : last; }
+    }
+    ninf = warp_sum_i<W>(ninf);
+    last = warp_max_i<W>(last);
+    if (ninf == 0) break;
+    bool block;
+    if (ninf < best) { best = ninf; patience = PATIENCE; block = true; }
+    else if (patience > 0) { --patience; block = true; }
+    else block = false;
+    BIK_SYNCWARP();
+    for (int i = lane; i < n; i += W) if (block || i == last) w.st[i] = w.idx[i];
+    for (int r = lane; r < np; r += W) if (block || n + r == last) w.gst[r] = w.gnew[r];
+    BIK_SYNCWARP();
+  }
+  if (it >= MAXIT) status |= 2;
+  if (iters_out) *iters_out = it + 1;
+  return status;
+}
+
+// One instance per warp: assemble, optionally dump (H, c) / (lo, hi), solve, write dq.
+template <typename T, int W>
+BIK_HD void k2_warp(const PView& P, const K2Args& a, int b, void* wsm, int lane) {
+  const PHeader& h = P.h();
+  const int n = h.nv;
+  K2Ws<T> w = k2_carve<T>(h, wsm);
+  k2_assemble<T, W>(P, a, b, w, lane);
+  if (a.Hout) {
+    for (int k = lane; k < n * n; k += W) { int i = k / n, j = k - i * n; a.Hout[(long long)b * n * n + k] = double(Hsym(w.Hp, i, j)); }
+    for (int d = lane; d < n; d += W) a.cout[(long long)b * n + d] = double(w.c[d]);
+  }
+  if (a.lo_out)
+    for (int d = lane; d < n; d += W) { a.lo_out[(long long)b * n + d] = float(w.lo[d]); a.hi_out[(long long)b * n + d] = float(w.hi[d]); }
+  if (!a.dq) return;
+  int iters = 0;
+  int st = k2_solve<T, W>(P, a, b, w, lane, &iters);
+  for (int d = lane; d < n; d += W) {
+    T v = w.x[d];
+    if (!(v == v)) st |= 4;
+    a.dq[(long long)b * n + d] = float(v);
+  }
+  st = warp_max_i<W>(st & 2) | warp_max_i<W>(st & 4) | warp_max_i<W>(st & 8);
+  if (lane == 0) {
+    if (a.status) a.status[b] |= st;
+    if (a.iters) a.iters[b] = iters;
+  }
+}
+
+}  // namespace bik

@@ -1,0 +1,66 @@
+// bik_layout.h -- the compiled problem image ("pimage") shared by host builder and device kernels.
+//
+// bik_problem_create lowers (model blob, task descs, limit descs) into ONE contiguous array of
+// 32-bit words: a header of word offsets followed by fp32/int32 tables.  Every CTA stages the image
+// into shared memory once (single bulk copy, cp.async.bulk + mbarrier) and then works out of
+// shared memory only; a few KB for the BASELINE robots (G1: ~5 KB).
+#pragma once
+#include <stdint.h>
+
+namespace bik {
+
+enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
+enum { MAX_CFG_LIMITS = 2 };
+
+// words per record
+enum { NODE_WORDS = 20, FRAME_WORDS = 20, COMNODE_WORDS = 8, GEOM_WORDS = 16 };
+
+struct NodeRec {  // 20 words, 16-byte aligned
+  int32_t parent, type, qadr, dadr;
+  float pos[3];
+  float quat[4];
+  float axis[3];
+  float jpos[3];
+  float pad[3];
+};
+struct FrameRec {  // 20 words
+  int32_t node;
+  float lpos[3];
+  float lquat[4];
+  float cost[6];
+  float gain, lm;
+  int32_t ncols, col_off, row0, pad;
+};
+struct ComNodeRec {  // 8 words: own mass of the node's weld group, its first moment in the node frame, subtree mass
+  float own_m, own_c[3], sub_m, pad[3];
+};
+struct GeomRec {  // 16 words
+  int32_t type, node;
+  float lpos[3], lquat[4], size[3];
+  float pad[4];
+};
+
+struct PHeader {  // all offsets in 32-bit words from the start of the image
+  int32_t words;       // total image size in words (multiple of 4)
+  int32_t nq, nv, nnode;
+  int32_t F, P, C, K;  // frame / posture / com task counts, stacked rows K = 6F + 3C
+  int32_t npairs, ngeoms, ncfg, has_vel;
+  int32_t G, nsteps;   // lane program: nsteps x G node ids (-1 idle)
+  int32_t off_nodes, off_qpos0, off_prog, off_frames, off_cols;
+  int32_t off_posture;  // P x { gain, lm, cost_eff[nv] }  (stride 2 + nv)
+  int32_t off_com;      // C x { cost[3], gain, lm, row0, pad, pad } (8 words each)
+  int32_t off_comnodes; // ComNodeRec[nnode]
+  int32_t com_cols_off, com_ncols;  // dofs with non-zero CoM column
+  int32_t off_cfg;      // ncfg x { gain, pad, lower[nv], upper[nv] } (stride 2 + 2 nv); +-inf where not listed
+  int32_t off_vmax;     // float[nv], +inf where not listed
+  int32_t off_dofnode;  // int[nv]
+  int32_t off_dofqadr;  // int[nv], -1 for free/ball dofs
+  int32_t off_range;    // float[2 nv] joint range lo|hi for check_limits (+-inf if unlimited)
+  int32_t off_geoms, off_pairs;  // GeomRec[ngeoms], int2[npairs]
+  float coll_gain, coll_dmin, coll_ddet, coll_relax;
+  float com_total_mass, com_fixed[3];  // total mass of subtree(body 1); first moment of its world-fixed part
+  int32_t reserved[9];
+};
+static_assert(sizeof(PHeader) % 16 == 0, "header must stay 16-byte aligned");
+
+}  // namespace bik

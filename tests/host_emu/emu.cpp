@@ -1,0 +1,87 @@
+// TEST INFRASTRUCTURE -- compiles the kernel headers (mink_b200/csrc/bik_k1.h, bik_k2.h) for the host
+// with one lane per instance (G = W = 1) so the device math can be checked against the oracle on a
+// machine without a GPU.  Never shipped, never loaded by mink_b200/: the product path is CUDA only.
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../mink_b200/csrc/bik_build.h"
+#include "../../mink_b200/csrc/bik_k2.h"
+
+using namespace bik;
+
+static std::string g_err;
+extern "C" const char* emu_last_error() { return g_err.c_str(); }
+
+struct EmuProblem {
+  std::vector<uint32_t> image;
+};
+
+extern "C" void* emu_problem_create(const void* blob, size_t nbytes, const bik_task_desc* tasks, int ntasks, const bik_limit_desc* limits, int nlimits) {
+  HostModel m;
+  if (!parse_model_blob(blob, nbytes, &m, &g_err)) return nullptr;
+  EmuProblem* p = new EmuProblem;
+  if (!build_image(m, tasks, ntasks, limits, nlimits, 1, &p->image, &g_err)) { delete p; return nullptr; }
+  return p;
+}
+extern "C" void emu_problem_destroy(void* p) { delete static_cast<EmuProblem*>(p); }
+
+extern "C" int emu_lane_program(const void* blob, size_t nbytes, int G, int32_t* out, int cap) {
+  HostModel m;
+  if (!parse_model_blob(blob, nbytes, &m, &g_err)) return -1;
+  std::vector<int32_t> prog; int nsteps;
+  lane_program(m, G, &prog, &nsteps);
+  if ((int)prog.size() > cap) return -2;
+  memcpy(out, prog.data(), prog.size() * 4);
+  return nsteps;
+}
+
+extern "C" int emu_fk_jac(void* prob, int B, const float* q, const float* ftgt, const float* ptgt, int pbatched, const float* ctgt, float dt,
+                          float* J, float* e, float* ep, float* Gc, float* hc) {
+  EmuProblem* p = static_cast<EmuProblem*>(prob);
+  PView P{p->image.data()};
+  K1Args a{B, q, ftgt, ptgt, ctgt, pbatched, dt, J, e, ep, Gc, hc};
+  std::vector<float> wsm(k1_warp_words(P.h(), 1) + 16);
+  for (int b = 0; b < B; ++b) k1_warp_tile<1, 1>(P, a, b, wsm.data(), 0);
+  return 0;
+}
+
+extern "C" int emu_solve(void* prob, int B, const float* q, const float* J, const float* e, const float* ep, const float* Gc, const float* hc,
+                         float dt, double damping, int use_double, float* dq, int32_t* status, int32_t* iters, double* H, double* c, float* lo, float* hi) {
+  EmuProblem* p = static_cast<EmuProblem*>(prob);
+  PView P{p->image.data()};
+  K2Args a{B, q, J, e, ep, Gc, hc, dt, damping, dq, status, iters, H, c, lo, hi};
+  std::vector<double> wsm(k2_warp_bytes(P.h(), 8) / 8 + 16);
+  for (int b = 0; b < B; ++b) {
+    if (status) status[b] = 0;
+    if (use_double) k2_warp<double, 1>(P, a, b, wsm.data(), 0); else k2_warp<float, 1>(P, a, b, wsm.data(), 0);
+  }
+  return 0;
+}
+
+extern "C" int emu_fk(void* prob, int B, const float* q, const bik_frame* frames, int nframes, float* poses, float* com, float* J) {
+  EmuProblem* p = static_cast<EmuProblem*>(prob);
+  PView P{p->image.data()};
+  if (nframes > 16) return -1;
+  FkArgs a; memset(&a, 0, sizeof a);
+  a.B = B; a.nframes = nframes; a.q = q; a.poses = poses; a.com = com; a.J = J;
+  for (int f = 0; f < nframes; ++f) put_frame(frames[f], &a.frames[f].node, a.frames[f].lpos, a.frames[f].lquat);
+  std::vector<float> wsm(7 * P.h().nnode + 16);
+  for (int b = 0; b < B; ++b) fk_warp_tile<1, 1>(P, a, b, wsm.data(), 0);
+  return 0;
+}
+
+extern "C" int emu_integrate(void* prob, int B, float* q, const float* dq) {
+  EmuProblem* p = static_cast<EmuProblem*>(prob);
+  PView P{p->image.data()};
+  for (int b = 0; b < B; ++b) integrate_instance(P, q + (size_t)b * P.h().nq, dq + (size_t)b * P.h().nv);
+  return 0;
+}
+extern "C" int emu_check_limits(void* prob, int B, const float* q, float tol, int32_t* status) {
+  EmuProblem* p = static_cast<EmuProblem*>(prob);
+  PView P{p->image.data()};
+  for (int b = 0; b < B; ++b) status[b] = check_limits_instance(P, q + (size_t)b * P.h().nq, tol);
+  return 0;
+}

@@ -1,0 +1,106 @@
+"""Kernel math (mink_b200/csrc headers compiled for the host, one lane) vs the golden vectors.
+
+fp32 device arithmetic against the fp64 reference: tolerances are the fp64->fp32 budget stated in
+BASELINE.json (dq within 1e-4 rad) and tighter where the quantity allows it.  The GPU tests repeat
+these checks through the real kernels; this file lets the math be debugged without a GPU.
+"""
+
+import numpy as np
+import pytest
+
+from tests.emu_lib import Emu
+from tests.helpers import load_case, quat_align, task_frames
+
+CASES = ["ur5e", "ur5e_dls", "g1", "shadow", "spot"]
+
+
+def _emu(name):
+    wl, fm, spec, g = load_case(name)
+    return wl, fm, spec, g, Emu(fm.to_blob(), spec, fm.nq, fm.nv)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_fk_and_body_jacobian(name):
+    wl, fm, spec, g, emu = _emu(name)
+    frames = task_frames(wl, fm)
+    poses, com, Jb = emu.fk(g["q"], frames, want_J=True)
+    ref = g["frame_pose"]
+    np.testing.assert_allclose(poses[..., 4:], ref[..., 4:], atol=5e-6)
+    np.testing.assert_allclose(quat_align(poses[..., :4].astype(np.float64), ref[..., :4]), ref[..., :4], atol=5e-6)
+    np.testing.assert_allclose(Jb, g["J_body"], atol=1e-5)
+    if fm.ncom:
+        np.testing.assert_allclose(com, g["com"], atol=5e-6)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_k1_errors_and_jacobians(name):
+    wl, fm, spec, g, emu = _emu(name)
+    J, e, ep, Gc, hc = emu.fk_jac(g["q"], g["frame_targets"], g["posture_target"], g.get("com_target"), dt=float(g["dt"]))
+    F = spec.nframe
+    np.testing.assert_allclose(e[:, :6 * F].reshape(-1, F, 6), g["e_frame"], atol=2e-5)
+    np.testing.assert_allclose(J[:, :6 * F].reshape(-1, F, 6, fm.nv), g["J_frame"], atol=5e-5)
+    if spec.nposture:
+        np.testing.assert_allclose(ep[:, 0], g["e_posture"], atol=1e-6)
+    if spec.ncom:
+        np.testing.assert_allclose(e[:, 6 * F:], g["e_com"], atol=5e-6)
+        np.testing.assert_allclose(J[:, 6 * F:], g["J_com"], atol=5e-6)
+    if spec.npairs:
+        fin = np.isfinite(g["h"])
+        assert np.array_equal(np.isfinite(hc), fin)
+        np.testing.assert_allclose(hc[fin], g["h"][fin], rtol=2e-4, atol=2e-3)
+        np.testing.assert_allclose(Gc, g["G"], atol=2e-5)
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("use_double", [True, False])
+def test_k2_from_golden_jacobians(name, use_double):
+    """K2 alone: feed the reference's own (J, e) cast to fp32, compare H, c, box and dq."""
+    wl, fm, spec, g, emu = _emu(name)
+    B, F = g["q"].shape[0], spec.nframe
+    J = np.concatenate([g["J_frame"].reshape(B, 6 * F, fm.nv)] + ([g["J_com"]] if spec.ncom else []), axis=1)
+    e = np.concatenate([g["e_frame"].reshape(B, 6 * F)] + ([g["e_com"]] if spec.ncom else []), axis=1)
+    ep = g["e_posture"][:, None, :] if spec.nposture else np.zeros((B, 0, fm.nv))
+    if spec.npairs:
+        Gc, hc = g["G"], g["h"]
+    else:
+        Gc, hc = np.zeros((B, 0, fm.nv)), np.zeros((B, 0))
+    dq, st, it, H, c, lo, hi = emu.solve(g["q"], J, e, ep, Gc, hc, float(g["dt"]), float(g["damping"]),
+                                         use_double=use_double, want_objective=True)
+    assert not st.any(), st
+    scale = np.abs(g["H"]).max()
+    np.testing.assert_allclose(H, g["H"], atol=(1e-6 if use_double else 1e-5) * scale)
+    np.testing.assert_allclose(c, g["c"], atol=1e-5 * max(1.0, np.abs(g["c"]).max()))
+    fin = np.isfinite(g["box_lo"])
+    np.testing.assert_allclose(lo[fin], g["box_lo"][fin], atol=1e-6)
+    fin = np.isfinite(g["box_hi"])
+    np.testing.assert_allclose(hi[fin], g["box_hi"][fin], atol=1e-6)
+    if name == "spot":
+        tol = 2e-3 if use_double else 5e-2   # cond(H) ~ 4e7: fp32 inputs alone move the optimum
+    else:
+        tol = 1e-5 if use_double else 1e-4
+    np.testing.assert_allclose(dq, g["dq"], atol=tol)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_full_step(name):
+    """K1 -> K2 -> integrate in fp32 I/O against the reference's solve_ik + integrate."""
+    wl, fm, spec, g, emu = _emu(name)
+    dt, damping = float(g["dt"]), float(g["damping"])
+    J, e, ep, Gc, hc = emu.fk_jac(g["q"], g["frame_targets"], g["posture_target"], g.get("com_target"), dt=dt)
+    dq, st, it, *_ = emu.solve(g["q"], J, e, ep, Gc, hc, dt, damping, use_double=True)
+    assert not st.any()
+    tol = 1e-4 if name != "spot" else 5e-3
+    err = np.abs(dq - g["dq"]).max()
+    print(name, "max |dq - dq_ref| =", err, "iters mean/max", it.mean(), it.max())
+    assert err < tol
+    qn = emu.integrate(g["q"], dq)
+    np.testing.assert_allclose(qn, g["q_next"], atol=2 * tol)
+
+
+def test_check_limits():
+    wl, fm, spec, g, emu = _emu("g1")
+    q = g["q"].copy()
+    assert not emu.check_limits(q).any()
+    q[3, 10] = 100.0
+    st = emu.check_limits(q)
+    assert st[3] == 1 and st.sum() == 1
