@@ -1,0 +1,514 @@
+// bik.cu -- sm_100a kernels and the C ABI of libbik (include/bik.h).
+//
+// Kernels (all persistent: grid = SMs x resident CTAs, CTAs loop over tiles):
+//   k1_kernel<G>    FK + task errors/Jacobians + collision rows; G lanes per instance, problem image
+//                   staged into shared memory by one bulk async copy (cp.async.bulk + mbarrier),
+//                   Jacobian rows staged per warp and flushed as contiguous runs.
+//   k2_kernel<T>    QP assembly + active-set solve, one warp per instance, packed H and Cholesky
+//                   factor in shared memory (T = double | float).
+//   fk_kernel<G>    frame poses / CoM / body-frame Jacobians for the Configuration API.
+//   integrate_kernel, check_limits_kernel: one thread per instance.
+//
+// There is no CPU fallback in this library: without a CUDA device every entry point fails.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "bik_build.h"
+#include "bik_k2.h"
+
+using namespace bik;
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk async copy (TMA engine; SASS: UBLKCP / SYNCS)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(phase)
+      : "memory");
+  return ok != 0;
+}
+
+// Stage the problem image into shared memory: one elected thread issues a single bulk copy and
+// everybody waits on the mbarrier (bounded spin; traps instead of hanging the GPU).
+__device__ __forceinline__ void stage_image(uint32_t* smem_image, const uint32_t* gimage, int words, uint64_t* bar, int use_tma) {
+  if (use_tma) {
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, (uint32_t)words * 4u);
+      bulk_g2s(smem_image, gimage, (uint32_t)words * 4u, bar);
+    }
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, 0)) {
+      if (++spins > (1u << 24)) __trap();
+    }
+  } else {
+    const uint4* src = reinterpret_cast<const uint4*>(gimage);
+    uint4* dst = reinterpret_cast<uint4*>(smem_image);
+    for (int k = threadIdx.x; k < words / 4; k += blockDim.x) dst[k] = src[k];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(128) k1_kernel(const uint32_t* __restrict__ gimage, int words, int use_tma, K1Args a) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  stage_image(smem, gimage, words, &bar, use_tma);
+  PView P{smem};
+  constexpr int IPW = 32 / G;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float* wsm = reinterpret_cast<float*>(smem + words) + warp * k1_warp_words(P.h(), IPW);
+  const int ntiles = (a.B + IPW - 1) / IPW;
+  for (int tile = blockIdx.x * nwarps + warp; tile < ntiles; tile += gridDim.x * nwarps) k1_warp_tile<G, 32>(P, a, tile * IPW, wsm, lane);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) k2_kernel(const uint32_t* __restrict__ gimage, int words, int use_tma, K2Args a) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  stage_image(smem, gimage, words, &bar, use_tma);
+  PView P{smem};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  char* wsm = reinterpret_cast<char*>(smem + words) + (size_t)warp * k2_warp_bytes(P.h(), sizeof(T));
+  for (int b = blockIdx.x * nwarps + warp; b < a.B; b += gridDim.x * nwarps) k2_warp<T, 32>(P, a, b, wsm, lane);
+}
+
+template <int G>
+__global__ void __launch_bounds__(128) fk_kernel(const uint32_t* __restrict__ gimage, int words, int use_tma, FkArgs a) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  stage_image(smem, gimage, words, &bar, use_tma);
+  PView P{smem};
+  constexpr int IPW = 32 / G;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int wwords = (IPW * ((7 * P.h().nnode) | 1) + 3) & ~3;
+  float* wsm = reinterpret_cast<float*>(smem + words) + warp * wwords;
+  const int ntiles = (a.B + IPW - 1) / IPW;
+  for (int tile = blockIdx.x * nwarps + warp; tile < ntiles; tile += gridDim.x * nwarps) fk_warp_tile<G, 32>(P, a, tile * IPW, wsm, lane);
+}
+
+__global__ void integrate_kernel(const uint32_t* __restrict__ gimage, int B, float* q, const float* dq) {
+  PView P{gimage};
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) integrate_instance(P, q + (size_t)b * P.h().nq, dq + (size_t)b * P.h().nv);
+}
+__global__ void check_limits_kernel(const uint32_t* __restrict__ gimage, int B, const float* q, float tol, int32_t* status, int accumulate) {
+  PView P{gimage};
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) {
+    int s = check_limits_instance(P, q + (size_t)b * P.h().nq, tol);
+    status[b] = accumulate ? (status[b] | s) : s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_OK(expr)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess) return fail(BIK_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
+
+struct bik_model {
+  int device = 0, nsm = 0, max_smem = 0;
+  int G = 4, use_tma = 1;
+  HostModel hm;
+  std::vector<uint32_t> image;  // model-only image (no tasks)
+  uint32_t* d_image = nullptr;
+};
+
+struct bik_problem {
+  const bik_model* model = nullptr;
+  std::vector<uint32_t> image;
+  uint32_t* d_image = nullptr;
+  PHeader h;
+  int solve_double = 1;
+  // lazily grown scratch between K1 and K2 (one caller at a time per problem)
+  std::mutex mu;
+  size_t ws_B = 0;
+  float *J = nullptr, *e = nullptr, *ep = nullptr, *Gc = nullptr, *hc = nullptr;
+  // bik_step_host staging
+  size_t host_B = 0;
+  float *hq = nullptr, *hft = nullptr, *hpt = nullptr, *hct = nullptr, *hdq = nullptr;
+  int32_t* hst = nullptr;
+  size_t host_pt_elems = 0;
+};
+
+static int valid_group(int G) { return G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32; }
+
+extern "C" int bik_version(void) { return BIK_VERSION; }
+extern "C" const char* bik_last_error(void) { return g_err.c_str(); }
+
+extern "C" int bik_model_create(const void* blob, size_t nbytes, int device, bik_model** out) {
+  if (!blob || !out) return fail(BIK_ERR_INVALID, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(BIK_ERR_CUDA, "no CUDA device: libbik has no CPU path");
+  if (device < 0 || device >= ndev) return fail(BIK_ERR_INVALID, "bad device index");
+  bik_model* m = new bik_model;
+  std::string err;
+  if (!parse_model_blob(blob, nbytes, &m->hm, &err)) { delete m; return fail(BIK_ERR_INVALID, err); }
+  m->device = device;
+  m->G = env_int("BIK_K1_GROUP", 4);
+  if (!valid_group(m->G)) { delete m; return fail(BIK_ERR_INVALID, "BIK_K1_GROUP must be 1,2,4,8,16 or 32"); }
+  m->use_tma = env_int("BIK_USE_TMA", 1);
+  if (!build_image(m->hm, nullptr, 0, nullptr, 0, m->G, &m->image, &err)) { delete m; return fail(BIK_ERR_UNSUPPORTED, err); }
+  DeviceGuard g(device);
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  m->nsm = prop.multiProcessorCount;
+  m->max_smem = (int)prop.sharedMemPerBlockOptin;
+  CUDA_OK(cudaMalloc(&m->d_image, m->image.size() * 4));
+  CUDA_OK(cudaMemcpy(m->d_image, m->image.data(), m->image.size() * 4, cudaMemcpyHostToDevice));
+  *out = m;
+  return BIK_OK;
+}
+extern "C" void bik_model_destroy(bik_model* m) {
+  if (!m) return;
+  DeviceGuard g(m->device);
+  cudaFree(m->d_image);
+  delete m;
+}
+
+extern "C" int bik_problem_create(const bik_model* model, const bik_task_desc* tasks, int ntasks, const bik_limit_desc* limits, int nlimits,
+                                  bik_problem** out) {
+  if (!model || !out || ntasks < 0 || nlimits < 0 || (ntasks && !tasks) || (nlimits && !limits)) return fail(BIK_ERR_INVALID, "null argument");
+  bik_problem* p = new bik_problem;
+  p->model = model;
+  std::string err;
+  if (!build_image(model->hm, tasks, ntasks, limits, nlimits, model->G, &p->image, &err)) { delete p; return fail(BIK_ERR_UNSUPPORTED, err); }
+  memcpy(&p->h, p->image.data(), sizeof(PHeader));
+  const char* prec = getenv("BIK_SOLVE_PRECISION");
+  p->solve_double = !(prec && (std::string(prec) == "f32" || std::string(prec) == "float"));
+  DeviceGuard g(model->device);
+  CUDA_OK(cudaMalloc(&p->d_image, p->image.size() * 4));
+  CUDA_OK(cudaMemcpy(p->d_image, p->image.data(), p->image.size() * 4, cudaMemcpyHostToDevice));
+  *out = p;
+  return BIK_OK;
+}
+extern "C" void bik_problem_destroy(bik_problem* p) {
+  if (!p) return;
+  DeviceGuard g(p->model->device);
+  cudaFree(p->d_image); cudaFree(p->J); cudaFree(p->e); cudaFree(p->ep); cudaFree(p->Gc); cudaFree(p->hc);
+  cudaFree(p->hq); cudaFree(p->hft); cudaFree(p->hpt); cudaFree(p->hct); cudaFree(p->hdq); cudaFree(p->hst);
+  delete p;
+}
+extern "C" int bik_problem_dims(const bik_problem* p, bik_dims* out) {
+  if (!p || !out) return fail(BIK_ERR_INVALID, "null argument");
+  out->nq = p->h.nq; out->nv = p->h.nv; out->nnode = p->h.nnode; out->nframe = p->h.F; out->nposture = p->h.P; out->ncom = p->h.C;
+  out->nrows = p->h.K; out->npairs = p->h.npairs;
+  return BIK_OK;
+}
+extern "C" size_t bik_workspace_bytes(const bik_problem* p, int B) {
+  if (!p || B <= 0) return 0;
+  const PHeader& h = p->h;
+  return (size_t)B * 4 * ((size_t)h.K * h.nv + h.K + (size_t)h.P * h.nv + (size_t)h.npairs * (h.nv + 1) + 4);
+}
+
+template <typename Kern>
+static int launch_geometry(Kern kern, const bik_model* m, size_t smem, int threads, long long work_ctas, int* grid) {
+  if ((int)smem > m->max_smem) return fail(BIK_ERR_UNSUPPORTED, "problem does not fit in shared memory (" + std::to_string(smem) + " B)");
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+  if (per_sm < 1) return fail(BIK_ERR_UNSUPPORTED, "kernel cannot be resident");
+  long long g = (long long)m->nsm * per_sm;  // persistent: one wave, CTAs loop over tiles
+  if (work_ctas < g) g = work_ctas;
+  *grid = (int)(g < 1 ? 1 : g);
+  return BIK_OK;
+}
+
+template <int G>
+static int launch_k1(const bik_problem* p, const K1Args& a, cudaStream_t st) {
+  const PHeader& h = p->h;
+  constexpr int IPW = 32 / G, THREADS = 128, NW = THREADS / 32;
+  size_t smem = (size_t)h.words * 4 + (size_t)NW * k1_warp_words(h, IPW) * 4;
+  int grid = 1;
+  long long tiles = ((long long)a.B + IPW - 1) / IPW;
+  int rc = launch_geometry(k1_kernel<G>, p->model, smem, THREADS, (tiles + NW - 1) / NW, &grid);
+  if (rc) return rc;
+  k1_kernel<G><<<grid, THREADS, smem, st>>>(p->d_image, h.words, p->model->use_tma, a);
+  CUDA_OK(cudaGetLastError());
+  return BIK_OK;
+}
+static int dispatch_k1(const bik_problem* p, const K1Args& a, cudaStream_t st) {
+  switch (p->h.G) {
+    case 1: return launch_k1<1>(p, a, st);
+    case 2: return launch_k1<2>(p, a, st);
+    case 4: return launch_k1<4>(p, a, st);
+    case 8: return launch_k1<8>(p, a, st);
+    case 16: return launch_k1<16>(p, a, st);
+    default: return launch_k1<32>(p, a, st);
+  }
+}
+template <typename T>
+static int launch_k2(const bik_problem* p, const K2Args& a, cudaStream_t st) {
+  const PHeader& h = p->h;
+  const int THREADS = 128, NW = THREADS / 32;
+  size_t smem = (size_t)h.words * 4 + (size_t)NW * k2_warp_bytes(h, sizeof(T));
+  int grid = 1;
+  int rc = launch_geometry(k2_kernel<T>, p->model, smem, THREADS, ((long long)a.B + NW - 1) / NW, &grid);
+  if (rc) return rc;
+  k2_kernel<T><<<grid, THREADS, smem, st>>>(p->d_image, h.words, p->model->use_tma, a);
+  CUDA_OK(cudaGetLastError());
+  return BIK_OK;
+}
+static int dispatch_k2(const bik_problem* p, const K2Args& a, cudaStream_t st) {
+  return p->solve_double ? launch_k2<double>(p, a, st) : launch_k2<float>(p, a, st);
+}
+
+template <int G>
+static int launch_fk(const bik_model* m, const FkArgs& a, cudaStream_t st) {
+  PHeader h;
+  memcpy(&h, m->image.data(), sizeof h);
+  constexpr int IPW = 32 / G, THREADS = 128, NW = THREADS / 32;
+  size_t wwords = (IPW * ((7 * h.nnode) | 1) + 3) & ~3;
+  size_t smem = (size_t)h.words * 4 + NW * wwords * 4;
+  int grid = 1;
+  long long tiles = ((long long)a.B + IPW - 1) / IPW;
+  int rc = launch_geometry(fk_kernel<G>, m, smem, THREADS, (tiles + NW - 1) / NW, &grid);
+  if (rc) return rc;
+  fk_kernel<G><<<grid, THREADS, smem, st>>>(m->d_image, h.words, m->use_tma, a);
+  CUDA_OK(cudaGetLastError());
+  return BIK_OK;
+}
+static int dispatch_fk(const bik_model* m, const FkArgs& a, cudaStream_t st) {
+  switch (m->G) {
+    case 1: return launch_fk<1>(m, a, st);
+    case 2: return launch_fk<2>(m, a, st);
+    case 4: return launch_fk<4>(m, a, st);
+    case 8: return launch_fk<8>(m, a, st);
+    case 16: return launch_fk<16>(m, a, st);
+    default: return launch_fk<32>(m, a, st);
+  }
+}
+
+static int fk_common(const bik_model* model, int B, const float* q, const bik_frame* frames, int nframes, float* poses, float* com, float* J, void* stream) {
+  if (!model || B < 0 || !q || nframes < 0 || (nframes && !frames)) return fail(BIK_ERR_INVALID, "null argument");
+  if (B == 0) return BIK_OK;
+  DeviceGuard g(model->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // frames travel by value in the kernel arguments (the Configuration API asks for one or two)
+  if (nframes > 16) return fail(BIK_ERR_UNSUPPORTED, "at most 16 frames per bik_fk / bik_frame_jacobian call");
+  FkArgs a;
+  memset(&a, 0, sizeof a);
+  a.B = B; a.nframes = nframes; a.q = q; a.poses = poses; a.com = com; a.J = J;
+  for (int f = 0; f < nframes; ++f) {
+    if (frames[f].node >= model->hm.nnode) return fail(BIK_ERR_INVALID, "frame node out of range");
+    put_frame(frames[f], &a.frames[f].node, a.frames[f].lpos, a.frames[f].lquat);
+  }
+  return dispatch_fk(model, a, st);
+}
+extern "C" int bik_fk(const bik_model* model, int B, const float* q, const bik_frame* frames, int nframes, float* poses, float* com, void* stream) {
+  return fk_common(model, B, q, frames, nframes, poses, com, nullptr, stream);
+}
+extern "C" int bik_frame_jacobian(const bik_model* model, int B, const float* q, const bik_frame* frames, int nframes, float* J, void* stream) {
+  return fk_common(model, B, q, frames, nframes, nullptr, nullptr, J, stream);
+}
+
+static int check_inputs(const bik_problem* p, const bik_inputs* in, bool need_q) {
+  if (!p || !in) return fail(BIK_ERR_INVALID, "null argument");
+  const PHeader& h = p->h;
+  if (need_q && !in->q) return fail(BIK_ERR_INVALID, "inputs.q is null");
+  if (h.F > 0 && !in->frame_targets) return fail(BIK_ERR_INVALID, "No target set for FrameTask");
+  if (h.P > 0 && !in->posture_targets) return fail(BIK_ERR_INVALID, "No target set for PostureTask");
+  if (h.C > 0 && !in->com_targets) return fail(BIK_ERR_INVALID, "No target set for ComTask");
+  return BIK_OK;
+}
+
+extern "C" int bik_fk_jac(const bik_problem* p, int B, const bik_inputs* in, float dt, float* J, float* e, float* e_posture, float* G_coll,
+                          float* h_coll, void* stream) {
+  int rc = check_inputs(p, in, true);
+  if (rc) return rc;
+  const PHeader& h = p->h;
+  if (B < 0 || (h.K > 0 && (!J || !e)) || (h.P > 0 && !e_posture) || (h.npairs > 0 && (!G_coll || !h_coll))) return fail(BIK_ERR_INVALID, "null output");
+  if (B == 0) return BIK_OK;
+  DeviceGuard g(p->model->device);
+  K1Args a{B, in->q, in->frame_targets, in->posture_targets, in->com_targets, in->posture_batched, dt, J, e, e_posture, G_coll, h_coll};
+  return dispatch_k1(p, a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bik_qp_objective(const bik_problem* p, int B, const float* J, const float* e, const float* e_posture, double damping, double* H,
+                                double* c, void* stream) {
+  if (!p || !H || !c || B < 0) return fail(BIK_ERR_INVALID, "null argument");
+  if (B == 0) return BIK_OK;
+  DeviceGuard g(p->model->device);
+  K2Args a;
+  memset(&a, 0, sizeof a);
+  a.B = B; a.J = J; a.e = e; a.ep = e_posture; a.dt = 1.f; a.damping = damping; a.Hout = H; a.cout = c;
+  a.skip_box = 1;
+  return dispatch_k2(p, a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bik_limits_box(const bik_problem* p, int B, const float* q, float dt, float* lo, float* hi, void* stream) {
+  if (!p || !q || !lo || !hi || B < 0) return fail(BIK_ERR_INVALID, "null argument");
+  if (B == 0) return BIK_OK;
+  DeviceGuard g(p->model->device);
+  K2Args a;
+  memset(&a, 0, sizeof a);
+  a.B = B; a.q = q; a.dt = dt; a.lo_out = lo; a.hi_out = hi; a.skip_objective = 1;
+  return dispatch_k2(p, a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bik_solve(const bik_problem* p, int B, const float* q, const float* J, const float* e, const float* e_posture, const float* G_coll,
+                         const float* h_coll, float dt, double damping, float* dq, int32_t* status, void* stream) {
+  if (!p || !q || !dq || B < 0) return fail(BIK_ERR_INVALID, "null argument");
+  const PHeader& h = p->h;
+  if ((h.K > 0 && (!J || !e)) || (h.P > 0 && !e_posture) || (h.npairs > 0 && (!G_coll || !h_coll))) return fail(BIK_ERR_INVALID, "null input");
+  if (B == 0) return BIK_OK;
+  DeviceGuard g(p->model->device);
+  K2Args a;
+  memset(&a, 0, sizeof a);
+  a.B = B; a.q = q; a.J = J; a.e = e; a.ep = e_posture; a.Gc = G_coll; a.hc = h_coll; a.dt = dt; a.damping = damping; a.dq = dq; a.status = status;
+  if (status) CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, static_cast<cudaStream_t>(stream)));
+  return dispatch_k2(p, a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bik_integrate(const bik_model* m, int B, float* q, const float* dq, void* stream) {
+  if (!m || !q || !dq || B < 0) return fail(BIK_ERR_INVALID, "null argument");
+  if (B == 0) return BIK_OK;
+  DeviceGuard g(m->device);
+  integrate_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(m->d_image, B, q, dq);
+  CUDA_OK(cudaGetLastError());
+  return BIK_OK;
+}
+extern "C" int bik_check_limits(const bik_model* m, int B, const float* q, float tol, int32_t* status, void* stream) {
+  if (!m || !q || !status || B < 0) return fail(BIK_ERR_INVALID, "null argument");
+  if (B == 0) return BIK_OK;
+  DeviceGuard g(m->device);
+  check_limits_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(m->d_image, B, q, tol, status, 0);
+  CUDA_OK(cudaGetLastError());
+  return BIK_OK;
+}
+
+static int ensure_workspace(bik_problem* p, int B) {
+  if ((size_t)B <= p->ws_B) return BIK_OK;
+  const PHeader& h = p->h;
+  cudaFree(p->J); cudaFree(p->e); cudaFree(p->ep); cudaFree(p->Gc); cudaFree(p->hc);
+  p->J = p->e = p->ep = p->Gc = p->hc = nullptr; p->ws_B = 0;
+  size_t b = (size_t)B;
+  CUDA_OK(cudaMalloc(&p->J, sizeof(float) * b * (h.K > 0 ? h.K : 1) * h.nv));
+  CUDA_OK(cudaMalloc(&p->e, sizeof(float) * b * (h.K > 0 ? h.K : 1)));
+  CUDA_OK(cudaMalloc(&p->ep, sizeof(float) * b * (h.P > 0 ? h.P : 1) * h.nv));
+  CUDA_OK(cudaMalloc(&p->Gc, sizeof(float) * b * (h.npairs > 0 ? h.npairs : 1) * h.nv));
+  CUDA_OK(cudaMalloc(&p->hc, sizeof(float) * b * (h.npairs > 0 ? h.npairs : 1)));
+  p->ws_B = b;
+  return BIK_OK;
+}
+
+extern "C" int bik_step(const bik_problem* cp, int B, float* q, const bik_inputs* in, float dt, double damping, int nsteps, int integrate, float* dq,
+                        int32_t* status, void* stream) {
+  int rc = check_inputs(cp, in, false);
+  if (rc) return rc;
+  if (!q || !dq || B < 0 || nsteps < 1) return fail(BIK_ERR_INVALID, "bad argument");
+  if (B == 0) return BIK_OK;
+  bik_problem* p = const_cast<bik_problem*>(cp);
+  std::lock_guard<std::mutex> lock(p->mu);
+  DeviceGuard g(p->model->device);
+  rc = ensure_workspace(p, B);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const PHeader& h = p->h;
+  for (int s = 0; s < nsteps; ++s) {
+    if (status) {  // Configuration.check_limits(safety_break=False) of solve_ik.py:99
+      check_limits_kernel<<<(B + 127) / 128, 128, 0, st>>>(p->d_image, B, q, 1e-6f, status, s > 0);
+      CUDA_OK(cudaGetLastError());
+    }
+    K1Args a1{B, q, in->frame_targets, in->posture_targets, in->com_targets, in->posture_batched, dt, p->J, p->e, p->ep, p->Gc, p->hc};
+    rc = dispatch_k1(p, a1, st);
+    if (rc) return rc;
+    K2Args a2;
+    memset(&a2, 0, sizeof a2);
+    a2.B = B; a2.q = q; a2.J = p->J; a2.e = p->e; a2.ep = p->ep; a2.Gc = p->Gc; a2.hc = p->hc; a2.dt = dt; a2.damping = damping; a2.dq = dq; a2.status = status;
+    rc = dispatch_k2(p, a2, st);
+    if (rc) return rc;
+    if (integrate) {
+      integrate_kernel<<<(B + 127) / 128, 128, 0, st>>>(p->d_image, B, q, dq);
+      CUDA_OK(cudaGetLastError());
+    }
+  }
+  (void)h;
+  return BIK_OK;
+}
+
+// Host-buffer variant: device staging lives in the problem's workspace region (separate allocations).
+extern "C" int bik_step_host(const bik_problem* cp, int B, float* q_host, const bik_inputs* in, float dt, double damping, int nsteps, int integrate,
+                             float* dq_host, int32_t* status_host, size_t* h2d_bytes, size_t* d2h_bytes) {
+  int rc = check_inputs(cp, in, false);
+  if (rc) return rc;
+  if (!q_host || !dq_host || B < 0) return fail(BIK_ERR_INVALID, "bad argument");
+  if (B == 0) return BIK_OK;
+  bik_problem* p = const_cast<bik_problem*>(cp);
+  const PHeader& h = p->h;
+  DeviceGuard g(p->model->device);
+  size_t nq = h.nq, nv = h.nv, b = (size_t)B;
+  size_t pt_elems = (in->posture_batched ? b : 1) * (size_t)h.P * nq;
+  {
+    std::lock_guard<std::mutex> lock(p->mu);
+    if (b > p->host_B || pt_elems > p->host_pt_elems) {
+      cudaFree(p->hq); cudaFree(p->hft); cudaFree(p->hpt); cudaFree(p->hct); cudaFree(p->hdq); cudaFree(p->hst);
+      p->hq = p->hft = p->hpt = p->hct = p->hdq = nullptr; p->hst = nullptr; p->host_B = 0;
+      CUDA_OK(cudaMalloc(&p->hq, 4 * b * nq));
+      CUDA_OK(cudaMalloc(&p->hft, 4 * b * (h.F > 0 ? h.F : 1) * 7));
+      CUDA_OK(cudaMalloc(&p->hpt, 4 * (pt_elems > 0 ? pt_elems : 1)));
+      CUDA_OK(cudaMalloc(&p->hct, 4 * b * (h.C > 0 ? h.C : 1) * 3));
+      CUDA_OK(cudaMalloc(&p->hdq, 4 * b * nv));
+      CUDA_OK(cudaMalloc(&p->hst, 4 * b));
+      p->host_B = b; p->host_pt_elems = pt_elems;
+    }
+  }
+  cudaStream_t st = 0;
+  size_t up = 0, down = 0;
+  CUDA_OK(cudaMemcpyAsync(p->hq, q_host, 4 * b * nq, cudaMemcpyHostToDevice, st)); up += 4 * b * nq;
+  if (h.F) { CUDA_OK(cudaMemcpyAsync(p->hft, in->frame_targets, 4 * b * h.F * 7, cudaMemcpyHostToDevice, st)); up += 4 * b * h.F * 7; }
+  if (h.P) { CUDA_OK(cudaMemcpyAsync(p->hpt, in->posture_targets, 4 * pt_elems, cudaMemcpyHostToDevice, st)); up += 4 * pt_elems; }
+  if (h.C) { CUDA_OK(cudaMemcpyAsync(p->hct, in->com_targets, 4 * b * h.C * 3, cudaMemcpyHostToDevice, st)); up += 4 * b * h.C * 3; }
+  bik_inputs din = *in;
+  din.q = p->hq; din.frame_targets = p->hft; din.posture_targets = p->hpt; din.com_targets = p->hct;
+  rc = bik_step(cp, B, p->hq, &din, dt, damping, nsteps, integrate, p->hdq, status_host ? p->hst : nullptr, st);
+  if (rc) return rc;
+  CUDA_OK(cudaMemcpyAsync(dq_host, p->hdq, 4 * b * nv, cudaMemcpyDeviceToHost, st)); down += 4 * b * nv;
+  if (integrate) { CUDA_OK(cudaMemcpyAsync(q_host, p->hq, 4 * b * nq, cudaMemcpyDeviceToHost, st)); down += 4 * b * nq; }
+  if (status_host) { CUDA_OK(cudaMemcpyAsync(status_host, p->hst, 4 * b, cudaMemcpyDeviceToHost, st)); down += 4 * b; }
+  CUDA_OK(cudaStreamSynchronize(st));
+  if (h2d_bytes) *h2d_bytes = up;
+  if (d2h_bytes) *d2h_bytes = down;
+  return BIK_OK;
+}

@@ -24,13 +24,17 @@
 #define BIK_SYNCWARP() ((void)0)
 #endif
 
-#if defined(__CUDACC__)
-#define BIK_INF_F (__int_as_float(0x7f800000))
-#else
-#define BIK_INF_F (INFINITY)
-#endif
+#define BIK_INF_F (bik::bik_inf())
 
 namespace bik {
+
+BIK_HD float bik_inf() {
+#if defined(__CUDA_ARCH__)
+  return __int_as_float(0x7f800000);
+#else
+  return INFINITY;
+#endif
+}
 
 typedef V3<float> F3;
 typedef Q4<float> FQ;

@@ -38,6 +38,8 @@ struct K2Args {
   double* cout;      // [B][nv] or null
   float* lo_out;     // [B][nv] or null      (bik_limits_box)
   float* hi_out;
+  int skip_objective;  // bik_limits_box: J/e/ep are not read
+  int skip_box;        // bik_qp_objective: q is not read
 };
 
 enum { K2_MAX_GEN = 16 };  // general (collision) rows that may be active at once
@@ -101,6 +103,15 @@ BIK_HD void k2_assemble(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int 
   const float* eb = a.e + (long long)b * K;
   const int32_t* cols = P.i(h.off_cols);
   for (int k = lane; k < tri(n); k += W) w.Hp[k] = T(0);
+  if (a.skip_objective) {
+    for (int d = lane; d < n; d += W) {
+      float lo, hi;
+      box_dof(P, d, a.q + (long long)b * h.nq, a.dt, &lo, &hi);
+      w.lo[d] = T(lo); w.hi[d] = T(hi); w.c[d] = T(0);
+    }
+    BIK_SYNCWARP();
+    return;
+  }
   // weighted rows  W J  and  W(-gain e)
   for (int f = 0; f < h.F; ++f) {
     const FrameRec& fr = P.frame(f);
@@ -162,8 +173,8 @@ BIK_HD void k2_assemble(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int 
     }
     w.Hp[tri(d) + d] += hd;
     w.c[d] = cd;
-    float lo, hi;
-    box_dof(P, d, a.q + (long long)b * h.nq, a.dt, &lo, &hi);
+    float lo = -BIK_INF_F, hi = BIK_INF_F;
+    if (!a.skip_box) box_dof(P, d, a.q + (long long)b * h.nq, a.dt, &lo, &hi);
     w.lo[d] = T(lo); w.hi[d] = T(hi);
   }
   BIK_SYNCWARP();

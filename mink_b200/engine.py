@@ -1,0 +1,210 @@
+"""Low-level batched engine: thin, typed wrapper over the C ABI using torch CUDA tensors for memory.
+
+`DeviceModel` owns a bik_model, `Problem` a bik_problem.  All methods enqueue kernels on torch's
+current stream and return torch tensors (fp32 on the model's device); nothing here computes --
+torch is used for allocation, streams and host<->device copies only.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._abi import BikDims, BikInputs, ProblemSpec, c_frames
+from .flatten import FlatModel, Frame
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class DeviceModel:
+    def __init__(self, flat: FlatModel, device: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("mink_b200 needs a CUDA device: the IK hot path has no CPU implementation")
+        self.flat = flat
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.lib = _lib.load()
+        blob = flat.to_blob()
+        h = C.c_void_p()
+        _lib.check(self.lib.bik_model_create(blob, len(blob), self.device, C.byref(h)))
+        self.handle = h
+        self.nq, self.nv = flat.nq, flat.nv
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            self.lib.bik_model_destroy(h)
+
+    def _f32(self, a, shape=None) -> torch.Tensor:
+        t = torch.as_tensor(a)
+        t = t.to(device=f"cuda:{self.device}", dtype=torch.float32).contiguous()
+        return t if shape is None else t.reshape(shape)
+
+    def _rows(self, a, *tail) -> torch.Tensor:
+        """fp32 CUDA tensor viewed as [-1, *tail] (well defined for empty batches too)."""
+        t = self._f32(a)
+        n = 1
+        for d in tail:
+            n *= d
+        return t.reshape((t.numel() // n,) + tuple(tail))
+
+    def fk(self, q, frames: Sequence[Frame], want_com: bool = False):
+        q = self._rows(q, self.nq)
+        B, F = q.shape[0], len(frames)
+        poses = torch.empty((B, F, 7), device=q.device, dtype=torch.float32)
+        com = torch.empty((B, 3), device=q.device, dtype=torch.float32) if want_com else None
+        _lib.check(self.lib.bik_fk(self.handle, B, q.data_ptr(), c_frames(frames), F, poses.data_ptr(), _ptr(com), _stream()))
+        return poses, com
+
+    def frame_jacobian(self, q, frames: Sequence[Frame]):
+        q = self._rows(q, self.nq)
+        B, F = q.shape[0], len(frames)
+        J = torch.empty((B, F, 6, self.nv), device=q.device, dtype=torch.float32)
+        _lib.check(self.lib.bik_frame_jacobian(self.handle, B, q.data_ptr(), c_frames(frames), F, J.data_ptr(), _stream()))
+        return J
+
+    def integrate(self, q: torch.Tensor, dq: torch.Tensor) -> torch.Tensor:
+        """In place on q ([B,nq] fp32 CUDA)."""
+        _lib.check(self.lib.bik_integrate(self.handle, q.shape[0], q.data_ptr(), dq.data_ptr(), _stream()))
+        return q
+
+    def check_limits(self, q: torch.Tensor, tol: float = 1e-6) -> torch.Tensor:
+        st = torch.empty(q.shape[0], device=q.device, dtype=torch.int32)
+        _lib.check(self.lib.bik_check_limits(self.handle, q.shape[0], q.data_ptr(), float(tol), st.data_ptr(), _stream()))
+        return st
+
+
+class Problem:
+    def __init__(self, model: DeviceModel, spec: ProblemSpec):
+        self.model, self.spec, self.lib = model, spec, model.lib
+        t, nt, l, nl, self._keep = spec.to_c()
+        h = C.c_void_p()
+        _lib.check(self.lib.bik_problem_create(model.handle, t, nt, l, nl, C.byref(h)))
+        self.handle = h
+        d = BikDims()
+        _lib.check(self.lib.bik_problem_dims(h, C.byref(d)))
+        self.nq, self.nv, self.F, self.P, self.Cn, self.K, self.npairs = d.nq, d.nv, d.nframe, d.nposture, d.ncom, d.nrows, d.npairs
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            self.lib.bik_problem_destroy(h)
+
+    # -- inputs --------------------------------------------------------------------------------
+    def _inputs(self, q, frame_targets, posture_targets, com_targets):
+        m = self.model
+        keep = []
+        inp = BikInputs()
+        B = None
+        if q is not None:
+            q = m._rows(q, self.nq)
+            B = q.shape[0]
+            inp.q = q.data_ptr()
+            keep.append(q)
+        if self.F:
+            if frame_targets is None:
+                raise ValueError("No target set for FrameTask")
+            ft = m._rows(frame_targets, self.F, 7)
+            inp.frame_targets = ft.data_ptr()
+            keep.append(ft)
+            B = ft.shape[0] if B is None else B
+        if self.P:
+            if posture_targets is None:
+                raise ValueError("No target set for PostureTask")
+            pt = m._rows(posture_targets, self.P, self.nq)
+            inp.posture_targets = pt.data_ptr()
+            inp.posture_batched = int(pt.shape[0] > 1)
+            keep.append(pt)
+        if self.Cn:
+            if com_targets is None:
+                raise ValueError("No target set for ComTask")
+            ct = m._rows(com_targets, self.Cn, 3)
+            inp.com_targets = ct.data_ptr()
+            keep.append(ct)
+        return inp, keep, B, q
+
+    def fk_jac(self, q, frame_targets=None, posture_targets=None, com_targets=None, dt: float = 1e-2):
+        inp, keep, B, q = self._inputs(q, frame_targets, posture_targets, com_targets)
+        dev, f32 = q.device, torch.float32
+        J = torch.empty((B, self.K, self.nv), device=dev, dtype=f32)
+        e = torch.empty((B, self.K), device=dev, dtype=f32)
+        ep = torch.empty((B, self.P, self.nv), device=dev, dtype=f32)
+        Gc = torch.empty((B, self.npairs, self.nv), device=dev, dtype=f32)
+        hc = torch.empty((B, self.npairs), device=dev, dtype=f32)
+        _lib.check(self.lib.bik_fk_jac(self.handle, B, C.byref(inp), float(dt), _ptr(J) if self.K else None,
+                                       _ptr(e) if self.K else None, _ptr(ep) if self.P else None,
+                                       _ptr(Gc) if self.npairs else None, _ptr(hc) if self.npairs else None, _stream()))
+        return J, e, ep, Gc, hc
+
+    def objective(self, J, e, ep, damping: float):
+        B = J.shape[0] if self.K else ep.shape[0]
+        dev = J.device if self.K else ep.device
+        H = torch.empty((B, self.nv, self.nv), device=dev, dtype=torch.float64)
+        c = torch.empty((B, self.nv), device=dev, dtype=torch.float64)
+        _lib.check(self.lib.bik_qp_objective(self.handle, B, _ptr(J) if self.K else None, _ptr(e) if self.K else None,
+                                             _ptr(ep) if self.P else None, float(damping), H.data_ptr(), c.data_ptr(), _stream()))
+        return H, c
+
+    def box(self, q, dt: float):
+        q = self.model._rows(q, self.nq)
+        lo = torch.empty((q.shape[0], self.nv), device=q.device, dtype=torch.float32)
+        hi = torch.empty_like(lo)
+        _lib.check(self.lib.bik_limits_box(self.handle, q.shape[0], q.data_ptr(), float(dt), lo.data_ptr(), hi.data_ptr(), _stream()))
+        return lo, hi
+
+    def solve(self, q, J, e, ep, Gc, hc, dt: float, damping: float):
+        q = self.model._rows(q, self.nq)
+        B = q.shape[0]
+        dq = torch.empty((B, self.nv), device=q.device, dtype=torch.float32)
+        st = torch.empty(B, device=q.device, dtype=torch.int32)
+        _lib.check(self.lib.bik_solve(self.handle, B, q.data_ptr(), _ptr(J) if self.K else None, _ptr(e) if self.K else None,
+                                      _ptr(ep) if self.P else None, _ptr(Gc) if self.npairs else None,
+                                      _ptr(hc) if self.npairs else None, float(dt), float(damping), dq.data_ptr(),
+                                      st.data_ptr(), _stream()))
+        return dq, st
+
+    def step(self, q: torch.Tensor, frame_targets=None, posture_targets=None, com_targets=None, dt: float = 1e-2,
+             damping: float = 1e-12, nsteps: int = 1, integrate: bool = False, dq: Optional[torch.Tensor] = None,
+             status: Optional[torch.Tensor] = None):
+        """solve_ik (x nsteps, optionally integrating q in place).  q: [B,nq] fp32 CUDA tensor."""
+        assert q.is_cuda and q.dtype == torch.float32 and q.is_contiguous()
+        inp, keep, _, _ = self._inputs(None, frame_targets, posture_targets, com_targets)
+        B = q.shape[0]
+        if dq is None:
+            dq = torch.empty((B, self.nv), device=q.device, dtype=torch.float32)
+        if status is None:
+            status = torch.empty(B, device=q.device, dtype=torch.int32)
+        _lib.check(self.lib.bik_step(self.handle, B, q.data_ptr(), C.byref(inp), float(dt), float(damping), int(nsteps),
+                                     int(bool(integrate)), dq.data_ptr(), status.data_ptr(), _stream()))
+        return dq, status
+
+    def step_host(self, q: np.ndarray, frame_targets=None, posture_targets=None, com_targets=None, dt: float = 1e-2,
+                  damping: float = 1e-12, nsteps: int = 1, integrate: bool = False):
+        """Host-buffer entry (numpy fp32 in, numpy fp32 out; copies inside).  Returns (dq, status, h2d, d2h)."""
+        f32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+        q = f32(q).reshape(-1, self.nq)
+        B = q.shape[0]
+        ft, pt, ct = f32(frame_targets), f32(posture_targets), f32(com_targets)
+        inp = BikInputs()
+        if self.F:
+            inp.frame_targets = ft.ctypes.data
+        if self.P:
+            inp.posture_targets = pt.ctypes.data
+            inp.posture_batched = int(pt.size == B * self.P * self.nq and B > 1)
+        if self.Cn:
+            inp.com_targets = ct.ctypes.data
+        dq = np.empty((B, self.nv), np.float32)
+        st = np.empty(B, np.int32)
+        up, down = C.c_size_t(0), C.c_size_t(0)
+        _lib.check(self.lib.bik_step_host(self.handle, B, q.ctypes.data, C.byref(inp), float(dt), float(damping), int(nsteps),
+                                          int(bool(integrate)), dq.ctypes.data, st.ctypes.data, C.byref(up), C.byref(down)))
+        return dq, st, q, int(up.value), int(down.value)

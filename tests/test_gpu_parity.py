@@ -1,0 +1,272 @@
+"""GPU parity: the CUDA path (through the C ABI) against the golden vectors and the C oracle.
+
+Tolerance: BASELINE.json north_star -- dq within 1e-4 rad of the fp64 reference (fp32 device I/O).
+Tighter bounds are used where the quantity allows.  Property tests cover BASELINE's full sizes.
+"""
+
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from mink_b200._abi import spec_from_workload  # noqa: E402
+from mink_b200.workloads import WORKLOADS, make_inputs  # noqa: E402
+from tests.helpers import load_case, load_flat, quat_align, task_frames  # noqa: E402
+
+CASES = ["ur5e", "ur5e_dls", "g1", "shadow", "spot"]
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def _engine(name, env=None):
+    _need_gpu()
+    from mink_b200.engine import DeviceModel, Problem
+
+    old = {}
+    for k, v in (env or {}).items():
+        old[k] = os.environ.get(k)
+        os.environ[k] = str(v)
+    try:
+        wl, fm, spec, g = load_case(name)
+        model = DeviceModel(fm, device=0)
+        prob = Problem(model, spec)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return wl, fm, spec, g, model, prob
+
+
+def _oracle(fm, spec):
+    from oracle.ikoracle import Oracle
+
+    return Oracle(fm.to_blob(), spec, fm.nq, fm.nv)
+
+
+def _np(t):
+    return t.detach().cpu().numpy().astype(np.float64)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_fk_and_frame_jacobian(name):
+    wl, fm, spec, g, model, prob = _engine(name)
+    frames = task_frames(wl, fm)
+    poses, com = model.fk(g["q"], frames, want_com=True)
+    poses, ref = _np(poses), g["frame_pose"]
+    np.testing.assert_allclose(poses[..., 4:], ref[..., 4:], atol=5e-6)
+    np.testing.assert_allclose(quat_align(poses[..., :4], ref[..., :4]), ref[..., :4], atol=5e-6)
+    if fm.ncom:
+        np.testing.assert_allclose(_np(com), g["com"], atol=5e-6)
+    np.testing.assert_allclose(_np(model.frame_jacobian(g["q"], frames)), g["J_body"], atol=1e-5)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_k1_task_errors_and_jacobians(name):
+    wl, fm, spec, g, model, prob = _engine(name)
+    J, e, ep, Gc, hc = prob.fk_jac(g["q"], g["frame_targets"], g["posture_target"], g.get("com_target"), dt=float(g["dt"]))
+    J, e, ep, Gc, hc = map(_np, (J, e, ep, Gc, hc))
+    F = spec.nframe
+    np.testing.assert_allclose(e[:, :6 * F].reshape(-1, F, 6), g["e_frame"], atol=2e-5)
+    np.testing.assert_allclose(J[:, :6 * F].reshape(-1, F, 6, fm.nv), g["J_frame"], atol=5e-5)
+    if spec.nposture:
+        np.testing.assert_allclose(ep[:, 0], g["e_posture"], atol=1e-6)
+    if spec.ncom:
+        np.testing.assert_allclose(e[:, 6 * F:], g["e_com"], atol=5e-6)
+        np.testing.assert_allclose(J[:, 6 * F:], g["J_com"], atol=5e-6)
+    if spec.npairs:
+        fin = np.isfinite(g["h"])
+        assert np.array_equal(np.isfinite(hc), fin)
+        np.testing.assert_allclose(hc[fin], g["h"][fin], rtol=2e-4, atol=2e-3)
+        np.testing.assert_allclose(Gc, g["G"], atol=2e-5)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_k2_objective_box_and_solve_from_reference_jacobians(name):
+    """K2 alone, fed with the reference's own (J, e) cast to fp32."""
+    wl, fm, spec, g, model, prob = _engine(name)
+    B, F = g["q"].shape[0], spec.nframe
+    f32 = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float32, device="cuda:0")
+    J = f32(np.concatenate([g["J_frame"].reshape(B, 6 * F, fm.nv)] + ([g["J_com"]] if spec.ncom else []), axis=1))
+    e = f32(np.concatenate([g["e_frame"].reshape(B, 6 * F)] + ([g["e_com"]] if spec.ncom else []), axis=1))
+    ep = f32(g["e_posture"][:, None, :]) if spec.nposture else torch.zeros((B, 0, fm.nv), device="cuda:0")
+    Gc = f32(g["G"]) if spec.npairs else torch.zeros((B, 0, fm.nv), device="cuda:0")
+    hc = f32(g["h"]) if spec.npairs else torch.zeros((B, 0), device="cuda:0")
+    H, c = prob.objective(J, e, ep, float(g["damping"]))
+    scale = np.abs(g["H"]).max()
+    np.testing.assert_allclose(_np(H), g["H"], atol=1e-6 * scale)
+    np.testing.assert_allclose(_np(c), g["c"], atol=1e-5 * max(1.0, np.abs(g["c"]).max()))
+    lo, hi = prob.box(g["q"], float(g["dt"]))
+    fin = np.isfinite(g["box_lo"])
+    np.testing.assert_allclose(_np(lo)[fin], g["box_lo"][fin], atol=1e-6)
+    assert np.all(np.isneginf(_np(lo)[~fin]))
+    fin = np.isfinite(g["box_hi"])
+    np.testing.assert_allclose(_np(hi)[fin], g["box_hi"][fin], atol=1e-6)
+    dq, st = prob.solve(g["q"], J, e, ep, Gc, hc, float(g["dt"]), float(g["damping"]))
+    assert int(st.max()) == 0
+    np.testing.assert_allclose(_np(dq), g["dq"], atol=1e-5 if name != "spot" else 2e-3)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_solve_ik_step_matches_reference(name):
+    """The whole step (check_limits -> K1 -> K2 -> integrate) vs reference solve_ik + integrate."""
+    wl, fm, spec, g, model, prob = _engine(name)
+    q = torch.tensor(g["q"], dtype=torch.float32, device="cuda:0")
+    dq, st = prob.step(q, g["frame_targets"], g["posture_target"], g.get("com_target"), dt=float(g["dt"]),
+                       damping=float(g["damping"]), nsteps=1, integrate=True)
+    assert int(st.max()) == 0
+    tol = 1e-4 if name != "spot" else 5e-3   # spot: cond(H) ~ 4e7, fp32 J alone moves the optimum
+    err = np.abs(_np(dq) - g["dq"]).max()
+    print(f"{name}: max|dq - dq_ref| = {err:.3e}")
+    assert err < tol
+    np.testing.assert_allclose(_np(q), g["q_next"], atol=2 * tol)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_rollout_matches_reference(name):
+    wl, fm, spec, g, model, prob = _engine(name)
+    traj = g["rollout_q"]
+    T, RB = traj.shape[0] - 1, traj.shape[1]
+    q = torch.tensor(traj[0], dtype=torch.float32, device="cuda:0")
+    ct = g["com_target"][:RB] if "com_target" in g else None
+    dq, st = prob.step(q, g["frame_targets"][:RB], g["posture_target"], ct, dt=float(g["dt"]), damping=float(g["damping"]),
+                       nsteps=T, integrate=True)
+    assert int(st.max()) == 0
+    np.testing.assert_allclose(_np(q), traj[-1], atol=5e-4 if name != "spot" else 2e-2)
+
+
+@pytest.mark.parametrize("group", [1, 2, 4, 8, 16, 32])
+def test_every_lane_group_size_against_oracle(group):
+    """K1's lanes-per-instance mapping (BIK_K1_GROUP) must not change results; ragged batch (tail tile)."""
+    wl, fm, spec, g, model, prob = _engine("g1", env={"BIK_K1_GROUP": group})
+    orc = _oracle(fm, spec)
+    frames = task_frames(wl, fm)
+    B = 263
+    inp = make_inputs(fm, wl, B, lambda qq: orc.fk(qq, frames), seed=7)
+    J, e, ep, _, _ = prob.fk_jac(inp["q"], inp["frame_targets"], inp["posture_target"], None, dt=wl["dt"])
+    Jr, er, epr = orc.fk_jac(inp["q"], inp["frame_targets"], inp["posture_target"], None)
+    np.testing.assert_allclose(_np(J), Jr, atol=5e-5)
+    np.testing.assert_allclose(_np(e), er, atol=2e-5)
+    np.testing.assert_allclose(_np(ep), epr, atol=1e-6)
+
+
+@pytest.mark.parametrize("env", [{"BIK_USE_TMA": 0}, {"BIK_SOLVE_PRECISION": "f32"}])
+def test_alternate_paths(env):
+    wl, fm, spec, g, model, prob = _engine("g1", env=env)
+    q = torch.tensor(g["q"], dtype=torch.float32, device="cuda:0")
+    dq, st = prob.step(q, g["frame_targets"], g["posture_target"], None, dt=float(g["dt"]), damping=float(g["damping"]))
+    assert int(st.max()) == 0
+    assert np.abs(_np(dq) - g["dq"]).max() < 1e-4
+
+
+@pytest.mark.parametrize("name,B", [("g1", 4099), ("shadow", 2050), ("ur5e_dls", 4096), ("spot", 1031)])
+def test_batch_against_oracle(name, B):
+    wl, fm, spec, g, model, prob = _engine(name)
+    orc = _oracle(fm, spec)
+    frames = task_frames(wl, fm)
+    inp = make_inputs(fm, wl, B, lambda qq: orc.fk(qq, frames), seed=3)
+    q = torch.tensor(inp["q"], dtype=torch.float32, device="cuda:0")
+    dq, st = prob.step(q, inp["frame_targets"], inp["posture_target"], inp.get("com_target"), dt=wl["dt"], damping=wl["damping"],
+                       nsteps=1, integrate=True)
+    dq_ref, q_ref, st_ref, nact = orc.step(inp["q"], inp["frame_targets"], inp["posture_target"], inp.get("com_target"), dt=wl["dt"],
+                                            damping=wl["damping"], nsteps=1, integrate=True)
+    assert int(st.max()) == 0 and not st_ref.any()
+    err = np.abs(_np(dq) - dq_ref).max(axis=1)
+    print(f"{name}: B={B} max|dq-dq_oracle|={err.max():.3e} median={np.median(err):.3e} active mean={nact.mean():.1f} max={nact.max()}")
+    assert err.max() < (1e-4 if name != "spot" else 2e-2)
+    np.testing.assert_allclose(_np(q), q_ref, atol=2e-4 if name != "spot" else 4e-2)
+
+
+def test_full_size_properties_g1():
+    """BASELINE config 3 at full size (65 536 instances): size-independent properties."""
+    wl, fm, spec, g, model, prob = _engine("g1")
+    frames = task_frames(wl, fm)
+
+    def fk(qq):
+        p, c = model.fk(qq, frames, want_com=False)
+        return _np(p), None
+
+    B = 65536
+    inp = make_inputs(fm, wl, B, fk, seed=11)
+    q0 = torch.tensor(inp["q"], dtype=torch.float32, device="cuda:0")
+    ft = torch.tensor(inp["frame_targets"], dtype=torch.float32, device="cuda:0")
+    q = q0.clone()
+    dq, st = prob.step(q, ft, inp["posture_target"], None, dt=wl["dt"], damping=wl["damping"], nsteps=1, integrate=False)
+    assert int(st.max()) == 0
+    assert torch.isfinite(dq).all()
+    # (1) feasibility: dq inside the box of configuration + velocity limits
+    lo, hi = prob.box(q0, wl["dt"])
+    assert bool(((dq >= lo - 1e-6) & (dq <= hi + 1e-6)).all())
+    # (2) KKT of the box QP in fp64 from the library's own H, c: projected gradient vanishes
+    J, e, ep, Gc, hc = prob.fk_jac(q0, ft, inp["posture_target"], None, dt=wl["dt"])
+    H, c = prob.objective(J, e, ep, wl["damping"])
+    x = dq.double()
+    grad = torch.einsum("bij,bj->bi", H, x) + c
+    at_lo = (x <= lo.double() + 1e-6)
+    at_hi = (x >= hi.double() - 1e-6)
+    free = ~(at_lo | at_hi)
+    scale = H.abs().amax(dim=(1, 2)).unsqueeze(1) * 1e-6 + 1e-4
+    assert bool((grad.abs()[free] <= scale.expand_as(grad)[free]).all())
+    assert bool((grad[at_lo & ~at_hi] >= -scale.expand_as(grad)[at_lo & ~at_hi]).all())
+    assert bool((grad[at_hi & ~at_lo] <= scale.expand_as(grad)[at_hi & ~at_lo]).all())
+    # (3) determinism
+    dq2, _ = prob.step(q0.clone(), ft, inp["posture_target"], None, dt=wl["dt"], damping=wl["damping"])
+    assert torch.equal(dq, dq2)
+    # (4) fixed point: targets at the current pose and posture target = q  =>  dq = 0
+    poses, _ = model.fk(q0, frames)
+    dq3, _ = prob.step(q0.clone(), poses, q0.unsqueeze(1), None, dt=wl["dt"], damping=wl["damping"])
+    assert float(dq3.abs().max()) < 2e-5
+    # (5) integrate keeps the free-joint quaternion on the unit sphere and moves scalar joints by dq
+    q1 = q0.clone()
+    model.integrate(q1, dq)
+    assert float((q1[:, 3:7].norm(dim=1) - 1).abs().max()) < 1e-5
+    np.testing.assert_allclose(_np(q1[:, 7:] - q0[:, 7:]), _np(dq[:, 6:]), atol=1e-6)
+
+
+def test_task_at_target_gives_zero_velocity_ur5e():
+    """reference tests/test_solve_ik.py:79-93."""
+    wl, fm, spec, g, model, prob = _engine("ur5e")
+    frames = task_frames(wl, fm)
+    q = torch.tensor(np.tile(fm.key("home"), (5, 1)), dtype=torch.float32, device="cuda:0")
+    poses, _ = model.fk(q, frames)
+    dq, st = prob.step(q, poses, fm.key("home"), None, dt=wl["dt"], damping=wl["damping"])
+    assert float(dq.abs().max()) < 1e-6
+
+
+def test_out_of_limits_sets_status_flag():
+    wl, fm, spec, g, model, prob = _engine("ur5e")
+    q = torch.tensor(g["q"], dtype=torch.float32, device="cuda:0")
+    q[2, 1] = 100.0
+    dq, st = prob.step(q, g["frame_targets"], g["posture_target"], None, dt=wl["dt"], damping=wl["damping"])
+    st = st.cpu().numpy()
+    assert st[2] & 1 and not (np.delete(st, 2) & 1).any()
+    assert (model.check_limits(q).cpu().numpy() != 0).sum() == 1
+
+
+def test_step_host_entry_point():
+    wl, fm, spec, g, model, prob = _engine("g1")
+    dq, st, q, up, down = prob.step_host(g["q"], g["frame_targets"], g["posture_target"], None, dt=float(g["dt"]),
+                                         damping=float(g["damping"]), nsteps=1, integrate=True)
+    assert not st.any()
+    assert np.abs(dq - g["dq"]).max() < 1e-4
+    np.testing.assert_allclose(q, g["q_next"], atol=2e-4)
+    B = g["q"].shape[0]
+    assert up == 4 * (B * fm.nq + B * 3 * 7 + fm.nq) and down == 4 * (B * fm.nv + B * fm.nq + B)
+
+
+def test_empty_batch_and_missing_target():
+    wl, fm, spec, g, model, prob = _engine("g1")
+    from mink_b200._lib import BikError
+
+    q = torch.zeros((0, fm.nq), dtype=torch.float32, device="cuda:0")
+    dq, st = prob.step(q, torch.zeros((0, 3, 7), device="cuda:0"), g["posture_target"], None, dt=0.01)
+    assert dq.shape == (0, fm.nv)
+    with pytest.raises((BikError, ValueError)):
+        prob.step(torch.zeros((2, fm.nq), device="cuda:0"), None, g["posture_target"], None)
