@@ -187,6 +187,11 @@ int bik_solve(const bik_problem* problem, int B, const float* q, const float* J,
               const float* e_posture, const float* G_coll, const float* h_coll, float dt,
               double damping, float* dq, int32_t* status, void* stream);
 
+/* bik_solve plus diagnostics: iters [B] (may be NULL) receives the number of active-set iterations. */
+int bik_solve_ex(const bik_problem* problem, int B, const float* q, const float* J, const float* e,
+                 const float* e_posture, const float* G_coll, const float* h_coll, float dt,
+                 double damping, float* dq, int32_t* status, int32_t* iters, void* stream);
+
 /* q <- q (+) dq : Configuration.integrate / integrate_inplace (configuration.py:214-236). */
 int bik_integrate(const bik_model* model, int B, float* q, const float* dq, void* stream);
 

@@ -12,7 +12,7 @@ _lib = None
 
 EXPORTS = ["bik_version", "bik_last_error", "bik_model_create", "bik_model_destroy", "bik_problem_create",
            "bik_problem_destroy", "bik_problem_dims", "bik_fk", "bik_frame_jacobian", "bik_fk_jac",
-           "bik_qp_objective", "bik_limits_box", "bik_solve", "bik_integrate", "bik_check_limits", "bik_step",
+           "bik_qp_objective", "bik_limits_box", "bik_solve", "bik_solve_ex", "bik_integrate", "bik_check_limits", "bik_step",
            "bik_step_host", "bik_workspace_bytes"]
 
 
@@ -51,6 +51,7 @@ def load():
     lib.bik_qp_objective.argtypes = [vp, ci, vp, vp, vp, cd, vp, vp, vp]
     lib.bik_limits_box.argtypes = [vp, ci, vp, cf, vp, vp, vp]
     lib.bik_solve.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp, cf, cd, vp, vp, vp]
+    lib.bik_solve_ex.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp, cf, cd, vp, vp, vp, vp]
     lib.bik_integrate.argtypes = [vp, ci, vp, vp, vp]
     lib.bik_check_limits.argtypes = [vp, ci, vp, cf, vp, vp]
     lib.bik_step.argtypes = [vp, ci, vp, C.POINTER(BikInputs), cf, cd, ci, ci, vp, vp, vp]

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(128) k1_kernel(const uint32_t* __restrict__ gi
   for (int tile = blockIdx.x * nwarps + warp; tile < ntiles; tile += gridDim.x * nwarps) k1_warp_tile<G, 32>(P, a, tile * IPW, wsm, lane);
 }
 
-template <typename T>
+template <typename T, int SLOTS>
 __global__ void __launch_bounds__(128) k2_kernel(const uint32_t* __restrict__ gimage, int words, int use_tma, K2Args a) {
   extern __shared__ __align__(16) uint32_t smem[];
   __shared__ __align__(8) uint64_t bar;
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(128) k2_kernel(const uint32_t* __restrict__ gi
   PView P{smem};
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   char* wsm = reinterpret_cast<char*>(smem + words) + (size_t)warp * k2_warp_bytes(P.h(), sizeof(T));
-  for (int b = blockIdx.x * nwarps + warp; b < a.B; b += gridDim.x * nwarps) k2_warp<T, 32>(P, a, b, wsm, lane);
+  for (int b = blockIdx.x * nwarps + warp; b < a.B; b += gridDim.x * nwarps) k2_warp<T, 32, SLOTS>(P, a, b, wsm, lane);
 }
 
 template <int G>
@@ -258,13 +258,16 @@ static int launch_geometry(Kern kern, const bik_model* m, size_t smem, int threa
 template <int G>
 static int launch_k1(const bik_problem* p, const K1Args& a, cudaStream_t st) {
   const PHeader& h = p->h;
-  constexpr int IPW = 32 / G, THREADS = 128, NW = THREADS / 32;
-  size_t smem = (size_t)h.words * 4 + (size_t)NW * k1_warp_words(h, IPW) * 4;
+  constexpr int IPW = 32 / G;
+  int NW = 4;  // warps per CTA: as many as fit next to the image in shared memory
+  auto need = [&](int nw) { return (size_t)h.words * 4 + (size_t)nw * k1_warp_words(h, IPW) * 4; };
+  while (NW > 1 && (int)need(NW) > p->model->max_smem) NW >>= 1;
+  size_t smem = need(NW);
   int grid = 1;
   long long tiles = ((long long)a.B + IPW - 1) / IPW;
-  int rc = launch_geometry(k1_kernel<G>, p->model, smem, THREADS, (tiles + NW - 1) / NW, &grid);
+  int rc = launch_geometry(k1_kernel<G>, p->model, smem, 32 * NW, (tiles + NW - 1) / NW, &grid);
   if (rc) return rc;
-  k1_kernel<G><<<grid, THREADS, smem, st>>>(p->d_image, h.words, p->model->use_tma, a);
+  k1_kernel<G><<<grid, 32 * NW, smem, st>>>(p->d_image, h.words, p->model->use_tma, a);
   CUDA_OK(cudaGetLastError());
   return BIK_OK;
 }
@@ -278,20 +281,29 @@ static int dispatch_k1(const bik_problem* p, const K1Args& a, cudaStream_t st) {
     default: return launch_k1<32>(p, a, st);
   }
 }
-template <typename T>
+template <typename T, int SLOTS>
 static int launch_k2(const bik_problem* p, const K2Args& a, cudaStream_t st) {
   const PHeader& h = p->h;
-  const int THREADS = 128, NW = THREADS / 32;
-  size_t smem = (size_t)h.words * 4 + (size_t)NW * k2_warp_bytes(h, sizeof(T));
+  int NW = 4;
+  auto need = [&](int nw) { return (size_t)h.words * 4 + (size_t)nw * k2_warp_bytes(h, sizeof(T)); };
+  while (NW > 1 && (int)need(NW) > p->model->max_smem) NW >>= 1;
+  size_t smem = need(NW);
   int grid = 1;
-  int rc = launch_geometry(k2_kernel<T>, p->model, smem, THREADS, ((long long)a.B + NW - 1) / NW, &grid);
+  int rc = launch_geometry(k2_kernel<T, SLOTS>, p->model, smem, 32 * NW, ((long long)a.B + NW - 1) / NW, &grid);
   if (rc) return rc;
-  k2_kernel<T><<<grid, THREADS, smem, st>>>(p->d_image, h.words, p->model->use_tma, a);
+  k2_kernel<T, SLOTS><<<grid, 32 * NW, smem, st>>>(p->d_image, h.words, p->model->use_tma, a);
   CUDA_OK(cudaGetLastError());
   return BIK_OK;
 }
+template <typename T>
+static int dispatch_k2_slots(const bik_problem* p, const K2Args& a, cudaStream_t st) {
+  int slots = (p->h.nv + 1 + 31) / 32;  // rows of the augmented factor per lane
+  if (slots <= 1) return launch_k2<T, 1>(p, a, st);
+  if (slots == 2) return launch_k2<T, 2>(p, a, st);
+  return launch_k2<T, 3>(p, a, st);
+}
 static int dispatch_k2(const bik_problem* p, const K2Args& a, cudaStream_t st) {
-  return p->solve_double ? launch_k2<double>(p, a, st) : launch_k2<float>(p, a, st);
+  return p->solve_double ? dispatch_k2_slots<double>(p, a, st) : dispatch_k2_slots<float>(p, a, st);
 }
 
 template <int G>
@@ -355,6 +367,7 @@ static int check_inputs(const bik_problem* p, const bik_inputs* in, bool need_q)
 
 extern "C" int bik_fk_jac(const bik_problem* p, int B, const bik_inputs* in, float dt, float* J, float* e, float* e_posture, float* G_coll,
                           float* h_coll, void* stream) {
+  if (B == 0 && p) return BIK_OK;
   int rc = check_inputs(p, in, true);
   if (rc) return rc;
   const PHeader& h = p->h;
@@ -387,8 +400,14 @@ extern "C" int bik_limits_box(const bik_problem* p, int B, const float* q, float
   return dispatch_k2(p, a, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int bik_solve_ex(const bik_problem* p, int B, const float* q, const float* J, const float* e, const float* e_posture, const float* G_coll,
+                            const float* h_coll, float dt, double damping, float* dq, int32_t* status, int32_t* iters, void* stream);
 extern "C" int bik_solve(const bik_problem* p, int B, const float* q, const float* J, const float* e, const float* e_posture, const float* G_coll,
                          const float* h_coll, float dt, double damping, float* dq, int32_t* status, void* stream) {
+  return bik_solve_ex(p, B, q, J, e, e_posture, G_coll, h_coll, dt, damping, dq, status, nullptr, stream);
+}
+extern "C" int bik_solve_ex(const bik_problem* p, int B, const float* q, const float* J, const float* e, const float* e_posture, const float* G_coll,
+                            const float* h_coll, float dt, double damping, float* dq, int32_t* status, int32_t* iters, void* stream) {
   if (!p || !q || !dq || B < 0) return fail(BIK_ERR_INVALID, "null argument");
   const PHeader& h = p->h;
   if ((h.K > 0 && (!J || !e)) || (h.P > 0 && !e_posture) || (h.npairs > 0 && (!G_coll || !h_coll))) return fail(BIK_ERR_INVALID, "null input");
@@ -396,7 +415,7 @@ extern "C" int bik_solve(const bik_problem* p, int B, const float* q, const floa
   DeviceGuard g(p->model->device);
   K2Args a;
   memset(&a, 0, sizeof a);
-  a.B = B; a.q = q; a.J = J; a.e = e; a.ep = e_posture; a.Gc = G_coll; a.hc = h_coll; a.dt = dt; a.damping = damping; a.dq = dq; a.status = status;
+  a.B = B; a.q = q; a.J = J; a.e = e; a.ep = e_posture; a.Gc = G_coll; a.hc = h_coll; a.dt = dt; a.damping = damping; a.dq = dq; a.status = status; a.iters = iters;
   if (status) CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, static_cast<cudaStream_t>(stream)));
   return dispatch_k2(p, a, static_cast<cudaStream_t>(stream));
 }
@@ -435,10 +454,10 @@ static int ensure_workspace(bik_problem* p, int B) {
 
 extern "C" int bik_step(const bik_problem* cp, int B, float* q, const bik_inputs* in, float dt, double damping, int nsteps, int integrate, float* dq,
                         int32_t* status, void* stream) {
+  if (B == 0 && cp) return BIK_OK;
   int rc = check_inputs(cp, in, false);
   if (rc) return rc;
   if (!q || !dq || B < 0 || nsteps < 1) return fail(BIK_ERR_INVALID, "bad argument");
-  if (B == 0) return BIK_OK;
   bik_problem* p = const_cast<bik_problem*>(cp);
   std::lock_guard<std::mutex> lock(p->mu);
   DeviceGuard g(p->model->device);

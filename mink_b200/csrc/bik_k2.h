@@ -46,17 +46,40 @@ enum { K2_MAX_GEN = 16 };  // general (collision) rows that may be active at onc
 
 BIK_HD int tri(int i) { return (i * (i + 1)) >> 1; }
 
-// per-warp scratch, in bytes, for scalar type of size `ts`
+// per-warp scratch, in bytes, for scalar type of size `ts`.
+// Layout: Hp | U | dinv c lo hi x | [general-row block] | ints.   U is a union: during assembly it
+// holds the weighted Jacobian rows (fp32), afterwards the packed factor augmented by the rhs row.
+BIK_HD int k2_union_bytes(const PHeader& h, int ts) {
+  int n = h.nv;
+  int lp = tri(n + 1) * ts + 16;                       // (n+1) rows: factor + fused right-hand side
+  int wj = 4 * ((h.K > 0 ? h.K : 1) * (n + 1)) + 16;  // wJ [K][n] + we [K]
+  return ((lp > wj ? lp : wj) + 15) & ~15;
+}
 BIK_HD int k2_warp_bytes(const PHeader& h, int ts) {
   int n = h.nv, np = h.npairs;
-  int words_T = 2 * tri(n) + 6 * n + (np > 0 ? (K2_MAX_GEN * n + K2_MAX_GEN * K2_MAX_GEN + 3 * K2_MAX_GEN + np) : 0);
-  int bytes = words_T * ts + 4 * (2 * n + 3 * np + 12) + 4 * ((h.K > 0 ? h.K : 1) * (n + 1));
+  int words_T = tri(n) + 5 * n + (np > 0 ? (K2_MAX_GEN * n + K2_MAX_GEN * K2_MAX_GEN + 3 * K2_MAX_GEN + np) : 0);
+  int bytes = ((words_T * ts + 15) & ~15) + k2_union_bytes(h, ts) + 4 * (2 * n + 3 * np + 12);
   return (bytes + 15) & ~15;
 }
 
 template <typename T> BIK_HD T bik_sqrt(T x);
 template <> BIK_HD float bik_sqrt<float>(float x) { return sqrtf(x); }
 template <> BIK_HD double bik_sqrt<double>(double x) { return sqrt(x); }
+template <typename T> BIK_HD T bik_rsqrt(T x);
+template <> BIK_HD float bik_rsqrt<float>(float x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+template <> BIK_HD double bik_rsqrt<double>(double x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
 
 template <int W> BIK_HD int warp_sum_i(int v) {
 #if defined(__CUDA_ARCH__)
@@ -70,9 +93,17 @@ template <int W> BIK_HD int warp_max_i(int v) {
 #endif
   return v;
 }
+template <typename T> BIK_HD T warp_bcast(T v, int src) {
+#if defined(__CUDA_ARCH__)
+  return __shfl_sync(0xffffffffu, v, src);
+#else
+  (void)src;
+  return v;
+#endif
+}
 
 template <typename T> struct K2Ws {
-  T *Hp, *Lp, *c, *lo, *hi, *x, *y, *g;
+  T *Hp, *Lp, *dinv, *c, *lo, *hi, *x;
   T *Y, *S, *lam, *rg, *hg, *sg;  // general rows: Y = L^-1 G_F^T (K2_MAX_GEN x n), S Schur, lam, rhs, h, slack
   int *st, *idx, *gst, *gidx, *gnew;
   float *wJ, *we;
@@ -80,15 +111,19 @@ template <typename T> struct K2Ws {
 template <typename T> BIK_HD K2Ws<T> k2_carve(const PHeader& h, void* mem) {
   K2Ws<T> w;
   int n = h.nv, np = h.npairs;
-  T* p = reinterpret_cast<T*>(mem);
-  w.Hp = p; p += tri(n); w.Lp = p; p += tri(n);
-  w.c = p; p += n; w.lo = p; p += n; w.hi = p; p += n; w.x = p; p += n; w.y = p; p += n; w.g = p; p += n;
+  char* base = reinterpret_cast<char*>(mem);
+  T* p = reinterpret_cast<T*>(base);
+  w.Hp = p; p += tri(n);
+  w.dinv = p; p += n; w.c = p; p += n; w.lo = p; p += n; w.hi = p; p += n; w.x = p; p += n;
   w.Y = w.S = w.lam = w.rg = w.hg = w.sg = nullptr;
   if (np > 0) { w.Y = p; p += K2_MAX_GEN * n; w.S = p; p += K2_MAX_GEN * K2_MAX_GEN; w.lam = p; p += K2_MAX_GEN; w.rg = p; p += K2_MAX_GEN; w.sg = p; p += K2_MAX_GEN; w.hg = p; p += np; }
-  int* ip = reinterpret_cast<int*>(p);
+  int words_T = (int)(p - reinterpret_cast<T*>(base));
+  char* u = base + ((words_T * (int)sizeof(T) + 15) & ~15);
+  w.Lp = reinterpret_cast<T*>(u);
+  w.wJ = reinterpret_cast<float*>(u);
+  w.we = w.wJ + (h.K > 0 ? h.K : 1) * n;
+  int* ip = reinterpret_cast<int*>(u + k2_union_bytes(h, sizeof(T)));
   w.st = ip; ip += n; w.idx = ip; ip += n; w.gst = ip; ip += np + 4; w.gidx = ip; ip += np + 4; w.gnew = ip; ip += np + 4;
-  float* fp = reinterpret_cast<float*>(ip);
-  w.wJ = fp; fp += (h.K > 0 ? h.K : 1) * n; w.we = fp;
   return w;
 }
 
@@ -180,62 +215,81 @@ BIK_HD void k2_assemble(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int 
   BIK_SYNCWARP();
 }
 
-// ---- packed Cholesky of the free block + solves ------------------------------------------------
-// Lp holds, on entry, the lower triangle of the nf x nf matrix to factor (compact indices).
-template <typename T, int W>
-BIK_HD int k2_cholesky(T* Lp, int nf, int lane) {
-  constexpr int SLOTS = (64 + W - 1) / W;
+// ---- packed Cholesky of the free block, right-hand side fused as row nf -------------------------
+// On entry Lp holds the lower triangle of the nf x nf block (compact indices) and, as row nf, the
+// right-hand side y.  On exit row i (< nf) holds L[i][0..i-1] (the diagonal is kept as its inverse in
+// dinv) and row nf holds L^-1 y: the forward substitution is just one more row of the same recurrence.
+// Lane i % W owns row i; one warp barrier per column; no division or square root on the critical
+// path (rsqrt once per column, by the lane that owns the next diagonal, from a running sum of squares).
+template <typename T, int W, int SLOTS>
+BIK_HD int k2_factor(T* Lp, T* dinv, int nf, int lane) {
   int bad = 0;
+  T ss[SLOTS];
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) ss[s] = T(0);
+  if (lane == 0 && nf > 0) {
+    T d = Lp[0];
+    if (!(d > T(0))) { bad = 1; d = T(1e-30); }
+    dinv[0] = bik_rsqrt<T>(d);
+  }
+  BIK_SYNCWARP();
   for (int j = 0; j < nf; ++j) {
-    T tmp[SLOTS];
     const T* Lj = Lp + tri(j);
+    const T inv = dinv[j];
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
-      int i = lane + s * W;
-      tmp[s] = T(0);
-      if (i >= j && i < nf) {
+      const int i = lane + s * W;
+      if (i > j && i <= nf) {
         T* Li = Lp + tri(i);
-        T v = Li[j];
-        for (int k = 0; k < j; ++k) v -= Li[k] * Lj[k];
-        tmp[s] = v;
-        if (i == j) { if (!(v > T(0))) { bad = 1; v = T(1e-30); } Li[j] = bik_sqrt<T>(v); }
+        T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+        int k = 0;
+        for (; k + 3 < j; k += 4) {
+          a0 += Li[k] * Lj[k]; a1 += Li[k + 1] * Lj[k + 1]; a2 += Li[k + 2] * Lj[k + 2]; a3 += Li[k + 3] * Lj[k + 3];
+        }
+        for (; k < j; ++k) a0 += Li[k] * Lj[k];
+        T l = (Li[j] - ((a0 + a1) + (a2 + a3))) * inv;
+        Li[j] = l;
+        ss[s] += l * l;
+        if (i == j + 1 && i < nf) {
+          T d = Li[i] - ss[s];
+          if (!(d > T(0))) { bad = 1; d = T(1e-30); }
+          dinv[i] = bik_rsqrt<T>(d);
+        }
       }
-    }
-    BIK_SYNCWARP();
-    T inv = T(1) / Lj[j];
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-      int i = lane + s * W;
-      if (i > j && i < nf) Lp[tri(i) + j] = tmp[s] * inv;
     }
     BIK_SYNCWARP();
   }
   return bad;
 }
-// y <- L^-1 y
-template <typename T, int W>
-BIK_HD void k2_forward(const T* Lp, T* y, int nf, int lane) {
-  constexpr int SLOTS = (64 + W - 1) / W;
-  for (int k = 0; k < nf; ++k) {
-    if (k % W == lane) y[k] = y[k] / Lp[tri(k) + k];
-    BIK_SYNCWARP();
-    T yk = y[k];
+// Back substitution x = L^-T y with y in row nf of Lp; each lane keeps its entries in registers and
+// the pivot value travels by shuffle.  Writes x_k into out[k] (compact indices).
+template <typename T, int W, int SLOTS>
+BIK_HD void k2_backsub(const T* Lp, const T* dinv, int nf, T* out, int lane) {
+  T y[SLOTS];
+  const T* rhs = Lp + tri(nf);
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s) { int i = lane + s * W; if (i > k && i < nf) y[i] -= Lp[tri(i) + k] * yk; }
+  for (int s = 0; s < SLOTS; ++s) { int i = lane + s * W; y[s] = (i < nf) ? rhs[i] : T(0); }
+  for (int k = nf - 1; k >= 0; --k) {
+    const int ks = k / W, kl = k - ks * W;
+    T cand = y[0];
+#pragma unroll
+    for (int s = 1; s < SLOTS; ++s) if (ks == s) cand = y[s];
+    T xk = warp_bcast<T>(cand, kl) * dinv[k];
+    if (lane == kl) out[k] = xk;
+    const T* Lk = Lp + tri(k);
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) { int i = lane + s * W; if (i < k) y[s] -= Lk[i] * xk; }
   }
   BIK_SYNCWARP();
 }
-// y <- L^-T y
+// y <- L^-1 y for a separate vector (general-row path only)
 template <typename T, int W>
-BIK_HD void k2_backward(const T* Lp, T* y, int nf, int lane) {
-  constexpr int SLOTS = (64 + W - 1) / W;
-  for (int k = nf - 1; k >= 0; --k) {
-    if (k % W == lane) y[k] = y[k] / Lp[tri(k) + k];
+BIK_HD void k2_forward(const T* Lp, const T* dinv, T* y, int nf, int lane) {
+  for (int k = 0; k < nf; ++k) {
+    if (k % W == lane) y[k] = y[k] * dinv[k];
     BIK_SYNCWARP();
-    T xk = y[k];
-    const T* Lk = Lp + tri(k);
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) { int i = lane + s * W; if (i < k) y[i] -= Lk[i] * xk; }
+    T yk = y[k];
+    for (int i = lane; i < nf; i += W) if (i > k) y[i] -= Lp[tri(i) + k] * yk;
   }
   BIK_SYNCWARP();
 }
@@ -245,7 +299,7 @@ template <> struct K2Tol<double> { static BIK_HD double x() { return 1e-12; } st
 template <> struct K2Tol<float> { static BIK_HD float x() { return 1e-7f; } static BIK_HD float g() { return 1e-4f; } };
 
 // Returns status bits.  On exit w.x holds dq.
-template <typename T, int W>
+template <typename T, int W, int SLOTS>
 BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane, int* iters_out) {
   const PHeader& h = P.h();
   const int n = h.nv, np = h.npairs;
@@ -265,36 +319,35 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
     // x on the bounds, rhs of the reduced system, copy of H_FF
     for (int i = lane; i < n; i += W) w.x[i] = w.st[i] == 1 ? w.lo[i] : (w.st[i] == 2 ? w.hi[i] : T(0));
     BIK_SYNCWARP();
+    T* rhs = w.Lp + tri(nf);
     for (int i = lane; i < nf; i += W) {
       int ii = w.idx[i];
+      const T* Hrow = w.Hp + tri(ii);
       T r = -w.c[ii];
-      for (int j = 0; j < n; ++j) if (w.st[j]) r -= Hsym(w.Hp, ii, j) * w.x[j];
-      w.y[i] = r;
+      for (int j = 0; j < ii; ++j) if (w.st[j]) r -= Hrow[j] * w.x[j];
+      for (int j = ii + 1; j < n; ++j) if (w.st[j]) r -= w.Hp[tri(j) + ii] * w.x[j];
+      rhs[i] = r;
       T* Li = w.Lp + tri(i);
-      for (int j = 0; j <= i; ++j) Li[j] = Hsym(w.Hp, ii, w.idx[j]);
+      for (int j = 0; j <= i; ++j) Li[j] = Hrow[w.idx[j]];
     }
     BIK_SYNCWARP();
-    if (k2_cholesky<T, W>(w.Lp, nf, lane)) status |= 4;
+    if (k2_factor<T, W, SLOTS>(w.Lp, w.dinv, nf, lane)) status |= 4;
     status = warp_max_i<W>(status);
-    if (ng == 0) {
-      k2_forward<T, W>(w.Lp, w.y, nf, lane);
-      k2_backward<T, W>(w.Lp, w.y, nf, lane);
-    } else {
+    if (ng > 0) {
       // KKT with active general rows R:  [H_FF G_RF^T; G_RF 0][x_F; lam] = [y; h_R - G_RA x_A]
       // Y_r = L^-1 G_rF^T,  S = Y Y^T,  lam = S^-1 (Y (L^-1 y) - rhs),  x_F = L^-T (L^-1 y - Y^T lam)
       for (int r = 0; r < ng; ++r) {
         const float* Gr = Gb + (long long)w.gidx[r] * n;
         T* Yr = w.Y + r * n;
         for (int i = lane; i < nf; i += W) Yr[i] = T(Gr[w.idx[i]]);
-        if (lane == 0) { T s = w.hg[w.gidx[r]]; for (int j = 0; j < n; ++j) if (w.st[j]) s -= T(Gr[j]) * w.x[j]; w.rg[r] = s; }
+        if (lane == 0) { T sv = w.hg[w.gidx[r]]; for (int j = 0; j < n; ++j) if (w.st[j]) sv -= T(Gr[j]) * w.x[j]; w.rg[r] = sv; }
         BIK_SYNCWARP();
-        k2_forward<T, W>(w.Lp, Yr, nf, lane);
+        k2_forward<T, W>(w.Lp, w.dinv, Yr, nf, lane);
       }
-      k2_forward<T, W>(w.Lp, w.y, nf, lane);
       if (lane == 0) {  // tiny dense solve, serial
         for (int r = 0; r < ng; ++r) {
-          for (int s = 0; s <= r; ++s) { T v = T(0); for (int i = 0; i < nf; ++i) v += w.Y[r * n + i] * w.Y[s * n + i]; w.S[r * K2_MAX_GEN + s] = v; w.S[s * K2_MAX_GEN + r] = v; }
-          T v = -w.rg[r]; for (int i = 0; i < nf; ++i) v += w.Y[r * n + i] * w.y[i]; w.lam[r] = v;
+          for (int q2 = 0; q2 <= r; ++q2) { T v = T(0); for (int i = 0; i < nf; ++i) v += w.Y[r * n + i] * w.Y[q2 * n + i]; w.S[r * K2_MAX_GEN + q2] = v; w.S[q2 * K2_MAX_GEN + r] = v; }
+          T v = -w.rg[r]; for (int i = 0; i < nf; ++i) v += w.Y[r * n + i] * rhs[i]; w.lam[r] = v;
         }
         for (int j = 0; j < ng; ++j) {  // Cholesky of S in place + solve
           T d = w.S[j * K2_MAX_GEN + j]; for (int k = 0; k < j; ++k) d -= w.S[j * K2_MAX_GEN + k] * w.S[j * K2_MAX_GEN + k];
@@ -305,11 +358,12 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
         for (int i = ng - 1; i >= 0; --i) { T v = w.lam[i]; for (int k = i + 1; k < ng; ++k) v -= w.S[k * K2_MAX_GEN + i] * w.lam[k]; w.lam[i] = v / w.S[i * K2_MAX_GEN + i]; }
       }
       BIK_SYNCWARP();
-      for (int i = lane; i < nf; i += W) { T v = w.y[i]; for (int r = 0; r < ng; ++r) v -= w.Y[r * n + i] * w.lam[r]; w.y[i] = v; }
+      for (int i = lane; i < nf; i += W) { T v = rhs[i]; for (int r = 0; r < ng; ++r) v -= w.Y[r * n + i] * w.lam[r]; rhs[i] = v; }
       BIK_SYNCWARP();
-      k2_backward<T, W>(w.Lp, w.y, nf, lane);
     }
-    for (int i = lane; i < nf; i += W) w.x[w.idx[i]] = w.y[i];
+    // x_F = L^-T (.), overwriting the rhs row in place
+    k2_backsub<T, W, SLOTS>(w.Lp, w.dinv, nf, rhs, lane);
+    for (int i = lane; i < nf; i += W) w.x[w.idx[i]] = rhs[i];
     BIK_SYNCWARP();
     // gradient on the active bounds, feasibility of free variables and of general rows.
     // Proposed new states go to w.idx (free after the scatter above) and w.gnew.
@@ -322,7 +376,9 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
         else if (xi > w.hi[i] + tolx * (T(1) + (w.hi[i] < 0 ? -w.hi[i] : w.hi[i]))) ns = 2;
       } else {
         T gi = w.c[i];
-        for (int j = 0; j < n; ++j) gi += Hsym(w.Hp, i, j) * w.x[j];
+        const T* Hrow = w.Hp + tri(i);
+        for (int j = 0; j <= i; ++j) gi += Hrow[j] * w.x[j];
+        for (int j = i + 1; j < n; ++j) gi += w.Hp[tri(j) + i] * w.x[j];
         for (int r = 0; r < ng; ++r) gi += T(Gb[(long long)w.gidx[r] * n + i]) * w.lam[r];
         if (cur == 1 && gi < -tolg) ns = 0;
         else if (cur == 2 && gi > tolg) ns = 0;
@@ -364,7 +420,7 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
 }
 
 // One instance per warp: assemble, optionally dump (H, c) / (lo, hi), solve, write dq.
-template <typename T, int W>
+template <typename T, int W, int SLOTS>
 BIK_HD void k2_warp(const PView& P, const K2Args& a, int b, void* wsm, int lane) {
   const PHeader& h = P.h();
   const int n = h.nv;
@@ -378,7 +434,7 @@ BIK_HD void k2_warp(const PView& P, const K2Args& a, int b, void* wsm, int lane)
     for (int d = lane; d < n; d += W) { a.lo_out[(long long)b * n + d] = float(w.lo[d]); a.hi_out[(long long)b * n + d] = float(w.hi[d]); }
   if (!a.dq) return;
   int iters = 0;
-  int st = k2_solve<T, W>(P, a, b, w, lane, &iters);
+  int st = k2_solve<T, W, SLOTS>(P, a, b, w, lane, &iters);
   for (int d = lane; d < n; d += W) {
     T v = w.x[d];
     if (!(v == v)) st |= 4;

@@ -161,16 +161,17 @@ class Problem:
         _lib.check(self.lib.bik_limits_box(self.handle, q.shape[0], q.data_ptr(), float(dt), lo.data_ptr(), hi.data_ptr(), _stream()))
         return lo, hi
 
-    def solve(self, q, J, e, ep, Gc, hc, dt: float, damping: float):
+    def solve(self, q, J, e, ep, Gc, hc, dt: float, damping: float, return_iters: bool = False):
         q = self.model._rows(q, self.nq)
         B = q.shape[0]
         dq = torch.empty((B, self.nv), device=q.device, dtype=torch.float32)
         st = torch.empty(B, device=q.device, dtype=torch.int32)
-        _lib.check(self.lib.bik_solve(self.handle, B, q.data_ptr(), _ptr(J) if self.K else None, _ptr(e) if self.K else None,
-                                      _ptr(ep) if self.P else None, _ptr(Gc) if self.npairs else None,
-                                      _ptr(hc) if self.npairs else None, float(dt), float(damping), dq.data_ptr(),
-                                      st.data_ptr(), _stream()))
-        return dq, st
+        it = torch.zeros(B, device=q.device, dtype=torch.int32) if return_iters else None
+        _lib.check(self.lib.bik_solve_ex(self.handle, B, q.data_ptr(), _ptr(J) if self.K else None, _ptr(e) if self.K else None,
+                                         _ptr(ep) if self.P else None, _ptr(Gc) if self.npairs else None,
+                                         _ptr(hc) if self.npairs else None, float(dt), float(damping), dq.data_ptr(),
+                                         st.data_ptr(), _ptr(it), _stream()))
+        return (dq, st, it) if return_iters else (dq, st)
 
     def step(self, q: torch.Tensor, frame_targets=None, posture_targets=None, com_targets=None, dt: float = 1e-2,
              damping: float = 1e-12, nsteps: int = 1, integrate: bool = False, dq: Optional[torch.Tensor] = None,

@@ -56,7 +56,7 @@ extern "C" int emu_solve(void* prob, int B, const float* q, const float* J, cons
   std::vector<double> wsm(k2_warp_bytes(P.h(), 8) / 8 + 16);
   for (int b = 0; b < B; ++b) {
     if (status) status[b] = 0;
-    if (use_double) k2_warp<double, 1>(P, a, b, wsm.data(), 0); else k2_warp<float, 1>(P, a, b, wsm.data(), 0);
+    if (use_double) k2_warp<double, 1, 65>(P, a, b, wsm.data(), 0); else k2_warp<float, 1, 65>(P, a, b, wsm.data(), 0);
   }
   return 0;
 }
