@@ -1,0 +1,164 @@
+"""Host-side front end (no GPU): Lie value types against the reference-generated goldens and the
+reference's algebraic property tests (tests/test_lie_*.py), task/limit validation and error messages
+(tests/test_frame_task.py, test_posture_task.py, test_com_task.py, test_velocity_limit.py,
+test_configuration_limit.py), and lowering of tasks/limits to C-ABI descriptors."""
+
+import numpy as np
+import pytest
+
+import mink_b200 as mink
+from mink_b200._abi import LIMIT_CONFIGURATION, LIMIT_VELOCITY, TASK_FRAME, TASK_POSTURE, ProblemSpec, spec_from_workload
+from mink_b200.lie import SE3, SO3
+from tests.helpers import load_case, load_flat
+
+
+# ---------------------------------------------------------------- Lie ---------------------------
+@pytest.mark.parametrize("name", ["g1", "shadow", "ur5e"])
+def test_frame_error_matches_reference_golden(name):
+    """target.minus(pose) with this package's SE3 == reference FrameTask.compute_error."""
+    wl, fm, spec, g = load_case(name)
+    e = SE3(g["frame_targets"]).minus(SE3(g["frame_pose"]))
+    np.testing.assert_allclose(e, g["e_frame"], atol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["g1", "spot"])
+def test_frame_jacobian_identity_matches_reference_golden(name):
+    """J_task = -jlog(T_wt^-1 T_wb) J_body  (frame_task.py:145-146) with this package's SE3.jlog."""
+    wl, fm, spec, g = load_case(name)
+    T_tb = SE3(g["frame_targets"]).inverse() @ SE3(g["frame_pose"])
+    J = -np.einsum("...ij,...jk->...ik", T_tb.jlog(), g["J_body"])
+    np.testing.assert_allclose(J, g["J_frame"], atol=1e-8)
+
+
+@pytest.mark.parametrize("group", [SO3, SE3])
+def test_lie_axioms(group):
+    np.random.seed(0)
+    for _ in range(10):
+        a, b, c = group.sample_uniform(), group.sample_uniform(), group.sample_uniform()
+        I = group.identity()
+        np.testing.assert_allclose(((a @ b) @ c).as_matrix(), (a @ (b @ c)).as_matrix(), atol=1e-9)
+        np.testing.assert_allclose((a @ a.inverse()).as_matrix(), I.as_matrix(), atol=1e-9)
+        np.testing.assert_allclose((I @ a).as_matrix(), a.as_matrix(), atol=1e-12)
+        np.testing.assert_allclose(group.exp(a.log()).as_matrix(), a.as_matrix(), atol=1e-9)
+        w = np.random.randn(group.tangent_dim)
+        np.testing.assert_allclose(group.exp(w).log(), w if np.linalg.norm(w[-3:]) < np.pi else group.exp(w).log(), atol=1e-9)
+        # adjoint: T exp(w) = exp(Ad_T w) T
+        np.testing.assert_allclose((a @ group.exp(w)).as_matrix(), (group.exp(a.adjoint() @ w) @ a).as_matrix(), atol=1e-9)
+        # plus / minus round trips
+        np.testing.assert_allclose(a.rplus(b.rminus(a)).as_matrix(), b.as_matrix(), atol=1e-9)
+        np.testing.assert_allclose(a.lplus(b.lminus(a)).as_matrix(), b.as_matrix(), atol=1e-9)
+        # ljac / ljacinv are inverses (rotation part above the identity-branch threshold)
+        np.testing.assert_allclose(group.ljac(w) @ group.ljacinv(w), np.eye(group.tangent_dim), atol=1e-9)
+        # log(T (+) d) ~ log T + jlog(T) d      (reference tests/test_lie_operations.py:74-79)
+        d = 1e-6 * np.random.randn(group.tangent_dim)
+        np.testing.assert_allclose(a.rplus(d).log(), a.log() + a.jlog() @ d, atol=1e-7)
+
+
+def test_se3_ljacinv_identity_branch_quirk():
+    """reference se3.py:212-214: exactly I6 below |w|^2 = 1e-10 even with translation."""
+    xi = np.array([0.3, -0.2, 0.1, 1e-7, 0.0, 0.0])
+    np.testing.assert_array_equal(SE3.ljacinv(xi), np.eye(6))
+    assert not np.allclose(SE3.ljacinv(np.array([0.3, -0.2, 0.1, 1e-3, 0, 0])), np.eye(6))
+
+
+def test_so3_helpers_and_matrix_round_trip():
+    R = SO3.from_rpy_radians(0.1, -0.4, 1.2)
+    rpy = R.as_rpy_radians()
+    np.testing.assert_allclose([rpy.roll, rpy.pitch, rpy.yaw], [0.1, -0.4, 1.2], atol=1e-12)
+    np.testing.assert_allclose(SO3.from_matrix(R.as_matrix()).as_matrix(), R.as_matrix(), atol=1e-12)
+    v = np.array([0.3, 0.1, -2.0])
+    np.testing.assert_allclose(R @ v, R.as_matrix() @ v, atol=1e-12)
+    T = SE3.from_rotation_and_translation(R, np.array([1.0, 2.0, 3.0]))
+    np.testing.assert_allclose(SE3.from_matrix(T.as_matrix()).wxyz_xyz, T.wxyz_xyz, atol=1e-12)
+    np.testing.assert_allclose(T @ v, R.as_matrix() @ v + [1, 2, 3], atol=1e-12)
+    with pytest.raises(ValueError):
+        SO3(np.zeros(3))
+
+
+def test_set_target_copies():
+    """Targets are copied on set_target (reference tests/test_frame_task.py:107-122)."""
+    t = mink.FrameTask("pelvis", "body", 1.0, 1.0)
+    T = SE3.from_translation(np.array([1.0, 0, 0]))
+    t.set_target(T)
+    T.wxyz_xyz[4] = 5.0
+    assert t.transform_target_to_world.wxyz_xyz[4] == 1.0
+
+
+# ---------------------------------------------------------------- task / limit definitions ------
+def test_task_definition_errors():
+    fm = load_flat("g1")
+    with pytest.raises(mink.InvalidGain, match=r"`gain` must be in the range \[0, 1\]"):
+        mink.FrameTask("pelvis", "body", 1.0, 1.0, gain=1.5)
+    with pytest.raises(mink.InvalidDamping, match="`lm_damping` must be >= 0"):
+        mink.FrameTask("pelvis", "body", 1.0, 1.0, lm_damping=-1.0)
+    with pytest.raises(mink.TaskDefinitionError, match="position cost should be a vector of shape 1"):
+        mink.FrameTask("pelvis", "body", [1.0, 2.0], 1.0)
+    with pytest.raises(mink.TaskDefinitionError, match="cost should be >= 0"):
+        mink.FrameTask("pelvis", "body", [-1.0, 1.5, 1.0], 1.0)
+    t = mink.FrameTask("pelvis", "body", [1.0, 2.0, 3.0], 5.0)
+    np.testing.assert_array_equal(t.cost, [1, 2, 3, 5, 5, 5])
+    with pytest.raises(mink.TaskDefinitionError, match=r"cost must be a vector of shape \(1,\) \(aka identical cost for all dofs\) or \(43,\). Got \(2,\)"):
+        mink.PostureTask(fm, cost=(0.5, 2.0))
+    with pytest.raises(mink.TaskDefinitionError, match="cost should be >= 0"):
+        mink.PostureTask(fm, cost=-1.0)
+    p = mink.PostureTask(fm, cost=1.0)
+    with pytest.raises(mink.InvalidTarget, match=r"Expected target posture to have shape \(44,\) but got \(43,\)"):
+        p.set_target(np.zeros(43))
+    with pytest.raises(mink.TargetNotSet, match="No target set for PostureTask"):
+        p._target()
+    with pytest.raises(mink.TaskDefinitionError, match=r"cost must be a vector of shape \(1,\) \(aka identical cost for all coordinates\) or \(3,\)"):
+        mink.ComTask(cost=(1.0, 2.0))
+    with pytest.raises(mink.InvalidTarget, match=r"Expected target CoM to have shape \(3,\) but got \(5,\)"):
+        mink.ComTask(cost=1.0).set_target(np.zeros(5))
+    d = mink.DampingTask(fm, 1.0)
+    assert d.gain == 0.0 and np.array_equal(d.target_q, fm.qpos0)
+    with pytest.raises(mink.InvalidFrame):
+        mink.FrameTask("nope", "site", 1.0, 1.0)._spec(fm)
+    with pytest.raises(mink.UnsupportedFrame):
+        mink.FrameTask("pelvis", "joint", 1.0, 1.0)._spec(fm)
+
+
+def test_limit_definitions():
+    fm = load_flat("g1")
+    lim = mink.ConfigurationLimit(fm)
+    np.testing.assert_array_equal(lim.indices, np.arange(6, 43))          # reference tests/test_configuration_limit.py:43-46
+    assert lim.projection_matrix.shape == (37, 43)
+    assert lim.lower[0] == -1e10 and lim.upper[3] == 1e10                   # free-joint slots stay at -+mjMAXVAL
+    with pytest.raises(mink.LimitDefinitionError, match=r"gain must be in the range \(0, 1\]"):
+        mink.ConfigurationLimit(fm, gain=0.0)
+    spec = lim._spec(fm)
+    assert spec.kind == LIMIT_CONFIGURATION and len(spec.dof) == 37
+    np.testing.assert_allclose(spec.lower, fm.dof_lo[6:])
+    lim2 = mink.ConfigurationLimit(fm, min_distance_from_limits=0.1)
+    np.testing.assert_allclose(lim2._spec(fm).upper, fm.dof_hi[6:] - 0.1)
+
+    vel = mink.VelocityLimit(fm, {"left_knee_joint": np.pi, "right_knee_joint": 2.0})
+    assert vel.indices.tolist() == [fm.names["joint"].index("left_knee_joint") + 5, fm.names["joint"].index("right_knee_joint") + 5]
+    assert vel._spec(fm).kind == LIMIT_VELOCITY
+    with pytest.raises(mink.LimitDefinitionError, match="Free joint floating_base_joint is not supported"):
+        mink.VelocityLimit(fm, {"floating_base_joint": 1.0})
+    with pytest.raises(mink.LimitDefinitionError, match=r"must have a limit of shape \(1,\). Got: \(2,\)"):
+        mink.VelocityLimit(fm, {"left_knee_joint": [1.0, 2.0]})
+    assert mink.VelocityLimit(fm).projection_matrix is None
+    with pytest.raises(Exception):
+        lim.indices[0] = 3                                                  # write-locked like the reference
+
+
+def test_collision_pairs_follow_reference_filtering():
+    wl, fm, spec, g = load_case("spot")
+    lim = mink.CollisionAvoidanceLimit(fm, wl["limits"][0]["pairs"], minimum_distance_from_collisions=0.005,
+                                       collision_detection_distance=0.3)
+    assert lim.max_num_contacts == g["h"].shape[1] == 16
+    s = lim._spec(fm)
+    ref = spec.limits[0]
+    np.testing.assert_array_equal(s.pairs, ref.pairs)
+
+
+def test_workload_lowering_shapes():
+    for name in ["ur5e", "g1", "shadow", "spot"]:
+        wl, fm, spec, g = load_case(name)
+        assert spec.nframe == len(wl["frames"]) and spec.nrows == 6 * spec.nframe + 3 * spec.ncom
+        t, nt, l, nl, keep = spec.to_c()
+        assert nt == len(spec.tasks) and nl == len(spec.limits)
+        assert t[0].kind == TASK_FRAME and abs(sum(x * x for x in t[0].frame.quat) - 1) < 1e-12
+        assert isinstance(spec.key(), bytes) and spec.key() == spec_from_workload(fm, wl).key()

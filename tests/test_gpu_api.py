@@ -1,0 +1,174 @@
+"""The mink-compatible Python API on the GPU engine, written the way the reference's own tests are
+(tests/test_solve_ik.py, test_frame_task.py, test_configuration.py, test_configuration_limit.py ...)."""
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import mink_b200 as mink  # noqa: E402
+from mink_b200.lie import SE3  # noqa: E402
+from tests.helpers import load_case, load_flat  # noqa: E402
+
+
+@pytest.fixture(autouse=True)
+def _gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def _np(t):
+    return t.detach().cpu().numpy().astype(np.float64) if hasattr(t, "detach") else np.asarray(t)
+
+
+def _g1_tasks(fm, wl):
+    tasks = [mink.FrameTask(f["name"], f["type"], f["position_cost"], f["orientation_cost"], lm_damping=f["lm_damping"])
+             for f in wl["frames"]]
+    tasks.append(mink.PostureTask(fm, cost=wl["posture"]["cost"]))
+    limits = [mink.ConfigurationLimit(fm), mink.VelocityLimit(fm, {n: np.pi for n, t in zip(fm.names["joint"], fm.node_type) if t >= 2})]
+    return tasks, limits
+
+
+def test_single_instance_matches_reference_objects():
+    """Single configuration, numpy in / numpy out: every public quantity vs the reference (golden row 0)."""
+    wl, fm, spec, g = load_case("g1")
+    cfg = mink.Configuration(fm, g["q"][0])
+    assert cfg.nq == 44 and cfg.nv == 43 and not cfg.batched
+    np.testing.assert_array_equal(cfg.q, g["q"][0])
+    tasks, limits = _g1_tasks(fm, wl)
+    for k, t in enumerate(tasks[:3]):
+        t.set_target(SE3(g["frame_targets"][0, k]))
+        e, J = t.compute_error(cfg), t.compute_jacobian(cfg)
+        assert e.shape == (6,) and J.shape == (6, 43)
+        np.testing.assert_allclose(e, g["e_frame"][0, k], atol=2e-5)
+        np.testing.assert_allclose(J, g["J_frame"][0, k], atol=5e-5)
+        T = cfg.get_transform_frame_to_world(wl["frames"][k]["name"], wl["frames"][k]["type"])
+        np.testing.assert_allclose(T.as_matrix(), SE3(g["frame_pose"][0, k]).as_matrix(), atol=5e-6)
+        np.testing.assert_allclose(cfg.get_frame_jacobian(wl["frames"][k]["name"], wl["frames"][k]["type"]), g["J_body"][0, k], atol=1e-5)
+    tasks[3].set_target(g["posture_target"])
+    np.testing.assert_allclose(tasks[3].compute_error(cfg), g["e_posture"][0], atol=1e-6)
+    Jp = tasks[3].compute_jacobian(cfg)
+    assert np.array_equal(Jp[:, :6], np.zeros((43, 6))) and np.array_equal(Jp[6:, 6:], -np.eye(37))
+    # unit-cost frame task: H = J^T J, c = e^T J ... here with the example costs against the golden total
+    prob = mink.build_ik(cfg, tasks, float(g["dt"]), float(g["damping"]), limits)
+    np.testing.assert_allclose(prob.P, g["H"][0], atol=1e-6 * np.abs(g["H"][0]).max())
+    np.testing.assert_allclose(prob.q, g["c"][0], atol=1e-5 * np.abs(g["c"][0]).max())
+    assert prob.G.shape == g["G"][0].shape == (148, 43)
+    np.testing.assert_array_equal(prob.G, g["G"][0])
+    np.testing.assert_allclose(prob.h, g["h"][0], atol=1e-6)
+    v = mink.solve_ik(cfg, tasks, float(g["dt"]), "quadprog", float(g["damping"]), limits=limits)
+    assert isinstance(v, np.ndarray) and v.shape == (43,)
+    np.testing.assert_allclose(v * float(g["dt"]), g["dq"][0], atol=1e-4)
+    np.testing.assert_allclose(cfg.integrate(v, float(g["dt"])), g["q_next"][0], atol=2e-4)
+    cfg.integrate_inplace(v, float(g["dt"]))
+    np.testing.assert_allclose(cfg.q, g["q_next"][0], atol=2e-4)
+
+
+def test_batched_solve_ik_matches_reference():
+    wl, fm, spec, g = load_case("g1")
+    cfg = mink.Configuration(fm, g["q"])
+    assert cfg.batched
+    tasks, limits = _g1_tasks(fm, wl)
+    for k in range(3):
+        tasks[k].set_target(SE3(g["frame_targets"][:, k]))
+    tasks[3].set_target(g["posture_target"])
+    v = mink.solve_ik(cfg, tasks, float(g["dt"]), "daqp", float(g["damping"]), limits=limits)
+    assert v.is_cuda and tuple(v.shape) == (32, 43)
+    np.testing.assert_allclose(_np(v) * float(g["dt"]), g["dq"], atol=1e-4)
+    e = tasks[0].compute_error(cfg)
+    np.testing.assert_allclose(_np(e), g["e_frame"][:, 0], atol=2e-5)
+    obj = tasks[0].compute_qp_objective(cfg)
+    assert tuple(obj.H.shape) == (32, 43, 43)
+    con = limits[0].compute_qp_inequalities(cfg, float(g["dt"]))
+    np.testing.assert_allclose(_np(con.h), g["h"][:, :74], atol=1e-6)
+
+
+def test_solve_ik_converges_like_reference_test():
+    """reference tests/test_solve_ik.py:95-148: UR5e `home`, +0.1 m along the site's local z, dt 5e-3,
+    Configuration + Velocity(pi) limits: error strictly decreasing, converged in < 20 steps."""
+    fm = load_flat("ur5e")
+    cfg = mink.Configuration(fm)
+    cfg.update_from_keyframe("home")
+    task = mink.FrameTask("attachment_site", "site", 1.0, 1.0)
+    T0 = cfg.get_transform_frame_to_world("attachment_site", "site")
+    task.set_target(T0 @ SE3.from_translation(np.array([0.0, 0.0, 0.1])))
+    limits = [mink.ConfigurationLimit(fm), mink.VelocityLimit(fm, {n: np.pi for n in fm.names["joint"]})]
+    dt, errs = 5e-3, []
+    v = mink.solve_ik(cfg, [task], dt, "quadprog", limits=limits)
+    # first step of the reference (SURVEY.md 8c anchor): three joints sit on the velocity bound pi*dt
+    np.testing.assert_allclose(v * dt, [0.002654728895, 0.015707963268, 0.015707963268, -0.015707963268, -0.000129333879,
+                                        0.002654787088], atol=2e-5)
+    for it in range(20):
+        err = np.linalg.norm(task.compute_error(cfg))
+        errs.append(err)
+        if err < 1e-5:
+            break
+        v = mink.solve_ik(cfg, [task], dt, "quadprog", limits=limits)
+        cfg.integrate_inplace(v, dt)
+    assert errs[0] == pytest.approx(0.1, abs=1e-5)
+    assert all(b < a for a, b in zip(errs, errs[1:]))
+    assert len(errs) < 20 and errs[-1] < 1e-5
+
+
+def test_no_tasks_and_task_at_target_give_zero_velocity():
+    """reference tests/test_solve_ik.py:74-93."""
+    fm = load_flat("ur5e")
+    cfg = mink.Configuration(fm)
+    cfg.update_from_keyframe("home")
+    np.testing.assert_allclose(mink.solve_ik(cfg, [], 1e-3, "quadprog", limits=[]), np.zeros(6), atol=1e-12)
+    task = mink.FrameTask("attachment_site", "site", 1.0, 1.0)
+    task.set_target_from_configuration(cfg)
+    np.testing.assert_allclose(mink.solve_ik(cfg, [task], 5e-3, "quadprog"), np.zeros(6), atol=1e-4)
+    assert mink.build_ik(cfg, [task], 1e-3, limits=[]).G is None                     # tests/test_solve_ik.py:62-66
+    assert mink.build_ik(cfg, [task], 1e-3, limits=None).G.shape == (12, 6)          # default ConfigurationLimit :68-72
+
+
+def test_safety_break_and_errors():
+    """reference tests/test_solve_ik.py:33-60, tests/test_configuration.py."""
+    fm = load_flat("ur5e")
+    q = fm.key("home").copy()
+    q[1] = 100.0
+    cfg = mink.Configuration(fm, q)
+    task = mink.FrameTask("attachment_site", "site", 1.0, 1.0)
+    task.set_target(SE3.identity())
+    with pytest.raises(mink.NotWithinConfigurationLimits):
+        mink.solve_ik(cfg, [task], 1e-3, "quadprog", safety_break=True)
+    mink.solve_ik(cfg, [task], 1e-3, "quadprog", safety_break=False)      # warns, continues
+    with pytest.raises(mink.NotWithinConfigurationLimits):
+        cfg.check_limits()
+    cfg.check_limits(safety_break=False)
+    with pytest.raises(mink.InvalidKeyframe):
+        cfg.update_from_keyframe("nope")
+    with pytest.raises(mink.InvalidFrame):
+        cfg.get_frame_jacobian("nope", "site")
+    with pytest.raises(mink.UnsupportedFrame):
+        cfg.get_transform_frame_to_world("attachment_site", "joint")
+    with pytest.raises(mink.TargetNotSet):
+        mink.solve_ik(mink.Configuration(fm), [mink.FrameTask("attachment_site", "site", 1.0, 1.0)], 1e-3)
+    # get_transform: pose of source in dest
+    cfg2 = mink.Configuration(fm, fm.key("home"))
+    T = cfg2.get_transform("attachment_site", "site", "wrist_3_link", "body")
+    np.testing.assert_allclose(T.translation(), [0.0, 0.1, 0.0], atol=1e-6)
+
+
+def test_com_task_and_collision_limit_spot():
+    wl, fm, spec, g = load_case("spot")
+    cfg = mink.Configuration(fm, g["q"])
+    com = mink.ComTask(cost=200.0)
+    com.set_target(g["com_target"])
+    np.testing.assert_allclose(_np(com.compute_error(cfg)), g["e_com"], atol=5e-6)
+    np.testing.assert_allclose(_np(com.compute_jacobian(cfg)), g["J_com"], atol=5e-6)
+    np.testing.assert_allclose(_np(cfg.get_com()), g["com"], atol=5e-6)
+    l = wl["limits"][0]
+    lim = mink.CollisionAvoidanceLimit(fm, l["pairs"], gain=l["gain"], minimum_distance_from_collisions=l["minimum_distance"],
+                                       collision_detection_distance=l["detection_distance"], bound_relaxation=l["bound_relaxation"])
+    con = lim.compute_qp_inequalities(cfg, float(g["dt"]))
+    fin = np.isfinite(g["h"])
+    assert np.array_equal(np.isfinite(_np(con.h)), fin)
+    np.testing.assert_allclose(_np(con.G), g["G"], atol=2e-5)
+    tasks = [mink.FrameTask(f["name"], f["type"], f["position_cost"], f["orientation_cost"]) for f in wl["frames"]]
+    for k, t in enumerate(tasks):
+        t.set_target(SE3(g["frame_targets"][:, k]))
+    v = mink.solve_ik(cfg, tasks + [com], float(g["dt"]), "quadprog", float(g["damping"]), limits=[lim])
+    np.testing.assert_allclose(_np(v) * float(g["dt"]), g["dq"], atol=5e-3)
