@@ -19,7 +19,7 @@
 #include <vector>
 
 #include "bik_build.h"
-#include "bik_k2.h"
+#include "bik_k2lr.h"
 
 using namespace bik;
 
@@ -100,6 +100,17 @@ __global__ void __launch_bounds__(128) k2_kernel(const uint32_t* __restrict__ gi
   for (int b = blockIdx.x * nwarps + warp; b < a.B; b += gridDim.x * nwarps) k2_warp<T, 32, SLOTS>(P, a, b, wsm, lane);
 }
 
+template <int SLOTS>
+__global__ void __launch_bounds__(128) k2lr_kernel(const uint32_t* __restrict__ gimage, int words, int use_tma, K2Args a) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  stage_image(smem, gimage, words, &bar, use_tma);
+  PView P{smem};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  char* wsm = reinterpret_cast<char*>(smem + words) + (size_t)warp * k2lr_warp_bytes(P.h());
+  for (int b = blockIdx.x * nwarps + warp; b < a.B; b += gridDim.x * nwarps) k2lr_warp<32, SLOTS>(P, a, b, wsm, lane);
+}
+
 template <int G>
 __global__ void __launch_bounds__(128) fk_kernel(const uint32_t* __restrict__ gimage, int words, int use_tma, FkArgs a) {
   extern __shared__ __align__(16) uint32_t smem[];
@@ -141,7 +152,11 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 struct DeviceGuard {
   int prev = -1;
-  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+    (void)cudaGetLastError();  // drop stale errors of earlier, unrelated calls on this thread
+  }
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
@@ -157,10 +172,12 @@ struct bik_model {
 
 struct bik_problem {
   const bik_model* model = nullptr;
+  int device = 0;  // copy: the model may be destroyed first
   std::vector<uint32_t> image;
   uint32_t* d_image = nullptr;
   PHeader h;
   int solve_double = 1;
+  int k2_path = 0;  // 0 auto, 1 dense only (BIK_K2_PATH=dense)
   // lazily grown scratch between K1 and K2 (one caller at a time per problem)
   std::mutex mu;
   size_t ws_B = 0;
@@ -212,11 +229,14 @@ extern "C" int bik_problem_create(const bik_model* model, const bik_task_desc* t
   if (!model || !out || ntasks < 0 || nlimits < 0 || (ntasks && !tasks) || (nlimits && !limits)) return fail(BIK_ERR_INVALID, "null argument");
   bik_problem* p = new bik_problem;
   p->model = model;
+  p->device = model->device;
   std::string err;
   if (!build_image(model->hm, tasks, ntasks, limits, nlimits, model->G, &p->image, &err)) { delete p; return fail(BIK_ERR_UNSUPPORTED, err); }
   memcpy(&p->h, p->image.data(), sizeof(PHeader));
   const char* prec = getenv("BIK_SOLVE_PRECISION");
   p->solve_double = !(prec && (std::string(prec) == "f32" || std::string(prec) == "float"));
+  const char* path = getenv("BIK_K2_PATH");
+  p->k2_path = (path && std::string(path) == "dense") ? 1 : 0;
   DeviceGuard g(model->device);
   CUDA_OK(cudaMalloc(&p->d_image, p->image.size() * 4));
   CUDA_OK(cudaMemcpy(p->d_image, p->image.data(), p->image.size() * 4, cudaMemcpyHostToDevice));
@@ -225,7 +245,7 @@ extern "C" int bik_problem_create(const bik_model* model, const bik_task_desc* t
 }
 extern "C" void bik_problem_destroy(bik_problem* p) {
   if (!p) return;
-  DeviceGuard g(p->model->device);
+  DeviceGuard g(p->device);
   cudaFree(p->d_image); cudaFree(p->J); cudaFree(p->e); cudaFree(p->ep); cudaFree(p->Gc); cudaFree(p->hc);
   cudaFree(p->hq); cudaFree(p->hft); cudaFree(p->hpt); cudaFree(p->hct); cudaFree(p->hdq); cudaFree(p->hst);
   delete p;
@@ -302,7 +322,29 @@ static int dispatch_k2_slots(const bik_problem* p, const K2Args& a, cudaStream_t
   if (slots == 2) return launch_k2<T, 2>(p, a, st);
   return launch_k2<T, 3>(p, a, st);
 }
+template <int SLOTS>
+static int launch_k2lr(const bik_problem* p, const K2Args& a, cudaStream_t st) {
+  const PHeader& h = p->h;
+  int NW = 4;
+  auto need = [&](int nw) { return (size_t)h.words * 4 + (size_t)nw * k2lr_warp_bytes(h); };
+  while (NW > 1 && (int)need(NW) > p->model->max_smem) NW >>= 1;
+  size_t smem = need(NW);
+  int grid = 1;
+  int rc = launch_geometry(k2lr_kernel<SLOTS>, p->model, smem, 32 * NW, ((long long)a.B + NW - 1) / NW, &grid);
+  if (rc) return rc;
+  k2lr_kernel<SLOTS><<<grid, 32 * NW, smem, st>>>(p->d_image, h.words, p->model->use_tma, a);
+  CUDA_OK(cudaGetLastError());
+  return BIK_OK;
+}
+// Low-rank path when the stacked task rows are well below nv, no general rows, D bounded away from 0.
+static bool use_low_rank(const bik_problem* p, const K2Args& a) {
+  const PHeader& h = p->h;
+  if (p->k2_path == 1 || !a.dq || a.Hout || a.lo_out) return false;
+  bool ok = h.npairs == 0 && h.K > 0 && h.K < 63 && 4 * h.K <= 3 * h.nv && a.damping >= 1e-6;
+  return ok;
+}
 static int dispatch_k2(const bik_problem* p, const K2Args& a, cudaStream_t st) {
+  if (use_low_rank(p, a)) return (p->h.K + 1 <= 32) ? launch_k2lr<1>(p, a, st) : launch_k2lr<2>(p, a, st);
   return p->solve_double ? dispatch_k2_slots<double>(p, a, st) : dispatch_k2_slots<float>(p, a, st);
 }
 

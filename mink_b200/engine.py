@@ -40,11 +40,16 @@ class DeviceModel:
         self.nq, self.nv = flat.nq, flat.nv
 
     def __del__(self):
+        # problems created through tasks.problem_for() reference this model: release them first
+        for prob in list(self.__dict__.get("_problems", {}).values()):
+            prob.close()
         h, self.handle = getattr(self, "handle", None), None
         if h:
             self.lib.bik_model_destroy(h)
 
     def _f32(self, a, shape=None) -> torch.Tensor:
+        if isinstance(a, np.ndarray) and not a.flags.writeable:
+            a = a.copy()
         t = torch.as_tensor(a)
         t = t.to(device=f"cuda:{self.device}", dtype=torch.float32).contiguous()
         return t if shape is None else t.reshape(shape)
@@ -94,10 +99,13 @@ class Problem:
         _lib.check(self.lib.bik_problem_dims(h, C.byref(d)))
         self.nq, self.nv, self.F, self.P, self.Cn, self.K, self.npairs = d.nq, d.nv, d.nframe, d.nposture, d.ncom, d.nrows, d.npairs
 
-    def __del__(self):
+    def close(self):
         h, self.handle = getattr(self, "handle", None), None
         if h:
             self.lib.bik_problem_destroy(h)
+
+    def __del__(self):
+        self.close()
 
     # -- inputs --------------------------------------------------------------------------------
     def _inputs(self, q, frame_targets, posture_targets, com_targets):

@@ -8,7 +8,7 @@
 #include <vector>
 
 #include "../../mink_b200/csrc/bik_build.h"
-#include "../../mink_b200/csrc/bik_k2.h"
+#include "../../mink_b200/csrc/bik_k2lr.h"
 
 using namespace bik;
 
@@ -53,10 +53,12 @@ extern "C" int emu_solve(void* prob, int B, const float* q, const float* J, cons
   EmuProblem* p = static_cast<EmuProblem*>(prob);
   PView P{p->image.data()};
   K2Args a{B, q, J, e, ep, Gc, hc, dt, damping, dq, status, iters, H, c, lo, hi, 0, 0};
-  std::vector<double> wsm(k2_warp_bytes(P.h(), 8) / 8 + 16);
+  std::vector<double> wsm((k2_warp_bytes(P.h(), 8) + k2lr_warp_bytes(P.h())) / 8 + 16);
   for (int b = 0; b < B; ++b) {
     if (status) status[b] = 0;
-    if (use_double) k2_warp<double, 1, 65>(P, a, b, wsm.data(), 0); else k2_warp<float, 1, 65>(P, a, b, wsm.data(), 0);
+    if (use_double == 2) k2lr_warp<1, 65>(P, a, b, wsm.data(), 0);   // low-rank (Woodbury) path
+    else if (use_double) k2_warp<double, 1, 65>(P, a, b, wsm.data(), 0);
+    else k2_warp<float, 1, 65>(P, a, b, wsm.data(), 0);
   }
   return 0;
 }

@@ -97,6 +97,21 @@ def test_full_step(name):
     np.testing.assert_allclose(qn, g["q_next"], atol=2 * tol)
 
 
+@pytest.mark.parametrize("name", ["g1", "ur5e", "ur5e_dls", "shadow"])
+def test_low_rank_path_matches_reference(name):
+    """K2 low-rank (Woodbury) path: same optimum as the dense path and the reference."""
+    wl, fm, spec, g, emu = _emu(name)
+    dt, damping = float(g["dt"]), float(g["damping"])
+    J, e, ep, Gc, hc = emu.fk_jac(g["q"], g["frame_targets"], g["posture_target"], None, dt=dt)
+    dq, st, it, *_ = emu.solve(g["q"], J, e, ep, Gc, hc, dt, damping, use_double=2)
+    assert not st.any()
+    err = np.abs(dq - g["dq"]).max()
+    print(name, "low-rank max |dq - dq_ref| =", err, "iters mean/max", it.mean(), it.max())
+    assert err < 1e-4
+    dq_dense, _, it_dense, *_ = emu.solve(g["q"], J, e, ep, Gc, hc, dt, damping, use_double=1)
+    np.testing.assert_allclose(dq, dq_dense, atol=2e-6)
+
+
 def test_check_limits():
     wl, fm, spec, g, emu = _emu("g1")
     q = g["q"].copy()
