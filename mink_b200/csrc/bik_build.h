@@ -227,6 +227,21 @@ inline bool build_image(const HostModel& m, const bik_task_desc* tasks, int ntas
     }
   }
 
+  // per-row (cost, gain, lm) table for the stacked rows
+  H.off_rowinfo = b.alloc(3 * std::max(H.K, 1));
+  {
+    int row = 0;
+    for (int t = 0; t < ntasks; ++t) {
+      int k = tasks[t].kind == BIK_TASK_FRAME ? 6 : (tasks[t].kind == BIK_TASK_COM ? 3 : 0);
+      for (int r = 0; r < k; ++r) {
+        b.f(H.off_rowinfo)[row + r] = (float)tasks[t].cost[r];
+        b.f(H.off_rowinfo)[H.K + row + r] = (float)tasks[t].gain;
+        b.f(H.off_rowinfo)[2 * H.K + row + r] = (float)tasks[t].lm_damping;
+      }
+      row += k;
+    }
+  }
+
   // limits
   int ncfg = 0;
   for (int l = 0; l < nlimits; ++l) if (limits[l].kind == BIK_LIMIT_CONFIGURATION) ++ncfg;

@@ -11,20 +11,33 @@
 // so one pivoting iteration costs a K x K Cholesky plus a few K x nv mat-vecs instead of an
 // nv x nv factorisation, and moving index i between F and B is the rank-one change M -+= u_i u_i^T.
 // The pivoting rule, tolerances and termination are those of the dense path (bik_k2.h): the result is
-// the same KKT point.  Arithmetic is fp64 except the storage of U (fp32, like J itself): Woodbury
-// subtracts nearly equal terms, which fp64 absorbs (cond(H) eps64 ~ 1e-11) and fp32 would not.
+// the same KKT point.  Everything is fp64: Woodbury subtracts nearly equal terms, which fp64 absorbs
+// (cond(H) eps64 ~ 1e-11) and fp32 would not.
+//
+// Code shape: the six mat-vecs of an iteration go through two small NON-inlined helpers so that the
+// pivoting loop stays inside the instruction cache (the first version, fully inlined, was fetch-bound:
+// profiles/r1_k2lr_v1.md).  Inactive entries are handled by zero-masked vectors, not by branches.
 //
 // Chosen by the dispatcher when K is well below nv, there are no general (collision) rows and
 // `damping` keeps D away from zero; otherwise the dense path runs.
 #pragma once
 #include "bik_k2.h"
 
+#if defined(__CUDACC__)
+#define BIK_NOINLINE __host__ __device__ __noinline__
+#else
+#define BIK_NOINLINE __attribute__((noinline))
+#endif
+
 namespace bik {
 
+enum { K2LR_MAX_PAIRS = 8 };  // packed-triangle entries of M per lane: tri(K) <= 32 * 8  (K <= 22); larger K loops
+
+BIK_HD int k2lr_ld(const PHeader& h) { return h.nv | 1; }
 BIK_HD int k2lr_warp_bytes(const PHeader& h) {
   int n = h.nv, K = h.K;
-  int words_T = tri(K) + tri(K + 1) + 3 * K + 5 * n + 4;
-  int bytes = words_T * 8 + 4 * (K * n + K + 4) + 4 * (2 * n + 4);
+  int words_T = K * k2lr_ld(h) + tri(K) + tri(K + 1) + 4 * K + 8 * n + 8;
+  int bytes = words_T * 8 + 4 * (2 * n + 8);
   return (bytes + 15) & ~15;
 }
 
@@ -35,65 +48,90 @@ BIK_HD void tri_unflatten(int p, int* r, int* s) {
   *r = rr; *s = p - tri(rr);
 }
 
+template <int W> BIK_HD double warp_sum_d(double v) {
+#if defined(__CUDA_ARCH__)
+  for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#endif
+  return v;
+}
+
+// out[r] = sum_j U[r][j] v[j]            (lane <-> row r)
+template <int W>
+BIK_NOINLINE void lr_rowop(const double* U, int ld, int K, int n, const double* v, double* out, int lane) {
+  for (int r = lane; r < K; r += W) {
+    const double* Ur = U + r * ld;
+    double a0 = 0, a1 = 0;
+    int j = 0;
+    for (; j + 1 < n; j += 2) { a0 += Ur[j] * v[j]; a1 += Ur[j + 1] * v[j + 1]; }
+    if (j < n) a0 += Ur[j] * v[j];
+    out[r] = a0 + a1;
+  }
+  BIK_SYNCWARP();
+}
+// out[i] = sum_r U[r][i] w[r]            (lane <-> column i)
+template <int W>
+BIK_NOINLINE void lr_colop(const double* U, int ld, int K, int n, const double* w, double* out, int lane) {
+  for (int i = lane; i < n; i += W) {
+    const double* Ui = U + i;
+    double a0 = 0, a1 = 0;
+    int r = 0;
+    for (; r + 1 < K; r += 2) { a0 += Ui[r * ld] * w[r]; a1 += Ui[(r + 1) * ld] * w[r + 1]; }
+    if (r < K) a0 += Ui[r * ld] * w[r];
+    out[i] = a0 + a1;
+  }
+  BIK_SYNCWARP();
+}
+// M[p] += sgn * U[r][i] U[s][i] over this lane's packed-triangle entries
+template <int W>
+BIK_NOINLINE void lr_rank1(double* M, const double* U, int ld, int npairs, int i, double sgn, int lane) {
+  for (int p = lane; p < npairs; p += W) {
+    int r, s;
+    tri_unflatten(p, &r, &s);
+    M[p] += sgn * U[r * ld + i] * U[s * ld + i];
+  }
+}
+
 template <int W, int SLOTS>
 BIK_HD void k2lr_warp(const PView& P, const K2Args& a, int b, void* wsm, int lane) {
   typedef double T;
   const PHeader& h = P.h();
-  const int n = h.nv, K = h.K;
+  const int n = h.nv, K = h.K, ld = k2lr_ld(h), NP = tri(K);
   // ---- carve ------------------------------------------------------------------------------------
-  T* M0 = reinterpret_cast<T*>(wsm);          // tri(K): I + U_F U_F^T, kept up to date across iterations
-  T* Lp = M0 + tri(K);                        // tri(K+1): factor workspace, row K = right-hand side
-  T* dM = Lp + tri(K + 1);                    // K: inverse diagonal of the factor
-  T* tv = dM + K;                             // K
-  T* yv = tv + K;                             // K
-  T* ct = yv + K;                             // n: c~
-  T* lo = ct + n; T* hi = lo + n; T* x = hi + n; T* sd = x + n;   // n each
-  float* U = reinterpret_cast<float*>(sd + n + 4);
-  float* we = U + K * n;
-  int* st = reinterpret_cast<int*>(we + K + 4);
+  T* U = reinterpret_cast<T*>(wsm);            // K x ld: scaled weighted Jacobian rows
+  T* M0 = U + K * ld;                           // tri(K): I + U_F U_F^T, maintained across iterations
+  T* Lp = M0 + NP;                              // tri(K+1): factor workspace, row K = right-hand side
+  T* dM = Lp + tri(K + 1);                      // K: inverse diagonal of the factor
+  T* tv = dM + K; T* yv = tv + K; T* we = yv + K;   // K each
+  T* ct = we + K;                               // n: c~
+  T* lo = ct + n; T* hi = lo + n; T* x = hi + n; T* sd = x + n; T* xb = sd + n; T* zf = xb + n; T* tmp = zf + n;
+  int* st = reinterpret_cast<int*>(tmp + n + 8);
   int* nst = st + n;
 
   const float* Jb = a.J + (long long)b * K * n;
   const float* eb = a.e + (long long)b * K;
-  // ---- weighted rows W J and W(-gain e) (task.py:128-129) -------------------------------------------
-  for (int f = 0; f < h.F; ++f) {
-    const FrameRec& fr = P.frame(f);
-    for (int k = lane; k < 6 * n; k += W) { int r = k / n; U[fr.row0 * n + k] = fr.cost[r] * Jb[fr.row0 * n + k]; }
-    for (int r = lane; r < 6; r += W) we[fr.row0 + r] = fr.cost[r] * (-fr.gain * eb[fr.row0 + r]);
-  }
-  for (int c = 0; c < h.C; ++c) {
-    const float* cr = P.f(h.off_com) + 8 * c;
-    int row0 = reinterpret_cast<const int32_t*>(cr)[5];
-    for (int k = lane; k < 3 * n; k += W) { int r = k / n; U[row0 * n + k] = cr[r] * Jb[row0 * n + k]; }
-    for (int r = lane; r < 3; r += W) we[row0 + r] = cr[r] * (-cr[3] * eb[row0 + r]);
-  }
-  BIK_SYNCWARP();
-  // ---- mu = damping + sum_t lm_t ||W(-gain e)||^2 (task.py:131), every lane in the same order ---------
-  T mu = T(a.damping);
-  for (int f = 0; f < h.F; ++f) {
-    const FrameRec& fr = P.frame(f);
-    if (fr.lm != 0.f) { T s = 0; for (int r = 0; r < 6; ++r) s += T(we[fr.row0 + r]) * T(we[fr.row0 + r]); mu += T(fr.lm) * s; }
-  }
-  for (int c = 0; c < h.C; ++c) {
-    const float* cr = P.f(h.off_com) + 8 * c;
-    int row0 = reinterpret_cast<const int32_t*>(cr)[5];
-    if (cr[4] != 0.f) { T s = 0; for (int r = 0; r < 3; ++r) s += T(we[row0 + r]) * T(we[row0 + r]); mu += T(cr[4]) * s; }
+  const float* rowcost = P.f(h.off_rowinfo);
+  const float* rowgain = rowcost + K;
+  const float* rowlm = rowgain + K;
+  // ---- W(-gain e) and mu = damping + sum_t lm_t ||W(-gain e)||^2 (task.py:128-131) --------------------
+  T mu_part = 0;
+  for (int r = lane; r < K; r += W) {
+    T w = T(rowcost[r]) * (-T(rowgain[r]) * T(eb[r]));
+    we[r] = w;
+    mu_part += T(rowlm[r]) * w * w;
   }
   for (int p = 0; p < h.P; ++p) {
     const float* pr = P.f(h.off_posture) + p * (2 + n);
     if (pr[1] != 0.f) {
       const float* epb = a.ep + ((long long)b * h.P + p) * n;
-      T s = 0;
-      for (int d = 0; d < n; ++d) { T v = T(pr[2 + d]) * T(pr[0]) * T(epb[d]); s += v * v; }
-      mu += T(pr[1]) * s;
+      for (int d = lane; d < n; d += W) { T v = T(pr[2 + d]) * T(pr[0]) * T(epb[d]); mu_part += T(pr[1]) * v * v; }
     }
   }
-  // ---- per dof: diagonal d, linear term, box; then scale to x~ = sqrt(d) x --------------------------
+  const T mu = T(a.damping) + warp_sum_d<W>(mu_part);
+  BIK_SYNCWARP();
+  // ---- per dof: diagonal d, linear term, box, scaled column of U -------------------------------------
   int status = 0;
   for (int d = lane; d < n; d += W) {
-    T cd = 0;
-    for (int r = 0; r < K; ++r) cd -= T(we[r]) * T(U[r * n + d]);
-    T hd = mu;
+    T hd = mu, cd = 0;
     for (int p = 0; p < h.P; ++p) {
       const float* pr = P.f(h.off_posture) + p * (2 + n);
       T wgt = T(pr[2 + d]);
@@ -101,23 +139,27 @@ BIK_HD void k2lr_warp(const PView& P, const K2Args& a, int b, void* wsm, int lan
       cd -= T(pr[0]) * wgt * wgt * T(a.ep[((long long)b * h.P + p) * n + d]);
     }
     if (!(hd > T(0))) { status |= 4; hd = T(1); }
-    T s = bik_sqrt<T>(hd), is = T(1) / s;
+    const T is = bik_rsqrt<T>(hd), s = hd * is;
+    for (int r = 0; r < K; ++r) {
+      T wj = T(rowcost[r]) * T(Jb[r * n + d]);
+      cd -= we[r] * wj;
+      U[r * ld + d] = wj * is;
+    }
     float blo, bhi;
     box_dof(P, d, a.q + (long long)b * h.nq, a.dt, &blo, &bhi);
     sd[d] = s; ct[d] = cd * is; lo[d] = T(blo) * s; hi[d] = T(bhi) * s;
-    st[d] = 0;
-    for (int r = 0; r < K; ++r) U[r * n + d] = float(T(U[r * n + d]) * is);
+    st[d] = 0; xb[d] = T(0);
   }
   BIK_SYNCWARP();
   // ---- M0 = I + U U^T over all dofs (everything free) -------------------------------------------
-  for (int p = lane; p < tri(K); p += W) {
+  for (int p = lane; p < NP; p += W) {
     int r, s;
     tri_unflatten(p, &r, &s);
-    const float* Ur = U + r * n; const float* Us = U + s * n;
+    const T* Ur = U + r * ld; const T* Us = U + s * ld;
     T a0 = 0, a1 = 0;
     int i = 0;
-    for (; i + 1 < n; i += 2) { a0 += T(Ur[i]) * T(Us[i]); a1 += T(Ur[i + 1]) * T(Us[i + 1]); }
-    if (i < n) a0 += T(Ur[i]) * T(Us[i]);
+    for (; i + 1 < n; i += 2) { a0 += Ur[i] * Us[i]; a1 += Ur[i + 1] * Us[i + 1]; }
+    if (i < n) a0 += Ur[i] * Us[i];
     M0[p] = a0 + a1 + (r == s ? T(1) : T(0));
   }
   BIK_SYNCWARP();
@@ -126,40 +168,27 @@ BIK_HD void k2lr_warp(const PView& P, const K2Args& a, int b, void* wsm, int lan
   const T tolx = K2Tol<T>::x(), tolg = K2Tol<T>::g();
   int best = n + 1, patience = PATIENCE, it = 0, nactive = 0;
   for (; it < MAXIT; ++it) {
-    // t = U_B x~_B
-    for (int r = lane; r < K; r += W) {
-      T t = 0;
-      if (nactive) { const float* Ur = U + r * n; for (int j = 0; j < n; ++j) if (st[j]) t += T(Ur[j]) * (st[j] == 1 ? lo[j] : hi[j]); }
-      tv[r] = t;
+    // t = U xb  (xb = bound value on the active set, 0 elsewhere);  z = -c~ - U^T t on the free set
+    if (nactive) {
+      lr_rowop<W>(U, ld, K, n, xb, tv, lane);
+      lr_colop<W>(U, ld, K, n, tv, tmp, lane);
     }
+    for (int i = lane; i < n; i += W) zf[i] = st[i] == 0 ? -ct[i] - (nactive ? tmp[i] : T(0)) : T(0);
     BIK_SYNCWARP();
-    // z on the free set (kept in x), bounds on the active set
-    for (int i = lane; i < n; i += W) {
-      T v;
-      if (st[i] == 0) { v = -ct[i]; if (nactive) for (int r = 0; r < K; ++r) v -= T(U[r * n + i]) * tv[r]; }
-      else v = st[i] == 1 ? lo[i] : hi[i];
-      x[i] = v;
-    }
-    BIK_SYNCWARP();
-    // right-hand side r = U_F z and a fresh copy of M0 for the factorisation
-    for (int r = lane; r < K; r += W) {
-      const float* Ur = U + r * n;
-      T acc = 0;
-      for (int j = 0; j < n; ++j) if (st[j] == 0) acc += T(Ur[j]) * x[j];
-      Lp[tri(K) + r] = acc;
-      for (int s = 0; s <= r; ++s) Lp[tri(r) + s] = M0[tri(r) + s];
-    }
+    // right-hand side r = U zf (row K of the factor workspace) and a fresh copy of M0
+    lr_rowop<W>(U, ld, K, n, zf, Lp + tri(K), lane);
+    for (int p = lane; p < NP; p += W) Lp[p] = M0[p];
     BIK_SYNCWARP();
     if (k2_factor<T, W, SLOTS>(Lp, dM, K, lane)) status |= 4;
     k2_backsub<T, W, SLOTS>(Lp, dM, K, yv, lane);
-    // x~_F = z - U_F^T y
-    for (int i = lane; i < n; i += W)
-      if (st[i] == 0) { T v = x[i]; for (int r = 0; r < K; ++r) v -= T(U[r * n + i]) * yv[r]; x[i] = v; }
+    // x~ = zf - U^T y on the free set, bounds on the active set
+    lr_colop<W>(U, ld, K, n, yv, tmp, lane);
+    for (int i = lane; i < n; i += W) x[i] = st[i] == 0 ? zf[i] - tmp[i] : xb[i];
     BIK_SYNCWARP();
-    // s = U x~ for the gradient on the active set
+    // gradient on the active set: g~ = c~ + x~ + U^T (U x~)
     if (nactive) {
-      for (int r = lane; r < K; r += W) { const float* Ur = U + r * n; T acc = 0; for (int j = 0; j < n; ++j) acc += T(Ur[j]) * x[j]; tv[r] = acc; }
-      BIK_SYNCWARP();
+      lr_rowop<W>(U, ld, K, n, x, tv, lane);
+      lr_colop<W>(U, ld, K, n, tv, tmp, lane);
     }
     int ninf = 0, last = -1;
     for (int i = lane; i < n; i += W) {
@@ -169,8 +198,7 @@ BIK_HD void k2lr_warp(const PView& P, const K2Args& a, int b, void* wsm, int lan
         if (xi < lo[i] - tolx * (T(1) + (lo[i] < 0 ? -lo[i] : lo[i]))) ns = 1;
         else if (xi > hi[i] + tolx * (T(1) + (hi[i] < 0 ? -hi[i] : hi[i]))) ns = 2;
       } else {
-        T gi = ct[i] + x[i];
-        for (int r = 0; r < K; ++r) gi += T(U[r * n + i]) * tv[r];
+        T gi = ct[i] + x[i] + tmp[i];
         if (cur == 1 && gi < -tolg) ns = 0;
         else if (cur == 2 && gi > tolg) ns = 0;
       }
@@ -185,23 +213,21 @@ BIK_HD void k2lr_warp(const PView& P, const K2Args& a, int b, void* wsm, int lan
     else if (patience > 0) { --patience; block = true; }
     else block = false;
     BIK_SYNCWARP();
-    // apply the flips: rank-one up/down-dates of M0, then the state itself
-    for (int i = 0; i < n; ++i) {
-      int cur = st[i], ns = nst[i];
-      if (ns == cur || !(block || i == last)) continue;
-      if ((cur == 0) != (ns == 0)) {
-        T sgn = (ns == 0) ? T(1) : T(-1);
-        for (int p = lane; p < tri(K); p += W) { int r, s; tri_unflatten(p, &r, &s); M0[p] += sgn * T(U[r * n + i]) * T(U[s * n + i]); }
-      }
-    }
-    BIK_SYNCWARP();
+    // apply the flips: rank-one up/down-dates of M0 (lanes over packed entries), then the state itself
     nactive = 0;
     for (int i = 0; i < n; ++i) {
-      int v = (nst[i] != st[i] && (block || i == last)) ? nst[i] : st[i];
-      nactive += v != 0;
+      int cur = st[i], ns = nst[i];
+      if (ns != cur && (block || i == last)) {
+        if ((cur == 0) != (ns == 0)) lr_rank1<W>(M0, U, ld, NP, i, ns == 0 ? T(1) : T(-1), lane);
+        cur = ns;
+      }
+      nactive += cur != 0;
     }
     BIK_SYNCWARP();
-    for (int i = lane; i < n; i += W) if (block || i == last) st[i] = nst[i];
+    for (int i = lane; i < n; i += W) {
+      if (block || i == last) st[i] = nst[i];
+      xb[i] = st[i] == 1 ? lo[i] : (st[i] == 2 ? hi[i] : T(0));
+    }
     BIK_SYNCWARP();
   }
   if (it >= MAXIT) status |= 2;
@@ -215,6 +241,7 @@ BIK_HD void k2lr_warp(const PView& P, const K2Args& a, int b, void* wsm, int lan
     if (a.status) a.status[b] |= status;
     if (a.iters) a.iters[b] = it + 1;
   }
+  BIK_SYNCWARP();
 }
 
 }  // namespace bik

@@ -59,7 +59,8 @@ struct PHeader {  // all offsets in 32-bit words from the start of the image
   int32_t off_geoms, off_pairs;  // GeomRec[ngeoms], int2[npairs]
   float coll_gain, coll_dmin, coll_ddet, coll_relax;
   float com_total_mass, com_fixed[3];  // total mass of subtree(body 1); first moment of its world-fixed part
-  int32_t reserved[9];
+  int32_t off_rowinfo;  // float[3 K]: per stacked row cost | gain | lm_damping of its task
+  int32_t reserved[8];
 };
 static_assert(sizeof(PHeader) % 16 == 0, "header must stay 16-byte aligned");
 
