@@ -107,8 +107,13 @@ __global__ void __launch_bounds__(128) k2lr_kernel(const uint32_t* __restrict__ 
   stage_image(smem, gimage, words, &bar, use_tma);
   PView P{smem};
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  char* wsm = reinterpret_cast<char*>(smem + words) + (size_t)warp * k2lr_warp_bytes(P.h());
-  for (int b = blockIdx.x * nwarps + warp; b < a.B; b += gridDim.x * nwarps) k2lr_warp<32, SLOTS>(P, a, b, wsm, lane);
+  // packed-triangle index -> (row, col) table of the K x K capacitance matrix, shared by the CTA
+  const int K = P.h().K, NP = tri(K);
+  uint16_t* pairtab = reinterpret_cast<uint16_t*>(smem + words);
+  for (int p = threadIdx.x; p < NP; p += blockDim.x) { int r, s; tri_unflatten(p, &r, &s); pairtab[p] = (uint16_t)((r << 8) | s); }
+  __syncthreads();
+  char* wsm = reinterpret_cast<char*>(smem + words) + ((NP * 2 + 15) & ~15) + (size_t)warp * k2lr_warp_bytes(P.h());
+  for (int b = blockIdx.x * nwarps + warp; b < a.B; b += gridDim.x * nwarps) k2lr_warp<32, SLOTS>(P, a, b, wsm, pairtab, lane);
 }
 
 template <int G>
@@ -326,7 +331,7 @@ template <int SLOTS>
 static int launch_k2lr(const bik_problem* p, const K2Args& a, cudaStream_t st) {
   const PHeader& h = p->h;
   int NW = 4;
-  auto need = [&](int nw) { return (size_t)h.words * 4 + (size_t)nw * k2lr_warp_bytes(h); };
+  auto need = [&](int nw) { return (size_t)h.words * 4 + ((tri(h.K) * 2 + 15) & ~15) + (size_t)nw * k2lr_warp_bytes(h); };
   while (NW > 1 && (int)need(NW) > p->model->max_smem) NW >>= 1;
   size_t smem = need(NW);
   int grid = 1;

@@ -57,7 +57,7 @@ template <int W> BIK_HD double warp_sum_d(double v) {
 
 // out[r] = sum_j U[r][j] v[j]            (lane <-> row r)
 template <int W>
-BIK_NOINLINE void lr_rowop(const double* U, int ld, int K, int n, const double* v, double* out, int lane) {
+BIK_NOINLINE void lr_rowop(const double* __restrict__ U, int ld, int K, int n, const double* __restrict__ v, double* __restrict__ out, int lane) {
   for (int r = lane; r < K; r += W) {
     const double* Ur = U + r * ld;
     double a0 = 0, a1 = 0;
@@ -70,7 +70,7 @@ BIK_NOINLINE void lr_rowop(const double* U, int ld, int K, int n, const double* 
 }
 // out[i] = sum_r U[r][i] w[r]            (lane <-> column i)
 template <int W>
-BIK_NOINLINE void lr_colop(const double* U, int ld, int K, int n, const double* w, double* out, int lane) {
+BIK_NOINLINE void lr_colop(const double* __restrict__ U, int ld, int K, int n, const double* __restrict__ w, double* __restrict__ out, int lane) {
   for (int i = lane; i < n; i += W) {
     const double* Ui = U + i;
     double a0 = 0, a1 = 0;
@@ -81,18 +81,18 @@ BIK_NOINLINE void lr_colop(const double* U, int ld, int K, int n, const double* 
   }
   BIK_SYNCWARP();
 }
-// M[p] += sgn * U[r][i] U[s][i] over this lane's packed-triangle entries
+// M[p] += sgn * U[r][i] U[s][i] over this lane's packed-triangle entries; pairtab[p] = r << 8 | s
 template <int W>
-BIK_NOINLINE void lr_rank1(double* M, const double* U, int ld, int npairs, int i, double sgn, int lane) {
+BIK_NOINLINE void lr_rank1(double* __restrict__ M, const double* __restrict__ U, const uint16_t* __restrict__ pairtab, int ld, int npairs, int i,
+                           double sgn, int lane) {
   for (int p = lane; p < npairs; p += W) {
-    int r, s;
-    tri_unflatten(p, &r, &s);
-    M[p] += sgn * U[r * ld + i] * U[s * ld + i];
+    int rs = pairtab[p];
+    M[p] += sgn * U[(rs >> 8) * ld + i] * U[(rs & 0xff) * ld + i];
   }
 }
 
 template <int W, int SLOTS>
-BIK_HD void k2lr_warp(const PView& P, const K2Args& a, int b, void* wsm, int lane) {
+BIK_HD void k2lr_warp(const PView& P, const K2Args& a, int b, void* wsm, const uint16_t* pairtab, int lane) {
   typedef double T;
   const PHeader& h = P.h();
   const int n = h.nv, K = h.K, ld = k2lr_ld(h), NP = tri(K);
@@ -153,14 +153,16 @@ BIK_HD void k2lr_warp(const PView& P, const K2Args& a, int b, void* wsm, int lan
   BIK_SYNCWARP();
   // ---- M0 = I + U U^T over all dofs (everything free) -------------------------------------------
   for (int p = lane; p < NP; p += W) {
-    int r, s;
-    tri_unflatten(p, &r, &s);
+    const int rs = pairtab[p], r = rs >> 8, s = rs & 0xff;
     const T* Ur = U + r * ld; const T* Us = U + s * ld;
-    T a0 = 0, a1 = 0;
+    T a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     int i = 0;
-    for (; i + 1 < n; i += 2) { a0 += Ur[i] * Us[i]; a1 += Ur[i + 1] * Us[i + 1]; }
-    if (i < n) a0 += Ur[i] * Us[i];
-    M0[p] = a0 + a1 + (r == s ? T(1) : T(0));
+    for (; i + 3 < n; i += 4) {
+      T u0 = Ur[i], u1 = Ur[i + 1], u2 = Ur[i + 2], u3 = Ur[i + 3], v0 = Us[i], v1 = Us[i + 1], v2 = Us[i + 2], v3 = Us[i + 3];
+      a0 += u0 * v0; a1 += u1 * v1; a2 += u2 * v2; a3 += u3 * v3;
+    }
+    for (; i < n; ++i) a0 += Ur[i] * Us[i];
+    M0[p] = (a0 + a1) + (a2 + a3) + (r == s ? T(1) : T(0));
   }
   BIK_SYNCWARP();
 
@@ -218,7 +220,7 @@ BIK_HD void k2lr_warp(const PView& P, const K2Args& a, int b, void* wsm, int lan
     for (int i = 0; i < n; ++i) {
       int cur = st[i], ns = nst[i];
       if (ns != cur && (block || i == last)) {
-        if ((cur == 0) != (ns == 0)) lr_rank1<W>(M0, U, ld, NP, i, ns == 0 ? T(1) : T(-1), lane);
+        if ((cur == 0) != (ns == 0)) lr_rank1<W>(M0, U, pairtab, ld, NP, i, ns == 0 ? T(1) : T(-1), lane);
         cur = ns;
       }
       nactive += cur != 0;

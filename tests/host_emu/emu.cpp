@@ -56,7 +56,11 @@ extern "C" int emu_solve(void* prob, int B, const float* q, const float* J, cons
   std::vector<double> wsm((k2_warp_bytes(P.h(), 8) + k2lr_warp_bytes(P.h())) / 8 + 16);
   for (int b = 0; b < B; ++b) {
     if (status) status[b] = 0;
-    if (use_double == 2) k2lr_warp<1, 65>(P, a, b, wsm.data(), 0);   // low-rank (Woodbury) path
+    if (use_double == 2) {   // low-rank (Woodbury) path
+      std::vector<uint16_t> pairtab(tri(P.h().K) + 1);
+      for (int p = 0; p < tri(P.h().K); ++p) { int r, s; tri_unflatten(p, &r, &s); pairtab[p] = (uint16_t)((r << 8) | s); }
+      k2lr_warp<1, 65>(P, a, b, wsm.data(), pairtab.data(), 0);
+    }
     else if (use_double) k2_warp<double, 1, 65>(P, a, b, wsm.data(), 0);
     else k2_warp<float, 1, 65>(P, a, b, wsm.data(), 0);
   }
