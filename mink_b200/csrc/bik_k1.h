@@ -28,6 +28,10 @@
 
 namespace bik {
 
+// plain 8/16-byte carriers for vectorised shared/global moves (float2/float4 only exist under nvcc)
+struct alignas(8) F2 { float x, y; };
+struct alignas(16) F4 { float x, y, z, w; };
+
 BIK_HD float bik_inf() {
 #if defined(__CUDA_ARCH__)
   return __int_as_float(0x7f800000);
@@ -72,8 +76,9 @@ BIK_HD int k1_state_stride(const PHeader& h) {  // pose (7) + CoM first moment (
   return s | 1;
 }
 BIK_HD int k1_stage_rows(const PHeader& h) { return 6; }
+BIK_HD int k1_state_words(const PHeader& h, int ipw) { return (ipw * k1_state_stride(h) + 3) & ~3; }  // keeps the stage 16-byte aligned
 BIK_HD int k1_warp_words(const PHeader& h, int ipw) {
-  int w = ipw * k1_state_stride(h) + ipw * k1_stage_rows(h) * h.nv + ipw * (h.K > 0 ? h.K : 1);
+  int w = k1_state_words(h, ipw) + ipw * k1_stage_rows(h) * h.nv + ipw * (h.K > 0 ? h.K : 1) + ipw * (h.F > 0 ? h.F : 1) * 24;
   return (w + 3) & ~3;
 }
 
@@ -221,11 +226,29 @@ BIK_HD float geom_distance(const GeomRec& g1, const GeomRec& g2, const float* xs
 // ---- staging flush: IPW x (R*nv) floats -> global rows [inst][row0 .. row0+R) ----------------
 template <int W>
 BIK_HD void flush_rows(const float* stage, int chunk, int nvalid, float* out, long long inst_stride, int lane) {
+  const bool vec2 = ((chunk | (int)(inst_stride & 1)) & 1) == 0 && ((reinterpret_cast<size_t>(out) | reinterpret_cast<size_t>(stage)) & 7) == 0;
+  if (vec2) {  // 8-byte stores: every run starts on an 8-byte boundary
+    const int c2 = chunk >> 1;
+    for (int li = 0; li < nvalid; ++li) {
+      F2* o = reinterpret_cast<F2*>(out + li * inst_stride);
+      const F2* s = reinterpret_cast<const F2*>(stage + li * chunk);
+      for (int k = lane; k < c2; k += W) o[k] = s[k];
+    }
+    return;
+  }
   for (int li = 0; li < nvalid; ++li) {
     float* o = out + li * inst_stride;
     const float* s = stage + li * chunk;
     for (int k = lane; k < chunk; k += W) o[k] = s[k];
   }
+}
+template <int W>
+BIK_HD void zero_words(float* p, int count, int lane) {  // p is 16-byte aligned, count a multiple of 4 or handled by the tail
+  F4* p4 = reinterpret_cast<F4*>(p);
+  const int c4 = count >> 2;
+  const F4 z = {0.f, 0.f, 0.f, 0.f};
+  for (int k = lane; k < c4; k += W) p4[k] = z;
+  for (int k = (c4 << 2) + lane; k < count; k += W) p[k] = 0.f;
 }
 
 // One warp tile: instances [inst0, inst0 + IPW) clipped to B.
@@ -240,8 +263,9 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, float* wsm,
   const bool valid = li < nvalid;
   const int SS = k1_state_stride(h);
   float* state = wsm;
-  float* stage = wsm + IPW * SS;
+  float* stage = wsm + k1_state_words(h, IPW);
   float* estage = stage + IPW * 6 * nv;
+  float* fsc = estage + IPW * (K > 0 ? K : 1);  // per (instance, frame): pf[3], A1[9], A2[9]
   float* xs = state + li * SS;
   const float* qb = a.q + (long long)(valid ? b : inst0) * nq;
 
@@ -254,19 +278,32 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, float* wsm,
   }
 
   // ---- frame tasks -------------------------------------------------------------------------
+  // (1) the G lanes of an instance evaluate different frames' SE(3) algebra (error, jlog blocks) in parallel
   const int32_t* cols = P.i(h.off_cols);
-  for (int f = 0; f < h.F; ++f) {
-    const FrameRec& fr = P.frame(f);
-    for (int k = lane; k < IPW * 6 * nv; k += W) stage[k] = 0.f;
-    BIK_SYNCWARP();
-    if (valid) {
+  if (valid) {
+    for (int f = g; f < h.F; f += G) {
+      const FrameRec& fr = P.frame(f);
       FQ qf; F3 pf, ev, ew; FM A1, A2;
       frame_pose(fr.node, fr.lpos, fr.lquat, xs, &qf, &pf);
       frame_task(qf, pf, a.ftgt + ((long long)b * h.F + f) * 7, &ev, &ew, &A1, &A2);
-      if (g == 0) {
-        float* eo = estage + li * K + fr.row0;
-        eo[0] = ev.x; eo[1] = ev.y; eo[2] = ev.z; eo[3] = ew.x; eo[4] = ew.y; eo[5] = ew.z;
-      }
+      float* eo = estage + li * K + fr.row0;
+      eo[0] = ev.x; eo[1] = ev.y; eo[2] = ev.z; eo[3] = ew.x; eo[4] = ew.y; eo[5] = ew.z;
+      float* sc = fsc + (li * h.F + f) * 24;
+      sc[0] = pf.x; sc[1] = pf.y; sc[2] = pf.z;
+      for (int k = 0; k < 9; ++k) { sc[3 + k] = A1.m[k]; sc[12 + k] = A2.m[k]; }
+    }
+  }
+  BIK_SYNCWARP();
+  // (2) per frame: Jacobian columns into the staging tile, then one coalesced flush
+  for (int f = 0; f < h.F; ++f) {
+    const FrameRec& fr = P.frame(f);
+    zero_words<W>(stage, IPW * 6 * nv, lane);
+    BIK_SYNCWARP();
+    if (valid) {
+      const float* sc = fsc + (li * h.F + f) * 24;
+      F3 pf = ld_v(sc);
+      FM A1, A2;
+      for (int k = 0; k < 9; ++k) { A1.m[k] = sc[3 + k]; A2.m[k] = sc[12 + k]; }
       float* st = stage + li * 6 * nv;
       for (int c = g; c < fr.ncols; c += G) {
         int ent = cols[fr.col_off + c], d = ent & 0xffff, n = ent >> 16;
@@ -301,7 +338,7 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, float* wsm,
     for (int c = 0; c < h.C; ++c) {
       const float* cr = P.f(h.off_com) + 8 * c;
       const int row0 = reinterpret_cast<const int32_t*>(cr)[5];
-      for (int k = lane; k < IPW * 3 * nv; k += W) stage[k] = 0.f;
+      zero_words<W>(stage, IPW * 3 * nv, lane);
       BIK_SYNCWARP();
       if (valid) {
         if (g == 0) {
@@ -347,22 +384,26 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, float* wsm,
   if (h.P > 0) {
     const int32_t* dofnode = P.i(h.off_dofnode);
     const int32_t* dofqadr = P.i(h.off_dofqadr);
-    for (int k = lane; k < nvalid * h.P * nv; k += W) {
-      int l2 = k / (h.P * nv), rem = k - l2 * (h.P * nv), p = rem / nv, d = rem - p * nv;
+    for (int l2 = 0; l2 < nvalid; ++l2) {
       const float* qq = a.q + (long long)(inst0 + l2) * nq;
-      const float* tg = a.ptgt + ((long long)(a.pbatched ? (inst0 + l2) : 0) * h.P + p) * nq;
-      float val = 0.f;
-      int qa = dofqadr[d];
-      if (qa >= 0) val = tg[qa] - qq[qa];
-      else {
-        const NodeRec& r = P.node(dofnode[d]);
-        if (r.type == JNT_BALL) {
-          F3 w = quat_sub<float>(qnormalize(ld_q(tg + r.qadr)), qnormalize(ld_q(qq + r.qadr)));
-          int c = d - r.dadr;
-          val = c == 0 ? w.x : (c == 1 ? w.y : w.z);
+      for (int p = 0; p < h.P; ++p) {
+        const float* tg = a.ptgt + ((long long)(a.pbatched ? (inst0 + l2) : 0) * h.P + p) * nq;
+        float* o = a.ep + ((long long)(inst0 + l2) * h.P + p) * nv;
+        for (int d = lane; d < nv; d += W) {
+          float val = 0.f;
+          int qa = dofqadr[d];
+          if (qa >= 0) val = tg[qa] - qq[qa];
+          else {
+            const NodeRec& r = P.node(dofnode[d]);
+            if (r.type == JNT_BALL) {
+              F3 w = quat_sub<float>(qnormalize(ld_q(tg + r.qadr)), qnormalize(ld_q(qq + r.qadr)));
+              int c = d - r.dadr;
+              val = c == 0 ? w.x : (c == 1 ? w.y : w.z);
+            }
+          }
+          o[d] = val;
         }
       }
-      a.ep[(long long)inst0 * h.P * nv + k] = val;
     }
   }
 
@@ -371,7 +412,7 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, float* wsm,
     const int32_t* pairs = P.i(h.off_pairs);
     for (int p0 = 0; p0 < h.npairs; p0 += 6) {
       int np_ = h.npairs - p0 < 6 ? h.npairs - p0 : 6;
-      for (int k = lane; k < IPW * np_ * nv; k += W) stage[k] = 0.f;
+      zero_words<W>(stage, IPW * np_ * nv, lane);
       BIK_SYNCWARP();
       if (valid) {
         for (int pi = g; pi < np_; pi += G) {

@@ -41,10 +41,17 @@ template <typename T> BIK_HD Q4<T> qmul(Q4<T> a, Q4<T> b) {
                a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x, a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w);
 }
 template <typename T> BIK_HD Q4<T> qconj(Q4<T> a) { return q4<T>(a.w, -a.x, -a.y, -a.z); }
+template <typename T> BIK_HD T inv_sqrt(T x) { return T(1) / sqrt(x); }
+#if defined(__CUDA_ARCH__)
+template <> BIK_HD float inv_sqrt<float>(float x) {  // MUFU.RSQ + one Newton step: < 1 ulp, no division
+  float r = rsqrtf(x);
+  return r * (1.5f - 0.5f * x * r * r);
+}
+#endif
 template <typename T> BIK_HD Q4<T> qnormalize(Q4<T> a) {
   T n2 = a.w * a.w + a.x * a.x + a.y * a.y + a.z * a.z;
   if (!(n2 > T(1e-30))) return q4<T>(T(1), T(0), T(0), T(0));
-  T s = T(1) / sqrt(n2);
+  T s = inv_sqrt<T>(n2);
   return q4<T>(a.w * s, a.x * s, a.y * s, a.z * s);
 }
 // rotate v by unit quaternion q:  v + 2 w (u x v) + 2 u x (u x v)
