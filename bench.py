@@ -96,6 +96,13 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(args, rank, world):
     """CPU arm: oracle port (oracle/ik_oracle.c, fp64, OpenMP over instances) = the reference's algorithm
     restated in C, because the reference itself (Python + mujoco + qpsolvers) cannot be installed here."""
@@ -110,11 +117,11 @@ def run_reference(args, rank, world):
     frames = task_frames(wl, fm)
     B = args.cpu_sample
     inp = make_inputs(fm, wl, B, lambda qq: orc.fk(qq, frames), seed=0)
-    threads = num_threads()
+    threads = host_threads()   # torchrun exports OMP_NUM_THREADS=1: ask for every core we may run on explicitly
 
     def step():
         return orc.step(inp["q"], inp["frame_targets"], inp["posture_target"], inp.get("com_target"), dt=wl["dt"],
-                        damping=wl["damping"], nsteps=1, integrate=True)
+                        damping=wl["damping"], nsteps=1, integrate=True, nthreads=threads)
 
     for _ in range(args.warmup):
         step()
@@ -265,9 +272,9 @@ def main():
         ctn = None if inp.get("com_target") is None else inp["com_target"][sl]
         t0 = time.perf_counter()
         dq_ref, _, st_ref, nact = orc.step(inp["q"][sl], inp["frame_targets"][sl], inp["posture_target"], ctn, dt=dt_, damping=damping,
-                                           nsteps=1, integrate=True)
+                                           nsteps=1, integrate=True, nthreads=host_threads())
         tc = time.perf_counter() - t0
-        cpu = {"value": Bc / tc, "unit": UNIT, "cores": num_threads(), "kind": "port",
+        cpu = {"value": Bc / tc, "unit": UNIT, "cores": host_threads(), "kind": "port",
                "sample": f"first {Bc} instances of rank 0's batch, 1 step, oracle/ik_oracle.c (fp64, OpenMP)",
                "mean_active_constraints": float(nact.mean())}
         # parity on the same sample (reported, asserted in tests)
@@ -276,15 +283,21 @@ def main():
         torch.cuda.synchronize()
         cpu["max_abs_dq_err_vs_oracle"] = float(np.abs(dq[:Bc].cpu().numpy() - dq_ref).max())
     prec = os.environ.get("BIK_SOLVE_PRECISION", "f64")
+    prec = "f32" if prec in ("f32", "float") else "f64"
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     fma_per_clk_sm = 64 if prec == "f64" else 128
     k2_peak = 148 * fma_per_clk_sm * 2 * sm_mhz * 1e6 / 1e12
     est_iters = 4.0  # block-pivoting iterations per solve on this workload (tests/test_host_emu.py prints 3.9)
     flops_k2 = k2_flops_per_instance(fm, spec, est_iters) * B
-    roofline_k2 = {"kernel": f"k2_kernel<{prec}> (assembly + active-set Cholesky)", "bound": "fma", "achieved": flops_k2 / k2_s / 1e12,
+    path = os.environ.get("BIK_K2_PATH", "auto")
+    lowrank = path == "lowrank" and spec.npairs == 0 and spec.nrows > 0   # auto picks dense for this workload (K = coupled dofs = 18)
+    k2_name = "k2lr_kernel (fp64 low-rank/Woodbury active set)" if lowrank else f"k2_kernel<{prec}> (dense packed Cholesky active set)"
+    if lowrank:
+        prec = "f64"
+    roofline_k2 = {"kernel": k2_name, "bound": "fma", "achieved": flops_k2 / k2_s / 1e12,
                    "peak": k2_peak, "unit": "TFLOP/s", "frac": flops_k2 / k2_s / 1e12 / k2_peak,
                    "peak_source": f"148 SM x {fma_per_clk_sm} FMA/clk x 2 x {sm_mhz:.0f} MHz (nominal CUDA-core rate at the sampled clock)",
-                   "flops_per_instance": flops_k2 / B, "assumed_iterations": est_iters, "ms": k2_s * 1e3,
+                   "flops_per_instance": flops_k2 / B, "flops_note": "dense-solver count of SURVEY 8(d), kept as the yardstick for both paths", "assumed_iterations": est_iters, "ms": k2_s * 1e3,
                    "share_of_step": k2_s / (k1_s + k2_s)}
 
     # ---- e2e through the host-buffer C-ABI entry (H2D + kernels + D2H inside the timing) -------------

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(128) k1_kernel(const uint32_t* __restrict__ gi
 }
 
 template <typename T, int SLOTS>
-__global__ void __launch_bounds__(128) k2_kernel(const uint32_t* __restrict__ gimage, int words, int use_tma, K2Args a) {
+__global__ void __launch_bounds__(256) k2_kernel(const uint32_t* __restrict__ gimage, int words, int use_tma, K2Args a) {
   extern __shared__ __align__(16) uint32_t smem[];
   __shared__ __align__(8) uint64_t bar;
   stage_image(smem, gimage, words, &bar, use_tma);
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(128) k2_kernel(const uint32_t* __restrict__ gi
 }
 
 template <int SLOTS>
-__global__ void __launch_bounds__(128) k2lr_kernel(const uint32_t* __restrict__ gimage, int words, int use_tma, K2Args a) {
+__global__ void __launch_bounds__(256) k2lr_kernel(const uint32_t* __restrict__ gimage, int words, int use_tma, K2Args a) {
   extern __shared__ __align__(16) uint32_t smem[];
   __shared__ __align__(8) uint64_t bar;
   stage_image(smem, gimage, words, &bar, use_tma);
@@ -182,7 +182,8 @@ struct bik_problem {
   uint32_t* d_image = nullptr;
   PHeader h;
   int solve_double = 1;
-  int k2_path = 0;  // 0 auto, 1 dense only (BIK_K2_PATH=dense)
+  int k2_path = 0;  // 0 auto, 1 dense only (BIK_K2_PATH=dense), 2 low-rank whenever valid (BIK_K2_PATH=lowrank)
+  int k2_warps = 4; // warps per CTA of the K2 kernels (BIK_K2_WARPS)
   // lazily grown scratch between K1 and K2 (one caller at a time per problem)
   std::mutex mu;
   size_t ws_B = 0;
@@ -241,7 +242,9 @@ extern "C" int bik_problem_create(const bik_model* model, const bik_task_desc* t
   const char* prec = getenv("BIK_SOLVE_PRECISION");
   p->solve_double = !(prec && (std::string(prec) == "f32" || std::string(prec) == "float"));
   const char* path = getenv("BIK_K2_PATH");
-  p->k2_path = (path && std::string(path) == "dense") ? 1 : 0;
+  p->k2_path = (path && std::string(path) == "dense") ? 1 : ((path && std::string(path) == "lowrank") ? 2 : 0);
+  p->k2_warps = env_int("BIK_K2_WARPS", 4);
+  if (p->k2_warps != 1 && p->k2_warps != 2 && p->k2_warps != 4 && p->k2_warps != 8) p->k2_warps = 4;
   DeviceGuard g(model->device);
   CUDA_OK(cudaMalloc(&p->d_image, p->image.size() * 4));
   CUDA_OK(cudaMemcpy(p->d_image, p->image.data(), p->image.size() * 4, cudaMemcpyHostToDevice));
@@ -309,7 +312,7 @@ static int dispatch_k1(const bik_problem* p, const K1Args& a, cudaStream_t st) {
 template <typename T, int SLOTS>
 static int launch_k2(const bik_problem* p, const K2Args& a, cudaStream_t st) {
   const PHeader& h = p->h;
-  int NW = 4;
+  int NW = p->k2_warps;
   auto need = [&](int nw) { return (size_t)h.words * 4 + (size_t)nw * k2_warp_bytes(h, sizeof(T)); };
   while (NW > 1 && (int)need(NW) > p->model->max_smem) NW >>= 1;
   size_t smem = need(NW);
@@ -322,7 +325,7 @@ static int launch_k2(const bik_problem* p, const K2Args& a, cudaStream_t st) {
 }
 template <typename T>
 static int dispatch_k2_slots(const bik_problem* p, const K2Args& a, cudaStream_t st) {
-  int slots = (p->h.nv + 1 + 31) / 32;  // rows of the augmented factor per lane
+  int slots = (p->h.nu + 1 + 31) / 32;  // rows of the augmented factor (coupled dofs + rhs) per lane
   if (slots <= 1) return launch_k2<T, 1>(p, a, st);
   if (slots == 2) return launch_k2<T, 2>(p, a, st);
   return launch_k2<T, 3>(p, a, st);
@@ -330,7 +333,7 @@ static int dispatch_k2_slots(const bik_problem* p, const K2Args& a, cudaStream_t
 template <int SLOTS>
 static int launch_k2lr(const bik_problem* p, const K2Args& a, cudaStream_t st) {
   const PHeader& h = p->h;
-  int NW = 4;
+  int NW = p->k2_warps;
   auto need = [&](int nw) { return (size_t)h.words * 4 + ((tri(h.K) * 2 + 15) & ~15) + (size_t)nw * k2lr_warp_bytes(h); };
   while (NW > 1 && (int)need(NW) > p->model->max_smem) NW >>= 1;
   size_t smem = need(NW);
@@ -341,12 +344,14 @@ static int launch_k2lr(const bik_problem* p, const K2Args& a, cudaStream_t st) {
   CUDA_OK(cudaGetLastError());
   return BIK_OK;
 }
-// Low-rank path when the stacked task rows are well below nv, no general rows, D bounded away from 0.
+// Low-rank path when the stacked task rows are well below the number of COUPLED dofs (e.g. a CoM task:
+// 3 rows coupling every dof), no general rows, D bounded away from 0.  Otherwise the dense path on the
+// coupled block wins (G1 config: K = 18 rows, 18 coupled dofs of 43).
 static bool use_low_rank(const bik_problem* p, const K2Args& a) {
   const PHeader& h = p->h;
   if (p->k2_path == 1 || !a.dq || a.Hout || a.lo_out) return false;
-  bool ok = h.npairs == 0 && h.K > 0 && h.K < 63 && 4 * h.K <= 3 * h.nv && a.damping >= 1e-6;
-  return ok;
+  if (p->k2_path == 2) return h.npairs == 0 && h.K > 0 && h.K < 63 && a.damping > 0;
+  return h.npairs == 0 && h.K > 0 && h.K < 63 && 2 * h.K <= h.nu && a.damping >= 1e-6;
 }
 static int dispatch_k2(const bik_problem* p, const K2Args& a, cudaStream_t st) {
   if (use_low_rank(p, a)) return (p->h.K + 1 <= 32) ? launch_k2lr<1>(p, a, st) : launch_k2lr<2>(p, a, st);

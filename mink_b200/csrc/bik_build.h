@@ -293,6 +293,23 @@ inline bool build_image(const HostModel& m, const bik_task_desc* tasks, int ntas
     } else { *err = "unknown limit kind"; return false; }
   }
   if (!H.off_geoms) { H.off_geoms = b.alloc(GEOM_WORDS); H.off_pairs = b.alloc(4); }
+  // coupled dofs: a dof whose column is zero in every task Jacobian and every general row only sees the
+  // diagonal of H, so its optimum is a closed-form clamp; the QP proper runs on the coupled set.
+  {
+    std::vector<char> coupled(m.nv, 0);
+    for (size_t k = 0; k < cols.size(); ++k) {
+      bool is_com = (int)k >= H.com_cols_off && (int)k < H.com_cols_off + H.com_ncols;
+      if (is_com && H.C == 0) continue;
+      coupled[cols[k] & 0xffff] = 1;
+    }
+    if (H.npairs > 0) std::fill(coupled.begin(), coupled.end(), 1);
+    H.off_umap = b.alloc(std::max(m.nv, 1));
+    std::vector<int32_t> ucols;
+    for (int d = 0; d < m.nv; ++d) { b.i(H.off_umap)[d] = coupled[d] ? (int)ucols.size() : -1; if (coupled[d]) ucols.push_back(d); }
+    H.nu = (int)ucols.size();
+    H.off_ucols = b.alloc(std::max(H.nu, 1));
+    for (int k = 0; k < H.nu; ++k) b.i(H.off_ucols)[k] = ucols[k];
+  }
   H.words = (int)b.w.size();
   memcpy(b.w.data() + hoff, &H, sizeof H);
   *image = b.w;

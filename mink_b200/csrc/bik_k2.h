@@ -50,14 +50,14 @@ BIK_HD int tri(int i) { return (i * (i + 1)) >> 1; }
 // Layout: Hp | U | dinv c lo hi x | [general-row block] | ints.   U is a union: during assembly it
 // holds the weighted Jacobian rows (fp32), afterwards the packed factor augmented by the rhs row.
 BIK_HD int k2_union_bytes(const PHeader& h, int ts) {
-  int n = h.nv;
+  int n = h.nu;
   int lp = tri(n + 1) * ts + 16;                       // (n+1) rows: factor + fused right-hand side
-  int wj = 4 * ((h.K > 0 ? h.K : 1) * (n + 1)) + 16;  // wJ [K][n] + we [K]
+  int wj = 4 * ((h.K > 0 ? h.K : 1) * (h.nv + 1)) + 16;  // wJ [K][nv] + we [K]
   return ((lp > wj ? lp : wj) + 15) & ~15;
 }
 BIK_HD int k2_warp_bytes(const PHeader& h, int ts) {
-  int n = h.nv, np = h.npairs;
-  int words_T = tri(n) + 5 * n + (np > 0 ? (K2_MAX_GEN * n + K2_MAX_GEN * K2_MAX_GEN + 3 * K2_MAX_GEN + np) : 0);
+  int n = h.nu, np = h.npairs;
+  int words_T = tri(n) + 5 * n + h.nv + (np > 0 ? (K2_MAX_GEN * n + K2_MAX_GEN * K2_MAX_GEN + 3 * K2_MAX_GEN + np) : 0);
   int bytes = ((words_T * ts + 15) & ~15) + k2_union_bytes(h, ts) + 4 * (2 * n + 3 * np + 12);
   return (bytes + 15) & ~15;
 }
@@ -103,25 +103,25 @@ template <typename T> BIK_HD T warp_bcast(T v, int src) {
 }
 
 template <typename T> struct K2Ws {
-  T *Hp, *Lp, *dinv, *c, *lo, *hi, *x;
+  T *Hp, *Lp, *dinv, *c, *lo, *hi, *x, *xfull;
   T *Y, *S, *lam, *rg, *hg, *sg;  // general rows: Y = L^-1 G_F^T (K2_MAX_GEN x n), S Schur, lam, rhs, h, slack
   int *st, *idx, *gst, *gidx, *gnew;
   float *wJ, *we;
 };
 template <typename T> BIK_HD K2Ws<T> k2_carve(const PHeader& h, void* mem) {
   K2Ws<T> w;
-  int n = h.nv, np = h.npairs;
+  int n = h.nu, np = h.npairs;
   char* base = reinterpret_cast<char*>(mem);
   T* p = reinterpret_cast<T*>(base);
   w.Hp = p; p += tri(n);
-  w.dinv = p; p += n; w.c = p; p += n; w.lo = p; p += n; w.hi = p; p += n; w.x = p; p += n;
+  w.dinv = p; p += n; w.c = p; p += n; w.lo = p; p += n; w.hi = p; p += n; w.x = p; p += n; w.xfull = p; p += h.nv;
   w.Y = w.S = w.lam = w.rg = w.hg = w.sg = nullptr;
   if (np > 0) { w.Y = p; p += K2_MAX_GEN * n; w.S = p; p += K2_MAX_GEN * K2_MAX_GEN; w.lam = p; p += K2_MAX_GEN; w.rg = p; p += K2_MAX_GEN; w.sg = p; p += K2_MAX_GEN; w.hg = p; p += np; }
   int words_T = (int)(p - reinterpret_cast<T*>(base));
   char* u = base + ((words_T * (int)sizeof(T) + 15) & ~15);
   w.Lp = reinterpret_cast<T*>(u);
   w.wJ = reinterpret_cast<float*>(u);
-  w.we = w.wJ + (h.K > 0 ? h.K : 1) * n;
+  w.we = w.wJ + (h.K > 0 ? h.K : 1) * h.nv;
   int* ip = reinterpret_cast<int*>(u + k2_union_bytes(h, sizeof(T)));
   w.st = ip; ip += n; w.idx = ip; ip += n; w.gst = ip; ip += np + 4; w.gidx = ip; ip += np + 4; w.gnew = ip; ip += np + 4;
   return w;
@@ -133,20 +133,20 @@ template <typename T> BIK_HD T Hsym(const T* Hp, int i, int j) { return i >= j ?
 template <typename T, int W>
 BIK_HD void k2_assemble(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane) {
   const PHeader& h = P.h();
-  const int n = h.nv, K = h.K;
+  const int n = h.nv, nu = h.nu, K = h.K;
   const float* Jb = a.J + (long long)b * K * n;
   const float* eb = a.e + (long long)b * K;
   const int32_t* cols = P.i(h.off_cols);
-  for (int k = lane; k < tri(n); k += W) w.Hp[k] = T(0);
-  if (a.skip_objective) {
+  const int32_t* umap = P.i(h.off_umap);
+  if (a.skip_objective) {  // bik_limits_box: only the box, for every dof
     for (int d = lane; d < n; d += W) {
       float lo, hi;
       box_dof(P, d, a.q + (long long)b * h.nq, a.dt, &lo, &hi);
-      w.lo[d] = T(lo); w.hi[d] = T(hi); w.c[d] = T(0);
+      a.lo_out[(long long)b * n + d] = lo; a.hi_out[(long long)b * n + d] = hi;
     }
-    BIK_SYNCWARP();
     return;
   }
+  for (int k = lane; k < tri(nu); k += W) w.Hp[k] = T(0);
   // weighted rows  W J  and  W(-gain e)
   for (int f = 0; f < h.F; ++f) {
     const FrameRec& fr = P.frame(f);
@@ -160,7 +160,7 @@ BIK_HD void k2_assemble(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int 
     for (int r = lane; r < 3; r += W) w.we[row0 + r] = cr[r] * (-cr[3] * eb[row0 + r]);
   }
   BIK_SYNCWARP();
-  // block contributions (W J)^T (W J), lower triangle, only over each task's non-zero columns
+  // block contributions (W J)^T (W J), lower triangle of the COUPLED block, per task over its non-zero columns
   for (int t = 0; t < h.F + h.C; ++t) {
     int row0, nr, nc, coff;
     if (t < h.F) { const FrameRec& fr = P.frame(t); row0 = fr.row0; nr = 6; nc = fr.ncols; coff = fr.col_off; }
@@ -171,7 +171,7 @@ BIK_HD void k2_assemble(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int 
       int ca = cols[coff + ia] & 0xffff, cb = cols[coff + ib] & 0xffff;
       T s = T(0);
       for (int r = 0; r < nr; ++r) s += T(w.wJ[(row0 + r) * n + ca]) * T(w.wJ[(row0 + r) * n + cb]);
-      w.Hp[tri(ca) + cb] += s;
+      w.Hp[tri(umap[ca]) + umap[cb]] += s;   // column lists are ascending, so umap[ca] >= umap[cb]
     }
     BIK_SYNCWARP();
   }
@@ -195,10 +195,12 @@ BIK_HD void k2_assemble(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int 
       mu += T(pr[1]) * s;
     }
   }
-  // linear term and diagonal
+  // linear term, diagonal and box.  A DECOUPLED dof (zero column in every task Jacobian) only sees
+  // the diagonal: its optimum is the clamp of -c/h, written straight to xfull.
   for (int d = lane; d < n; d += W) {
+    const int u = umap[d];
     T cd = T(0);
-    for (int r = 0; r < K; ++r) cd -= T(w.we[r]) * T(w.wJ[r * n + d]);
+    if (u >= 0) for (int r = 0; r < K; ++r) cd -= T(w.we[r]) * T(w.wJ[r * n + d]);
     T hd = mu;
     for (int p = 0; p < h.P; ++p) {
       const float* pr = P.f(h.off_posture) + p * (2 + n);
@@ -206,11 +208,18 @@ BIK_HD void k2_assemble(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int 
       hd += wgt * wgt;                                                        // (W J)^T (W J), J = -I
       cd -= T(pr[0]) * wgt * wgt * T(a.ep[((long long)b * h.P + p) * n + d]);  // -(W(-g e))^T W (-I)
     }
-    w.Hp[tri(d) + d] += hd;
-    w.c[d] = cd;
     float lo = -BIK_INF_F, hi = BIK_INF_F;
     if (!a.skip_box) box_dof(P, d, a.q + (long long)b * h.nq, a.dt, &lo, &hi);
-    w.lo[d] = T(lo); w.hi[d] = T(hi);
+    if (a.lo_out) { a.lo_out[(long long)b * n + d] = lo; a.hi_out[(long long)b * n + d] = hi; }
+    if (u >= 0) {
+      w.Hp[tri(u) + u] += hd;
+      w.c[u] = cd; w.lo[u] = T(lo); w.hi[u] = T(hi);
+    } else {
+      T v = -cd / hd;
+      v = v < T(lo) ? T(lo) : (v > T(hi) ? T(hi) : v);
+      w.xfull[d] = v;
+      if (a.Hout) { a.Hout[((long long)b * n + d) * n + d] = double(hd); a.cout[(long long)b * n + d] = double(cd); }
+    }
   }
   BIK_SYNCWARP();
 }
@@ -302,7 +311,7 @@ template <> struct K2Tol<float> { static BIK_HD float x() { return 1e-7f; } stat
 template <typename T, int W, int SLOTS>
 BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane, int* iters_out) {
   const PHeader& h = P.h();
-  const int n = h.nv, np = h.npairs;
+  const int n = h.nu, np = h.npairs;   // coupled dofs only (n == nv whenever there are general rows)
   const int MAXIT = 60, PATIENCE = 3;
   const T tolx = K2Tol<T>::x(), tolg = K2Tol<T>::g();
   const float* Gb = np > 0 ? a.Gc + (long long)b * np * n : nullptr;
@@ -423,20 +432,24 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
 template <typename T, int W, int SLOTS>
 BIK_HD void k2_warp(const PView& P, const K2Args& a, int b, void* wsm, int lane) {
   const PHeader& h = P.h();
-  const int n = h.nv;
+  const int n = h.nv, nu = h.nu;
+  const int32_t* umap = P.i(h.off_umap);
   K2Ws<T> w = k2_carve<T>(h, wsm);
   k2_assemble<T, W>(P, a, b, w, lane);
+  if (a.skip_objective) return;
   if (a.Hout) {
-    for (int k = lane; k < n * n; k += W) { int i = k / n, j = k - i * n; a.Hout[(long long)b * n * n + k] = double(Hsym(w.Hp, i, j)); }
-    for (int d = lane; d < n; d += W) a.cout[(long long)b * n + d] = double(w.c[d]);
+    for (int k = lane; k < n * n; k += W) {
+      int i = k / n, j = k - i * n, ui = umap[i], uj = umap[j];
+      if (ui >= 0 && uj >= 0) a.Hout[(long long)b * n * n + k] = double(Hsym(w.Hp, ui, uj));
+      else if (i != j) a.Hout[(long long)b * n * n + k] = 0.0;
+    }
+    for (int d = lane; d < n; d += W) if (umap[d] >= 0) a.cout[(long long)b * n + d] = double(w.c[umap[d]]);
   }
-  if (a.lo_out)
-    for (int d = lane; d < n; d += W) { a.lo_out[(long long)b * n + d] = float(w.lo[d]); a.hi_out[(long long)b * n + d] = float(w.hi[d]); }
   if (!a.dq) return;
-  int iters = 0;
-  int st = k2_solve<T, W, SLOTS>(P, a, b, w, lane, &iters);
+  int iters = 0, st = 0;
+  if (nu > 0) st = k2_solve<T, W, SLOTS>(P, a, b, w, lane, &iters);
   for (int d = lane; d < n; d += W) {
-    T v = w.x[d];
+    T v = umap[d] >= 0 ? w.x[umap[d]] : w.xfull[d];
     if (!(v == v)) st |= 4;
     a.dq[(long long)b * n + d] = float(v);
   }
@@ -445,6 +458,7 @@ BIK_HD void k2_warp(const PView& P, const K2Args& a, int b, void* wsm, int lane)
     if (a.status) a.status[b] |= st;
     if (a.iters) a.iters[b] = iters;
   }
+  BIK_SYNCWARP();
 }
 
 }  // namespace bik

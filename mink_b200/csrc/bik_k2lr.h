@@ -29,6 +29,17 @@
 #define BIK_NOINLINE __attribute__((noinline))
 #endif
 
+#ifndef BIK_LR_UNROLL
+#define BIK_LR_UNROLL 2
+#endif
+#define BIK_PRAGMA_(x) _Pragma(#x)
+#define BIK_UNROLL(n) BIK_PRAGMA_(unroll n)
+#ifndef BIK_LR_U64
+typedef float lr_u_t;   // U stored in fp32, products accumulated in fp64 (more warps per SM, one convert per load)
+#else
+typedef double lr_u_t;
+#endif
+
 namespace bik {
 
 enum { K2LR_MAX_PAIRS = 8 };  // packed-triangle entries of M per lane: tri(K) <= 32 * 8  (K <= 22); larger K loops
@@ -36,8 +47,8 @@ enum { K2LR_MAX_PAIRS = 8 };  // packed-triangle entries of M per lane: tri(K) <
 BIK_HD int k2lr_ld(const PHeader& h) { return h.nv | 1; }
 BIK_HD int k2lr_warp_bytes(const PHeader& h) {
   int n = h.nv, K = h.K;
-  int words_T = K * k2lr_ld(h) + tri(K) + tri(K + 1) + 4 * K + 8 * n + 8;
-  int bytes = words_T * 8 + 4 * (2 * n + 8);
+  int words_T = tri(K) + tri(K + 1) + 4 * K + 8 * n + 8;
+  int bytes = words_T * 8 + ((K * k2lr_ld(h) * (int)sizeof(lr_u_t) + 15) & ~15) + 4 * (2 * n + 8);
   return (bytes + 15) & ~15;
 }
 
@@ -57,37 +68,39 @@ template <int W> BIK_HD double warp_sum_d(double v) {
 
 // out[r] = sum_j U[r][j] v[j]            (lane <-> row r)
 template <int W>
-BIK_NOINLINE void lr_rowop(const double* __restrict__ U, int ld, int K, int n, const double* __restrict__ v, double* __restrict__ out, int lane) {
+BIK_NOINLINE void lr_rowop(const lr_u_t* __restrict__ U, int ld, int K, int n, const double* __restrict__ v, double* __restrict__ out, int lane) {
   for (int r = lane; r < K; r += W) {
-    const double* Ur = U + r * ld;
+    const lr_u_t* Ur = U + r * ld;
     double a0 = 0, a1 = 0;
     int j = 0;
-    for (; j + 1 < n; j += 2) { a0 += Ur[j] * v[j]; a1 += Ur[j + 1] * v[j + 1]; }
-    if (j < n) a0 += Ur[j] * v[j];
+BIK_UNROLL(BIK_LR_UNROLL)
+    for (; j + 1 < n; j += 2) { a0 += double(Ur[j]) * v[j]; a1 += double(Ur[j + 1]) * v[j + 1]; }
+    if (j < n) a0 += double(Ur[j]) * v[j];
     out[r] = a0 + a1;
   }
   BIK_SYNCWARP();
 }
 // out[i] = sum_r U[r][i] w[r]            (lane <-> column i)
 template <int W>
-BIK_NOINLINE void lr_colop(const double* __restrict__ U, int ld, int K, int n, const double* __restrict__ w, double* __restrict__ out, int lane) {
+BIK_NOINLINE void lr_colop(const lr_u_t* __restrict__ U, int ld, int K, int n, const double* __restrict__ w, double* __restrict__ out, int lane) {
   for (int i = lane; i < n; i += W) {
-    const double* Ui = U + i;
+    const lr_u_t* Ui = U + i;
     double a0 = 0, a1 = 0;
     int r = 0;
-    for (; r + 1 < K; r += 2) { a0 += Ui[r * ld] * w[r]; a1 += Ui[(r + 1) * ld] * w[r + 1]; }
-    if (r < K) a0 += Ui[r * ld] * w[r];
+BIK_UNROLL(BIK_LR_UNROLL)
+    for (; r + 1 < K; r += 2) { a0 += double(Ui[r * ld]) * w[r]; a1 += double(Ui[(r + 1) * ld]) * w[r + 1]; }
+    if (r < K) a0 += double(Ui[r * ld]) * w[r];
     out[i] = a0 + a1;
   }
   BIK_SYNCWARP();
 }
 // M[p] += sgn * U[r][i] U[s][i] over this lane's packed-triangle entries; pairtab[p] = r << 8 | s
 template <int W>
-BIK_NOINLINE void lr_rank1(double* __restrict__ M, const double* __restrict__ U, const uint16_t* __restrict__ pairtab, int ld, int npairs, int i,
+BIK_NOINLINE void lr_rank1(double* __restrict__ M, const lr_u_t* __restrict__ U, const uint16_t* __restrict__ pairtab, int ld, int npairs, int i,
                            double sgn, int lane) {
   for (int p = lane; p < npairs; p += W) {
     int rs = pairtab[p];
-    M[p] += sgn * U[(rs >> 8) * ld + i] * U[(rs & 0xff) * ld + i];
+    M[p] += sgn * double(U[(rs >> 8) * ld + i]) * double(U[(rs & 0xff) * ld + i]);
   }
 }
 
@@ -97,14 +110,14 @@ BIK_HD void k2lr_warp(const PView& P, const K2Args& a, int b, void* wsm, const u
   const PHeader& h = P.h();
   const int n = h.nv, K = h.K, ld = k2lr_ld(h), NP = tri(K);
   // ---- carve ------------------------------------------------------------------------------------
-  T* U = reinterpret_cast<T*>(wsm);            // K x ld: scaled weighted Jacobian rows
-  T* M0 = U + K * ld;                           // tri(K): I + U_F U_F^T, maintained across iterations
+  T* M0 = reinterpret_cast<T*>(wsm);           // tri(K): I + U_F U_F^T, maintained across iterations
   T* Lp = M0 + NP;                              // tri(K+1): factor workspace, row K = right-hand side
   T* dM = Lp + tri(K + 1);                      // K: inverse diagonal of the factor
   T* tv = dM + K; T* yv = tv + K; T* we = yv + K;   // K each
   T* ct = we + K;                               // n: c~
   T* lo = ct + n; T* hi = lo + n; T* x = hi + n; T* sd = x + n; T* xb = sd + n; T* zf = xb + n; T* tmp = zf + n;
-  int* st = reinterpret_cast<int*>(tmp + n + 8);
+  lr_u_t* U = reinterpret_cast<lr_u_t*>(tmp + n + 8);   // K x ld: scaled weighted Jacobian rows
+  int* st = reinterpret_cast<int*>(reinterpret_cast<char*>(U) + ((K * ld * (int)sizeof(lr_u_t) + 15) & ~15));
   int* nst = st + n;
 
   const float* Jb = a.J + (long long)b * K * n;
@@ -143,7 +156,7 @@ BIK_HD void k2lr_warp(const PView& P, const K2Args& a, int b, void* wsm, const u
     for (int r = 0; r < K; ++r) {
       T wj = T(rowcost[r]) * T(Jb[r * n + d]);
       cd -= we[r] * wj;
-      U[r * ld + d] = wj * is;
+      U[r * ld + d] = lr_u_t(wj * is);
     }
     float blo, bhi;
     box_dof(P, d, a.q + (long long)b * h.nq, a.dt, &blo, &bhi);
@@ -154,14 +167,14 @@ BIK_HD void k2lr_warp(const PView& P, const K2Args& a, int b, void* wsm, const u
   // ---- M0 = I + U U^T over all dofs (everything free) -------------------------------------------
   for (int p = lane; p < NP; p += W) {
     const int rs = pairtab[p], r = rs >> 8, s = rs & 0xff;
-    const T* Ur = U + r * ld; const T* Us = U + s * ld;
+    const lr_u_t* Ur = U + r * ld; const lr_u_t* Us = U + s * ld;
     T a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     int i = 0;
     for (; i + 3 < n; i += 4) {
-      T u0 = Ur[i], u1 = Ur[i + 1], u2 = Ur[i + 2], u3 = Ur[i + 3], v0 = Us[i], v1 = Us[i + 1], v2 = Us[i + 2], v3 = Us[i + 3];
+      T u0 = T(Ur[i]), u1 = T(Ur[i + 1]), u2 = T(Ur[i + 2]), u3 = T(Ur[i + 3]), v0 = T(Us[i]), v1 = T(Us[i + 1]), v2 = T(Us[i + 2]), v3 = T(Us[i + 3]);
       a0 += u0 * v0; a1 += u1 * v1; a2 += u2 * v2; a3 += u3 * v3;
     }
-    for (; i < n; ++i) a0 += Ur[i] * Us[i];
+    for (; i < n; ++i) a0 += T(Ur[i]) * T(Us[i]);
     M0[p] = (a0 + a1) + (a2 + a3) + (r == s ? T(1) : T(0));
   }
   BIK_SYNCWARP();

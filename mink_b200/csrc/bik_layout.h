@@ -60,7 +60,10 @@ struct PHeader {  // all offsets in 32-bit words from the start of the image
   float coll_gain, coll_dmin, coll_ddet, coll_relax;
   float com_total_mass, com_fixed[3];  // total mass of subtree(body 1); first moment of its world-fixed part
   int32_t off_rowinfo;  // float[3 K]: per stacked row cost | gain | lm_damping of its task
-  int32_t reserved[8];
+  int32_t nu;           // number of COUPLED dofs: columns touched by some task Jacobian or general row
+  int32_t off_umap;     // int[nv]: compact index of a coupled dof, -1 for a decoupled one (H row is diagonal there)
+  int32_t off_ucols;    // int[nu]: dof of each compact index
+  int32_t reserved[5];
 };
 static_assert(sizeof(PHeader) % 16 == 0, "header must stay 16-byte aligned");
 

@@ -157,7 +157,8 @@ def test_every_lane_group_size_against_oracle(group):
     np.testing.assert_allclose(_np(ep), epr, atol=1e-6)
 
 
-@pytest.mark.parametrize("env", [{"BIK_USE_TMA": 0}, {"BIK_SOLVE_PRECISION": "f32", "BIK_K2_PATH": "dense"}, {"BIK_K2_PATH": "dense"}])
+@pytest.mark.parametrize("env", [{"BIK_USE_TMA": 0}, {"BIK_SOLVE_PRECISION": "f32", "BIK_K2_PATH": "dense"}, {"BIK_K2_PATH": "dense"},
+                                 {"BIK_K2_PATH": "lowrank"}, {"BIK_K2_WARPS": 8}])
 def test_alternate_paths(env):
     wl, fm, spec, g, model, prob = _engine("g1", env=env)
     q = torch.tensor(g["q"], dtype=torch.float32, device="cuda:0")
