@@ -270,13 +270,33 @@ extern "C" size_t bik_workspace_bytes(const bik_problem* p, int B) {
   return (size_t)B * 4 * ((size_t)h.K * h.nv + h.K + (size_t)h.P * h.nv + (size_t)h.npairs * (h.nv + 1) + 4);
 }
 
+// (kernel, smem, threads) -> resident CTAs per SM; the attribute/occupancy queries run once per combination.
+struct GeomKey { const void* kern; size_t smem; int threads; int device; };
+static std::mutex g_geom_mu;
+static std::vector<std::pair<GeomKey, int>> g_geom;
+
 template <typename Kern>
 static int launch_geometry(Kern kern, const bik_model* m, size_t smem, int threads, long long work_ctas, int* grid) {
   if ((int)smem > m->max_smem) return fail(BIK_ERR_UNSUPPORTED, "problem does not fit in shared memory (" + std::to_string(smem) + " B)");
-  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-  if (per_sm < 1) return fail(BIK_ERR_UNSUPPORTED, "kernel cannot be resident");
+  {
+    std::lock_guard<std::mutex> lock(g_geom_mu);
+    for (auto& e : g_geom)
+      if (e.first.kern == (const void*)kern && e.first.smem == smem && e.first.threads == threads && e.first.device == m->device) per_sm = e.second;
+  }
+  if (per_sm == 0) {
+    // the opt-in limit is per kernel and must never shrink below what an earlier, cached combination needs
+    size_t prev_max = 0;
+    {
+      std::lock_guard<std::mutex> lock(g_geom_mu);
+      for (auto& e : g_geom) if (e.first.kern == (const void*)kern && e.first.device == m->device && e.first.smem > prev_max) prev_max = e.first.smem;
+    }
+    if (smem > prev_max) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+    if (per_sm < 1) return fail(BIK_ERR_UNSUPPORTED, "kernel cannot be resident");
+    std::lock_guard<std::mutex> lock(g_geom_mu);
+    g_geom.push_back({GeomKey{(const void*)kern, smem, threads, m->device}, per_sm});
+  }
   long long g = (long long)m->nsm * per_sm;  // persistent: one wave, CTAs loop over tiles
   if (work_ctas < g) g = work_ctas;
   *grid = (int)(g < 1 ? 1 : g);

@@ -19,6 +19,12 @@
 #pragma once
 #include "bik_k1.h"
 
+#if defined(__CUDACC__)
+#define BIK_NOINLINE __host__ __device__ __noinline__
+#else
+#define BIK_NOINLINE __attribute__((noinline))
+#endif
+
 namespace bik {
 
 struct K2Args {
@@ -231,7 +237,7 @@ BIK_HD void k2_assemble(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int 
 // Lane i % W owns row i; one warp barrier per column; no division or square root on the critical
 // path (rsqrt once per column, by the lane that owns the next diagonal, from a running sum of squares).
 template <typename T, int W, int SLOTS>
-BIK_HD int k2_factor(T* Lp, T* dinv, int nf, int lane) {
+BIK_NOINLINE int k2_factor(T* __restrict__ Lp, T* __restrict__ dinv, int nf, int lane) {
   int bad = 0;
   T ss[SLOTS];
 #pragma unroll
@@ -242,6 +248,7 @@ BIK_HD int k2_factor(T* Lp, T* dinv, int nf, int lane) {
     dinv[0] = bik_rsqrt<T>(d);
   }
   BIK_SYNCWARP();
+#pragma unroll 1
   for (int j = 0; j < nf; ++j) {
     const T* Lj = Lp + tri(j);
     const T inv = dinv[j];
@@ -250,13 +257,12 @@ BIK_HD int k2_factor(T* Lp, T* dinv, int nf, int lane) {
       const int i = lane + s * W;
       if (i > j && i <= nf) {
         T* Li = Lp + tri(i);
-        T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+        T a0 = T(0), a1 = T(0);
         int k = 0;
-        for (; k + 3 < j; k += 4) {
-          a0 += Li[k] * Lj[k]; a1 += Li[k + 1] * Lj[k + 1]; a2 += Li[k + 2] * Lj[k + 2]; a3 += Li[k + 3] * Lj[k + 3];
-        }
-        for (; k < j; ++k) a0 += Li[k] * Lj[k];
-        T l = (Li[j] - ((a0 + a1) + (a2 + a3))) * inv;
+#pragma unroll 2
+        for (; k + 1 < j; k += 2) { a0 += Li[k] * Lj[k]; a1 += Li[k + 1] * Lj[k + 1]; }
+        if (k < j) a0 += Li[k] * Lj[k];
+        T l = (Li[j] - (a0 + a1)) * inv;
         Li[j] = l;
         ss[s] += l * l;
         if (i == j + 1 && i < nf) {
@@ -273,7 +279,7 @@ BIK_HD int k2_factor(T* Lp, T* dinv, int nf, int lane) {
 // Back substitution x = L^-T y with y in row nf of Lp; each lane keeps its entries in registers and
 // the pivot value travels by shuffle.  Writes x_k into out[k] (compact indices).
 template <typename T, int W, int SLOTS>
-BIK_HD void k2_backsub(const T* Lp, const T* dinv, int nf, T* out, int lane) {
+BIK_NOINLINE void k2_backsub(const T* __restrict__ Lp, const T* __restrict__ dinv, int nf, T* out, int lane) {
   T y[SLOTS];
   const T* rhs = Lp + tri(nf);
 #pragma unroll
@@ -293,13 +299,44 @@ BIK_HD void k2_backsub(const T* Lp, const T* dinv, int nf, T* out, int lane) {
 }
 // y <- L^-1 y for a separate vector (general-row path only)
 template <typename T, int W>
-BIK_HD void k2_forward(const T* Lp, const T* dinv, T* y, int nf, int lane) {
+BIK_NOINLINE void k2_forward(const T* Lp, const T* dinv, T* y, int nf, int lane) {
   for (int k = 0; k < nf; ++k) {
     if (k % W == lane) y[k] = y[k] * dinv[k];
     BIK_SYNCWARP();
     T yk = y[k];
     for (int i = lane; i < nf; i += W) if (i > k) y[i] -= Lp[tri(i) + k] * yk;
   }
+  BIK_SYNCWARP();
+}
+
+// Active general rows R (collision): KKT  [H_FF G_RF^T; G_RF 0][x_F; lam] = [y; h_R - G_RA x_A] through the
+// factor:  Y_r = L^-1 G_rF^T,  S = Y Y^T,  lam = S^-1 (Y (L^-1 y) - rhs),  rhs row <- L^-1 y - Y^T lam.
+// Cold for box-only problems: kept out of line so it does not occupy the instruction cache.
+template <typename T, int W>
+BIK_NOINLINE void k2_general_rows(K2Ws<T>& w, const float* Gb, T* rhs, int n, int nf, int ng, int lane) {
+  for (int r = 0; r < ng; ++r) {
+    const float* Gr = Gb + (long long)w.gidx[r] * n;
+    T* Yr = w.Y + r * n;
+    for (int i = lane; i < nf; i += W) Yr[i] = T(Gr[w.idx[i]]);
+    if (lane == 0) { T sv = w.hg[w.gidx[r]]; for (int j = 0; j < n; ++j) if (w.st[j]) sv -= T(Gr[j]) * w.x[j]; w.rg[r] = sv; }
+    BIK_SYNCWARP();
+    k2_forward<T, W>(w.Lp, w.dinv, Yr, nf, lane);
+  }
+  if (lane == 0) {  // tiny dense solve, serial
+    for (int r = 0; r < ng; ++r) {
+      for (int q2 = 0; q2 <= r; ++q2) { T v = T(0); for (int i = 0; i < nf; ++i) v += w.Y[r * n + i] * w.Y[q2 * n + i]; w.S[r * K2_MAX_GEN + q2] = v; w.S[q2 * K2_MAX_GEN + r] = v; }
+      T v = -w.rg[r]; for (int i = 0; i < nf; ++i) v += w.Y[r * n + i] * rhs[i]; w.lam[r] = v;
+    }
+    for (int j = 0; j < ng; ++j) {  // Cholesky of S in place + solve
+      T d = w.S[j * K2_MAX_GEN + j]; for (int k = 0; k < j; ++k) d -= w.S[j * K2_MAX_GEN + k] * w.S[j * K2_MAX_GEN + k];
+      d = bik_sqrt<T>(d > T(0) ? d : T(1e-30)); w.S[j * K2_MAX_GEN + j] = d;
+      for (int i = j + 1; i < ng; ++i) { T v = w.S[i * K2_MAX_GEN + j]; for (int k = 0; k < j; ++k) v -= w.S[i * K2_MAX_GEN + k] * w.S[j * K2_MAX_GEN + k]; w.S[i * K2_MAX_GEN + j] = v / d; }
+    }
+    for (int i = 0; i < ng; ++i) { T v = w.lam[i]; for (int k = 0; k < i; ++k) v -= w.S[i * K2_MAX_GEN + k] * w.lam[k]; w.lam[i] = v / w.S[i * K2_MAX_GEN + i]; }
+    for (int i = ng - 1; i >= 0; --i) { T v = w.lam[i]; for (int k = i + 1; k < ng; ++k) v -= w.S[k * K2_MAX_GEN + i] * w.lam[k]; w.lam[i] = v / w.S[i * K2_MAX_GEN + i]; }
+  }
+  BIK_SYNCWARP();
+  for (int i = lane; i < nf; i += W) { T v = rhs[i]; for (int r = 0; r < ng; ++r) v -= w.Y[r * n + i] * w.lam[r]; rhs[i] = v; }
   BIK_SYNCWARP();
 }
 
@@ -342,34 +379,7 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
     BIK_SYNCWARP();
     if (k2_factor<T, W, SLOTS>(w.Lp, w.dinv, nf, lane)) status |= 4;
     status = warp_max_i<W>(status);
-    if (ng > 0) {
-      // KKT with active general rows R:  [H_FF G_RF^T; G_RF 0][x_F; lam] = [y; h_R - G_RA x_A]
-      // Y_r = L^-1 G_rF^T,  S = Y Y^T,  lam = S^-1 (Y (L^-1 y) - rhs),  x_F = L^-T (L^-1 y - Y^T lam)
-      for (int r = 0; r < ng; ++r) {
-        const float* Gr = Gb + (long long)w.gidx[r] * n;
-        T* Yr = w.Y + r * n;
-        for (int i = lane; i < nf; i += W) Yr[i] = T(Gr[w.idx[i]]);
-        if (lane == 0) { T sv = w.hg[w.gidx[r]]; for (int j = 0; j < n; ++j) if (w.st[j]) sv -= T(Gr[j]) * w.x[j]; w.rg[r] = sv; }
-        BIK_SYNCWARP();
-        k2_forward<T, W>(w.Lp, w.dinv, Yr, nf, lane);
-      }
-      if (lane == 0) {  // tiny dense solve, serial
-        for (int r = 0; r < ng; ++r) {
-          for (int q2 = 0; q2 <= r; ++q2) { T v = T(0); for (int i = 0; i < nf; ++i) v += w.Y[r * n + i] * w.Y[q2 * n + i]; w.S[r * K2_MAX_GEN + q2] = v; w.S[q2 * K2_MAX_GEN + r] = v; }
-          T v = -w.rg[r]; for (int i = 0; i < nf; ++i) v += w.Y[r * n + i] * rhs[i]; w.lam[r] = v;
-        }
-        for (int j = 0; j < ng; ++j) {  // Cholesky of S in place + solve
-          T d = w.S[j * K2_MAX_GEN + j]; for (int k = 0; k < j; ++k) d -= w.S[j * K2_MAX_GEN + k] * w.S[j * K2_MAX_GEN + k];
-          d = bik_sqrt<T>(d > T(0) ? d : T(1e-30)); w.S[j * K2_MAX_GEN + j] = d;
-          for (int i = j + 1; i < ng; ++i) { T v = w.S[i * K2_MAX_GEN + j]; for (int k = 0; k < j; ++k) v -= w.S[i * K2_MAX_GEN + k] * w.S[j * K2_MAX_GEN + k]; w.S[i * K2_MAX_GEN + j] = v / d; }
-        }
-        for (int i = 0; i < ng; ++i) { T v = w.lam[i]; for (int k = 0; k < i; ++k) v -= w.S[i * K2_MAX_GEN + k] * w.lam[k]; w.lam[i] = v / w.S[i * K2_MAX_GEN + i]; }
-        for (int i = ng - 1; i >= 0; --i) { T v = w.lam[i]; for (int k = i + 1; k < ng; ++k) v -= w.S[k * K2_MAX_GEN + i] * w.lam[k]; w.lam[i] = v / w.S[i * K2_MAX_GEN + i]; }
-      }
-      BIK_SYNCWARP();
-      for (int i = lane; i < nf; i += W) { T v = rhs[i]; for (int r = 0; r < ng; ++r) v -= w.Y[r * n + i] * w.lam[r]; rhs[i] = v; }
-      BIK_SYNCWARP();
-    }
+    if (ng > 0) k2_general_rows<T, W>(w, Gb, rhs, n, nf, ng, lane);
     // x_F = L^-T (.), overwriting the rhs row in place
     k2_backsub<T, W, SLOTS>(w.Lp, w.dinv, nf, rhs, lane);
     for (int i = lane; i < nf; i += W) w.x[w.idx[i]] = rhs[i];

@@ -23,12 +23,6 @@
 #pragma once
 #include "bik_k2.h"
 
-#if defined(__CUDACC__)
-#define BIK_NOINLINE __host__ __device__ __noinline__
-#else
-#define BIK_NOINLINE __attribute__((noinline))
-#endif
-
 #ifndef BIK_LR_UNROLL
 #define BIK_LR_UNROLL 2
 #endif

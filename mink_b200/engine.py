@@ -197,8 +197,11 @@ class Problem:
         return dq, status
 
     def step_host(self, q: np.ndarray, frame_targets=None, posture_targets=None, com_targets=None, dt: float = 1e-2,
-                  damping: float = 1e-12, nsteps: int = 1, integrate: bool = False):
-        """Host-buffer entry (numpy fp32 in, numpy fp32 out; copies inside).  Returns (dq, status, h2d, d2h)."""
+                  damping: float = 1e-12, nsteps: int = 1, integrate: bool = False, out_dq: np.ndarray = None,
+                  out_status: np.ndarray = None):
+        """Host-buffer entry (numpy fp32 in, numpy fp32 out; copies inside).  `q` is updated in place when
+        integrating.  Pass page-locked arrays (e.g. torch pinned tensors' .numpy()) for full copy bandwidth.
+        Returns (dq, status, q, h2d_bytes, d2h_bytes)."""
         f32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)
         q = f32(q).reshape(-1, self.nq)
         B = q.shape[0]
@@ -211,8 +214,9 @@ class Problem:
             inp.posture_batched = int(pt.size == B * self.P * self.nq and B > 1)
         if self.Cn:
             inp.com_targets = ct.ctypes.data
-        dq = np.empty((B, self.nv), np.float32)
-        st = np.empty(B, np.int32)
+        dq = out_dq if out_dq is not None else np.empty((B, self.nv), np.float32)
+        st = out_status if out_status is not None else np.empty(B, np.int32)
+        assert dq.dtype == np.float32 and dq.flags.c_contiguous and st.dtype == np.int32
         up, down = C.c_size_t(0), C.c_size_t(0)
         _lib.check(self.lib.bik_step_host(self.handle, B, q.ctypes.data, C.byref(inp), float(dt), float(damping), int(nsteps),
                                           int(bool(integrate)), dq.ctypes.data, st.ctypes.data, C.byref(up), C.byref(down)))
