@@ -97,6 +97,13 @@ __global__ void __launch_bounds__(256) k2_kernel(const uint32_t* __restrict__ gi
   PView P{smem};
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   char* wsm = reinterpret_cast<char*>(smem + words) + (size_t)warp * k2_warp_bytes(P.h(), sizeof(T));
+  if (a.lockstep && a.dq) {  // block-uniform trip count: every warp reaches every CTA-wide vote
+    for (int base = blockIdx.x * nwarps; base < a.B; base += gridDim.x * nwarps) {
+      __syncthreads();
+      k2_warp<T, 32, SLOTS>(P, a, base + warp, wsm, lane, base + warp < a.B);
+    }
+    return;
+  }
   for (int b = blockIdx.x * nwarps + warp; b < a.B; b += gridDim.x * nwarps) k2_warp<T, 32, SLOTS>(P, a, b, wsm, lane);
 }
 
@@ -183,7 +190,8 @@ struct bik_problem {
   PHeader h;
   int solve_double = 1;
   int k2_path = 0;  // 0 auto, 1 dense only (BIK_K2_PATH=dense), 2 low-rank whenever valid (BIK_K2_PATH=lowrank)
-  int k2_warps = 4; // warps per CTA of the K2 kernels (BIK_K2_WARPS)
+  int k2_warps = 8; // warps per CTA of the K2 kernels (BIK_K2_WARPS)
+  int k2_lockstep = 1; // BIK_K2_LOCKSTEP=0 disables: CTA-wide lock-step pivoting iterations
   // lazily grown scratch between K1 and K2 (one caller at a time per problem)
   std::mutex mu;
   size_t ws_B = 0;
@@ -243,8 +251,9 @@ extern "C" int bik_problem_create(const bik_model* model, const bik_task_desc* t
   p->solve_double = !(prec && (std::string(prec) == "f32" || std::string(prec) == "float"));
   const char* path = getenv("BIK_K2_PATH");
   p->k2_path = (path && std::string(path) == "dense") ? 1 : ((path && std::string(path) == "lowrank") ? 2 : 0);
-  p->k2_warps = env_int("BIK_K2_WARPS", 4);
-  if (p->k2_warps != 1 && p->k2_warps != 2 && p->k2_warps != 4 && p->k2_warps != 8) p->k2_warps = 4;
+  p->k2_warps = env_int("BIK_K2_WARPS", 8);
+  p->k2_lockstep = env_int("BIK_K2_LOCKSTEP", 1);
+  if (p->k2_warps != 1 && p->k2_warps != 2 && p->k2_warps != 4 && p->k2_warps != 8) p->k2_warps = 8;
   DeviceGuard g(model->device);
   CUDA_OK(cudaMalloc(&p->d_image, p->image.size() * 4));
   CUDA_OK(cudaMemcpy(p->d_image, p->image.data(), p->image.size() * 4, cudaMemcpyHostToDevice));
@@ -487,7 +496,7 @@ extern "C" int bik_solve_ex(const bik_problem* p, int B, const float* q, const f
   DeviceGuard g(p->model->device);
   K2Args a;
   memset(&a, 0, sizeof a);
-  a.B = B; a.q = q; a.J = J; a.e = e; a.ep = e_posture; a.Gc = G_coll; a.hc = h_coll; a.dt = dt; a.damping = damping; a.dq = dq; a.status = status; a.iters = iters;
+  a.B = B; a.q = q; a.J = J; a.e = e; a.ep = e_posture; a.Gc = G_coll; a.hc = h_coll; a.dt = dt; a.damping = damping; a.dq = dq; a.status = status; a.iters = iters; a.lockstep = p->k2_lockstep;
   if (status) CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, static_cast<cudaStream_t>(stream)));
   return dispatch_k2(p, a, static_cast<cudaStream_t>(stream));
 }
@@ -547,7 +556,7 @@ extern "C" int bik_step(const bik_problem* cp, int B, float* q, const bik_inputs
     if (rc) return rc;
     K2Args a2;
     memset(&a2, 0, sizeof a2);
-    a2.B = B; a2.q = q; a2.J = p->J; a2.e = p->e; a2.ep = p->ep; a2.Gc = p->Gc; a2.hc = p->hc; a2.dt = dt; a2.damping = damping; a2.dq = dq; a2.status = status;
+    a2.B = B; a2.q = q; a2.J = p->J; a2.e = p->e; a2.ep = p->ep; a2.Gc = p->Gc; a2.hc = p->hc; a2.dt = dt; a2.damping = damping; a2.dq = dq; a2.status = status; a2.lockstep = p->k2_lockstep;
     rc = dispatch_k2(p, a2, st);
     if (rc) return rc;
     if (integrate) {

@@ -25,6 +25,14 @@
 #define BIK_NOINLINE __attribute__((noinline))
 #endif
 
+// CTA-wide "does any warp still have work" vote (lock-step mode keeps the warps of a CTA in the same
+// solver phase so that they share instruction-cache lines); identity on the host.
+#if defined(__CUDA_ARCH__)
+#define BIK_BLOCK_ANY(x) __syncthreads_or(x)
+#else
+#define BIK_BLOCK_ANY(x) (x)
+#endif
+
 namespace bik {
 
 struct K2Args {
@@ -46,6 +54,7 @@ struct K2Args {
   float* hi_out;
   int skip_objective;  // bik_limits_box: J/e/ep are not read
   int skip_box;        // bik_qp_objective: q is not read
+  int lockstep;        // warps of a CTA advance through the pivoting iterations together (block barriers)
 };
 
 enum { K2_MAX_GEN = 16 };  // general (collision) rows that may be active at once
@@ -346,7 +355,7 @@ template <> struct K2Tol<float> { static BIK_HD float x() { return 1e-7f; } stat
 
 // Returns status bits.  On exit w.x holds dq.
 template <typename T, int W, int SLOTS>
-BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane, int* iters_out) {
+BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane, int* iters_out, bool active = true) {
   const PHeader& h = P.h();
   const int n = h.nu, np = h.npairs;   // coupled dofs only (n == nv whenever there are general rows)
   const int MAXIT = 60, PATIENCE = 3;
@@ -356,7 +365,11 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
   for (int r = lane; r < np; r += W) { w.gst[r] = 0; w.hg[r] = T(a.hc[(long long)b * np + r]); }
   BIK_SYNCWARP();
   int status = 0, best = n + np + 1, patience = PATIENCE, it = 0;
-  for (; it < MAXIT; ++it) {
+  bool done = !active || n == 0;
+  for (;; ++it) {
+    if (a.lockstep) { if (!BIK_BLOCK_ANY(!done && it < MAXIT)) break; }
+    else if (done || it >= MAXIT) break;
+    if (done || it >= MAXIT) continue;
     // compact free list / active general rows (every lane writes the same values)
     int nf = 0, ng = 0;
     for (int i = 0; i < n; ++i) if (w.st[i] == 0) { w.idx[nf] = i; ++nf; }
@@ -423,7 +436,7 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
     }
     ninf = warp_sum_i<W>(ninf);
     last = warp_max_i<W>(last);
-    if (ninf == 0) break;
+    if (ninf == 0) { done = true; continue; }
     bool block;
     if (ninf < best) { best = ninf; patience = PATIENCE; block = true; }
     else if (patience > 0) { --patience; block = true; }
@@ -433,18 +446,22 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
     for (int r = lane; r < np; r += W) if (block || n + r == last) w.gst[r] = w.gnew[r];
     BIK_SYNCWARP();
   }
-  if (it >= MAXIT) status |= 2;
-  if (iters_out) *iters_out = it + 1;
+  if (!done) status |= 2;
+  if (iters_out) *iters_out = it;
   return status;
 }
 
 // One instance per warp: assemble, optionally dump (H, c) / (lo, hi), solve, write dq.
 template <typename T, int W, int SLOTS>
-BIK_HD void k2_warp(const PView& P, const K2Args& a, int b, void* wsm, int lane) {
+BIK_HD void k2_warp(const PView& P, const K2Args& a, int b, void* wsm, int lane, bool active = true) {
   const PHeader& h = P.h();
   const int n = h.nv, nu = h.nu;
   const int32_t* umap = P.i(h.off_umap);
   K2Ws<T> w = k2_carve<T>(h, wsm);
+  if (!active) {  // lock-step tail: no instance for this warp, but it must take part in the CTA votes
+    if (a.dq && nu > 0) { int it = 0; k2_solve<T, W, SLOTS>(P, a, b, w, lane, &it, false); }
+    return;
+  }
   k2_assemble<T, W>(P, a, b, w, lane);
   if (a.skip_objective) return;
   if (a.Hout) {
