@@ -58,14 +58,16 @@ typedef struct bik_frame {
   double quat[4];
 } bik_frame;
 
-enum { BIK_TASK_FRAME = 0, BIK_TASK_POSTURE = 1, BIK_TASK_COM = 2 };
+enum { BIK_TASK_FRAME = 0, BIK_TASK_POSTURE = 1, BIK_TASK_COM = 2, BIK_TASK_RELATIVE_FRAME = 3 };
 
 /* One kinematic task (reference mink/tasks/task.py:54-79 holds cost/gain/lm_damping).
  *   FRAME   : FrameTask   (frame_task.py:28-45)   rows = 6, cost = position xyz | orientation xyz
  *   POSTURE : PostureTask (posture_task.py:27-50) rows = nv (never materialised as a Jacobian:
  *             J = -I with free-joint dofs zeroed, posture_task.py:137-141); dof_cost[nv] host array.
  *             DampingTask (damping_task.py:19-20) = POSTURE with gain 0 and target qpos0.
- *   COM     : ComTask     (com_task.py:25-33)     rows = 3, cost[0..2] */
+ *   COM     : ComTask     (com_task.py:25-33)     rows = 3, cost[0..2]
+ *   RELATIVE_FRAME : RelativeFrameTask (relative_frame_task.py:24-45) rows = 6; pose of `frame` expressed
+ *             in `root`; its target (one slot of frame_targets, in task order) is T_root<-target. */
 typedef struct bik_task_desc {
   int32_t kind;
   int32_t reserved;
@@ -74,6 +76,7 @@ typedef struct bik_task_desc {
   const double* dof_cost;
   double gain;
   double lm_damping;
+  bik_frame root; /* RELATIVE_FRAME only */
 } bik_task_desc;
 
 enum { BIK_LIMIT_CONFIGURATION = 0, BIK_LIMIT_VELOCITY = 1, BIK_LIMIT_COLLISION = 2 };
@@ -117,7 +120,7 @@ typedef struct bik_limit_desc {
  * com_task.py:61), one per instance. */
 typedef struct bik_inputs {
   const float* q;               /* [B][nq] */
-  const float* frame_targets;   /* [B][F][7]  F = number of FRAME tasks, in task-list order */
+  const float* frame_targets;   /* [B][F][7]  F = number of FRAME + RELATIVE_FRAME tasks, in task-list order */
   const float* posture_targets; /* [B or 1][P][nq]  P = number of POSTURE tasks */
   const float* com_targets;     /* [B][C][3]  C = number of COM tasks */
   int32_t posture_batched;      /* 0: one posture target shared by the batch, 1: per instance */

@@ -23,7 +23,7 @@ def __getattr__(name):
     table = {
         "Configuration": "configuration", "SUPPORTED_FRAMES": "configuration",
         "Task": "tasks", "Objective": "tasks", "FrameTask": "tasks", "PostureTask": "tasks", "DampingTask": "tasks",
-        "ComTask": "tasks",
+        "ComTask": "tasks", "RelativeFrameTask": "tasks",
         "Limit": "limits", "Constraint": "limits", "ConfigurationLimit": "limits", "VelocityLimit": "limits",
         "CollisionAvoidanceLimit": "limits",
         "build_ik": "ik", "solve_ik": "ik",

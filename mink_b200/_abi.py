@@ -15,7 +15,7 @@ import numpy as np
 
 from .flatten import FlatModel, Frame
 
-TASK_FRAME, TASK_POSTURE, TASK_COM = 0, 1, 2
+TASK_FRAME, TASK_POSTURE, TASK_COM, TASK_RELATIVE_FRAME = 0, 1, 2, 3
 LIMIT_CONFIGURATION, LIMIT_VELOCITY, LIMIT_COLLISION = 0, 1, 2
 GEOM_PLANE, GEOM_SPHERE, GEOM_CAPSULE = 0, 2, 3
 
@@ -32,7 +32,7 @@ class BikFrame(C.Structure):
 
 class BikTaskDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("frame", BikFrame), ("cost", C.c_double * 6),
-                ("dof_cost", _pd), ("gain", C.c_double), ("lm_damping", C.c_double)]
+                ("dof_cost", _pd), ("gain", C.c_double), ("lm_damping", C.c_double), ("root", BikFrame)]
 
 
 class BikGeom(C.Structure):
@@ -79,6 +79,7 @@ class TaskSpec:
     dof_cost: Optional[np.ndarray] = None
     gain: float = 1.0
     lm_damping: float = 0.0
+    root: Optional[Frame] = None   # RELATIVE_FRAME
 
 
 @dataclass
@@ -103,7 +104,7 @@ class ProblemSpec:
 
     @property
     def nframe(self):
-        return sum(t.kind == TASK_FRAME for t in self.tasks)
+        return sum(t.kind in (TASK_FRAME, TASK_RELATIVE_FRAME) for t in self.tasks)
 
     @property
     def nposture(self):
@@ -127,8 +128,9 @@ class ProblemSpec:
         for t in self.tasks:
             parts.append(np.array([t.kind, t.gain, t.lm_damping], dtype=np.float64).tobytes())
             parts.append(np.asarray(t.cost, dtype=np.float64).tobytes())
-            if t.frame is not None:
-                parts.append(np.concatenate([[t.frame.node], t.frame.pos, t.frame.quat]).astype(np.float64).tobytes())
+            for fr in (t.frame, t.root):
+                if fr is not None:
+                    parts.append(np.concatenate([[fr.node], fr.pos, fr.quat]).astype(np.float64).tobytes())
             if t.dof_cost is not None:
                 parts.append(np.asarray(t.dof_cost, dtype=np.float64).tobytes())
         for l in self.limits:
@@ -150,6 +152,8 @@ class ProblemSpec:
             d.kind = t.kind
             if t.frame is not None:
                 d.frame = c_frame(t.frame)
+            if t.root is not None:
+                d.root = c_frame(t.root)
             d.cost[:] = [float(x) for x in np.asarray(t.cost, dtype=np.float64)]
             if t.dof_cost is not None:
                 buf = np.ascontiguousarray(t.dof_cost, dtype=np.float64)
@@ -226,6 +230,11 @@ def spec_from_workload(fm: FlatModel, wl: dict) -> ProblemSpec:
                                np.broadcast_to(np.atleast_1d(f["orientation_cost"]).astype(float), 3)])
         tasks.append(TaskSpec(TASK_FRAME, frame=fm.frame(f["name"], f["type"]), cost=cost,
                               gain=f.get("gain", 1.0), lm_damping=f.get("lm_damping", 0.0)))
+    for f in wl.get("relative_frames", []):
+        cost = np.concatenate([np.broadcast_to(np.atleast_1d(f["position_cost"]).astype(float), 3),
+                               np.broadcast_to(np.atleast_1d(f["orientation_cost"]).astype(float), 3)])
+        tasks.append(TaskSpec(TASK_RELATIVE_FRAME, frame=fm.frame(f["name"], f["type"]), root=fm.frame(f["root_name"], f["root_type"]),
+                              cost=cost, gain=f.get("gain", 1.0), lm_damping=f.get("lm_damping", 0.0)))
     if wl.get("posture") is not None:
         p = wl["posture"]
         tasks.append(TaskSpec(TASK_POSTURE, dof_cost=np.broadcast_to(np.atleast_1d(p["cost"]).astype(float), fm.nv).copy(),

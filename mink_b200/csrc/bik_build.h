@@ -114,7 +114,7 @@ inline bool build_image(const HostModel& m, const bik_task_desc* tasks, int ntas
   if (m.nv > 64) { *err = "nv > 64 is not supported by the warp-per-problem solver"; return false; }
   if (m.nnode > 32767) { *err = "too many nodes"; return false; }
   for (int t = 0; t < ntasks; ++t) {
-    if (tasks[t].kind == BIK_TASK_FRAME) H.F++;
+    if (tasks[t].kind == BIK_TASK_FRAME || tasks[t].kind == BIK_TASK_RELATIVE_FRAME) H.F++;
     else if (tasks[t].kind == BIK_TASK_POSTURE) H.P++;
     else if (tasks[t].kind == BIK_TASK_COM) H.C++;
     else { *err = "unknown task kind"; return false; }
@@ -153,19 +153,31 @@ inline bool build_image(const HostModel& m, const bik_task_desc* tasks, int ntas
   {
     int fi = 0, ci = 0, row = 0;
     for (int t = 0; t < ntasks; ++t) {
-      if (tasks[t].kind == BIK_TASK_FRAME) {
+      if (tasks[t].kind == BIK_TASK_FRAME || tasks[t].kind == BIK_TASK_RELATIVE_FRAME) {
         FrameRec r; memset(&r, 0, sizeof r);
         put_frame(tasks[t].frame, &r.node, r.lpos, r.lquat);
         if (r.node >= m.nnode) { *err = "frame node out of range"; return false; }
         for (int k = 0; k < 6; ++k) { if (tasks[t].cost[k] < 0) { *err = "cost should be >= 0"; return false; } r.cost[k] = (float)tasks[t].cost[k]; }
         r.gain = (float)tasks[t].gain; r.lm = (float)tasks[t].lm_damping; r.row0 = row;
         r.col_off = (int)cols.size();
-        std::vector<int32_t> mine;
-        for (int n = r.node; n >= 0; n = m.node_parent[n]) {
-          int nd = m.node_type[n] == JNT_FREE ? 6 : (m.node_type[n] == JNT_BALL ? 3 : 1);
-          for (int k = nd - 1; k >= 0; --k) mine.push_back((m.node_dadr[n] + k) | (n << 16));
+        r.relative = tasks[t].kind == BIK_TASK_RELATIVE_FRAME;
+        r.rnode = -1;
+        std::vector<int> chain_f, chain_r;
+        for (int n = r.node; n >= 0; n = m.node_parent[n]) chain_f.push_back(n);
+        if (r.relative) {
+          put_frame(tasks[t].root, &r.rnode, r.rlpos, r.rlquat);
+          if (r.rnode >= m.nnode) { *err = "root frame node out of range"; return false; }
+          for (int n = r.rnode; n >= 0; n = m.node_parent[n]) chain_r.push_back(n);
+          // dofs of common ancestors move both frames rigidly: their columns vanish identically
+          while (!chain_f.empty() && !chain_r.empty() && chain_f.back() == chain_r.back()) { chain_f.pop_back(); chain_r.pop_back(); }
         }
-        std::reverse(mine.begin(), mine.end());
+        std::vector<int32_t> mine;
+        for (int side = 0; side < 2; ++side)
+          for (int n : (side ? chain_r : chain_f)) {
+            int nd = m.node_type[n] == JNT_FREE ? 6 : (m.node_type[n] == JNT_BALL ? 3 : 1);
+            for (int k = 0; k < nd; ++k) mine.push_back((m.node_dadr[n] + k) | (n << 16) | (side ? (int32_t)0x80000000 : 0));
+          }
+        std::sort(mine.begin(), mine.end(), [](int32_t a, int32_t b) { return (a & 0xffff) < (b & 0xffff); });
         r.ncols = (int)mine.size();
         cols.insert(cols.end(), mine.begin(), mine.end());
         memcpy(b.w.data() + H.off_frames + FRAME_WORDS * fi, &r, sizeof r);
@@ -206,7 +218,7 @@ inline bool build_image(const HostModel& m, const bik_task_desc* tasks, int ntas
   {
     int pi = 0, ci = 0, row = 0;
     for (int t = 0; t < ntasks; ++t) {
-      if (tasks[t].kind == BIK_TASK_FRAME) { row += 6; continue; }
+      if (tasks[t].kind == BIK_TASK_FRAME || tasks[t].kind == BIK_TASK_RELATIVE_FRAME) { row += 6; continue; }
       if (tasks[t].kind == BIK_TASK_POSTURE) {
         float* p = b.f(H.off_posture) + pi * (2 + m.nv);
         p[0] = (float)tasks[t].gain; p[1] = (float)tasks[t].lm_damping;
@@ -232,7 +244,7 @@ inline bool build_image(const HostModel& m, const bik_task_desc* tasks, int ntas
   {
     int row = 0;
     for (int t = 0; t < ntasks; ++t) {
-      int k = tasks[t].kind == BIK_TASK_FRAME ? 6 : (tasks[t].kind == BIK_TASK_COM ? 3 : 0);
+      int k = (tasks[t].kind == BIK_TASK_FRAME || tasks[t].kind == BIK_TASK_RELATIVE_FRAME) ? 6 : (tasks[t].kind == BIK_TASK_COM ? 3 : 0);
       for (int r = 0; r < k; ++r) {
         b.f(H.off_rowinfo)[row + r] = (float)tasks[t].cost[r];
         b.f(H.off_rowinfo)[H.K + row + r] = (float)tasks[t].gain;

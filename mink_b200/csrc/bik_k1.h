@@ -78,7 +78,7 @@ BIK_HD int k1_state_stride(const PHeader& h) {  // pose (7) + CoM first moment (
 BIK_HD int k1_stage_rows(const PHeader& h) { return 6; }
 BIK_HD int k1_state_words(const PHeader& h, int ipw) { return (ipw * k1_state_stride(h) + 3) & ~3; }  // keeps the stage 16-byte aligned
 BIK_HD int k1_warp_words(const PHeader& h, int ipw) {
-  int w = k1_state_words(h, ipw) + ipw * k1_stage_rows(h) * h.nv + ipw * (h.K > 0 ? h.K : 1) + ipw * (h.F > 0 ? h.F : 1) * 24;
+  int w = k1_state_words(h, ipw) + ipw * k1_stage_rows(h) * h.nv + ipw * (h.K > 0 ? h.K : 1) + ipw * (h.F > 0 ? h.F : 1) * 32;
   return (w + 3) & ~3;
 }
 
@@ -175,6 +175,18 @@ BIK_HD void frame_task(FQ qf, F3 pf, const float* tgt, F3* ev, F3* ew, FM* A1, F
   for (int i = 0; i < 9; ++i) { A1->m[i] = -A1->m[i]; A2->m[i] = -A2->m[i]; }
 }
 
+// RelativeFrameTask (reference mink/tasks/relative_frame_task.py:106-142): pose of frame f in root r,
+//   e = log(T_rt^-1 T_rf),   J = jlog(T_tf) (J_f - Ad(T_rf^-1) J_r),   T_tf = T_rt^-1 T_rf.
+// Returns e and the blocks (Ji, Mi) of jlog(T_tf) = ljacinv(-log T_tf).
+BIK_HD void relative_frame_task(FQ qf, F3 pf, FQ qr, F3 pr, const float* tgt, F3* ev, F3* ew, FM* Ji, FM* Mi) {
+  FQ q_rf = qmul(qconj(qr), qf);
+  F3 t_rf = qrot_inv(qr, pf - pr);
+  FQ tq = qnormalize(ld_q(tgt));
+  F3 tp = ld_v(tgt + 4);
+  se3_log<float>(qmul(qconj(tq), q_rf), qrot_inv(tq, t_rf - tp), ev, ew);
+  se3_ljacinv_blocks<float>(v3<float>(-ev->x, -ev->y, -ev->z), v3<float>(-ew->x, -ew->y, -ew->z), Ji, Mi);
+}
+
 // ---- primitive geom distance (plane / sphere / capsule) ------------------------------------
 BIK_HD void seg_closest(F3 p1, F3 d1, F3 p2, F3 d2, F3* a, F3* b) {
   F3 r = p1 - p2;
@@ -265,7 +277,7 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, float* wsm,
   float* state = wsm;
   float* stage = wsm + k1_state_words(h, IPW);
   float* estage = stage + IPW * 6 * nv;
-  float* fsc = estage + IPW * (K > 0 ? K : 1);  // per (instance, frame): pf[3], A1[9], A2[9]
+  float* fsc = estage + IPW * (K > 0 ? K : 1);  // per (instance, frame): 32 floats of per-frame SE(3) results
   float* xs = state + li * SS;
   const float* qb = a.q + (long long)(valid ? b : inst0) * nq;
 
@@ -285,11 +297,21 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, float* wsm,
       const FrameRec& fr = P.frame(f);
       FQ qf; F3 pf, ev, ew; FM A1, A2;
       frame_pose(fr.node, fr.lpos, fr.lquat, xs, &qf, &pf);
-      frame_task(qf, pf, a.ftgt + ((long long)b * h.F + f) * 7, &ev, &ew, &A1, &A2);
+      float* sc = fsc + (li * h.F + f) * 32;
+      if (!fr.relative) {
+        frame_task(qf, pf, a.ftgt + ((long long)b * h.F + f) * 7, &ev, &ew, &A1, &A2);
+        sc[0] = pf.x; sc[1] = pf.y; sc[2] = pf.z;
+      } else {   // A1 = Ji, A2 = Mi of jlog(T_tf); plus both frames' poses for the column phase
+        FQ qr; F3 pr;
+        frame_pose(fr.rnode, fr.rlpos, fr.rlquat, xs, &qr, &pr);
+        relative_frame_task(qf, pf, qr, pr, a.ftgt + ((long long)b * h.F + f) * 7, &ev, &ew, &A1, &A2);
+        sc[0] = pf.x; sc[1] = pf.y; sc[2] = pf.z;
+        sc[21] = qf.w; sc[22] = qf.x; sc[23] = qf.y; sc[24] = qf.z;
+        sc[25] = qr.w; sc[26] = qr.x; sc[27] = qr.y; sc[28] = qr.z;
+        sc[29] = pr.x; sc[30] = pr.y; sc[31] = pr.z;
+      }
       float* eo = estage + li * K + fr.row0;
       eo[0] = ev.x; eo[1] = ev.y; eo[2] = ev.z; eo[3] = ew.x; eo[4] = ew.y; eo[5] = ew.z;
-      float* sc = fsc + (li * h.F + f) * 24;
-      sc[0] = pf.x; sc[1] = pf.y; sc[2] = pf.z;
       for (int k = 0; k < 9; ++k) { sc[3 + k] = A1.m[k]; sc[12 + k] = A2.m[k]; }
     }
   }
@@ -300,18 +322,43 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, float* wsm,
     zero_words<W>(stage, IPW * 6 * nv, lane);
     BIK_SYNCWARP();
     if (valid) {
-      const float* sc = fsc + (li * h.F + f) * 24;
+      const float* sc = fsc + (li * h.F + f) * 32;
       F3 pf = ld_v(sc);
       FM A1, A2;
       for (int k = 0; k < 9; ++k) { A1.m[k] = sc[3 + k]; A2.m[k] = sc[12 + k]; }
       float* st = stage + li * 6 * nv;
-      for (int c = g; c < fr.ncols; c += G) {
-        int ent = cols[fr.col_off + c], d = ent & 0xffff, n = ent >> 16;
-        F3 jp, jr;
-        jac_column(P, d, n, xs, pf, &jp, &jr);
-        F3 top = mmul(A1, jp) + mmul(A2, jr), bot = mmul(A1, jr);
-        st[d] = top.x; st[nv + d] = top.y; st[2 * nv + d] = top.z;
-        st[3 * nv + d] = bot.x; st[4 * nv + d] = bot.y; st[5 * nv + d] = bot.z;
+      if (!fr.relative) {
+        for (int c = g; c < fr.ncols; c += G) {
+          int ent = cols[fr.col_off + c], d = ent & 0xffff, n = (ent >> 16) & 0x7fff;
+          F3 jp, jr;
+          jac_column(P, d, n, xs, pf, &jp, &jr);
+          F3 top = mmul(A1, jp) + mmul(A2, jr), bot = mmul(A1, jr);
+          st[d] = top.x; st[nv + d] = top.y; st[2 * nv + d] = top.z;
+          st[3 * nv + d] = bot.x; st[4 * nv + d] = bot.y; st[5 * nv + d] = bot.z;
+        }
+      } else {
+        FQ qf = ld_q(sc + 21), qr = ld_q(sc + 25);
+        F3 pr = ld_v(sc + 29);
+        FQ q_fr = qmul(qconj(qf), qr);          // rotation of T_rf^-1 = T_fr
+        F3 t_fr = qrot_inv(qf, pr - pf);        // translation of T_fr
+        for (int c = g; c < fr.ncols; c += G) {
+          int ent = cols[fr.col_off + c], d = ent & 0xffff, n = (ent >> 16) & 0x7fff;
+          bool root_side = ent < 0;
+          F3 jp, jr, tv, tw;
+          if (!root_side) {                       // column of J_f (body frame of f)
+            jac_column(P, d, n, xs, pf, &jp, &jr);
+            tv = qrot_inv(qf, jp); tw = qrot_inv(qf, jr);
+          } else {                                // minus Ad(T_fr) applied to the column of J_r
+            jac_column(P, d, n, xs, pr, &jp, &jr);
+            F3 bv = qrot(q_fr, qrot_inv(qr, jp)), bw = qrot(q_fr, qrot_inv(qr, jr));
+            F3 x = cross(t_fr, bw);
+            tv = v3<float>(-(bv.x + x.x), -(bv.y + x.y), -(bv.z + x.z));
+            tw = v3<float>(-bw.x, -bw.y, -bw.z);
+          }
+          F3 top = mmul(A1, tv) + mmul(A2, tw), bot = mmul(A1, tw);
+          st[d] = top.x; st[nv + d] = top.y; st[2 * nv + d] = top.z;
+          st[3 * nv + d] = bot.x; st[4 * nv + d] = bot.y; st[5 * nv + d] = bot.z;
+        }
       }
     }
     BIK_SYNCWARP();
@@ -350,7 +397,7 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, float* wsm,
         }
         float* st = stage + li * 3 * nv;
         for (int ci = g; ci < h.com_ncols; ci += G) {
-          int ent = cols[h.com_cols_off + ci], d = ent & 0xffff, n = ent >> 16;
+          int ent = cols[h.com_cols_off + ci], d = ent & 0xffff, n = (ent >> 16) & 0x7fff;
           const NodeRec& r = P.node(n);
           float Ms = P.comnode(n).sub_m;
           FQ nq_ = ld_q(xs + 7 * n); F3 np = ld_v(xs + 7 * n + 4), Sn = ld_v(S + 3 * n), col;

@@ -13,7 +13,7 @@ enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
 enum { MAX_CFG_LIMITS = 2 };
 
 // words per record
-enum { NODE_WORDS = 20, FRAME_WORDS = 20, COMNODE_WORDS = 8, GEOM_WORDS = 16 };
+enum { NODE_WORDS = 20, FRAME_WORDS = 32, COMNODE_WORDS = 8, GEOM_WORDS = 16 };
 
 struct NodeRec {  // 20 words, 16-byte aligned
   int32_t parent, type, qadr, dadr;
@@ -23,13 +23,18 @@ struct NodeRec {  // 20 words, 16-byte aligned
   float jpos[3];
   float pad[3];
 };
-struct FrameRec {  // 20 words
+struct FrameRec {  // 32 words.  Column entries: dof | node << 16 | (belongs to the ROOT chain) << 31
   int32_t node;
   float lpos[3];
   float lquat[4];
   float cost[6];
   float gain, lm;
-  int32_t ncols, col_off, row0, pad;
+  int32_t ncols, col_off, row0;
+  int32_t relative;   // 1: RelativeFrameTask, pose of this frame in the root frame below
+  int32_t rnode;
+  float rlpos[3];
+  float rlquat[4];
+  float pad[3];
 };
 struct ComNodeRec {  // 8 words: own mass of the node's weld group, its first moment in the node frame, subtree mass
   float own_m, own_c[3], sub_m, pad[3];

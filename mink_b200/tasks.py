@@ -13,7 +13,7 @@ from typing import NamedTuple, Optional
 
 import numpy as np
 
-from ._abi import LIMIT_CONFIGURATION, TASK_COM, TASK_FRAME, TASK_POSTURE, ProblemSpec, TaskSpec
+from ._abi import LIMIT_CONFIGURATION, TASK_COM, TASK_FRAME, TASK_POSTURE, TASK_RELATIVE_FRAME, ProblemSpec, TaskSpec
 from .configuration import SUPPORTED_FRAMES, Configuration, as_flat, device_model
 from .exceptions import (InvalidDamping, InvalidFrame, InvalidGain, InvalidTarget, TargetNotSet, TaskDefinitionError,
                          UnsupportedFrame)
@@ -156,6 +156,41 @@ class FrameTask(Task):
         """J = -jlog(T_wt^-1 T_wb) J_b (frame_task.py:124-146)."""
         _, J, e, _ = self._evaluate(configuration)
         return _out(configuration, J)
+
+
+class RelativeFrameTask(FrameTask):
+    """Regulate the pose of a frame relative to another (root) frame -- reference
+    mink/tasks/relative_frame_task.py.  The target is T_root<-target; e = log(T_rt^-1 T_rf),
+    J = jlog(T_tf)(J_f - Ad(T_rf^-1) J_r)."""
+
+    def __init__(self, frame_name: str, frame_type: str, root_name: str, root_type: str, position_cost, orientation_cost,
+                 gain: float = 1.0, lm_damping: float = 0.0):
+        super().__init__(frame_name, frame_type, position_cost, orientation_cost, gain=gain, lm_damping=lm_damping)
+        self.root_name = root_name
+        self.root_type = root_type
+        self.transform_target_to_root: Optional[SE3] = None
+
+    def set_target(self, transform_target_to_root: SE3) -> None:
+        self.transform_target_to_root = transform_target_to_root.copy()
+
+    def set_target_from_configuration(self, configuration: Configuration) -> None:
+        self.set_target(configuration.get_transform(self.frame_name, self.frame_type, self.root_name, self.root_type))
+
+    def _spec(self, flat) -> TaskSpec:
+        base = super()._spec(flat)
+        if self.root_type not in SUPPORTED_FRAMES:
+            raise UnsupportedFrame(self.root_type, SUPPORTED_FRAMES)
+        try:
+            root = flat.frame(self.root_name, self.root_type)
+        except KeyError:
+            raise InvalidFrame(self.root_name, self.root_type, flat) from None
+        return TaskSpec(TASK_RELATIVE_FRAME, frame=base.frame, root=root, cost=self.cost.copy(), gain=self.gain,
+                        lm_damping=self.lm_damping)
+
+    def _target(self):
+        if self.transform_target_to_root is None:
+            raise TargetNotSet(self.__class__.__name__)
+        return self.transform_target_to_root.wxyz_xyz
 
 
 class PostureTask(Task):

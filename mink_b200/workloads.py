@@ -67,6 +67,17 @@ WORKLOADS: Dict[str, dict] = {
                      gain=0.85, minimum_distance=0.005, detection_distance=0.3, bound_relaxation=0.0)],
         dt=2e-3, damping=1e-3, batch=32768,
     ),
+    # Not a BASELINE config: exercises RelativeFrameTask (SURVEY.md 8f "next" row 1) -- left palm regulated
+    # relative to the right palm, as the bimanual examples do (examples/arm_hand_iiwa_allegro.py:75-83).
+    "g1_rel": dict(
+        robot="g1", scene="unitree_g1/scene.xml", key="stand",
+        frames=[dict(name="pelvis", type="body", position_cost=0.0, orientation_cost=10.0, lm_damping=0.0)],
+        relative_frames=[dict(name="left_palm", type="site", root_name="right_palm", root_type="site",
+                              position_cost=5.0, orientation_cost=1.0, lm_damping=0.5)],
+        posture=dict(cost=1.0), com=None,
+        limits=[dict(kind="configuration", gain=0.95)],
+        dt=5e-3, damping=1e-2, batch=4096,
+    ),
 }
 
 

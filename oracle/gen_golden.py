@@ -26,7 +26,7 @@ from mink_b200.flatten import flatten  # noqa: E402
 from mink_b200.workloads import WORKLOADS, make_inputs  # noqa: E402
 
 OUT = os.path.join(REPO, "tests", "golden")
-GOLDEN_B = {"ur5e": 8, "ur5e_dls": 16, "g1": 32, "shadow": 24, "spot": 24}
+GOLDEN_B = {"ur5e": 8, "ur5e_dls": 16, "g1": 32, "shadow": 24, "spot": 24, "g1_rel": 16}
 ROLLOUT_T, ROLLOUT_B = 8, 4
 
 
@@ -35,6 +35,10 @@ def build_reference_problem(model, wl):
     for f in wl["frames"]:
         t = mink.FrameTask(f["name"], f["type"], f["position_cost"], f["orientation_cost"],
                            lm_damping=f["lm_damping"])
+        frame_tasks.append(t)
+    for f in wl.get("relative_frames", []):
+        t = mink.RelativeFrameTask(f["name"], f["type"], f["root_name"], f["root_type"], f["position_cost"],
+                                   f["orientation_cost"], lm_damping=f["lm_damping"])
         frame_tasks.append(t)
     tasks.extend(frame_tasks)
     posture = com = None
@@ -77,6 +81,9 @@ def main():
         cfg = mink.Configuration(model)
         nv, nq, F = model.nv, model.nq, len(frame_tasks)
 
+        rel = wl.get("relative_frames", [])
+        nabs = len(wl["frames"])
+
         def fk(qb):
             poses = np.zeros((qb.shape[0], F, 7))
             coms = np.zeros((qb.shape[0], 3))
@@ -84,6 +91,8 @@ def main():
                 cfg.update(qb[b])
                 for k, f in enumerate(wl["frames"]):
                     poses[b, k] = cfg.get_transform_frame_to_world(f["name"], f["type"]).wxyz_xyz
+                for k, f in enumerate(rel):   # relative tasks are targeted in the root frame
+                    poses[b, nabs + k] = cfg.get_transform(f["name"], f["type"], f["root_name"], f["root_type"]).wxyz_xyz
                 coms[b] = cfg.data.subtree_com[1]
             return poses, coms
 
@@ -104,12 +113,17 @@ def main():
         Gs, hs, nact = [], [], np.zeros(B, dtype=np.int32)
         for b in range(B):
             cfg.update(q[b])
-            for k, (t, f) in enumerate(zip(frame_tasks, wl["frames"])):
+            for k, t in enumerate(frame_tasks):
                 t.set_target(mink.SE3(wxyz_xyz=inp["frame_targets"][b, k]))
-                poses[b, k] = cfg.get_transform_frame_to_world(f["name"], f["type"]).wxyz_xyz
                 eF[b, k] = t.compute_error(cfg)
                 JF[b, k] = t.compute_jacobian(cfg)
-                JB[b, k] = cfg.get_frame_jacobian(f["name"], f["type"])
+                if k < nabs:
+                    f = wl["frames"][k]
+                    poses[b, k] = cfg.get_transform_frame_to_world(f["name"], f["type"]).wxyz_xyz
+                    JB[b, k] = cfg.get_frame_jacobian(f["name"], f["type"])
+                else:
+                    f = rel[k - nabs]
+                    poses[b, k] = cfg.get_transform(f["name"], f["type"], f["root_name"], f["root_type"]).wxyz_xyz
             comp[b] = cfg.data.subtree_com[1]
             if posture is not None:
                 posture.set_target(inp["posture_target"])

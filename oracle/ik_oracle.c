@@ -362,7 +362,7 @@ int iko_frame_jacobian(const void* blob, int B, const double* q, const bik_frame
 typedef struct { int F, P, C, K; } Counts;
 static Counts count_tasks(const bik_task_desc* t, int n) {
   Counts c = {0, 0, 0, 0};
-  for (int i = 0; i < n; ++i) { if (t[i].kind == BIK_TASK_FRAME) c.F++; else if (t[i].kind == BIK_TASK_POSTURE) c.P++; else c.C++; }
+  for (int i = 0; i < n; ++i) { if (t[i].kind == BIK_TASK_FRAME || t[i].kind == BIK_TASK_RELATIVE_FRAME) c.F++; else if (t[i].kind == BIK_TASK_POSTURE) c.P++; else c.C++; }
   c.K = 6 * c.F + 3 * c.C; return c;
 }
 
@@ -403,6 +403,33 @@ static void tasks_instance(const Model* m, const Kin* k, const bik_task_desc* ta
           J[(row + i) * nv + d] = -s;
         }
       row += 6; fi++;
+    } else if (T->kind == BIK_TASK_RELATIVE_FRAME) { /* relative_frame_task.py:106-142 */
+      double pf[3], Rf[9], pr[3], Rr[9]; double* Jf = scratch + 6 * nv; double* Jr = scratch + 12 * nv;
+      body_jacobian(m, k, &T->frame, Jf, pf, Rf, scratch);
+      body_jacobian(m, k, &T->root, Jr, pr, Rr, scratch);
+      double qf[4], qr[4]; mat2quat(Rf, qf); mat2quat(Rr, qr);
+      /* T_rf = T_wr^-1 T_wf */
+      double qri[4] = {qr[0], -qr[1], -qr[2], -qr[3]}, q_rf[4], d_[3] = {pf[0] - pr[0], pf[1] - pr[1], pf[2] - pr[2]}, t_rf[3];
+      qmul(qri, qf, q_rf); matT_vec(Rr, d_, t_rf);
+      const double* tg = ftgt + 7 * fi;
+      double tq[4] = {tg[0], tg[1], tg[2], tg[3]}, tqi[4] = {tg[0], -tg[1], -tg[2], -tg[3]}, Rt[9], q_tf[4], dd[3] = {t_rf[0] - tg[4], t_rf[1] - tg[5], t_rf[2] - tg[6]}, t_tf[3];
+      q2mat(tq, Rt); qmul(tqi, q_rf, q_tf); matT_vec(Rt, dd, t_tf);
+      double xi[6], nxi[6], L[36];
+      se3_log(q_tf, t_tf, xi);                       /* e = T_rf.rminus(T_rt) = log(T_rt^-1 T_rf) */
+      memcpy(e + row, xi, sizeof xi);
+      for (int i = 0; i < 6; ++i) nxi[i] = -xi[i];
+      se3_ljacinv(nxi, L);                           /* jlog(T_tf) */
+      /* Ad(T_fr), T_fr = T_rf^-1: R = R_rf^T, t = -R_rf^T t_rf */
+      double Rrf[9], Rfr[9], tfr[3], S[9], SR[9];
+      q2mat(q_rf, Rrf); tr3(Rrf, Rfr); mat_vec(Rfr, t_rf, tfr); for (int i = 0; i < 3; ++i) tfr[i] = -tfr[i];
+      skew(tfr, S); mm3(S, Rfr, SR);
+      for (int d = 0; d < nv; ++d) {
+        double vr[3] = {Jr[d], Jr[nv + d], Jr[2 * nv + d]}, wr[3] = {Jr[3 * nv + d], Jr[4 * nv + d], Jr[5 * nv + d]}, a1[3], a2[3], a3[3], tw[6];
+        mat_vec(Rfr, vr, a1); mat_vec(SR, wr, a2); mat_vec(Rfr, wr, a3);
+        for (int i = 0; i < 3; ++i) { tw[i] = Jf[i * nv + d] - (a1[i] + a2[i]); tw[3 + i] = Jf[(3 + i) * nv + d] - a3[i]; }
+        for (int i = 0; i < 6; ++i) { double sacc = 0; for (int j = 0; j < 6; ++j) sacc += L[6 * i + j] * tw[j]; J[(row + i) * nv + d] = sacc; }
+      }
+      row += 6; fi++;
     } else if (T->kind == BIK_TASK_COM) {
       double com[3], M; com_of(m, k, com, &M);
       const double* tg = ctgt + 3 * ci;
@@ -434,7 +461,7 @@ int iko_fk_jac(const void* blob, const bik_task_desc* tasks, int ntasks, int B, 
   Counts c = count_tasks(tasks, ntasks);
 #pragma omp parallel
   {
-    Kin k = kin_alloc(m.nnode); double* s = (double*)malloc(sizeof(double) * 12 * m.nv);
+    Kin k = kin_alloc(m.nnode); double* s = (double*)malloc(sizeof(double) * 18 * m.nv);
 #pragma omp for
     for (int b = 0; b < B; ++b) {
       const double* qb = q + (size_t)b * m.nq;
@@ -469,7 +496,7 @@ static void objective_instance(const Model* m, const bik_task_desc* tasks, int n
       for (int d = 0; d < nv; ++d) H[d * nv + d] += mu;
       pi++; continue;
     }
-    int k = (T->kind == BIK_TASK_FRAME) ? 6 : 3; double we[6], mu = 0;
+    int k = (T->kind == BIK_TASK_FRAME || T->kind == BIK_TASK_RELATIVE_FRAME) ? 6 : 3; double we[6], mu = 0;
     for (int i = 0; i < k; ++i) { we[i] = T->cost[i] * (-T->gain * e[row + i]); mu += we[i] * we[i]; }
     mu *= T->lm_damping;
     for (int a = 0; a < nv; ++a) {
@@ -733,7 +760,7 @@ int iko_step(const void* blob, const bik_task_desc* tasks, int ntasks, const bik
 #pragma omp parallel
   {
     Kin k = kin_alloc(m.nnode);
-    double* s = (double*)malloc(sizeof(double) * 12 * nv);
+    double* s = (double*)malloc(sizeof(double) * 18 * nv);
     double* J = (double*)malloc(sizeof(double) * ((size_t)(cn.K + 1) * nv + cn.K + (size_t)(cn.P + 1) * nv));
     double* e = J + (size_t)(cn.K + 1) * nv; double* ep = e + cn.K;
     double* H = (double*)malloc(sizeof(double) * ((size_t)nv * nv + 3 * nv + (size_t)(npairs + 1) * (nv + 1)));
@@ -772,7 +799,7 @@ int iko_collision(const void* blob, const bik_limit_desc* limits, int nlimits, i
   int npairs = 0; for (int l = 0; l < nlimits; ++l) if (limits[l].kind == BIK_LIMIT_COLLISION) npairs += limits[l].n;
 #pragma omp parallel
   {
-    Kin k = kin_alloc(m.nnode); double* s = (double*)malloc(sizeof(double) * 12 * m.nv);
+    Kin k = kin_alloc(m.nnode); double* s = (double*)malloc(sizeof(double) * 18 * m.nv);
 #pragma omp for
     for (int b = 0; b < B; ++b) {
       fk_nodes(&m, q + (size_t)b * m.nq, &k); int row = 0;

@@ -172,3 +172,34 @@ def test_com_task_and_collision_limit_spot():
         t.set_target(SE3(g["frame_targets"][:, k]))
     v = mink.solve_ik(cfg, tasks + [com], float(g["dt"]), "quadprog", float(g["damping"]), limits=[lim])
     np.testing.assert_allclose(_np(v) * float(g["dt"]), g["dq"], atol=5e-3)
+
+
+def test_relative_frame_task_matches_reference_and_world_root_identity():
+    """RelativeFrameTask vs the reference golden (g1_rel), and the reference's own cross-check
+    (tests/test_relative_frame_task.py:128-154): with root = world it equals minus the FrameTask."""
+    wl, fm, spec, g = load_case("g1_rel")
+    cfg = mink.Configuration(fm, g["q"])
+    f = wl["relative_frames"][0]
+    rel = mink.RelativeFrameTask(f["name"], f["type"], f["root_name"], f["root_type"], f["position_cost"], f["orientation_cost"],
+                                 lm_damping=f["lm_damping"])
+    with pytest.raises(mink.TargetNotSet):
+        rel.compute_error(cfg)
+    rel.set_target(SE3(g["frame_targets"][:, 1]))
+    np.testing.assert_allclose(_np(rel.compute_error(cfg)), g["e_frame"][:, 1], atol=5e-5)
+    np.testing.assert_allclose(_np(rel.compute_jacobian(cfg)), g["J_frame"][:, 1], atol=1e-4)
+    pel = mink.FrameTask("pelvis", "body", 0.0, 10.0)
+    pel.set_target(SE3(g["frame_targets"][:, 0]))
+    post = mink.PostureTask(fm, cost=1.0)
+    post.set_target(g["posture_target"])
+    v = mink.solve_ik(cfg, [pel, rel, post], float(g["dt"]), "quadprog", float(g["damping"]), limits=[mink.ConfigurationLimit(fm)])
+    np.testing.assert_allclose(_np(v) * float(g["dt"]), g["dq"], atol=1e-4 * max(1.0, np.abs(g["dq"]).max()))
+    # root = world  ==>  error and Jacobian are minus the FrameTask's
+    one = mink.Configuration(fm, g["q"][3])
+    T = SE3(g["frame_targets"][3, 0])
+    a = mink.RelativeFrameTask("pelvis", "body", "world", "body", 1.0, 1.0)
+    b = mink.FrameTask("pelvis", "body", 1.0, 1.0)
+    a.set_target(T); b.set_target(T)
+    np.testing.assert_allclose(a.compute_error(one), -b.compute_error(one), atol=2e-6)
+    np.testing.assert_allclose(a.compute_jacobian(one), -b.compute_jacobian(one), atol=2e-5)
+    a.set_target_from_configuration(one)
+    np.testing.assert_allclose(a.compute_error(one), np.zeros(6), atol=2e-6)

@@ -16,7 +16,7 @@ from mink_b200._abi import spec_from_workload  # noqa: E402
 from mink_b200.workloads import WORKLOADS, make_inputs  # noqa: E402
 from tests.helpers import load_case, load_flat, quat_align, task_frames  # noqa: E402
 
-CASES = ["ur5e", "ur5e_dls", "g1", "shadow", "spot"]
+CASES = ["ur5e", "ur5e_dls", "g1", "shadow", "spot", "g1_rel"]
 
 
 def _need_gpu():
@@ -60,12 +60,12 @@ def test_fk_and_frame_jacobian(name):
     wl, fm, spec, g, model, prob = _engine(name)
     frames = task_frames(wl, fm)
     poses, com = model.fk(g["q"], frames, want_com=True)
-    poses, ref = _np(poses), g["frame_pose"]
+    poses, ref = _np(poses), g["frame_pose"][:, :len(frames)]
     np.testing.assert_allclose(poses[..., 4:], ref[..., 4:], atol=5e-6)
     np.testing.assert_allclose(quat_align(poses[..., :4], ref[..., :4]), ref[..., :4], atol=5e-6)
     if fm.ncom:
         np.testing.assert_allclose(_np(com), g["com"], atol=5e-6)
-    np.testing.assert_allclose(_np(model.frame_jacobian(g["q"], frames)), g["J_body"], atol=1e-5)
+    np.testing.assert_allclose(_np(model.frame_jacobian(g["q"], frames)), g["J_body"][:, :len(frames)], atol=1e-5)
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -122,7 +122,8 @@ def test_solve_ik_step_matches_reference(name):
     dq, st = prob.step(q, g["frame_targets"], g["posture_target"], g.get("com_target"), dt=float(g["dt"]),
                        damping=float(g["damping"]), nsteps=1, integrate=True)
     assert int(st.max()) == 0
-    tol = 1e-4 if name != "spot" else 5e-3   # spot: cond(H) ~ 4e7, fp32 J alone moves the optimum
+    # spot: cond(H) ~ 4e7, fp32 J alone moves the optimum; g1_rel: |dq| up to 2.3 rad (no velocity limit) -> relative 1e-4
+    tol = {"spot": 5e-3, "g1_rel": 1e-4 * max(1.0, np.abs(g["dq"]).max())}.get(name, 1e-4)
     err = np.abs(_np(dq) - g["dq"]).max()
     print(f"{name}: max|dq - dq_ref| = {err:.3e}")
     assert err < tol

@@ -11,7 +11,7 @@ import pytest
 from tests.emu_lib import Emu
 from tests.helpers import load_case, quat_align, task_frames
 
-CASES = ["ur5e", "ur5e_dls", "g1", "shadow", "spot"]
+CASES = ["ur5e", "ur5e_dls", "g1", "shadow", "spot", "g1_rel"]
 
 
 def _emu(name):
@@ -24,10 +24,10 @@ def test_fk_and_body_jacobian(name):
     wl, fm, spec, g, emu = _emu(name)
     frames = task_frames(wl, fm)
     poses, com, Jb = emu.fk(g["q"], frames, want_J=True)
-    ref = g["frame_pose"]
+    ref = g["frame_pose"][:, :len(frames)]
     np.testing.assert_allclose(poses[..., 4:], ref[..., 4:], atol=5e-6)
     np.testing.assert_allclose(quat_align(poses[..., :4].astype(np.float64), ref[..., :4]), ref[..., :4], atol=5e-6)
-    np.testing.assert_allclose(Jb, g["J_body"], atol=1e-5)
+    np.testing.assert_allclose(Jb, g["J_body"][:, :len(frames)], atol=1e-5)
     if fm.ncom:
         np.testing.assert_allclose(com, g["com"], atol=5e-6)
 
@@ -89,7 +89,7 @@ def test_full_step(name):
     J, e, ep, Gc, hc = emu.fk_jac(g["q"], g["frame_targets"], g["posture_target"], g.get("com_target"), dt=dt)
     dq, st, it, *_ = emu.solve(g["q"], J, e, ep, Gc, hc, dt, damping, use_double=True)
     assert not st.any()
-    tol = 1e-4 if name != "spot" else 5e-3
+    tol = {"spot": 5e-3, "g1_rel": 1e-4 * max(1.0, np.abs(g["dq"]).max())}.get(name, 1e-4)
     err = np.abs(dq - g["dq"]).max()
     print(name, "max |dq - dq_ref| =", err, "iters mean/max", it.mean(), it.max())
     assert err < tol

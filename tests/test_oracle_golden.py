@@ -10,7 +10,7 @@ import pytest
 from oracle.ikoracle import Oracle
 from tests.helpers import load_case, quat_align, task_frames
 
-CASES = ["ur5e", "ur5e_dls", "g1", "shadow", "spot"]
+CASES = ["ur5e", "ur5e_dls", "g1", "shadow", "spot", "g1_rel"]
 
 
 def _oracle(name):
@@ -23,13 +23,13 @@ def test_fk_and_body_jacobian(name):
     wl, fm, spec, g, orc = _oracle(name)
     frames = task_frames(wl, fm)
     poses, com = orc.fk(g["q"], frames)
-    ref = g["frame_pose"]
+    ref = g["frame_pose"][:, :len(frames)]
     np.testing.assert_allclose(poses[..., 4:], ref[..., 4:], atol=1e-12)
     np.testing.assert_allclose(quat_align(poses[..., :4], ref[..., :4]), ref[..., :4], atol=1e-12)
     if fm.ncom:
         np.testing.assert_allclose(com, g["com"], atol=1e-12)
     Jb = orc.frame_jacobian(g["q"], frames)
-    np.testing.assert_allclose(Jb, g["J_body"], atol=1e-12)
+    np.testing.assert_allclose(Jb, g["J_body"][:, :len(frames)], atol=1e-12)
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -73,7 +73,7 @@ def test_solve_and_integrate(name):
                                 dt=float(g["dt"]), damping=float(g["damping"]), nsteps=1, integrate=True)
     assert not st.any()
     # exact-QP optimum: both sides are fp64 active-set solves
-    tol = 1e-9 if name != "spot" else 1e-6   # spot: cond(H) ~ 4e7 (posture-free, damping 1e-3)
+    tol = {"spot": 1e-6, "g1_rel": 1e-8}.get(name, 1e-9)   # spot: cond(H) ~ 4e7 (posture-free, damping 1e-3)
     np.testing.assert_allclose(dq, g["dq"], atol=tol)
     np.testing.assert_array_equal(nact, g["n_active"])
     np.testing.assert_allclose(qn, g["q_next"], atol=tol)
@@ -88,5 +88,5 @@ def test_rollout(name):
     _, q, st, _ = orc.step(traj[0], g["frame_targets"][:RB], g["posture_target"], ct, dt=float(g["dt"]),
                            damping=float(g["damping"]), nsteps=T, integrate=True)
     assert not st.any()
-    tol = 1e-8 if name != "spot" else 1e-5
+    tol = {"spot": 1e-5, "g1_rel": 1e-6}.get(name, 1e-8)
     np.testing.assert_allclose(q, traj[-1], atol=tol)
