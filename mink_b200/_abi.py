@@ -252,7 +252,7 @@ def spec_from_workload(fm: FlatModel, wl: dict) -> ProblemSpec:
             limits.append(LimitSpec(LIMIT_CONFIGURATION, dof=dof, lower=fm.dof_lo[dof] + mind,
                                     upper=fm.dof_hi[dof] - mind, gain=l.get("gain", 0.95)))
         elif l["kind"] == "velocity":
-            dof = np.nonzero(fm.dof_qadr >= 0)[0].astype(np.int32)
+            dof = np.array([d for d in range(fm.nv) if fm.node_type[fm.dof_node[d]] != 0], dtype=np.int32)  # all but free joints
             limits.append(LimitSpec(LIMIT_VELOCITY, dof=dof, vmax=np.full(len(dof), float(l["vmax"]))))
         elif l["kind"] == "collision":
             names = fm.names["geom"]

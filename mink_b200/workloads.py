@@ -78,6 +78,21 @@ WORKLOADS: Dict[str, dict] = {
         limits=[dict(kind="configuration", gain=0.95)],
         dt=5e-3, damping=1e-2, batch=4096,
     ),
+    # Not a BASELINE config: edge-case model authored for this repository (tests/golden/models/edge.xml):
+    # ball joint with off-centre anchor, slide joint with ref, two joints on one body, a second floating
+    # root, capsule/sphere/plane collision pairs, every task and limit kind at once.
+    "edge": dict(
+        robot="edge", scene="@tests/golden/models/edge.xml", key="home",
+        frames=[dict(name="tool", type="site", position_cost=[3.0, 2.0, 1.0], orientation_cost=0.7, lm_damping=0.3, gain=0.8),
+                dict(name="float_site", type="site", position_cost=1.0, orientation_cost=[0.5, 0.0, 0.2], lm_damping=0.0)],
+        relative_frames=[dict(name="side_tip", type="site", root_name="tool", root_type="site",
+                              position_cost=2.0, orientation_cost=0.0, lm_damping=0.1)],
+        posture=dict(cost=0.5), com=dict(cost=2.0),
+        limits=[dict(kind="configuration", gain=0.9), dict(kind="velocity", vmax=2.0),
+                dict(kind="collision", pairs=[(["g_hand", "g_fore", "g_upper"], ["g_side"]), (["g_float"], ["floor", "g_hand"])],
+                     gain=0.85, minimum_distance=0.01, detection_distance=0.6, bound_relaxation=0.0)],
+        dt=1e-2, damping=1e-3, batch=1024,
+    ),
 }
 
 

@@ -26,7 +26,7 @@ from mink_b200.flatten import flatten  # noqa: E402
 from mink_b200.workloads import WORKLOADS, make_inputs  # noqa: E402
 
 OUT = os.path.join(REPO, "tests", "golden")
-GOLDEN_B = {"ur5e": 8, "ur5e_dls": 16, "g1": 32, "shadow": 24, "spot": 24, "g1_rel": 16}
+GOLDEN_B = {"ur5e": 8, "ur5e_dls": 16, "g1": 32, "shadow": 24, "spot": 24, "g1_rel": 16, "edge": 48}
 ROLLOUT_T, ROLLOUT_B = 8, 4
 
 
@@ -34,7 +34,7 @@ def build_reference_problem(model, wl):
     tasks, frame_tasks = [], []
     for f in wl["frames"]:
         t = mink.FrameTask(f["name"], f["type"], f["position_cost"], f["orientation_cost"],
-                           lm_damping=f["lm_damping"])
+                           gain=f.get("gain", 1.0), lm_damping=f["lm_damping"])
         frame_tasks.append(t)
     for f in wl.get("relative_frames", []):
         t = mink.RelativeFrameTask(f["name"], f["type"], f["root_name"], f["root_type"], f["position_cost"],
@@ -53,8 +53,8 @@ def build_reference_problem(model, wl):
         if l["kind"] == "configuration":
             limits.append(mink.ConfigurationLimit(model, gain=l["gain"]))
         elif l["kind"] == "velocity":
-            vel = {model.joint_names[j]: l["vmax"] for j in range(model.njnt)
-                   if model.jnt_type[j] in (2, 3)}
+            vel = {model.joint_names[j]: (np.full(3, l["vmax"]) if model.jnt_type[j] == 1 else l["vmax"])
+                   for j in range(model.njnt) if model.jnt_type[j] in (1, 2, 3)}
             limits.append(mink.VelocityLimit(model, vel))
         elif l["kind"] == "collision":
             limits.append(mink.CollisionAvoidanceLimit(
@@ -69,7 +69,8 @@ def main():
     os.makedirs(os.path.join(OUT, "models"), exist_ok=True)
     done_models = set()
     for name, wl in WORKLOADS.items():
-        model = mujoco.MjModel.from_xml_path(os.path.join(REF, "examples", wl["scene"]))
+        scene = os.path.join(REPO, wl["scene"][1:]) if wl["scene"].startswith("@") else os.path.join(REF, "examples", wl["scene"])
+        model = mujoco.MjModel.from_xml_path(scene)
         fm = flatten(model)
         if wl["robot"] not in done_models:
             with open(os.path.join(OUT, "models", wl["robot"] + ".bikm"), "wb") as f:

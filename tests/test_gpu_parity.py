@@ -16,7 +16,7 @@ from mink_b200._abi import spec_from_workload  # noqa: E402
 from mink_b200.workloads import WORKLOADS, make_inputs  # noqa: E402
 from tests.helpers import load_case, load_flat, quat_align, task_frames  # noqa: E402
 
-CASES = ["ur5e", "ur5e_dls", "g1", "shadow", "spot", "g1_rel"]
+CASES = ["ur5e", "ur5e_dls", "g1", "shadow", "spot", "g1_rel", "edge"]
 
 
 def _need_gpu():
@@ -82,10 +82,13 @@ def test_k1_task_errors_and_jacobians(name):
         np.testing.assert_allclose(e[:, 6 * F:], g["e_com"], atol=5e-6)
         np.testing.assert_allclose(J[:, 6 * F:], g["J_com"], atol=5e-6)
     if spec.npairs:
-        fin = np.isfinite(g["h"])
+        Gr, hr = g["G"][:, -spec.npairs:], g["h"][:, -spec.npairs:]   # collision rows are stacked last
+        fin = np.isfinite(hr)
         assert np.array_equal(np.isfinite(hc), fin)
-        np.testing.assert_allclose(hc[fin], g["h"][fin], rtol=2e-4, atol=2e-3)
-        np.testing.assert_allclose(Gc, g["G"], atol=2e-5)
+        np.testing.assert_allclose(hc[fin], hr[fin], rtol=2e-4, atol=2e-3)
+        # capsule-capsule closest POINTS are ill-conditioned when the axes are nearly parallel (the distance is
+        # not): fp32 poses move the contact point along the segment, hence the looser bound for that model
+        np.testing.assert_allclose(Gc, Gr, atol=2e-5 if name != "edge" else 5e-3)
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -97,8 +100,8 @@ def test_k2_objective_box_and_solve_from_reference_jacobians(name):
     J = f32(np.concatenate([g["J_frame"].reshape(B, 6 * F, fm.nv)] + ([g["J_com"]] if spec.ncom else []), axis=1))
     e = f32(np.concatenate([g["e_frame"].reshape(B, 6 * F)] + ([g["e_com"]] if spec.ncom else []), axis=1))
     ep = f32(g["e_posture"][:, None, :]) if spec.nposture else torch.zeros((B, 0, fm.nv), device="cuda:0")
-    Gc = f32(g["G"]) if spec.npairs else torch.zeros((B, 0, fm.nv), device="cuda:0")
-    hc = f32(g["h"]) if spec.npairs else torch.zeros((B, 0), device="cuda:0")
+    Gc = f32(g["G"][:, -spec.npairs:]) if spec.npairs else torch.zeros((B, 0, fm.nv), device="cuda:0")
+    hc = f32(g["h"][:, -spec.npairs:]) if spec.npairs else torch.zeros((B, 0), device="cuda:0")
     H, c = prob.objective(J, e, ep, float(g["damping"]))
     scale = np.abs(g["H"]).max()
     np.testing.assert_allclose(_np(H), g["H"], atol=1e-6 * scale)
@@ -111,7 +114,7 @@ def test_k2_objective_box_and_solve_from_reference_jacobians(name):
     np.testing.assert_allclose(_np(hi)[fin], g["box_hi"][fin], atol=1e-6)
     dq, st = prob.solve(g["q"], J, e, ep, Gc, hc, float(g["dt"]), float(g["damping"]))
     assert int(st.max()) == 0
-    np.testing.assert_allclose(_np(dq), g["dq"], atol=1e-5 if name != "spot" else 2e-3)
+    np.testing.assert_allclose(_np(dq), g["dq"], atol={"spot": 2e-3, "g1_rel": 5e-5}.get(name, 1e-5))
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -123,7 +126,8 @@ def test_solve_ik_step_matches_reference(name):
                        damping=float(g["damping"]), nsteps=1, integrate=True)
     assert int(st.max()) == 0
     # spot: cond(H) ~ 4e7, fp32 J alone moves the optimum; g1_rel: |dq| up to 2.3 rad (no velocity limit) -> relative 1e-4
-    tol = {"spot": 5e-3, "g1_rel": 1e-4 * max(1.0, np.abs(g["dq"]).max())}.get(name, 1e-4)
+    tol = {"spot": 5e-3, "g1_rel": 1e-4 * max(1.0, np.abs(g["dq"]).max()),
+           "edge": 2e-3}.get(name, 1e-4)   # edge: an active near-parallel capsule pair (ill-conditioned contact point)
     err = np.abs(_np(dq) - g["dq"]).max()
     print(f"{name}: max|dq - dq_ref| = {err:.3e}")
     assert err < tol
@@ -140,7 +144,7 @@ def test_rollout_matches_reference(name):
     dq, st = prob.step(q, g["frame_targets"][:RB], g["posture_target"], ct, dt=float(g["dt"]), damping=float(g["damping"]),
                        nsteps=T, integrate=True)
     assert int(st.max()) == 0
-    np.testing.assert_allclose(_np(q), traj[-1], atol=5e-4 if name != "spot" else 2e-2)
+    np.testing.assert_allclose(_np(q), traj[-1], atol={"spot": 2e-2, "edge": 1e-2, "g1_rel": 2e-3}.get(name, 5e-4))
 
 
 @pytest.mark.parametrize("group", [1, 2, 4, 8, 16, 32])

@@ -11,7 +11,7 @@ import pytest
 from tests.emu_lib import Emu
 from tests.helpers import load_case, quat_align, task_frames
 
-CASES = ["ur5e", "ur5e_dls", "g1", "shadow", "spot", "g1_rel"]
+CASES = ["ur5e", "ur5e_dls", "g1", "shadow", "spot", "g1_rel", "edge"]
 
 
 def _emu(name):
@@ -45,10 +45,13 @@ def test_k1_errors_and_jacobians(name):
         np.testing.assert_allclose(e[:, 6 * F:], g["e_com"], atol=5e-6)
         np.testing.assert_allclose(J[:, 6 * F:], g["J_com"], atol=5e-6)
     if spec.npairs:
-        fin = np.isfinite(g["h"])
+        Gr, hr = g["G"][:, -spec.npairs:], g["h"][:, -spec.npairs:]   # collision rows are stacked last
+        fin = np.isfinite(hr)
         assert np.array_equal(np.isfinite(hc), fin)
-        np.testing.assert_allclose(hc[fin], g["h"][fin], rtol=2e-4, atol=2e-3)
-        np.testing.assert_allclose(Gc, g["G"], atol=2e-5)
+        np.testing.assert_allclose(hc[fin], hr[fin], rtol=2e-4, atol=2e-3)
+        # capsule-capsule closest POINTS are ill-conditioned when the axes are nearly parallel (the distance is
+        # not): fp32 poses move the contact point along the segment, hence the looser bound for that model
+        np.testing.assert_allclose(Gc, Gr, atol=2e-5 if name != "edge" else 5e-3)
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -61,7 +64,7 @@ def test_k2_from_golden_jacobians(name, use_double):
     e = np.concatenate([g["e_frame"].reshape(B, 6 * F)] + ([g["e_com"]] if spec.ncom else []), axis=1)
     ep = g["e_posture"][:, None, :] if spec.nposture else np.zeros((B, 0, fm.nv))
     if spec.npairs:
-        Gc, hc = g["G"], g["h"]
+        Gc, hc = g["G"][:, -spec.npairs:], g["h"][:, -spec.npairs:]
     else:
         Gc, hc = np.zeros((B, 0, fm.nv)), np.zeros((B, 0))
     dq, st, it, H, c, lo, hi = emu.solve(g["q"], J, e, ep, Gc, hc, float(g["dt"]), float(g["damping"]),
@@ -89,7 +92,8 @@ def test_full_step(name):
     J, e, ep, Gc, hc = emu.fk_jac(g["q"], g["frame_targets"], g["posture_target"], g.get("com_target"), dt=dt)
     dq, st, it, *_ = emu.solve(g["q"], J, e, ep, Gc, hc, dt, damping, use_double=True)
     assert not st.any()
-    tol = {"spot": 5e-3, "g1_rel": 1e-4 * max(1.0, np.abs(g["dq"]).max())}.get(name, 1e-4)
+    tol = {"spot": 5e-3, "g1_rel": 1e-4 * max(1.0, np.abs(g["dq"]).max()),
+           "edge": 2e-3}.get(name, 1e-4)   # edge: an active near-parallel capsule pair (ill-conditioned contact point)
     err = np.abs(dq - g["dq"]).max()
     print(name, "max |dq - dq_ref| =", err, "iters mean/max", it.mean(), it.max())
     assert err < tol
