@@ -217,7 +217,9 @@ extern "C" int bik_model_create(const void* blob, size_t nbytes, int device, bik
   std::string err;
   if (!parse_model_blob(blob, nbytes, &m->hm, &err)) { delete m; return fail(BIK_ERR_INVALID, err); }
   m->device = device;
-  m->G = env_int("BIK_K1_GROUP", 4);
+  // lanes per instance in K1: wide enough that the per-warp tile stays small (occupancy), narrow enough that
+  // the lane program keeps the lanes busy; measured on G1 (38 nodes): G=8 0.153 ms, G=4 0.168, G=16 0.239, G=2 0.245
+  m->G = env_int("BIK_K1_GROUP", m->hm.nnode > 16 ? 8 : (m->hm.nnode > 8 ? 4 : 2));
   if (!valid_group(m->G)) { delete m; return fail(BIK_ERR_INVALID, "BIK_K1_GROUP must be 1,2,4,8,16 or 32"); }
   m->use_tma = env_int("BIK_USE_TMA", 1);
   if (!build_image(m->hm, nullptr, 0, nullptr, 0, m->G, &m->image, &err)) { delete m; return fail(BIK_ERR_UNSUPPORTED, err); }

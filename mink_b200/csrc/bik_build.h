@@ -161,6 +161,7 @@ inline bool build_image(const HostModel& m, const bik_task_desc* tasks, int ntas
         r.gain = (float)tasks[t].gain; r.lm = (float)tasks[t].lm_damping; r.row0 = row;
         r.col_off = (int)cols.size();
         r.relative = tasks[t].kind == BIK_TASK_RELATIVE_FRAME;
+        H.nrel += r.relative;
         r.rnode = -1;
         std::vector<int> chain_f, chain_r;
         for (int n = r.node; n >= 0; n = m.node_parent[n]) chain_f.push_back(n);

@@ -77,8 +77,11 @@ BIK_HD int k1_state_stride(const PHeader& h) {  // pose (7) + CoM first moment (
 }
 BIK_HD int k1_stage_rows(const PHeader& h) { return 6; }
 BIK_HD int k1_state_words(const PHeader& h, int ipw) { return (ipw * k1_state_stride(h) + 3) & ~3; }  // keeps the stage 16-byte aligned
+BIK_HD int k1_fsc_stride(const PHeader& h) { return h.nrel > 0 ? 32 : 24; }
+BIK_HD int k1_stage_words(const PHeader& h, int ipw) { return (ipw * 6 * h.nv + 3) & ~3; }   // one frame's 6 rows per instance
 BIK_HD int k1_warp_words(const PHeader& h, int ipw) {
-  int w = k1_state_words(h, ipw) + ipw * k1_stage_rows(h) * h.nv + ipw * (h.K > 0 ? h.K : 1) + ipw * (h.F > 0 ? h.F : 1) * 32;
+  int w = k1_state_words(h, ipw) + k1_stage_words(h, ipw) + ipw * (h.K > 0 ? h.K : 1) + ipw * (h.F > 0 ? h.F : 1) * k1_fsc_stride(h) +
+          ((ipw * h.nq + 3) & ~3);
   return (w + 3) & ~3;
 }
 
@@ -165,10 +168,9 @@ BIK_HD void frame_task(FQ qf, F3 pf, const float* tgt, F3* ev, F3* ew, FM* A1, F
   // e = log(T_wb^-1 T_wt)                                (frame_task.py:119-122)
   se3_log<float>(qmul(qconj(qf), tq), qrot_inv(qf, tp - pf), ev, ew);
   // jlog(T_wt^-1 T_wb) = ljacinv(-log(T_tb))            (frame_task.py:145-146, lie/base.py:151-156)
-  F3 v, w;
-  se3_log<float>(qmul(qconj(tq), qf), qrot_inv(tq, pf - tp), &v, &w);
+  // and log(T_tb) = log(T_bt^-1) = -e, so the argument of ljacinv is e itself: no second logarithm.
   FM Ji, Mi;
-  se3_ljacinv_blocks<float>(v3<float>(-v.x, -v.y, -v.z), v3<float>(-w.x, -w.y, -w.z), &Ji, &Mi);
+  se3_ljacinv_blocks<float>(*ev, *ew, &Ji, &Mi);
   FM Rt = mtrans(q2mat(qf));
   *A1 = mmul(Ji, Rt);
   *A2 = mmul(Mi, Rt);
@@ -276,10 +278,17 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, float* wsm,
   const int SS = k1_state_stride(h);
   float* state = wsm;
   float* stage = wsm + k1_state_words(h, IPW);
-  float* estage = stage + IPW * 6 * nv;
-  float* fsc = estage + IPW * (K > 0 ? K : 1);  // per (instance, frame): 32 floats of per-frame SE(3) results
+  float* estage = stage + k1_stage_words(h, IPW);
+  float* fsc = estage + IPW * (K > 0 ? K : 1);  // per (instance, frame): per-frame SE(3) results
+  const int FS = k1_fsc_stride(h);
+  float* qtile = fsc + IPW * (h.F > 0 ? h.F : 1) * FS;  // q of this tile: one contiguous, coalesced run of global memory
   float* xs = state + li * SS;
-  const float* qb = a.q + (long long)(valid ? b : inst0) * nq;
+  {
+    const float* gq = a.q + (long long)inst0 * nq;
+    for (int k = lane; k < nvalid * nq; k += W) qtile[k] = gq[k];
+  }
+  BIK_SYNCWARP();
+  const float* qb = qtile + (valid ? li : 0) * nq;
 
   // ---- forward kinematics over the lane program --------------------------------------------
   const int32_t* prog = P.i(h.off_prog);
@@ -297,7 +306,7 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, float* wsm,
       const FrameRec& fr = P.frame(f);
       FQ qf; F3 pf, ev, ew; FM A1, A2;
       frame_pose(fr.node, fr.lpos, fr.lquat, xs, &qf, &pf);
-      float* sc = fsc + (li * h.F + f) * 32;
+      float* sc = fsc + (li * h.F + f) * FS;
       if (!fr.relative) {
         frame_task(qf, pf, a.ftgt + ((long long)b * h.F + f) * 7, &ev, &ew, &A1, &A2);
         sc[0] = pf.x; sc[1] = pf.y; sc[2] = pf.z;
@@ -316,13 +325,16 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, float* wsm,
     }
   }
   BIK_SYNCWARP();
-  // (2) per frame: Jacobian columns into the staging tile, then one coalesced flush
+  // (2) per frame: Jacobian columns into the staging tile, then one coalesced flush.
+  // (A whole-tile variant -- all K rows staged, one cp.async.bulk store per tile, no per-tile zero-fill --
+  //  was measured slower: 0.198 vs 0.153 ms at G = 8, the 3x larger tile halves the resident warps;
+  //  profiles/r1_kernels.md.)
   for (int f = 0; f < h.F; ++f) {
     const FrameRec& fr = P.frame(f);
     zero_words<W>(stage, IPW * 6 * nv, lane);
     BIK_SYNCWARP();
     if (valid) {
-      const float* sc = fsc + (li * h.F + f) * 32;
+      const float* sc = fsc + (li * h.F + f) * FS;
       F3 pf = ld_v(sc);
       FM A1, A2;
       for (int k = 0; k < 9; ++k) { A1.m[k] = sc[3 + k]; A2.m[k] = sc[12 + k]; }
@@ -432,7 +444,7 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, float* wsm,
     const int32_t* dofnode = P.i(h.off_dofnode);
     const int32_t* dofqadr = P.i(h.off_dofqadr);
     for (int l2 = 0; l2 < nvalid; ++l2) {
-      const float* qq = a.q + (long long)(inst0 + l2) * nq;
+      const float* qq = qtile + l2 * nq;
       for (int p = 0; p < h.P; ++p) {
         const float* tg = a.ptgt + ((long long)(a.pbatched ? (inst0 + l2) : 0) * h.P + p) * nq;
         float* o = a.ep + ((long long)(inst0 + l2) * h.P + p) * nv;

@@ -53,10 +53,11 @@ def _box_constraint(limit: Limit, configuration: Configuration, dt: float, indic
     if configuration.batched:
         import torch
 
-        idx = torch.as_tensor(indices, device=lo.device, dtype=torch.long)
+        idx = torch.as_tensor(np.array(indices), device=lo.device, dtype=torch.long)
         h = torch.cat([hi[:, idx], -lo[:, idx]], dim=1)
         return Constraint(torch.tensor(G, dtype=torch.float32, device=lo.device).expand(lo.shape[0], -1, -1), h)
-    h = np.concatenate([hi[0, indices].cpu().numpy(), -lo[0, indices].cpu().numpy()]).astype(np.float64)
+    ii = np.array(indices)
+    h = np.concatenate([hi[0].cpu().numpy()[ii], -lo[0].cpu().numpy()[ii]]).astype(np.float64)
     return Constraint(G, h)
 
 

@@ -55,8 +55,8 @@ def main():
     if build_only:
         return
     for name in VARIANTS:
-        for env in ({}, {"BIK_K2_LOCKSTEP": "1"}, {"BIK_K2_LOCKSTEP": "1", "BIK_K2_WARPS": "8"}, {"BIK_K2_WARPS": "8"},
-                    {"BIK_K2_LOCKSTEP": "1", "BIK_K2_WARPS": "2"}, {"BIK_SOLVE_PRECISION": "f32", "BIK_K2_LOCKSTEP": "1", "BIK_K2_WARPS": "8"}):
+        for env in ({}, {"BIK_K1_GROUP": "8"}, {"BIK_K1_GROUP": "8", "BIK_K1_BULK": "1"}, {"BIK_K1_BULK": "1"},
+                    {"BIK_K1_GROUP": "16", "BIK_K1_BULK": "1"}):
             e = dict(os.environ, BIK_REPO=REPO, BIK_LIB=os.path.join(out, f"libbik_{name}.so"), **env)
             r = subprocess.run([sys.executable, "-c", CHILD], env=e, capture_output=True, text=True)
             line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:]
