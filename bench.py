@@ -144,7 +144,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="g1", choices=list(WORKLOADS))
@@ -245,6 +245,25 @@ def main():
         k1_ms.append(a.elapsed_time(b)); k2_ms.append(b.elapsed_time(c))
     k1_s, k2_s = statistics.median(k1_ms) * 1e-3, statistics.median(k2_ms) * 1e-3
 
+    # ---- SURVEY 8(d) second regime: T = 100 timesteps with targets held, q integrated on the device --------
+    T = 100
+    q.copy_(q0)
+    prob.step(q, ft, pt, ct, dt=dt_, damping=damping, nsteps=2, integrate=True, dq=dq, status=status)   # warm
+    q.copy_(q0)
+    flush.fill_(3.0)
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    r0.record()
+    prob.step(q, ft, pt, ct, dt=dt_, damping=damping, nsteps=T, integrate=True, dq=dq, status=status)
+    r1.record()
+    barrier()
+    roll_ms = torch.tensor([r0.elapsed_time(r1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(roll_ms, op=dist.ReduceOp.MAX)
+    rollout = {"timesteps": T, "value": world * B * T / (float(roll_ms.item()) * 1e-3), "unit": UNIT,
+               "ms_per_timestep": float(roll_ms.item()) / T,
+               "note": "one bik_step call with nsteps=100 from q0, targets held: instances converge, bounds deactivate"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -337,7 +356,7 @@ def main():
                        "step": "check_limits + FK/Jacobian (K1) + QP assemble/solve (K2) + integrate, every step from the same q0",
                        "l2": "256 MB flush between timed steps", "parallelism": f"dp{world} (independent instances, no collective)"},
             "gpu_launches": 4 * args.steps, "clocks": clocks, "roofline": roofline, "roofline_k2": roofline_k2,
-            "cpu_baseline": cpu, "e2e": e2e, "wall_s_timed_region": wall}
+            "cpu_baseline": cpu, "e2e": e2e, "rollout_T100": rollout, "wall_s_timed_region": wall}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
