@@ -196,6 +196,7 @@ struct bik_problem {
   std::mutex mu;
   size_t ws_B = 0;
   float *J = nullptr, *e = nullptr, *ep = nullptr, *Gc = nullptr, *hc = nullptr;
+  signed char* warm = nullptr;  // [B][nu] active-set guess carried between the steps of one bik_step call
   // bik_step_host staging
   size_t host_B = 0;
   float *hq = nullptr, *hft = nullptr, *hpt = nullptr, *hct = nullptr, *hdq = nullptr;
@@ -265,7 +266,7 @@ extern "C" int bik_problem_create(const bik_model* model, const bik_task_desc* t
 extern "C" void bik_problem_destroy(bik_problem* p) {
   if (!p) return;
   DeviceGuard g(p->device);
-  cudaFree(p->d_image); cudaFree(p->J); cudaFree(p->e); cudaFree(p->ep); cudaFree(p->Gc); cudaFree(p->hc);
+  cudaFree(p->d_image); cudaFree(p->J); cudaFree(p->e); cudaFree(p->ep); cudaFree(p->Gc); cudaFree(p->hc); cudaFree(p->warm);
   cudaFree(p->hq); cudaFree(p->hft); cudaFree(p->hpt); cudaFree(p->hct); cudaFree(p->hdq); cudaFree(p->hst);
   delete p;
 }
@@ -383,6 +384,12 @@ static bool use_low_rank(const bik_problem* p, const K2Args& a) {
   if (p->k2_path == 1 || !a.dq || a.Hout || a.lo_out) return false;
   if (p->k2_path == 2) return h.npairs == 0 && h.K > 0 && h.K < 63 && a.damping > 0;
   return h.npairs == 0 && h.K > 0 && h.K < 63 && 2 * h.K <= h.nu && a.damping >= 1e-6;
+}
+static bool use_low_rank_static(const bik_problem* p, double damping) {
+  K2Args a;
+  memset(&a, 0, sizeof a);
+  a.dq = reinterpret_cast<float*>(1); a.damping = damping;
+  return use_low_rank(p, a);
 }
 static int dispatch_k2(const bik_problem* p, const K2Args& a, cudaStream_t st) {
   if (use_low_rank(p, a)) return (p->h.K + 1 <= 32) ? launch_k2lr<1>(p, a, st) : launch_k2lr<2>(p, a, st);
@@ -523,14 +530,15 @@ extern "C" int bik_check_limits(const bik_model* m, int B, const float* q, float
 static int ensure_workspace(bik_problem* p, int B) {
   if ((size_t)B <= p->ws_B) return BIK_OK;
   const PHeader& h = p->h;
-  cudaFree(p->J); cudaFree(p->e); cudaFree(p->ep); cudaFree(p->Gc); cudaFree(p->hc);
-  p->J = p->e = p->ep = p->Gc = p->hc = nullptr; p->ws_B = 0;
+  cudaFree(p->J); cudaFree(p->e); cudaFree(p->ep); cudaFree(p->Gc); cudaFree(p->hc); cudaFree(p->warm);
+  p->J = p->e = p->ep = p->Gc = p->hc = nullptr; p->warm = nullptr; p->ws_B = 0;
   size_t b = (size_t)B;
   CUDA_OK(cudaMalloc(&p->J, sizeof(float) * b * (h.K > 0 ? h.K : 1) * h.nv));
   CUDA_OK(cudaMalloc(&p->e, sizeof(float) * b * (h.K > 0 ? h.K : 1)));
   CUDA_OK(cudaMalloc(&p->ep, sizeof(float) * b * (h.P > 0 ? h.P : 1) * h.nv));
   CUDA_OK(cudaMalloc(&p->Gc, sizeof(float) * b * (h.npairs > 0 ? h.npairs : 1) * h.nv));
   CUDA_OK(cudaMalloc(&p->hc, sizeof(float) * b * (h.npairs > 0 ? h.npairs : 1)));
+  CUDA_OK(cudaMalloc(&p->warm, b * (size_t)(h.nu > 0 ? h.nu : 1)));
   p->ws_B = b;
   return BIK_OK;
 }
@@ -548,6 +556,8 @@ extern "C" int bik_step(const bik_problem* cp, int B, float* q, const bik_inputs
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const PHeader& h = p->h;
+  const bool warm = nsteps > 1 && !use_low_rank_static(p, damping);   // rollouts: carry the active set from step to step
+  if (warm) CUDA_OK(cudaMemsetAsync(p->warm, 0, (size_t)B * (size_t)(h.nu > 0 ? h.nu : 1), st));
   for (int s = 0; s < nsteps; ++s) {
     if (status) {  // Configuration.check_limits(safety_break=False) of solve_ik.py:99
       check_limits_kernel<<<(B + 127) / 128, 128, 0, st>>>(p->d_image, B, q, 1e-6f, status, s > 0);
@@ -559,6 +569,7 @@ extern "C" int bik_step(const bik_problem* cp, int B, float* q, const bik_inputs
     K2Args a2;
     memset(&a2, 0, sizeof a2);
     a2.B = B; a2.q = q; a2.J = p->J; a2.e = p->e; a2.ep = p->ep; a2.Gc = p->Gc; a2.hc = p->hc; a2.dt = dt; a2.damping = damping; a2.dq = dq; a2.status = status; a2.lockstep = p->k2_lockstep;
+    a2.warm = warm ? p->warm : nullptr;
     rc = dispatch_k2(p, a2, st);
     if (rc) return rc;
     if (integrate) {

@@ -55,6 +55,7 @@ struct K2Args {
   int skip_objective;  // bik_limits_box: J/e/ep are not read
   int skip_box;        // bik_qp_objective: q is not read
   int lockstep;        // warps of a CTA advance through the pivoting iterations together (block barriers)
+  signed char* warm;   // [B][nu] or null: active-set guess in (0 free, 1 lower, 2 upper), read at entry, updated at exit
 };
 
 enum { K2_MAX_GEN = 16 };  // general (collision) rows that may be active at once
@@ -361,7 +362,11 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
   const int MAXIT = 60, PATIENCE = 3;
   const T tolx = K2Tol<T>::x(), tolg = K2Tol<T>::g();
   const float* Gb = np > 0 ? a.Gc + (long long)b * np * n : nullptr;
-  for (int i = lane; i < n; i += W) w.st[i] = 0;
+  for (int i = lane; i < n; i += W) {
+    int s0 = (a.warm && active) ? a.warm[(long long)b * n + i] : 0;   // warm start: last step's active set
+    if ((s0 == 1 && !(w.lo[i] > T(-1e30))) || (s0 == 2 && !(w.hi[i] < T(1e30)))) s0 = 0;
+    w.st[i] = s0;
+  }
   for (int r = lane; r < np; r += W) { w.gst[r] = 0; w.hg[r] = T(a.hc[(long long)b * np + r]); }
   BIK_SYNCWARP();
   int status = 0, best = n + np + 1, patience = PATIENCE, it = 0;
@@ -447,6 +452,7 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
     BIK_SYNCWARP();
   }
   if (!done) status |= 2;
+  if (a.warm && active) for (int i = lane; i < n; i += W) a.warm[(long long)b * n + i] = (signed char)w.st[i];
   if (iters_out) *iters_out = it;
   return status;
 }

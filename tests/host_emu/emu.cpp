@@ -52,7 +52,7 @@ extern "C" int emu_solve(void* prob, int B, const float* q, const float* J, cons
                          float dt, double damping, int use_double, float* dq, int32_t* status, int32_t* iters, double* H, double* c, float* lo, float* hi) {
   EmuProblem* p = static_cast<EmuProblem*>(prob);
   PView P{p->image.data()};
-  K2Args a{B, q, J, e, ep, Gc, hc, dt, damping, dq, status, iters, H, c, lo, hi, 0, 0, 0};
+  K2Args a{B, q, J, e, ep, Gc, hc, dt, damping, dq, status, iters, H, c, lo, hi, 0, 0, 0, nullptr};
   std::vector<double> wsm((k2_warp_bytes(P.h(), 8) + k2lr_warp_bytes(P.h())) / 8 + 16);
   for (int b = 0; b < B; ++b) {
     if (status) status[b] = 0;
