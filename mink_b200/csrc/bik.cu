@@ -218,10 +218,8 @@ extern "C" int bik_model_create(const void* blob, size_t nbytes, int device, bik
   std::string err;
   if (!parse_model_blob(blob, nbytes, &m->hm, &err)) { delete m; return fail(BIK_ERR_INVALID, err); }
   m->device = device;
-  // lanes per instance in K1: wide enough that the per-warp tile stays small (occupancy), narrow enough that
-  // the lane program keeps the lanes busy; measured on G1 (38 nodes): G=8 0.153 ms, G=4 0.168, G=16 0.239, G=2 0.245
-  m->G = env_int("BIK_K1_GROUP", m->hm.nnode > 16 ? 8 : (m->hm.nnode > 8 ? 4 : 2));
-  if (!valid_group(m->G)) { delete m; return fail(BIK_ERR_INVALID, "BIK_K1_GROUP must be 1,2,4,8,16 or 32"); }
+  m->G = env_int("BIK_K1_GROUP", 0);  // 0: chosen per problem from the visited tree (bik_build.h)
+  if (m->G != 0 && !valid_group(m->G)) { delete m; return fail(BIK_ERR_INVALID, "BIK_K1_GROUP must be 1,2,4,8,16 or 32"); }
   m->use_tma = env_int("BIK_USE_TMA", 1);
   if (!build_image(m->hm, nullptr, 0, nullptr, 0, m->G, &m->image, &err)) { delete m; return fail(BIK_ERR_UNSUPPORTED, err); }
   DeviceGuard g(device);
@@ -412,7 +410,9 @@ static int launch_fk(const bik_model* m, const FkArgs& a, cudaStream_t st) {
   return BIK_OK;
 }
 static int dispatch_fk(const bik_model* m, const FkArgs& a, cudaStream_t st) {
-  switch (m->G) {
+  PHeader mh;
+  memcpy(&mh, m->image.data(), sizeof mh);
+  switch (mh.G) {
     case 1: return launch_fk<1>(m, a, st);
     case 2: return launch_fk<2>(m, a, st);
     case 4: return launch_fk<4>(m, a, st);

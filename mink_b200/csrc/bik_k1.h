@@ -384,7 +384,8 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, float* wsm,
     if (valid && g == 0) {
       for (int n = 0; n < h.nnode; ++n) {
         const ComNodeRec& cn = P.comnode(n);
-        F3 m = cn.own_m * ld_v(xs + 7 * n + 4) + qrot(ld_q(xs + 7 * n), ld_v(cn.own_c));
+        F3 m = v3<float>(0.f, 0.f, 0.f);   // nodes without mass below them are not visited by the lane program
+        if (cn.sub_m > 0.f) m = cn.own_m * ld_v(xs + 7 * n + 4) + qrot(ld_q(xs + 7 * n), ld_v(cn.own_c));
         S[3 * n] = m.x; S[3 * n + 1] = m.y; S[3 * n + 2] = m.z;
       }
       for (int n = h.nnode - 1; n >= 0; --n) {

@@ -69,7 +69,8 @@ struct PHeader {  // all offsets in 32-bit words from the start of the image
   int32_t off_umap;     // int[nv]: compact index of a coupled dof, -1 for a decoupled one (H row is diagonal there)
   int32_t off_ucols;    // int[nu]: dof of each compact index
   int32_t nrel;         // number of RelativeFrameTasks among the F frame-like tasks
-  int32_t reserved[4];
+  int32_t nneeded;      // nodes visited by the lane program (ancestors of frames / masses / collision geoms)
+  int32_t reserved[3];
 };
 static_assert(sizeof(PHeader) % 16 == 0, "header must stay 16-byte aligned");
 

@@ -16,7 +16,8 @@ static std::string g_err;
 extern "C" const char* emu_last_error() { return g_err.c_str(); }
 
 struct EmuProblem {
-  std::vector<uint32_t> image;
+  std::vector<uint32_t> image;        // problem image (tasks + limits; FK visits only the nodes they need)
+  std::vector<uint32_t> model_image;  // model-only image, as bik_model_create builds it (FK visits every node)
 };
 
 extern "C" void* emu_problem_create(const void* blob, size_t nbytes, const bik_task_desc* tasks, int ntasks, const bik_limit_desc* limits, int nlimits) {
@@ -24,6 +25,7 @@ extern "C" void* emu_problem_create(const void* blob, size_t nbytes, const bik_t
   if (!parse_model_blob(blob, nbytes, &m, &g_err)) return nullptr;
   EmuProblem* p = new EmuProblem;
   if (!build_image(m, tasks, ntasks, limits, nlimits, 1, &p->image, &g_err)) { delete p; return nullptr; }
+  if (!build_image(m, nullptr, 0, nullptr, 0, 1, &p->model_image, &g_err)) { delete p; return nullptr; }
   return p;
 }
 extern "C" void emu_problem_destroy(void* p) { delete static_cast<EmuProblem*>(p); }
@@ -69,7 +71,7 @@ extern "C" int emu_solve(void* prob, int B, const float* q, const float* J, cons
 
 extern "C" int emu_fk(void* prob, int B, const float* q, const bik_frame* frames, int nframes, float* poses, float* com, float* J) {
   EmuProblem* p = static_cast<EmuProblem*>(prob);
-  PView P{p->image.data()};
+  PView P{p->model_image.data()};
   if (nframes > 16) return -1;
   FkArgs a; memset(&a, 0, sizeof a);
   a.B = B; a.nframes = nframes; a.q = q; a.poses = poses; a.com = com; a.J = J;
