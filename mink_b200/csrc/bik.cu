@@ -20,6 +20,8 @@
 
 #include "bik_build.h"
 #include "bik_k2lr.h"
+#include "bik_k2t.h"
+#include "bik_k2x.h"
 
 using namespace bik;
 
@@ -107,6 +109,34 @@ __global__ void __launch_bounds__(256) k2_kernel(const uint32_t* __restrict__ gi
   for (int b = blockIdx.x * nwarps + warp; b < a.B; b += gridDim.x * nwarps) k2_warp<T, 32, SLOTS>(P, a, b, wsm, lane);
 }
 
+// Small-group K2 (bik_k2t.h): G lanes per problem, 32/G problems per warp, tables read straight from the (L1-resident)
+// global image so that all of shared memory goes to the per-problem triangles; warps are independent.
+template <typename T, int G, int MAXT>
+__global__ void __launch_bounds__(MAXT) k2t_kernel(const uint32_t* __restrict__ gimage, int warp_bytes, K2Args a) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  constexpr int NS = 32 / G;
+  PView P{gimage};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  char* wsm = reinterpret_cast<char*>(smem) + (size_t)warp * warp_bytes;
+  const long long ntiles = ((long long)a.B + NS - 1) / NS;
+  for (long long tile = (long long)blockIdx.x * nwarps + warp; tile < ntiles; tile += (long long)gridDim.x * nwarps)
+    k2t_warp_tile<T, G, NS>(P, a, tile * NS, wsm, lane);
+}
+
+// Fixed-size thread-per-problem K2 (bik_k2x.h): 32 problems per warp, factor in shared memory, H / c / box in a per-warp
+// global scratch (L2 resident), tables read straight from the global image; warps are independent.
+template <typename T, int N>
+__global__ void __launch_bounds__(256) k2x_kernel(const uint32_t* __restrict__ gimage, int warp_smem, unsigned char* scratch, unsigned long long warp_scratch, K2Args a) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  PView P{gimage};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  char* wsm = reinterpret_cast<char*>(smem) + (size_t)warp * warp_smem;
+  unsigned char* wsc = scratch + ((size_t)blockIdx.x * nwarps + warp) * warp_scratch;
+  const long long ntiles = ((long long)a.B + 31) / 32;
+  for (long long tile = (long long)blockIdx.x * nwarps + warp; tile < ntiles; tile += (long long)gridDim.x * nwarps)
+    k2x_warp_tile<T, N, 32>(P, a, tile * 32, wsm, wsc, lane);
+}
+
 template <int SLOTS>
 __global__ void __launch_bounds__(256) k2lr_kernel(const uint32_t* __restrict__ gimage, int words, int use_tma, K2Args a) {
   extern __shared__ __align__(16) uint32_t smem[];
@@ -189,7 +219,11 @@ struct bik_problem {
   uint32_t* d_image = nullptr;
   PHeader h;
   int solve_double = 1;
-  int k2_path = 0;  // 0 auto, 1 dense only (BIK_K2_PATH=dense), 2 low-rank whenever valid (BIK_K2_PATH=lowrank)
+  int k2_path = 0;  // 0 auto, 1 warp-per-instance dense only (BIK_K2_PATH=dense), 2 low-rank whenever valid (=lowrank),
+                    // 3 small-group path whenever valid (=group), 4 fixed-size thread-per-problem path whenever valid (=fixed)
+  mutable unsigned char* k2x_scratch = nullptr;  // per-warp H / c / box scratch of the fixed-size path
+  mutable size_t k2x_scratch_bytes = 0;
+  int k2_group = 4; // lanes per problem on the small-group path (BIK_K2_GROUP = 4 | 8)
   int k2_warps = 8; // warps per CTA of the K2 kernels (BIK_K2_WARPS)
   int k2_lockstep = 1; // BIK_K2_LOCKSTEP=0 disables: CTA-wide lock-step pivoting iterations
   // lazily grown scratch between K1 and K2 (one caller at a time per problem)
@@ -251,7 +285,8 @@ extern "C" int bik_problem_create(const bik_model* model, const bik_task_desc* t
   const char* prec = getenv("BIK_SOLVE_PRECISION");
   p->solve_double = !(prec && (std::string(prec) == "f32" || std::string(prec) == "float"));
   const char* path = getenv("BIK_K2_PATH");
-  p->k2_path = (path && std::string(path) == "dense") ? 1 : ((path && std::string(path) == "lowrank") ? 2 : 0);
+  p->k2_path = (path && std::string(path) == "dense") ? 1 : ((path && std::string(path) == "lowrank") ? 2 : ((path && std::string(path) == "group") ? 3 : ((path && std::string(path) == "fixed") ? 4 : 0)));
+  p->k2_group = env_int("BIK_K2_GROUP", p->h.nu > 8 ? 8 : 4) == 8 ? 8 : 4;
   p->k2_warps = env_int("BIK_K2_WARPS", 8);
   p->k2_lockstep = env_int("BIK_K2_LOCKSTEP", 1);
   if (p->k2_warps != 1 && p->k2_warps != 2 && p->k2_warps != 4 && p->k2_warps != 8) p->k2_warps = 8;
@@ -264,7 +299,7 @@ extern "C" int bik_problem_create(const bik_model* model, const bik_task_desc* t
 extern "C" void bik_problem_destroy(bik_problem* p) {
   if (!p) return;
   DeviceGuard g(p->device);
-  cudaFree(p->d_image); cudaFree(p->J); cudaFree(p->e); cudaFree(p->ep); cudaFree(p->Gc); cudaFree(p->hc); cudaFree(p->warm);
+  cudaFree(p->d_image); cudaFree(p->J); cudaFree(p->e); cudaFree(p->ep); cudaFree(p->Gc); cudaFree(p->hc); cudaFree(p->warm); cudaFree(p->k2x_scratch);
   cudaFree(p->hq); cudaFree(p->hft); cudaFree(p->hpt); cudaFree(p->hct); cudaFree(p->hdq); cudaFree(p->hst);
   delete p;
 }
@@ -389,7 +424,87 @@ static bool use_low_rank_static(const bik_problem* p, double damping) {
   a.dq = reinterpret_cast<float*>(1); a.damping = damping;
   return use_low_rank(p, a);
 }
+template <typename T, int G>
+static int launch_k2t(const bik_problem* p, const K2Args& a, cudaStream_t st) {
+  constexpr int NS = 32 / G, MAXT = sizeof(T) == 8 ? 256 : 512;
+  PView P{p->image.data()};
+  const size_t wb = (size_t)k2t_warp_bytes(P, sizeof(T), NS);
+  int NW = MAXT / 32;
+  while (NW > 1 && NW * wb > (size_t)p->model->max_smem) --NW;
+  const size_t smem = NW * wb;
+  int grid = 1;
+  long long tiles = ((long long)a.B + NS - 1) / NS;
+  int rc = launch_geometry(k2t_kernel<T, G, MAXT>, p->model, smem, 32 * NW, (tiles + NW - 1) / NW, &grid);
+  if (rc) return rc;
+  k2t_kernel<T, G, MAXT><<<grid, 32 * NW, smem, st>>>(p->d_image, (int)wb, a);
+  CUDA_OK(cudaGetLastError());
+  return BIK_OK;
+}
+template <typename T>
+static int dispatch_k2t(const bik_problem* p, const K2Args& a, cudaStream_t st) {
+  return p->k2_group == 8 ? launch_k2t<T, 8>(p, a, st) : launch_k2t<T, 4>(p, a, st);
+}
+static int k2x_size(int nu) {
+  const int sizes[] = {6, 8, 12, 16, 18, 20, 24};
+  for (int n : sizes) if (nu <= n) return n;
+  return 0;
+}
+template <typename T, int N>
+static int launch_k2x(const bik_problem* p, const K2Args& a, cudaStream_t st) {
+  PView P{p->image.data()};
+  const size_t wb = (size_t)k2x_warp_smem_bytes(P, sizeof(T), N, 32);
+  int NW = 8;
+  while (NW > 1 && NW * wb > (size_t)p->model->max_smem) --NW;
+  const size_t smem = NW * wb;
+  int grid = 1;
+  long long tiles = ((long long)a.B + 31) / 32;
+  int rc = launch_geometry(k2x_kernel<T, N>, p->model, smem, 32 * NW, (tiles + NW - 1) / NW, &grid);
+  if (rc) return rc;
+  const size_t ws = k2x_warp_scratch_bytes(sizeof(T), N, 32), need = ws * NW * (size_t)grid;
+  if (need > p->k2x_scratch_bytes) {
+    CUDA_OK(cudaStreamSynchronize(st));
+    cudaFree(p->k2x_scratch); p->k2x_scratch = nullptr; p->k2x_scratch_bytes = 0;
+    CUDA_OK(cudaMalloc(&p->k2x_scratch, need));
+    p->k2x_scratch_bytes = need;
+  }
+  k2x_kernel<T, N><<<grid, 32 * NW, smem, st>>>(p->d_image, (int)wb, p->k2x_scratch, (unsigned long long)ws, a);
+  CUDA_OK(cudaGetLastError());
+  return BIK_OK;
+}
+template <typename T>
+static int dispatch_k2x(const bik_problem* p, const K2Args& a, cudaStream_t st) {
+  switch (k2x_size(p->h.nu)) {
+    case 6: return launch_k2x<T, 6>(p, a, st);
+    case 8: return launch_k2x<T, 8>(p, a, st);
+    case 12: return launch_k2x<T, 12>(p, a, st);
+    case 16: return launch_k2x<T, 16>(p, a, st);
+    case 18: return launch_k2x<T, 18>(p, a, st);
+    case 20: return launch_k2x<T, 20>(p, a, st);
+    default: return launch_k2x<T, 24>(p, a, st);
+  }
+}
+// Fixed-size path: box-only problems with at most 24 coupled dofs, fp32 solves only (BIK_SOLVE_PRECISION=f32): measured
+// on the G1 batch it is the fastest fp32 path (0.72 ms against 1.2 ms for the small-group path), while in fp64 its
+// register-resident rows spill and the small-group path wins (1.5 ms against 2.2 ms), so fp64 is not instantiated.
+static bool use_fixed(const bik_problem* p, const K2Args& a) {
+  const PHeader& h = p->h;
+  if (p->solve_double || p->k2_path == 1 || p->k2_path == 2 || p->k2_path == 3 || !a.dq || a.Hout || a.lo_out) return false;
+  if (h.npairs != 0 || h.nu < 1 || k2x_size(h.nu) == 0) return false;
+  PView P{p->image.data()};
+  return k2x_warp_smem_bytes(P, 4, k2x_size(h.nu), 32) <= p->model->max_smem;
+}
+// Small-group path: box-only problems whose coupled block is small enough (at least one warp of them must fit in
+// an SM's shared memory).
+static bool use_thread(const bik_problem* p, const K2Args& a) {
+  const PHeader& h = p->h;
+  if (p->k2_path == 1 || p->k2_path == 2 || p->k2_path == 4 || !a.dq || a.Hout || a.lo_out) return false;
+  if (h.npairs != 0 || h.nu < 1 || h.nu > K2T_NMAX) return false;
+  PView P{p->image.data()};
+  return k2t_warp_bytes(P, p->solve_double ? 8 : 4, 32 / (p->k2_group == 8 ? 8 : 4)) <= p->model->max_smem;
+}
 static int dispatch_k2(const bik_problem* p, const K2Args& a, cudaStream_t st) {
+  if (use_fixed(p, a)) return dispatch_k2x<float>(p, a, st);
+  if (use_thread(p, a)) return p->solve_double ? dispatch_k2t<double>(p, a, st) : dispatch_k2t<float>(p, a, st);
   if (use_low_rank(p, a)) return (p->h.K + 1 <= 32) ? launch_k2lr<1>(p, a, st) : launch_k2lr<2>(p, a, st);
   return p->solve_double ? dispatch_k2_slots<double>(p, a, st) : dispatch_k2_slots<float>(p, a, st);
 }
@@ -530,7 +645,7 @@ extern "C" int bik_check_limits(const bik_model* m, int B, const float* q, float
 static int ensure_workspace(bik_problem* p, int B) {
   if ((size_t)B <= p->ws_B) return BIK_OK;
   const PHeader& h = p->h;
-  cudaFree(p->J); cudaFree(p->e); cudaFree(p->ep); cudaFree(p->Gc); cudaFree(p->hc); cudaFree(p->warm);
+  cudaFree(p->J); cudaFree(p->e); cudaFree(p->ep); cudaFree(p->Gc); cudaFree(p->hc); cudaFree(p->warm); cudaFree(p->k2x_scratch);
   p->J = p->e = p->ep = p->Gc = p->hc = nullptr; p->warm = nullptr; p->ws_B = 0;
   size_t b = (size_t)B;
   CUDA_OK(cudaMalloc(&p->J, sizeof(float) * b * (h.K > 0 ? h.K : 1) * h.nv));

@@ -1,0 +1,384 @@
+// bik_k2t.h -- K2, small-group path: the same QP as bik_k2.h (same objective, same block principal
+// pivoting rule, same tolerances), laid out for coupled blocks of up to 24 dofs.
+//
+// Why: with a whole warp per instance the 18-dof coupled block of the G1 configuration keeps half the
+// lanes idle and spends most instructions on run-time index arithmetic, shuffles and barriers
+// (14 k warp-instructions per instance, ~45 k cycles per pivoting iteration).  Here G adjacent lanes
+// (4 or 8) share one problem, so a warp carries NS = 32/G problems; the loops are compact run-time loops
+// over shared memory so that a whole pivoting iteration stays resident in the instruction cache:
+//
+//   * per-instance vectors and packed triangles live in shared memory, word w of slot s at [w*NS + s]
+//     (the G lanes of a group broadcast-read one address; the NS groups read one 8*NS-byte segment);
+//   * instance data from K1 (J, e, e_posture, q) is staged a task at a time through an instance-major
+//     tile with odd row stride: coalesced global reads by the whole warp, conflict-free private reads;
+//   * pivoting iterations refactor the FULL coupled block with clamped dofs turned into identity
+//     rows/columns (masked loads): every group executes the same instruction stream whatever its active
+//     set is, so groups never diverge; a group that has converged idles until its warp is done;
+//   * the factorisation is left-looking by blocks of G rows: lane l owns row i0+l, finished rows are
+//     broadcast-read from shared memory, the right-hand side rides along as the last row (forward
+//     substitution for free), diagonals are kept as reciprocal square roots, entries masked out by the
+//     active set are known to be zero and skipped; one warp barrier per row;
+//   * back substitution in dot-product form: every lane sums the columns it owns, a G-lane butterfly
+//     adds the partial sums (no barrier); multipliers are only evaluated on clamped dofs.
+//
+// Reference semantics: mink/solve_ik.py:13-65,101 (build_ik + qpsolvers), mink/tasks/task.py:105-138.
+// Device: G in {4, 8}, NS = 32 / G.  Host emulation (tests/host_emu): G = NS = 1.
+#pragma once
+#include "bik_k2.h"
+
+#if defined(__CUDA_ARCH__)
+#define BIK_WARP_ANY(x) __any_sync(0xffffffffu, (x))
+#else
+#define BIK_WARP_ANY(x) (x)
+#endif
+
+namespace bik {
+
+enum { K2T_NMAX = 32 };  // largest coupled block this path takes (active sets are 32-bit masks)
+
+// ---- group reductions over G adjacent lanes (every lane of the warp must call them) --------------------
+template <int G> BIK_HD int grp_or(int v) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+#endif
+  return v;
+}
+template <int G> BIK_HD int grp_add(int v) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#endif
+  return v;
+}
+template <int G> BIK_HD int grp_max(int v) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) { int t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+#endif
+  return v;
+}
+template <typename T, int G> BIK_HD T grp_sum(T v) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#endif
+  return v;
+}
+
+// ---- per-warp scratch ------------------------------------------------------------------------------
+// T words per slot:   Hp tri(nu) | U (factor incl. rhs row; aliased by the staging tiles) | c nu | vs nu
+// float words / slot: lo nu | hi nu
+BIK_HD int k2t_task_tile_words(const PView& P) {  // widest task tile, in T words per instance (odd)
+  const PHeader& h = P.h();
+  int m = 1;
+  for (int f = 0; f < h.F; ++f) { int ne = 6 * P.frame(f).ncols + 6; m = ne > m ? ne : m; }
+  if (h.C > 0) { int ne = 3 * h.com_ncols + 3; m = ne > m ? ne : m; }
+  return m | 1;
+}
+BIK_HD int k2t_union_words(const PView& P, int ts) {
+  const PHeader& h = P.h();
+  int u = tri(h.nu + 1);
+  int t = k2t_task_tile_words(P);
+  u = t > u ? t : u;
+  int sq = ((h.nq + h.P * h.nv) | 1) * 4;
+  int fw = (sq + ts - 1) / ts;
+  return fw > u ? fw : u;
+}
+BIK_HD int k2t_slot_T_words(const PView& P, int ts) { return tri(P.h().nu) + k2t_union_words(P, ts) + 2 * P.h().nu; }
+BIK_HD int k2t_slot_bytes(const PView& P, int ts) { return k2t_slot_T_words(P, ts) * ts + 2 * P.h().nu * 4; }
+BIK_HD int k2t_warp_bytes(const PView& P, int ts, int NS) { return (NS * k2t_slot_bytes(P, ts) + 15) & ~15; }
+
+// ---- staging (warp-cooperative, W lanes, NS instances) -------------------------------------------------
+// One task's weighted rows:  tile[i][r*nc + ia] = cost_r J[row0+r][col_ia],  tile[i][nr*nc + r] = cost_r (-gain e[row0+r]);
+// fp32 products as in the warp path, converted to T once.
+template <typename T, int W, int NS>
+BIK_HD void k2t_stage_task(T* tile, int S, int lane, int cnt, long long b0, const K2Args& a, int K, int nv, const int32_t* cols,
+                           int row0, int nr, int nc, const float* cost, float gain) {
+  const int ne = nr * nc + nr;
+  for (int k = lane; k < ne; k += W) {
+    const bool isj = k < nr * nc;
+    int r, gofs;
+    long long stride;
+    const float* src;
+    if (isj) { r = k / nc; int ia = k - r * nc; gofs = (row0 + r) * nv + (cols[ia] & 0xffff); src = a.J; stride = (long long)K * nv; }
+    else { r = k - nr * nc; gofs = row0 + r; src = a.e; stride = K; }
+    const float cr = cost[r];
+    const float* s0 = src + b0 * stride + gofs;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      float v = 0.f;
+      if (i < cnt) { float g = s0[i * stride]; v = isj ? cr * g : cr * (-gain * g); }
+      tile[i * S + k] = T(v);
+    }
+  }
+}
+template <int W, int NS>
+BIK_HD void k2t_stage_rows(float* tile, int S, int off, int lane, int cnt, const float* src, long long stride, int n) {
+  for (int k = lane; k < n; k += W) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) tile[i * S + off + k] = i < cnt ? src[i * stride + k] : 0.f;
+  }
+}
+
+// ---- assembly: (W J)^T (W J) and -(W(-g e))^T W J of one task, lower-triangle entries dealt to the G lanes ----
+template <typename T, int G, int NS>
+BIK_HD void k2t_task_accumulate(const T* tr, int nr, int nc, const int32_t* cols, const int32_t* umap, T* Hp, T* c, float lm, T* mu, int l) {
+  const T* wev = tr + nr * nc;
+  if (lm != 0.f) { T s = T(0); for (int r = 0; r < nr; ++r) s += wev[r] * wev[r]; *mu += T(lm) * s; }
+  int ia = 0, ib = l;
+  while (ib > ia) { ib -= ia + 1; ++ia; }
+  while (ia < nc) {
+    T s = T(0);
+    for (int r = 0; r < nr; ++r) s += tr[r * nc + ia] * tr[r * nc + ib];
+    const int ua = umap[cols[ia] & 0xffff], ub = umap[cols[ib] & 0xffff];
+    const int hi = ua > ub ? ua : ub, lo = ua > ub ? ub : ua;
+    Hp[(tri(hi) + lo) * NS] += s;
+    ib += G;
+    while (ib > ia) { ib -= ia + 1; ++ia; }
+  }
+  for (int ja = l; ja < nc; ja += G) {
+    T s = T(0);
+    for (int r = 0; r < nr; ++r) s += wev[r] * tr[r * nc + ja];
+    c[umap[cols[ja] & 0xffff] * NS] -= s;
+  }
+}
+
+// ---- solver pieces: compact run-time loops (the whole pivoting iteration must stay resident in the
+// instruction cache -- the fully unrolled variants of these routines were instruction-fetch bound) --------
+// Dot product of row i of the symmetric packed matrix with a vector (both slot-strided in shared memory).
+template <typename T, int NS>
+BIK_HD T k2t_row_dot(const T* __restrict__ Hp, const T* __restrict__ v, int i, int nu) {
+  const T* row = Hp + tri(i) * NS;
+  T a0 = T(0), a1 = T(0);
+  int k = 0;
+  for (; k + 1 <= i; k += 2) { a0 += row[k * NS] * v[k * NS]; a1 += row[(k + 1) * NS] * v[(k + 1) * NS]; }
+  if (k <= i) a0 += row[k * NS] * v[k * NS];
+  const T* col = Hp + (tri(i + 1) + i) * NS;   // entries (m, i), m > i, sit at tri(m) + i
+  for (int m = i + 1; m < nu; ++m) { a1 += col[0] * v[m * NS]; col += (m + 1) * NS; }
+  return a0 + a1;
+}
+// Masked factorisation of the coupled block, left-looking by blocks of G rows (lane l owns row i0 + l); rows
+// 0..nu-1 are matrix rows, row nu is the right-hand side (already stored in Lp's row nu).  Active dofs (bit set in
+// `act`) become identity rows/columns.  On exit Lp row i holds L[i][0..i-1] and 1/L[i][i], row nu holds L^-1 rhs.
+// Every lane of the warp must call it (it contains warp barriers).
+template <typename T, int G, int NS>
+BIK_HD int k2t_factor(const T* __restrict__ Hp, T* __restrict__ Lp, int nu, uint32_t act, int l) {
+  int bad = 0;
+  T* const rhsrow = Lp + tri(nu) * NS;
+  for (int i0 = 0; i0 <= nu; i0 += G) {
+    const int i = i0 + l;
+    const bool has = i <= nu, rhs = i == nu;
+    const bool ai = has && !rhs && ((act >> i) & 1u);
+    const uint32_t msk = rhs ? 0u : (ai ? ~0u : act);
+    const int ir = has ? i : 0;
+    const T* src = rhs ? rhsrow : Hp + tri(ir) * NS;
+    T* dst = Lp + tri(ir) * NS;
+    T ss = T(0);
+    // one entry of my row: L[i][k] = (A[i][k] - sum_m L[i][m] L[k][m]) / L[k][k]; a masked entry is exactly zero
+    auto step = [&](int k) {
+      T s = T(0);
+      if (!((msk >> k) & 1u)) {
+        const T* Lk = Lp + tri(k) * NS;
+        T a0 = T(0), a1 = T(0);
+        int m = 0;
+        for (; m + 1 < k; m += 2) { a0 += dst[m * NS] * Lk[m * NS]; a1 += dst[(m + 1) * NS] * Lk[(m + 1) * NS]; }
+        if (m < k) a0 += dst[m * NS] * Lk[m * NS];
+        s = (src[k * NS] - (a0 + a1)) * Lk[k * NS];
+      }
+      dst[k * NS] = s;
+      ss += s * s;
+    };
+    if (has) for (int k = 0; k < i0; ++k) step(k);   // rows above the block are complete
+    for (int j = 0; j < G; ++j) {                     // diagonal block: the owner of row k closes it, then the rows below use it
+      const int k = i0 + j;
+      if (has && !rhs && l == j) {
+        T d = (ai ? T(1) : src[k * NS]) - ss;
+        if (!(d > T(0))) { bad = 1; d = T(1e-30); }
+        dst[k * NS] = bik_rsqrt<T>(d);
+      }
+      if (G > 1) BIK_SYNCWARP();
+      if (has && k < i) step(k);
+    }
+  }
+  return bad;
+}
+// x = L^-T y (y = row nu of Lp), dot-product form: x_k needs sum_{m>k} L[m][k] x_m; every lane sums the m it owns
+// (m = l mod G, kept in its own entries of xs), a butterfly adds the partial sums.  No barrier inside.
+template <typename T, int G, int NS>
+BIK_HD void k2t_backsub(const T* __restrict__ Lp, int nu, int l, T* __restrict__ xs) {
+  const T* y = Lp + tri(nu) * NS;
+  for (int k = nu - 1; k >= 0; --k) {
+    int m = (k + 1) + ((l - (k + 1)) & (G - 1));
+    T p = T(0);
+    for (; m < nu; m += G) p += Lp[(tri(m) + k) * NS] * xs[m * NS];
+    p = grp_sum<T, G>(p);
+    const T xk = (y[k * NS] - p) * Lp[(tri(k) + k) * NS];
+    if ((k & (G - 1)) == l) xs[k * NS] = xk;
+  }
+}
+
+// ---- one tile of NS instances per warp ----------------------------------------------------------------
+template <typename T, int G, int NS>
+BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* wsm, int lane) {
+  constexpr int W = G * NS;
+  const PHeader& h = P.h();
+  const int nv = h.nv, nu = h.nu, K = h.K, nq = h.nq, NP = h.P;
+  const int32_t* cols = P.i(h.off_cols);
+  const int32_t* umap = P.i(h.off_umap);
+  const int32_t* ucols = P.i(h.off_ucols);
+  const int cnt = (a.B - b0) < NS ? (int)(a.B - b0) : NS;
+  const int slot = lane / G, l = lane - slot * G;
+  const bool live = slot < cnt;
+  const long long b = b0 + slot;
+  const int uw = k2t_union_words(P, sizeof(T));
+  T* const Tb = reinterpret_cast<T*>(wsm);
+  T* const Hp = Tb + slot;
+  T* const U = Tb + (size_t)tri(nu) * NS;   // warp-wide base of the union region
+  T* const Lp = U + slot;
+  T* const c = Tb + (size_t)(tri(nu) + uw) * NS + slot;
+  T* const vs = c + (size_t)nu * NS;
+  float* const Fb = reinterpret_cast<float*>(Tb + (size_t)k2t_slot_T_words(P, sizeof(T)) * NS);
+  float* const lo = Fb + slot;
+  float* const hi = Fb + (size_t)nu * NS + slot;
+
+  // ---- assembly ----
+  for (int k = l; k < tri(nu); k += G) Hp[k * NS] = T(0);
+  for (int k = l; k < nu; k += G) c[k * NS] = T(0);
+  T mu = T(a.damping);
+  const int St = k2t_task_tile_words(P);
+  for (int t = 0; t < h.F + h.C; ++t) {
+    int row0, nr, nc, coff; const float* cost; float gain, lm;
+    if (t < h.F) { const FrameRec& fr = P.frame(t); row0 = fr.row0; nr = 6; nc = fr.ncols; coff = fr.col_off; cost = fr.cost; gain = fr.gain; lm = fr.lm; }
+    else { const float* cr = P.f(h.off_com) + 8 * (t - h.F); row0 = reinterpret_cast<const int32_t*>(cr)[5]; nr = 3; nc = h.com_ncols; coff = h.com_cols_off; cost = cr; gain = cr[3]; lm = cr[4]; }
+    BIK_SYNCWARP();
+    k2t_stage_task<T, W, NS>(U, St, lane, cnt, b0, a, K, nv, cols + coff, row0, nr, nc, cost, gain);
+    BIK_SYNCWARP();
+    k2t_task_accumulate<T, G, NS>(U + (size_t)slot * St, nr, nc, cols + coff, umap, Hp, c, lm, &mu, l);
+  }
+  // q and posture errors: stage, then diagonal / linear term / box; decoupled dofs are finished on the spot
+  BIK_SYNCWARP();
+  float* const ft = reinterpret_cast<float*>(U);
+  const int Sq = (nq + NP * nv) | 1;
+  k2t_stage_rows<W, NS>(ft, Sq, 0, lane, cnt, a.q + b0 * nq, nq, nq);
+  if (NP > 0) k2t_stage_rows<W, NS>(ft, Sq, nq, lane, cnt, a.ep + b0 * NP * nv, (long long)NP * nv, NP * nv);
+  BIK_SYNCWARP();
+  int st = 0;
+  {
+    const float* qrow = ft + (size_t)slot * Sq;
+    const float* eprow = qrow + nq;
+    for (int p = 0; p < NP; ++p) {
+      const float* pr = P.f(h.off_posture) + p * (2 + nv);
+      if (pr[1] != 0.f) {
+        T s = T(0);
+        for (int d = 0; d < nv; ++d) { T v = T(pr[2 + d]) * T(pr[0]) * T(eprow[p * nv + d]); s += v * v; }
+        mu += T(pr[1]) * s;
+      }
+    }
+    for (int d = l; d < nv; d += G) {
+      const int u = umap[d];
+      T hd = mu, cd = T(0);
+      for (int p = 0; p < NP; ++p) {
+        const float* pr = P.f(h.off_posture) + p * (2 + nv);
+        const T wgt = T(pr[2 + d]);
+        hd += wgt * wgt;
+        cd -= T(pr[0]) * wgt * wgt * T(eprow[p * nv + d]);
+      }
+      float bl, bu;
+      box_dof(P, d, qrow, a.dt, &bl, &bu);
+      if (u >= 0) { Hp[(tri(u) + u) * NS] += hd; c[u * NS] += cd; lo[u * NS] = bl; hi[u * NS] = bu; }
+      else {
+        T v = -cd / hd;
+        v = v < T(bl) ? T(bl) : (v > T(bu) ? T(bu) : v);
+        if (!(v == v)) st |= 4;
+        if (live) a.dq[b * nv + d] = float(v);
+      }
+    }
+  }
+  BIK_SYNCWARP();   // the tile is dead; the union region becomes each slot's factor
+
+  // ---- block principal pivoting ----
+  const int MAXIT = 60, PATIENCE = 3;
+  const T tolx = K2Tol<T>::x(), tolg = K2Tol<T>::g();
+  uint32_t lom = 0u, upm = 0u;
+  if (a.warm && live) {
+    const signed char* wm = a.warm + b * nu;
+    for (int i = 0; i < nu; ++i) {
+      int s0 = wm[i];
+      if (s0 == 1 && lo[i * NS] > -1e30f) lom |= 1u << i;
+      else if (s0 == 2 && hi[i * NS] < 1e30f) upm |= 1u << i;
+    }
+  }
+  int best = nu + 1, patience = PATIENCE, it = 0;
+  bool done = false;
+  T* const rhsrow = Lp + tri(nu) * NS;
+  for (;;) {
+    if (!BIK_WARP_ANY(!done && it < MAXIT)) break;
+    const bool run = !done && it < MAXIT;   // a finished group keeps executing (idempotently) until its warp is done
+    const uint32_t act = lom | upm;
+    // x on the bounds
+    for (int k = l; k < nu; k += G) vs[k * NS] = ((lom >> k) & 1u) ? T(lo[k * NS]) : (((upm >> k) & 1u) ? T(hi[k * NS]) : T(0));
+    BIK_SYNCWARP();
+    // right-hand side of the masked system: bound value on clamped dofs, -(c + H_FA x_A) on free ones
+    for (int k = l; k < nu; k += G) {
+      T rv;
+      if ((act >> k) & 1u) rv = vs[k * NS];
+      else { rv = -c[k * NS]; if (act) rv -= k2t_row_dot<T, NS>(Hp, vs, k, nu); }
+      rhsrow[k * NS] = rv;
+    }
+    BIK_SYNCWARP();
+    if (k2t_factor<T, G, NS>(Hp, Lp, nu, act, l)) st |= 4;
+    BIK_SYNCWARP();
+    k2t_backsub<T, G, NS>(Lp, nu, l, vs);
+    BIK_SYNCWARP();
+    // gradient on the clamped dofs, feasibility of the free ones
+    int ninf = 0, last = -1;
+    uint32_t nlo = 0u, nup = 0u;
+    for (int k = l; k < nu; k += G) {
+      const int cur = ((lom >> k) & 1u) ? 1 : (((upm >> k) & 1u) ? 2 : 0);
+      int ns = cur;
+      if (cur == 0) {
+        const T xi = vs[k * NS], bl = T(lo[k * NS]), bu = T(hi[k * NS]);
+        if (xi < bl - tolx * (T(1) + (bl < 0 ? -bl : bl))) ns = 1;
+        else if (xi > bu + tolx * (T(1) + (bu < 0 ? -bu : bu))) ns = 2;
+      } else {
+        const T gi = c[k * NS] + k2t_row_dot<T, NS>(Hp, vs, k, nu);
+        if (cur == 1 && gi < -tolg) ns = 0;
+        else if (cur == 2 && gi > tolg) ns = 0;
+      }
+      if (ns == 1) nlo |= 1u << k; else if (ns == 2) nup |= 1u << k;
+      if (ns != cur) { ++ninf; last = k > last ? k : last; }
+    }
+    nlo = (uint32_t)grp_or<G>((int)nlo); nup = (uint32_t)grp_or<G>((int)nup);
+    ninf = grp_add<G>(ninf); last = grp_max<G>(last);
+    BIK_SYNCWARP();   // every lane has read x before the next iteration overwrites vs
+    if (run) {
+      ++it;
+      if (ninf == 0) done = true;
+      else {
+        bool block;
+        if (ninf < best) { best = ninf; patience = PATIENCE; block = true; }
+        else if (patience > 0) { --patience; block = true; }
+        else block = false;
+        if (block) { lom = nlo; upm = nup; }
+        else { const uint32_t bit = 1u << last; lom = (lom & ~bit) | (nlo & bit); upm = (upm & ~bit) | (nup & bit); }
+      }
+    }
+  }
+  if (!done) st |= 2;
+  // ---- outputs: coupled dofs from vs (the last solve), status, warm-start state ----
+  for (int k = l; k < nu; k += G) {
+    const float v = float(vs[k * NS]);
+    if (!(v == v)) st |= 4;
+    if (live) a.dq[b * nv + ucols[k]] = v;
+  }
+  st = grp_or<G>(st);
+  if (live && l == 0) {
+    if (a.status) a.status[b] |= st;
+    if (a.iters) a.iters[b] = it;
+    if (a.warm) { signed char* wm = a.warm + b * nu; for (int i = 0; i < nu; ++i) wm[i] = (signed char)(((lom >> i) & 1u) ? 1 : (((upm >> i) & 1u) ? 2 : 0)); }
+  }
+  BIK_SYNCWARP();
+}
+
+}  // namespace bik

@@ -9,6 +9,7 @@
 
 #include "../../mink_b200/csrc/bik_build.h"
 #include "../../mink_b200/csrc/bik_k2lr.h"
+#include "../../mink_b200/csrc/bik_k2x.h"
 
 using namespace bik;
 
@@ -56,6 +57,37 @@ extern "C" int emu_solve(void* prob, int B, const float* q, const float* J, cons
   PView P{p->image.data()};
   K2Args a{B, q, J, e, ep, Gc, hc, dt, damping, dq, status, iters, H, c, lo, hi, 0, 0, 0, nullptr};
   std::vector<double> wsm((k2_warp_bytes(P.h(), 8) + k2lr_warp_bytes(P.h())) / 8 + 16);
+  if (use_double == 3 || use_double == 4) {   // small-group path (3: fp64, 4: fp32), one lane per problem on the host
+    if (P.h().npairs != 0 || P.h().nu < 1 || P.h().nu > K2T_NMAX) { g_err = "thread path not applicable"; return -1; }
+    std::vector<double> tw(k2t_warp_bytes(P, 8, 1) / 8 + 16);
+    for (int b = 0; b < B; ++b) {
+      if (status) status[b] = 0;
+      if (use_double == 3) k2t_warp_tile<double, 1, 1>(P, a, b, tw.data(), 0);
+      else k2t_warp_tile<float, 1, 1>(P, a, b, tw.data(), 0);
+    }
+    return 0;
+  }
+  if (use_double == 5 || use_double == 6) {   // fixed-size thread-per-problem path (5: fp64, 6: fp32)
+    const int nu = P.h().nu;
+    if (P.h().npairs != 0 || nu < 1 || nu > 24) { g_err = "fixed-size path not applicable"; return -1; }
+    const int N = nu <= 6 ? 6 : (nu <= 12 ? 12 : (nu <= 18 ? 18 : 24));
+    std::vector<double> tw(k2x_warp_smem_bytes(P, 8, N, 1) / 8 + 16), sc(k2x_warp_scratch_bytes(8, N, 1) / 8 + 16);
+    for (int b = 0; b < B; ++b) {
+      if (status) status[b] = 0;
+      if (use_double == 5) {
+        if (N == 6) k2x_warp_tile<double, 6, 1>(P, a, b, tw.data(), sc.data(), 0);
+        else if (N == 12) k2x_warp_tile<double, 12, 1>(P, a, b, tw.data(), sc.data(), 0);
+        else if (N == 18) k2x_warp_tile<double, 18, 1>(P, a, b, tw.data(), sc.data(), 0);
+        else k2x_warp_tile<double, 24, 1>(P, a, b, tw.data(), sc.data(), 0);
+      } else {
+        if (N == 6) k2x_warp_tile<float, 6, 1>(P, a, b, tw.data(), sc.data(), 0);
+        else if (N == 12) k2x_warp_tile<float, 12, 1>(P, a, b, tw.data(), sc.data(), 0);
+        else if (N == 18) k2x_warp_tile<float, 18, 1>(P, a, b, tw.data(), sc.data(), 0);
+        else k2x_warp_tile<float, 24, 1>(P, a, b, tw.data(), sc.data(), 0);
+      }
+    }
+    return 0;
+  }
   for (int b = 0; b < B; ++b) {
     if (status) status[b] = 0;
     if (use_double == 2) {   // low-rank (Woodbury) path

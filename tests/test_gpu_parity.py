@@ -163,13 +163,51 @@ def test_every_lane_group_size_against_oracle(group):
 
 
 @pytest.mark.parametrize("env", [{"BIK_USE_TMA": 0}, {"BIK_SOLVE_PRECISION": "f32", "BIK_K2_PATH": "dense"}, {"BIK_K2_PATH": "dense"},
-                                 {"BIK_K2_PATH": "lowrank"}, {"BIK_K2_WARPS": 8}])
+                                 {"BIK_K2_PATH": "lowrank"}, {"BIK_K2_WARPS": 8}, {"BIK_K2_PATH": "group", "BIK_K2_GROUP": 4},
+                                 {"BIK_K2_PATH": "group", "BIK_K2_GROUP": 8}, {"BIK_K2_PATH": "group", "BIK_SOLVE_PRECISION": "f32"},
+                                 {"BIK_K2_PATH": "fixed", "BIK_SOLVE_PRECISION": "f32"}])
 def test_alternate_paths(env):
     wl, fm, spec, g, model, prob = _engine("g1", env=env)
     q = torch.tensor(g["q"], dtype=torch.float32, device="cuda:0")
     dq, st = prob.step(q, g["frame_targets"], g["posture_target"], None, dt=float(g["dt"]), damping=float(g["damping"]))
     assert int(st.max()) == 0
     assert np.abs(_np(dq) - g["dq"]).max() < 1e-4
+
+
+@pytest.mark.parametrize("path", ["dense", "group", "fixed"])
+def test_k2_paths_on_relative_frame_golden(path):
+    env = {"BIK_K2_PATH": path}
+    if path == "fixed":
+        env["BIK_SOLVE_PRECISION"] = "f32"
+    wl, fm, spec, g, model, prob = _engine("g1_rel", env=env)
+    rep = 5   # 80 instances: more than one tile of every path, ragged tail
+    q = torch.tensor(np.tile(g["q"], (rep, 1)), dtype=torch.float32, device="cuda:0")
+    dq, st = prob.step(q, np.tile(g["frame_targets"], (rep, 1, 1)), g["posture_target"], None, dt=float(g["dt"]), damping=float(g["damping"]))
+    assert int(st.max()) == 0
+    tol = 1e-4 * max(1.0, np.abs(g["dq"]).max())
+    assert np.abs(_np(dq) - np.tile(g["dq"], (rep, 1))).max() < (tol if path != "fixed" else 20 * tol)
+
+
+@pytest.mark.parametrize("name", ["g1", "shadow", "ur5e"])
+@pytest.mark.parametrize("path", ["dense", "group", "fixed"])
+def test_k2_paths_agree_on_a_ragged_batch(name, path):
+    """Every K2 path that applies to a box-only problem returns the same optimum (ragged batch: tail tiles of each path)."""
+    env = {"BIK_K2_PATH": path}
+    if path == "fixed":
+        env["BIK_SOLVE_PRECISION"] = "f32"   # the fixed-size path is fp32 only
+    wl, fm, spec, g, model, prob = _engine(name, env=env)
+    orc = _oracle(fm, spec)
+    frames = task_frames(wl, fm)
+    B = 1000 + 37
+    inp = make_inputs(fm, wl, B, lambda qq: orc.fk(qq, frames), seed=11)
+    q = torch.tensor(inp["q"], dtype=torch.float32, device="cuda:0")
+    dq, st = prob.step(q, inp["frame_targets"], inp["posture_target"], inp.get("com_target"), dt=wl["dt"], damping=wl["damping"])
+    dq_ref, _, st_ref, _ = orc.step(inp["q"], inp["frame_targets"], inp["posture_target"], inp.get("com_target"), dt=wl["dt"],
+                                    damping=wl["damping"], nsteps=1, integrate=False)
+    assert int(st.max()) == 0 and not st_ref.any()
+    err = np.abs(_np(dq) - dq_ref).max()
+    print(f"{name}/{path}: max|dq-dq_oracle|={err:.3e}")
+    assert err < (1e-4 if path != "fixed" else 2e-3)
 
 
 @pytest.mark.parametrize("name,B", [("g1", 4099), ("shadow", 2050), ("ur5e_dls", 4096), ("spot", 1031)])

@@ -116,6 +116,25 @@ def test_low_rank_path_matches_reference(name):
     np.testing.assert_allclose(dq, dq_dense, atol=2e-6)
 
 
+@pytest.mark.parametrize("name", ["g1", "ur5e", "ur5e_dls", "shadow", "g1_rel"])
+@pytest.mark.parametrize("code", [3, 4, 5, 6])
+def test_small_paths_match_reference(name, code):
+    """K2 small-group path (3/4) and fixed-size thread-per-problem path (5/6), fp64/fp32: same optimum as the warp path and the reference."""
+    wl, fm, spec, g, emu = _emu(name)
+    dt, damping = float(g["dt"]), float(g["damping"])
+    J, e, ep, Gc, hc = emu.fk_jac(g["q"], g["frame_targets"], g["posture_target"], None, dt=dt)
+    dq, st, it, *_ = emu.solve(g["q"], J, e, ep, Gc, hc, dt, damping, use_double=code)
+    assert not st.any()
+    err = np.abs(dq - g["dq"]).max()
+    print(name, "thread path max |dq - dq_ref| =", err, "iters mean/max", it.mean(), it.max())
+    tol = 1e-4 * max(1.0, np.abs(g["dq"]).max())
+    assert err < (tol if code in (3, 5) else 20 * tol)
+    dq_dense, _, it_dense, *_ = emu.solve(g["q"], J, e, ep, Gc, hc, dt, damping, use_double=1)
+    if code in (3, 5):
+        np.testing.assert_allclose(dq, dq_dense, atol=2e-6)
+        assert (it == it_dense).all()
+
+
 def test_check_limits():
     wl, fm, spec, g, emu = _emu("g1")
     q = g["q"].copy()

@@ -20,11 +20,12 @@ from mink_b200._abi import spec_from_workload
 from mink_b200.engine import DeviceModel, Problem
 from mink_b200.workloads import WORKLOADS, make_inputs
 from tests.helpers import load_flat, task_frames
-wl = WORKLOADS["g1"]; fm = load_flat("g1"); spec = spec_from_workload(fm, wl)
+WL = os.environ.get("BIK_WL", "g1")
+wl = WORKLOADS[WL]; fm = load_flat(wl["robot"]); spec = spec_from_workload(fm, wl)
 model = DeviceModel(fm, 0); prob = Problem(model, spec); frames = task_frames(wl, fm)
 def fk(qq):
     p, c = model.fk(qq, frames); return p.cpu().numpy().astype(np.float64), None
-B = int(os.environ.get("BIK_B", "65536"))
+B = int(os.environ.get("BIK_B", str(wl["batch"])))
 inp = make_inputs(fm, wl, B, fk, seed=1000)
 f32 = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float32, device="cuda:0")
 q0, ft, pt = f32(inp["q"]), f32(inp["frame_targets"]), f32(inp["posture_target"])
@@ -38,7 +39,8 @@ for s in range(8):
     dq, st = prob.solve(q0, J, e, ep, Gc, hc, wl["dt"], wl["damping"]); c.record()
     torch.cuda.synchronize()
     k1.append(a.elapsed_time(b)); k2.append(b.elapsed_time(c))
-print(json.dumps({"k1_ms": statistics.median(k1[2:]), "k2_ms": statistics.median(k2[2:]), "status": int(st.max())}))
+dq2, st2, it = prob.solve(q0, J, e, ep, Gc, hc, wl["dt"], wl["damping"], return_iters=True)
+print(json.dumps({"wl": WL, "B": B, "k1_ms": statistics.median(k1[2:]), "k2_ms": statistics.median(k2[2:]), "status": int(st.max()), "iters_mean": float(it.float().mean()), "iters_max": int(it.max())}))
 '''
 
 
@@ -55,8 +57,9 @@ def main():
     if build_only:
         return
     for name in VARIANTS:
-        for env in ({}, {"BIK_K1_GROUP": "8"}, {"BIK_K1_GROUP": "8", "BIK_K1_BULK": "1"}, {"BIK_K1_BULK": "1"},
-                    {"BIK_K1_GROUP": "16", "BIK_K1_BULK": "1"}):
+        for env in ({"BIK_K2_PATH": "dense"}, {"BIK_K2_PATH": "group", "BIK_K2_GROUP": "8"}, {}, {"BIK_SOLVE_PRECISION": "f32"},
+                    {"BIK_WL": "shadow", "BIK_K2_PATH": "dense"}, {"BIK_WL": "shadow", "BIK_K2_PATH": "group"}, {"BIK_WL": "shadow"},
+                    {"BIK_WL": "ur5e_dls", "BIK_K2_PATH": "group"}, {"BIK_WL": "ur5e_dls"}, {"BIK_WL": "g1_rel", "BIK_K2_PATH": "group"}, {"BIK_WL": "g1_rel"}):
             e = dict(os.environ, BIK_REPO=REPO, BIK_LIB=os.path.join(out, f"libbik_{name}.so"), **env)
             r = subprocess.run([sys.executable, "-c", CHILD], env=e, capture_output=True, text=True)
             line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:]
