@@ -236,6 +236,8 @@ struct bik_problem {
   float *hq = nullptr, *hft = nullptr, *hpt = nullptr, *hct = nullptr, *hdq = nullptr;
   int32_t* hst = nullptr;
   size_t host_pt_elems = 0;
+  cudaStream_t hs[2] = {nullptr, nullptr};
+  cudaEvent_t hev = nullptr;
 };
 
 static int valid_group(int G) { return G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32; }
@@ -301,6 +303,7 @@ extern "C" void bik_problem_destroy(bik_problem* p) {
   DeviceGuard g(p->device);
   cudaFree(p->d_image); cudaFree(p->J); cudaFree(p->e); cudaFree(p->ep); cudaFree(p->Gc); cudaFree(p->hc); cudaFree(p->warm); cudaFree(p->k2x_scratch);
   cudaFree(p->hq); cudaFree(p->hft); cudaFree(p->hpt); cudaFree(p->hct); cudaFree(p->hdq); cudaFree(p->hst);
+  if (p->hs[0]) { cudaStreamDestroy(p->hs[0]); cudaStreamDestroy(p->hs[1]); cudaEventDestroy(p->hev); }
   delete p;
 }
 extern "C" int bik_problem_dims(const bik_problem* p, bik_dims* out) {
@@ -645,7 +648,7 @@ extern "C" int bik_check_limits(const bik_model* m, int B, const float* q, float
 static int ensure_workspace(bik_problem* p, int B) {
   if ((size_t)B <= p->ws_B) return BIK_OK;
   const PHeader& h = p->h;
-  cudaFree(p->J); cudaFree(p->e); cudaFree(p->ep); cudaFree(p->Gc); cudaFree(p->hc); cudaFree(p->warm); cudaFree(p->k2x_scratch);
+  cudaFree(p->J); cudaFree(p->e); cudaFree(p->ep); cudaFree(p->Gc); cudaFree(p->hc); cudaFree(p->warm);
   p->J = p->e = p->ep = p->Gc = p->hc = nullptr; p->warm = nullptr; p->ws_B = 0;
   size_t b = (size_t)B;
   CUDA_OK(cudaMalloc(&p->J, sizeof(float) * b * (h.K > 0 ? h.K : 1) * h.nv));
@@ -655,6 +658,39 @@ static int ensure_workspace(bik_problem* p, int B) {
   CUDA_OK(cudaMalloc(&p->hc, sizeof(float) * b * (h.npairs > 0 ? h.npairs : 1)));
   CUDA_OK(cudaMalloc(&p->warm, b * (size_t)(h.nu > 0 ? h.nu : 1)));
   p->ws_B = b;
+  return BIK_OK;
+}
+
+// One or more solve_ik steps on device buffers; the K1 -> K2 workspace rows [ws_off, ws_off + B) are used, so that
+// chunks of one batch can be in flight on different streams (bik_step_host).  Caller holds p->mu and has sized the workspace.
+static int step_core(bik_problem* p, int B, size_t ws_off, float* q, const bik_inputs* in, float dt, double damping, int nsteps, int integrate,
+                     float* dq, int32_t* status, cudaStream_t st) {
+  const PHeader& h = p->h;
+  const size_t Kd = h.K > 0 ? h.K : 1, Pd = h.P > 0 ? h.P : 1, Nd = h.npairs > 0 ? h.npairs : 1, Ud = h.nu > 0 ? h.nu : 1;
+  float* J = p->J + ws_off * Kd * h.nv; float* e = p->e + ws_off * Kd; float* ep = p->ep + ws_off * Pd * h.nv;
+  float* Gc = p->Gc + ws_off * Nd * h.nv; float* hc = p->hc + ws_off * Nd;
+  signed char* warm_buf = p->warm + ws_off * Ud;
+  const bool warm = nsteps > 1 && !use_low_rank_static(p, damping);   // rollouts: carry the active set from step to step
+  if (warm) CUDA_OK(cudaMemsetAsync(warm_buf, 0, (size_t)B * Ud, st));
+  for (int s = 0; s < nsteps; ++s) {
+    if (status) {  // Configuration.check_limits(safety_break=False) of solve_ik.py:99
+      check_limits_kernel<<<(B + 127) / 128, 128, 0, st>>>(p->d_image, B, q, 1e-6f, status, s > 0);
+      CUDA_OK(cudaGetLastError());
+    }
+    K1Args a1{B, q, in->frame_targets, in->posture_targets, in->com_targets, in->posture_batched, dt, J, e, ep, Gc, hc};
+    int rc = dispatch_k1(p, a1, st);
+    if (rc) return rc;
+    K2Args a2;
+    memset(&a2, 0, sizeof a2);
+    a2.B = B; a2.q = q; a2.J = J; a2.e = e; a2.ep = ep; a2.Gc = Gc; a2.hc = hc; a2.dt = dt; a2.damping = damping; a2.dq = dq; a2.status = status; a2.lockstep = p->k2_lockstep;
+    a2.warm = warm ? warm_buf : nullptr;
+    rc = dispatch_k2(p, a2, st);
+    if (rc) return rc;
+    if (integrate) {
+      integrate_kernel<<<(B + 127) / 128, 128, 0, st>>>(p->d_image, B, q, dq);
+      CUDA_OK(cudaGetLastError());
+    }
+  }
   return BIK_OK;
 }
 
@@ -669,31 +705,23 @@ extern "C" int bik_step(const bik_problem* cp, int B, float* q, const bik_inputs
   DeviceGuard g(p->model->device);
   rc = ensure_workspace(p, B);
   if (rc) return rc;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const PHeader& h = p->h;
-  const bool warm = nsteps > 1 && !use_low_rank_static(p, damping);   // rollouts: carry the active set from step to step
-  if (warm) CUDA_OK(cudaMemsetAsync(p->warm, 0, (size_t)B * (size_t)(h.nu > 0 ? h.nu : 1), st));
-  for (int s = 0; s < nsteps; ++s) {
-    if (status) {  // Configuration.check_limits(safety_break=False) of solve_ik.py:99
-      check_limits_kernel<<<(B + 127) / 128, 128, 0, st>>>(p->d_image, B, q, 1e-6f, status, s > 0);
-      CUDA_OK(cudaGetLastError());
-    }
-    K1Args a1{B, q, in->frame_targets, in->posture_targets, in->com_targets, in->posture_batched, dt, p->J, p->e, p->ep, p->Gc, p->hc};
-    rc = dispatch_k1(p, a1, st);
-    if (rc) return rc;
-    K2Args a2;
-    memset(&a2, 0, sizeof a2);
-    a2.B = B; a2.q = q; a2.J = p->J; a2.e = p->e; a2.ep = p->ep; a2.Gc = p->Gc; a2.hc = p->hc; a2.dt = dt; a2.damping = damping; a2.dq = dq; a2.status = status; a2.lockstep = p->k2_lockstep;
-    a2.warm = warm ? p->warm : nullptr;
-    rc = dispatch_k2(p, a2, st);
-    if (rc) return rc;
-    if (integrate) {
-      integrate_kernel<<<(B + 127) / 128, 128, 0, st>>>(p->d_image, B, q, dq);
-      CUDA_OK(cudaGetLastError());
-    }
-  }
-  (void)h;
-  return BIK_OK;
+  return step_core(p, B, 0, q, in, dt, damping, nsteps, integrate, dq, status, static_cast<cudaStream_t>(stream));
+}
+
+// Instances one resident wave of the K2 kernel covers (0 when unknown): bik_step_host cuts its chunks at multiples of it.
+static long long k2_wave_instances(const bik_problem* p) {
+  K2Args a;
+  memset(&a, 0, sizeof a);
+  a.dq = reinterpret_cast<float*>(1); a.damping = 1.0;
+  if (!use_thread(p, a) || use_fixed(p, a)) return 0;
+  PView P{p->image.data()};
+  const int G = p->k2_group == 8 ? 8 : 4, NS = 32 / G, ts = p->solve_double ? 8 : 4, maxt = p->solve_double ? 256 : 512;
+  const size_t wb = (size_t)k2t_warp_bytes(P, ts, NS);
+  int NW = maxt / 32;
+  while (NW > 1 && NW * wb > (size_t)p->model->max_smem) --NW;
+  int per_sm = (int)((size_t)p->model->max_smem / (NW * wb + 1024));   // estimate; only used to size chunks
+  if (per_sm < 1) per_sm = 1;
+  return (long long)p->model->nsm * per_sm * NW * NS;
 }
 
 // Host-buffer variant: device staging lives in the problem's workspace region (separate allocations).
@@ -722,20 +750,40 @@ extern "C" int bik_step_host(const bik_problem* cp, int B, float* q_host, const 
       p->host_B = b; p->host_pt_elems = pt_elems;
     }
   }
-  cudaStream_t st = 0;
-  size_t up = 0, down = 0;
-  CUDA_OK(cudaMemcpyAsync(p->hq, q_host, 4 * b * nq, cudaMemcpyHostToDevice, st)); up += 4 * b * nq;
-  if (h.F) { CUDA_OK(cudaMemcpyAsync(p->hft, in->frame_targets, 4 * b * h.F * 7, cudaMemcpyHostToDevice, st)); up += 4 * b * h.F * 7; }
-  if (h.P) { CUDA_OK(cudaMemcpyAsync(p->hpt, in->posture_targets, 4 * pt_elems, cudaMemcpyHostToDevice, st)); up += 4 * pt_elems; }
-  if (h.C) { CUDA_OK(cudaMemcpyAsync(p->hct, in->com_targets, 4 * b * h.C * 3, cudaMemcpyHostToDevice, st)); up += 4 * b * h.C * 3; }
-  bik_inputs din = *in;
-  din.q = p->hq; din.frame_targets = p->hft; din.posture_targets = p->hpt; din.com_targets = p->hct;
-  rc = bik_step(cp, B, p->hq, &din, dt, damping, nsteps, integrate, p->hdq, status_host ? p->hst : nullptr, st);
+  // The batch is cut into chunks that alternate between two streams: the copies of one chunk overlap the kernels of
+  // the other (BIK_HOST_CHUNKS, default 4; chunk boundaries at multiples of a resident K2 wave so no wave runs half empty).
+  std::lock_guard<std::mutex> lock(p->mu);
+  rc = ensure_workspace(p, B);
   if (rc) return rc;
-  CUDA_OK(cudaMemcpyAsync(dq_host, p->hdq, 4 * b * nv, cudaMemcpyDeviceToHost, st)); down += 4 * b * nv;
-  if (integrate) { CUDA_OK(cudaMemcpyAsync(q_host, p->hq, 4 * b * nq, cudaMemcpyDeviceToHost, st)); down += 4 * b * nq; }
-  if (status_host) { CUDA_OK(cudaMemcpyAsync(status_host, p->hst, 4 * b, cudaMemcpyDeviceToHost, st)); down += 4 * b; }
-  CUDA_OK(cudaStreamSynchronize(st));
+  if (!p->hs[0]) { CUDA_OK(cudaStreamCreateWithFlags(&p->hs[0], cudaStreamNonBlocking)); CUDA_OK(cudaStreamCreateWithFlags(&p->hs[1], cudaStreamNonBlocking)); CUDA_OK(cudaEventCreateWithFlags(&p->hev, cudaEventDisableTiming)); }
+  int NC = env_int("BIK_HOST_CHUNKS", 4);
+  if (NC < 1 || !p->solve_double) NC = 1;   // the fp32 fixed-size path shares one scratch per launch grid
+  size_t chunk = (b + NC - 1) / NC;
+  const long long wave = k2_wave_instances(p);
+  if (wave > 0 && NC > 1) chunk = (size_t)(((long long)chunk + wave - 1) / wave * wave);
+  if (chunk < 1024) chunk = b;
+  size_t up = 0, down = 0;
+  if (h.P) { CUDA_OK(cudaMemcpyAsync(p->hpt, in->posture_targets, 4 * pt_elems, cudaMemcpyHostToDevice, p->hs[0])); up += 4 * pt_elems; }
+  CUDA_OK(cudaEventRecord(p->hev, p->hs[0]));
+  CUDA_OK(cudaStreamWaitEvent(p->hs[1], p->hev, 0));
+  int ci = 0;
+  for (size_t o = 0; o < b; o += chunk, ++ci) {
+    const size_t n = b - o < chunk ? b - o : chunk;
+    cudaStream_t st = p->hs[ci & 1];
+    CUDA_OK(cudaMemcpyAsync(p->hq + o * nq, q_host + o * nq, 4 * n * nq, cudaMemcpyHostToDevice, st)); up += 4 * n * nq;
+    if (h.F) { CUDA_OK(cudaMemcpyAsync(p->hft + o * h.F * 7, in->frame_targets + o * h.F * 7, 4 * n * h.F * 7, cudaMemcpyHostToDevice, st)); up += 4 * n * h.F * 7; }
+    if (h.C) { CUDA_OK(cudaMemcpyAsync(p->hct + o * h.C * 3, in->com_targets + o * h.C * 3, 4 * n * h.C * 3, cudaMemcpyHostToDevice, st)); up += 4 * n * h.C * 3; }
+    bik_inputs din = *in;
+    din.q = p->hq + o * nq; din.frame_targets = p->hft + o * h.F * 7; din.com_targets = p->hct + o * h.C * 3;
+    din.posture_targets = in->posture_batched ? p->hpt + o * (size_t)h.P * nq : p->hpt;
+    rc = step_core(p, (int)n, o, p->hq + o * nq, &din, dt, damping, nsteps, integrate, p->hdq + o * nv, status_host ? p->hst + o : nullptr, st);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(dq_host + o * nv, p->hdq + o * nv, 4 * n * nv, cudaMemcpyDeviceToHost, st)); down += 4 * n * nv;
+    if (integrate) { CUDA_OK(cudaMemcpyAsync(q_host + o * nq, p->hq + o * nq, 4 * n * nq, cudaMemcpyDeviceToHost, st)); down += 4 * n * nq; }
+    if (status_host) { CUDA_OK(cudaMemcpyAsync(status_host + o, p->hst + o, 4 * n, cudaMemcpyDeviceToHost, st)); down += 4 * n; }
+  }
+  CUDA_OK(cudaStreamSynchronize(p->hs[0]));
+  CUDA_OK(cudaStreamSynchronize(p->hs[1]));
   if (h2d_bytes) *h2d_bytes = up;
   if (d2h_bytes) *d2h_bytes = down;
   return BIK_OK;
