@@ -276,8 +276,13 @@ def main():
         hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     bytes_k1 = k1_bytes_per_instance(fm, spec, posture_batched=False) * B
     achieved = bytes_k1 / k1_s / 1e9
+    traffic = None   # DRAM bytes per launch from the committed ncu --set full capture of this workload (never measured under the bench)
+    tpath = os.path.join(REPO, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath) and B == 65536 and args.workload == "g1":
+        tj = json.load(open(tpath))["k1_kernel"]
+        traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]
     roofline = {"kernel": "k1_kernel (FK + Jacobian sweep)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_instance": bytes_k1 // B, "ms": k1_s * 1e3, "share_of_step": k1_s / (k1_s + k2_s)}
     # K2: algorithmic FLOPs need the mean active-set iteration count -> measured by the oracle on a sample
     mean_iters = None
@@ -308,15 +313,15 @@ def main():
     k2_peak = 148 * fma_per_clk_sm * 2 * sm_mhz * 1e6 / 1e12
     est_iters = 4.0  # block-pivoting iterations per solve on this workload (tests/test_host_emu.py prints 3.9)
     flops_k2 = k2_flops_per_instance(fm, spec, est_iters) * B
-    path = os.environ.get("BIK_K2_PATH", "auto")
-    lowrank = path == "lowrank" and spec.npairs == 0 and spec.nrows > 0   # auto picks dense for this workload (K = coupled dofs = 18)
-    k2_name = "k2lr_kernel (fp64 low-rank/Woodbury active set)" if lowrank else f"k2_kernel<{prec}> (dense packed Cholesky active set)"
-    if lowrank:
-        prec = "f64"
+    mapping = prob.describe(damping)        # which K1 lane group / K2 path this problem runs on (bik_problem_describe)
+    k2_name = "K2 " + mapping.split("k2: ")[-1] + " (QP assembly + block-pivoting active set, packed Cholesky)"
+    _, _, it_dev = prob.solve(q0, J, e, ep, Gc, hc, dt_, damping, return_iters=True)
+    mean_iters_dev = float(it_dev.float().mean())
     roofline_k2 = {"kernel": k2_name, "bound": "fma", "achieved": flops_k2 / k2_s / 1e12,
                    "peak": k2_peak, "unit": "TFLOP/s", "frac": flops_k2 / k2_s / 1e12 / k2_peak,
                    "peak_source": f"148 SM x {fma_per_clk_sm} FMA/clk x 2 x {sm_mhz:.0f} MHz (nominal CUDA-core rate at the sampled clock)",
-                   "flops_per_instance": flops_k2 / B, "flops_note": "dense-solver count of SURVEY 8(d), kept as the yardstick for both paths", "assumed_iterations": est_iters, "ms": k2_s * 1e3,
+                   "flops_per_instance": flops_k2 / B, "flops_note": "dense-solver count of SURVEY 8(d), kept as the yardstick for both paths", "assumed_iterations": est_iters,
+                   "measured_iterations_mean": mean_iters_dev, "mapping": mapping, "ms": k2_s * 1e3,
                    "share_of_step": k2_s / (k1_s + k2_s)}
 
     # ---- e2e through the host-buffer C-ABI entry (H2D + kernels + D2H inside the timing) -------------

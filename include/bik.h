@@ -219,6 +219,11 @@ int bik_step_host(const bik_problem* problem, int B, float* q_host, const bik_in
 /* Bytes of device scratch a problem needs for a batch of B (J, e, ... between K1 and K2). */
 size_t bik_workspace_bytes(const bik_problem* problem, int B);
 
+/* One-line description of how a problem is mapped onto the device (lanes per instance and visited
+ * nodes in K1, coupled block size, K2 path and precision chosen for `damping`), for logs and
+ * benchmark labels.  Writes at most cap bytes including the terminator; returns the full length. */
+int bik_problem_describe(const bik_problem* problem, double damping, char* buf, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -708,6 +708,24 @@ extern "C" int bik_step(const bik_problem* cp, int B, float* q, const bik_inputs
   return step_core(p, B, 0, q, in, dt, damping, nsteps, integrate, dq, status, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int bik_problem_describe(const bik_problem* p, double damping, char* buf, size_t cap) {
+  if (!p) return fail(BIK_ERR_INVALID, "null argument");
+  const PHeader& h = p->h;
+  K2Args a;
+  memset(&a, 0, sizeof a);
+  a.dq = reinterpret_cast<float*>(1); a.damping = damping;
+  std::string k2;
+  if (use_fixed(p, a)) k2 = "fixed-size thread-per-problem N=" + std::to_string(k2x_size(h.nu));
+  else if (use_thread(p, a)) k2 = "small-group G=" + std::to_string(p->k2_group);
+  else if (use_low_rank(p, a)) k2 = "low-rank warp-per-problem";
+  else k2 = "dense warp-per-problem";
+  std::string d = "k1: " + std::to_string(h.G) + " lanes/instance, " + std::to_string(h.nneeded) + "/" + std::to_string(h.nnode) + " nodes visited; nv=" +
+                  std::to_string(h.nv) + " coupled=" + std::to_string(h.nu) + " rows=" + std::to_string(h.K) + " pairs=" + std::to_string(h.npairs) + "; k2: " + k2 +
+                  (p->solve_double ? " f64" : " f32");
+  if (buf && cap) { size_t n = d.size() < cap - 1 ? d.size() : cap - 1; memcpy(buf, d.c_str(), n); buf[n] = 0; }
+  return (int)d.size();
+}
+
 // Instances one resident wave of the K2 kernel covers (0 when unknown): bik_step_host cuts its chunks at multiples of it.
 static long long k2_wave_instances(const bik_problem* p) {
   K2Args a;

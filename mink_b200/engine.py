@@ -99,6 +99,12 @@ class Problem:
         _lib.check(self.lib.bik_problem_dims(h, C.byref(d)))
         self.nq, self.nv, self.F, self.P, self.Cn, self.K, self.npairs = d.nq, d.nv, d.nframe, d.nposture, d.ncom, d.nrows, d.npairs
 
+    def describe(self, damping: float = 1e-12) -> str:
+        """How the problem is mapped onto the device (K1 lanes, coupled block, K2 path); bik_problem_describe."""
+        buf = C.create_string_buffer(512)
+        self.lib.bik_problem_describe(self.handle, float(damping), buf, 512)
+        return buf.value.decode()
+
     def close(self):
         h, self.handle = getattr(self, "handle", None), None
         if h:
