@@ -166,9 +166,12 @@ template <typename T, int G, int NS>
 BIK_HD int k2t_factor(const T* __restrict__ Hp, T* __restrict__ Lp, int nu, uint32_t act, int l) {
   int bad = 0;
   T* const rhsrow = Lp + tri(nu) * NS;
-  for (int i0 = 0; i0 <= nu; i0 += G) {
+  // Row blocks are aligned to the END of the (nu+1)-row system: the last rows are the expensive ones (cost ~ i^2),
+  // so the partial block, if any, is the first one and every lane has a row in the last block.
+  const int first = (nu + 1) % G;
+  for (int i0 = first ? first - G : 0; i0 <= nu; i0 += G) {
     const int i = i0 + l;
-    const bool has = i <= nu, rhs = i == nu;
+    const bool has = i >= 0 && i <= nu, rhs = i == nu;
     const bool ai = has && !rhs && ((act >> i) & 1u);
     const uint32_t msk = rhs ? 0u : (ai ? ~0u : act);
     const int ir = has ? i : 0;
@@ -192,6 +195,7 @@ BIK_HD int k2t_factor(const T* __restrict__ Hp, T* __restrict__ Lp, int nu, uint
     if (has) for (int k = 0; k < i0; ++k) step(k);   // rows above the block are complete
     for (int j = 0; j < G; ++j) {                     // diagonal block: the owner of row k closes it, then the rows below use it
       const int k = i0 + j;
+      if (k < 0) continue;
       if (has && !rhs && l == j) {
         T d = (ai ? T(1) : src[k * NS]) - ss;
         if (!(d > T(0))) { bad = 1; d = T(1e-30); }
