@@ -44,6 +44,7 @@ typedef enum bik_status {
 #define BIK_STATUS_QP_MAXITER    2u  /* active-set iteration cap reached; dq is the last iterate */
 #define BIK_STATUS_NONFINITE     4u  /* NaN/Inf met in q, targets or the factorisation */
 #define BIK_STATUS_QP_INFEASIBLE 8u  /* inequality set inconsistent */
+#define BIK_STATUS_NOT_CONVERGED 16u /* bik_converge: thresholds not met within max_iters */
 
 typedef struct bik_model bik_model;     /* flattened kinematic tree resident on one device */
 typedef struct bik_problem bik_problem; /* static task + limit layout bound to a model */
@@ -215,6 +216,18 @@ int bik_step(const bik_problem* problem, int B, float* q, const bik_inputs* in, 
 int bik_step_host(const bik_problem* problem, int B, float* q_host, const bik_inputs* in_host,
                   float dt, double damping, int nsteps, int integrate, float* dq_host,
                   int32_t* status_host, size_t* h2d_bytes, size_t* d2h_bytes);
+
+/* Converge-until-threshold driver: the solve_ik + integrate inner loop of the reference's examples
+ * (examples/quadruped_spot.py:89-104, examples/arm_aloha.py:146-169), per instance:
+ *     for i in range(max_iters):  v = solve_ik(...); q = integrate(q, v, dt)
+ *                                 if all frame tasks: |e[:3]| <= pos_threshold and |e[3:]| <= ori_threshold: break
+ * q [B][nq] is updated in place; an instance that met the thresholds keeps its configuration while the
+ * others go on.  iters [B] receives the number of steps each instance took (1..max_iters); instances
+ * that never met the thresholds get BIK_STATUS_NOT_CONVERGED.  The batch loop stops as soon as no
+ * instance is left (the device counter is read back every `check_every` steps).  Device buffers. */
+int bik_converge(const bik_problem* problem, int B, float* q, const bik_inputs* in, float dt,
+                 double damping, int max_iters, float pos_threshold, float ori_threshold,
+                 int check_every, int32_t* iters, int32_t* status, void* stream);
 
 /* Bytes of device scratch a problem needs for a batch of B (J, e, ... between K1 and K2). */
 size_t bik_workspace_bytes(const bik_problem* problem, int B);

@@ -13,7 +13,7 @@ _lib = None
 EXPORTS = ["bik_version", "bik_last_error", "bik_model_create", "bik_model_destroy", "bik_problem_create",
            "bik_problem_destroy", "bik_problem_dims", "bik_fk", "bik_frame_jacobian", "bik_fk_jac",
            "bik_qp_objective", "bik_limits_box", "bik_solve", "bik_solve_ex", "bik_integrate", "bik_check_limits", "bik_step",
-           "bik_step_host", "bik_workspace_bytes", "bik_problem_describe"]
+           "bik_step_host", "bik_workspace_bytes", "bik_problem_describe", "bik_converge"]
 
 
 class BikError(RuntimeError):
@@ -59,6 +59,7 @@ def load():
                                   C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     lib.bik_workspace_bytes.argtypes = [vp, ci]
     lib.bik_workspace_bytes.restype = C.c_size_t
+    lib.bik_converge.argtypes = [vp, ci, vp, C.POINTER(BikInputs), cf, cd, ci, cf, cf, ci, vp, vp, vp]
     lib.bik_problem_describe.argtypes = [vp, cd, C.c_char_p, C.c_size_t]
     _lib = lib
     return lib

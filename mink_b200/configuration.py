@@ -169,6 +169,10 @@ class Configuration:
     def integrate_inplace(self, velocity, dt: float) -> None:
         """reference configuration.py:228-236."""
         self.dm.integrate(self._q, self._dq(velocity, dt))
+        self._sync_from_device()
+
+    def _sync_from_device(self) -> None:
+        """Refresh the host mirror of a single configuration after the device copy changed in place."""
         if self._q64 is not None:
             self._q64 = self._q[0].cpu().numpy().astype(np.float64)
             self.data.qpos = self._q64

@@ -172,6 +172,32 @@ __global__ void integrate_kernel(const uint32_t* __restrict__ gimage, int B, flo
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) integrate_instance(P, q + (size_t)b * P.h().nq, dq + (size_t)b * P.h().nv);
 }
+// Converge driver: instances whose every frame-task error is under the thresholds stop (done = 1, iters = steps taken so far);
+// the others are counted.  e is K1's unweighted error at the CURRENT q.
+__global__ void converge_check_kernel(const uint32_t* __restrict__ gimage, int B, const float* __restrict__ e, int it, float pos_thr, float ori_thr,
+                                      int32_t* done, int32_t* iters, int* not_done) {
+  PView P{gimage};
+  const PHeader& h = P.h();
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B || done[b]) return;
+  bool ok = true;
+  for (int f = 0; f < h.F; ++f) {
+    const float* eb = e + (size_t)b * h.K + P.frame(f).row0;
+    const float pos = sqrtf(eb[0] * eb[0] + eb[1] * eb[1] + eb[2] * eb[2]), ori = sqrtf(eb[3] * eb[3] + eb[4] * eb[4] + eb[5] * eb[5]);
+    ok = ok && pos <= pos_thr && ori <= ori_thr;
+  }
+  if (ok) { done[b] = 1; iters[b] = it; }
+  else atomicAdd(not_done, 1);
+}
+__global__ void integrate_masked_kernel(const uint32_t* __restrict__ gimage, int B, float* q, const float* dq, const int32_t* __restrict__ done) {
+  PView P{gimage};
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B && !done[b]) integrate_instance(P, q + (size_t)b * P.h().nq, dq + (size_t)b * P.h().nv);
+}
+__global__ void converge_finish_kernel(int B, int max_iters, const int32_t* __restrict__ done, int32_t* iters, int32_t* status) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B && !done[b]) { iters[b] = max_iters; if (status) status[b] |= 16; }
+}
 __global__ void check_limits_kernel(const uint32_t* __restrict__ gimage, int B, const float* q, float tol, int32_t* status, int accumulate) {
   PView P{gimage};
   int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -238,6 +264,12 @@ struct bik_problem {
   size_t host_pt_elems = 0;
   cudaStream_t hs[2] = {nullptr, nullptr};
   cudaEvent_t hev = nullptr;
+  // bik_converge state
+  size_t conv_B = 0;
+  int32_t* conv_done = nullptr;
+  float* conv_dq = nullptr;
+  int* conv_count = nullptr;
+  int* conv_host = nullptr;
 };
 
 static int valid_group(int G) { return G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32; }
@@ -303,6 +335,8 @@ extern "C" void bik_problem_destroy(bik_problem* p) {
   DeviceGuard g(p->device);
   cudaFree(p->d_image); cudaFree(p->J); cudaFree(p->e); cudaFree(p->ep); cudaFree(p->Gc); cudaFree(p->hc); cudaFree(p->warm); cudaFree(p->k2x_scratch);
   cudaFree(p->hq); cudaFree(p->hft); cudaFree(p->hpt); cudaFree(p->hct); cudaFree(p->hdq); cudaFree(p->hst);
+  cudaFree(p->conv_done); cudaFree(p->conv_dq); cudaFree(p->conv_count);
+  if (p->conv_host) cudaFreeHost(p->conv_host);
   if (p->hs[0]) { cudaStreamDestroy(p->hs[0]); cudaStreamDestroy(p->hs[1]); cudaEventDestroy(p->hev); }
   delete p;
 }
@@ -724,6 +758,72 @@ extern "C" int bik_problem_describe(const bik_problem* p, double damping, char* 
                   (p->solve_double ? " f64" : " f32");
   if (buf && cap) { size_t n = d.size() < cap - 1 ? d.size() : cap - 1; memcpy(buf, d.c_str(), n); buf[n] = 0; }
   return (int)d.size();
+}
+
+// solve_ik + integrate until every frame task of an instance is within (pos_threshold, ori_threshold) or max_iters steps were
+// taken -- the inner loop of the reference's examples (examples/quadruped_spot.py:89-104, examples/arm_aloha.py:146-169), per
+// instance.  An instance that has converged keeps its q; the batch loop ends as soon as the device counter of unconverged
+// instances reads zero (checked every `check_every` steps: one 4-byte D2H copy and a stream synchronisation).
+extern "C" int bik_converge(const bik_problem* cp, int B, float* q, const bik_inputs* in, float dt, double damping, int max_iters, float pos_threshold,
+                            float ori_threshold, int check_every, int32_t* iters, int32_t* status, void* stream) {
+  if (B == 0 && cp) return BIK_OK;
+  int rc = check_inputs(cp, in, false);
+  if (rc) return rc;
+  if (!q || !iters || B < 0 || max_iters < 1) return fail(BIK_ERR_INVALID, "bad argument");
+  if (check_every < 1) check_every = 1;
+  bik_problem* p = const_cast<bik_problem*>(cp);
+  std::lock_guard<std::mutex> lock(p->mu);
+  DeviceGuard g(p->model->device);
+  rc = ensure_workspace(p, B);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const PHeader& h = p->h;
+  if ((size_t)B > p->conv_B) {
+    cudaFree(p->conv_done); cudaFree(p->conv_dq); cudaFree(p->conv_count);
+    p->conv_done = nullptr; p->conv_dq = nullptr; p->conv_count = nullptr; p->conv_B = 0;
+    CUDA_OK(cudaMalloc(&p->conv_done, sizeof(int32_t) * (size_t)B));
+    CUDA_OK(cudaMalloc(&p->conv_dq, sizeof(float) * (size_t)B * h.nv));
+    CUDA_OK(cudaMalloc(&p->conv_count, sizeof(int)));
+    p->conv_B = (size_t)B;
+  }
+  if (!p->conv_host) CUDA_OK(cudaMallocHost(&p->conv_host, sizeof(int)));
+  CUDA_OK(cudaMemsetAsync(p->conv_done, 0, sizeof(int32_t) * (size_t)B, st));
+  const bool warm = !use_low_rank_static(p, damping);
+  if (warm) CUDA_OK(cudaMemsetAsync(p->warm, 0, (size_t)B * (size_t)(h.nu > 0 ? h.nu : 1), st));
+  const int blocks = (B + 127) / 128;
+  bool all_done = false;
+  for (int it = 0; it <= max_iters && !all_done; ++it) {
+    if (status && it < max_iters) {
+      check_limits_kernel<<<blocks, 128, 0, st>>>(p->d_image, B, q, 1e-6f, status, it > 0);
+      CUDA_OK(cudaGetLastError());
+    }
+    K1Args a1{B, q, in->frame_targets, in->posture_targets, in->com_targets, in->posture_batched, dt, p->J, p->e, p->ep, p->Gc, p->hc};
+    rc = dispatch_k1(p, a1, st);
+    if (rc) return rc;
+    if (it > 0) {   // errors at the configuration reached after `it` steps
+      CUDA_OK(cudaMemsetAsync(p->conv_count, 0, sizeof(int), st));
+      converge_check_kernel<<<blocks, 128, 0, st>>>(p->d_image, B, p->e, it, pos_threshold, ori_threshold, p->conv_done, iters, p->conv_count);
+      CUDA_OK(cudaGetLastError());
+      if (it == max_iters || it % check_every == 0) {
+        CUDA_OK(cudaMemcpyAsync(p->conv_host, p->conv_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        all_done = *p->conv_host == 0;
+      }
+    }
+    if (it == max_iters || all_done) break;
+    K2Args a2;
+    memset(&a2, 0, sizeof a2);
+    a2.B = B; a2.q = q; a2.J = p->J; a2.e = p->e; a2.ep = p->ep; a2.Gc = p->Gc; a2.hc = p->hc; a2.dt = dt; a2.damping = damping; a2.dq = p->conv_dq; a2.status = status;
+    a2.lockstep = p->k2_lockstep; a2.warm = warm ? p->warm : nullptr;
+    rc = dispatch_k2(p, a2, st);
+    if (rc) return rc;
+    integrate_masked_kernel<<<blocks, 128, 0, st>>>(p->d_image, B, q, p->conv_dq, p->conv_done);
+    CUDA_OK(cudaGetLastError());
+  }
+  // instances that never met the thresholds: iters = max_iters, status bit BIK_STATUS_NOT_CONVERGED
+  converge_finish_kernel<<<blocks, 128, 0, st>>>(B, max_iters, p->conv_done, iters, status);
+  CUDA_OK(cudaGetLastError());
+  return BIK_OK;
 }
 
 // Instances one resident wave of the K2 kernel covers (0 when unknown): bik_step_host cuts its chunks at multiples of it.

@@ -202,6 +202,21 @@ class Problem:
                                      int(bool(integrate)), dq.data_ptr(), status.data_ptr(), _stream()))
         return dq, status
 
+    def converge(self, q: torch.Tensor, frame_targets=None, posture_targets=None, com_targets=None, dt: float = 1e-2,
+                 damping: float = 1e-12, max_iters: int = 20, pos_threshold: float = 1e-4, ori_threshold: float = 1e-4,
+                 check_every: int = 1):
+        """solve_ik + integrate until every frame task is within the thresholds or max_iters steps were taken, per instance
+        (the inner loop of the reference's examples; bik_converge).  q is updated in place.  Returns (iters [B], status [B])."""
+        assert q.is_cuda and q.dtype == torch.float32 and q.is_contiguous()
+        inp, keep, _, _ = self._inputs(None, frame_targets, posture_targets, com_targets)
+        B = q.shape[0]
+        iters = torch.zeros(B, device=q.device, dtype=torch.int32)
+        status = torch.zeros(B, device=q.device, dtype=torch.int32)
+        _lib.check(self.lib.bik_converge(self.handle, B, q.data_ptr(), C.byref(inp), float(dt), float(damping), int(max_iters),
+                                         float(pos_threshold), float(ori_threshold), int(check_every), iters.data_ptr(), status.data_ptr(),
+                                         _stream()))
+        return iters, status
+
     def step_host(self, q: np.ndarray, frame_targets=None, posture_targets=None, com_targets=None, dt: float = 1e-2,
                   damping: float = 1e-12, nsteps: int = 1, integrate: bool = False, out_dq: np.ndarray = None,
                   out_status: np.ndarray = None):

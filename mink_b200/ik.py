@@ -99,3 +99,29 @@ def solve_ik(configuration: Configuration, tasks: Sequence[Task], dt: float, sol
     if configuration.batched:
         return v
     return v[0].cpu().numpy().astype(np.float64)
+
+
+def converge_ik(configuration: Configuration, tasks: Sequence[Task], dt: float, solver: str = "b200", damping: float = 1e-12,
+                limits: Optional[Sequence[Limit]] = None, max_iters: int = 20, pos_threshold: float = 1e-4,
+                ori_threshold: float = 1e-4, check_every: int = 1):
+    """The inner loop the reference's examples wrap around solve_ik (examples/arm_iiwa.py:63-70,
+    examples/quadruped_spot.py:89-104), run on the device per instance:
+
+        for i in range(max_iters):
+            vel = solve_ik(configuration, tasks, dt, solver, damping, limits=limits)
+            configuration.integrate_inplace(vel, dt)
+            if every FrameTask/RelativeFrameTask: |err[:3]| <= pos_threshold and |err[3:]| <= ori_threshold: break
+
+    The configuration is updated in place; returns (iters, converged): steps taken and whether the thresholds were
+    met, numpy scalars for a single configuration, [B] numpy arrays for a batch."""
+    prob, kw, limits = _lower(configuration, tasks, limits)
+    q = configuration.q_device
+    iters, status = prob.converge(q, dt=dt, damping=damping, max_iters=max_iters, pos_threshold=pos_threshold,
+                                  ori_threshold=ori_threshold, check_every=check_every, **kw)
+    configuration._sync_from_device()
+    st = status.cpu().numpy()
+    assert not (st & (2 | 4 | 8)).any(), f"QP not solved for {int(((st & 14) != 0).sum())} instance(s) (status bits {np.unique(st & 14)})"
+    it, ok = iters.cpu().numpy(), (st & 16) == 0
+    if configuration.batched:
+        return it, ok
+    return int(it[0]), bool(ok[0])

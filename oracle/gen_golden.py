@@ -28,6 +28,7 @@ from mink_b200.workloads import WORKLOADS, make_inputs  # noqa: E402
 OUT = os.path.join(REPO, "tests", "golden")
 GOLDEN_B = {"ur5e": 8, "ur5e_dls": 16, "g1": 32, "shadow": 24, "spot": 24, "g1_rel": 16, "edge": 48}
 ROLLOUT_T, ROLLOUT_B = 8, 4
+CONV_B, CONV_MAX_ITERS, CONV_POS, CONV_ORI = 8, 20, 2e-3, 2e-3
 
 
 def build_reference_problem(model, wl):
@@ -172,9 +173,32 @@ def main():
                 cfg.integrate_inplace(v, dt)
                 traj[s + 1, b] = cfg.q
         rec["rollout_q"] = traj
+        # Converge-until-threshold loop of the examples (examples/arm_iiwa.py:63-70, arm_ur5e_actuators.py:88-97): solve_ik +
+        # integrate, then every frame task's error at the new configuration against the thresholds.
+        CB = min(CONV_B, B)
+        conv_q = np.zeros((CB, nq)); conv_it = np.zeros(CB, dtype=np.int32); conv_ok = np.zeros(CB, dtype=np.int32)
+        for b in range(CB):
+            cfg.update(q[b])
+            for k, t in enumerate(frame_tasks):
+                t.set_target(mink.SE3(wxyz_xyz=inp["frame_targets"][b, k]))
+            if com is not None:
+                com.set_target(inp["com_target"][b])
+            for i in range(CONV_MAX_ITERS):
+                v = mink.solve_ik(cfg, tasks, dt, "quadprog", damping, limits=limits)
+                cfg.integrate_inplace(v, dt)
+                ok = True
+                for t in frame_tasks:
+                    err = t.compute_error(cfg)
+                    ok = ok and bool(np.linalg.norm(err[:3]) <= CONV_POS) and bool(np.linalg.norm(err[3:]) <= CONV_ORI)
+                conv_it[b] = i + 1
+                if ok:
+                    conv_ok[b] = 1
+                    break
+            conv_q[b] = cfg.q
+        rec.update(conv_q=conv_q, conv_iters=conv_it, conv_ok=conv_ok, conv_params=np.array([CONV_MAX_ITERS, CONV_POS, CONV_ORI]))
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
         print(f"{name}: B={B} nv={nv} F={F} rows={0 if not Gs else Gs[0].shape[0]} "
-              f"active mean={nact.mean():.1f} max={nact.max()} |dq|max={np.abs(dq).max():.4f} "
+              f"active mean={nact.mean():.1f} max={nact.max()} |dq|max={np.abs(dq).max():.4f} conv iters={conv_it.tolist()} ok={conv_ok.tolist()} "
               f"cond(H) median={np.median([np.linalg.cond(h) for h in H]):.2e}")
 
 

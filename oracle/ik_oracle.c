@@ -793,6 +793,71 @@ int iko_step(const void* blob, const bik_task_desc* tasks, int ntasks, const bik
   return 0;
 }
 
+/* Converge-until-threshold loop of the reference's examples (examples/arm_iiwa.py:63-70, examples/arm_ur5e_actuators.py:88-97,
+ * examples/quadruped_spot.py:89-104), per instance: solve_ik + integrate, then the frame-task errors at the NEW configuration are
+ * compared with the thresholds.  iters_out = steps taken (1..max_iters); converged_out = 1 when the thresholds were met. */
+int iko_converge(const void* blob, const bik_task_desc* tasks, int ntasks, const bik_limit_desc* limits, int nlimits, int B, double* q,
+                 const double* frame_targets, const double* posture_targets, int posture_batched, const double* com_targets, double dt,
+                 double damping, int max_iters, double pos_thr, double ori_thr, int32_t* iters_out, int32_t* converged_out, int32_t* status,
+                 int nthreads) {
+  Model m; if (model_from_blob(blob, &m)) return -1;
+  Counts cn = count_tasks(tasks, ntasks);
+  int nv = m.nv, npairs = 0;
+  for (int l = 0; l < nlimits; ++l) if (limits[l].kind == BIK_LIMIT_COLLISION) npairs += limits[l].n;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+  (void)nthreads;
+#pragma omp parallel
+  {
+    Kin k = kin_alloc(m.nnode);
+    double* s = (double*)malloc(sizeof(double) * 18 * nv);
+    double* J = (double*)malloc(sizeof(double) * ((size_t)(cn.K + 1) * nv + cn.K + (size_t)(cn.P + 1) * nv));
+    double* e = J + (size_t)(cn.K + 1) * nv; double* ep = e + cn.K;
+    double* H = (double*)malloc(sizeof(double) * ((size_t)nv * nv + 3 * nv + (size_t)(npairs + 1) * (nv + 1)));
+    double *c = H + (size_t)nv * nv, *lo = c + nv, *hi = lo + nv, *G = hi + nv, *h = G + (size_t)(npairs + 1) * nv;
+    double* work = (double*)malloc(sizeof(double) * qp_work_doubles(nv) + sizeof(int) * (nv + 4));
+    double* x = (double*)malloc(sizeof(double) * nv);
+#pragma omp for schedule(dynamic, 16)
+    for (int b = 0; b < B; ++b) {
+      double* qb = q + (size_t)b * m.nq; int st = 0, nact = 0, it = 0, conv = 0, steps = 0;
+      const double* ft = frame_targets ? frame_targets + (size_t)b * cn.F * 7 : NULL;
+      const double* pt = posture_targets ? posture_targets + (posture_batched ? (size_t)b * cn.P * m.nq : 0) : NULL;
+      const double* ct = com_targets ? com_targets + (size_t)b * cn.C * 3 : NULL;
+      fk_nodes(&m, qb, &k);
+      tasks_instance(&m, &k, tasks, ntasks, qb, ft, pt, ct, J, e, ep, s);
+      for (int step = 0; step < max_iters; ++step) {
+        objective_instance(&m, tasks, ntasks, J, e, ep, damping, H, c);
+        box_instance(&m, limits, nlimits, qb, dt, lo, hi);
+        int row = 0;
+        for (int l = 0; l < nlimits; ++l) if (limits[l].kind == BIK_LIMIT_COLLISION) { collision_rows(&m, &k, limits + l, dt, G + (size_t)row * nv, h + row, s); row += limits[l].n; }
+        Cons cons = {nv, npairs, lo, hi, G, h};
+        int rc = qp_solve(nv, H, c, &cons, x, &nact, &it, work);
+        if (rc == 1) st |= BIK_STATUS_QP_INFEASIBLE; else if (rc == 2) st |= BIK_STATUS_QP_MAXITER; else if (rc == 3) st |= BIK_STATUS_NONFINITE;
+        integrate_instance(&m, qb, x, 1.0);
+        steps = step + 1;
+        fk_nodes(&m, qb, &k);
+        tasks_instance(&m, &k, tasks, ntasks, qb, ft, pt, ct, J, e, ep, s);
+        int ok = 1, erow = 0;
+        for (int t = 0; t < ntasks; ++t) {
+          if (tasks[t].kind == BIK_TASK_FRAME || tasks[t].kind == BIK_TASK_RELATIVE_FRAME) {
+            const double* eb = e + erow;
+            double pos = sqrt(eb[0] * eb[0] + eb[1] * eb[1] + eb[2] * eb[2]), ori = sqrt(eb[3] * eb[3] + eb[4] * eb[4] + eb[5] * eb[5]);
+            if (!(pos <= pos_thr && ori <= ori_thr)) ok = 0;
+            erow += 6;
+          } else if (tasks[t].kind == BIK_TASK_COM) erow += 3;
+        }
+        if (ok) { conv = 1; break; }
+      }
+      if (iters_out) iters_out[b] = steps;
+      if (converged_out) converged_out[b] = conv;
+      if (status) status[b] = st;
+    }
+    kin_free(&k); free(s); free(J); free(H); free(work); free(x);
+  }
+  return 0;
+}
+
 /* collision rows for a batch (checker for bik_fk_jac's G_coll / h_coll) */
 int iko_collision(const void* blob, const bik_limit_desc* limits, int nlimits, int B, const double* q, double dt, double* G, double* h) {
   Model m; if (model_from_blob(blob, &m)) return -1;

@@ -108,6 +108,20 @@ class Oracle:
         assert rc == 0
         return dq, q, st, na
 
+    def converge(self, q, frame_targets=None, posture_target=None, com_targets=None, dt=1e-2, damping=1e-12, max_iters=20,
+                 pos_threshold=1e-4, ori_threshold=1e-4, nthreads=0):
+        """The examples' solve+integrate-until-threshold loop.  Returns (q_final [B,nq], iters [B], converged [B], status [B])."""
+        q = _f64(q).copy(); B = q.shape[0]; s = self.spec
+        ft, ct, pt = _f64(frame_targets), _f64(com_targets), _f64(posture_target)
+        batched = int(pt is not None and pt.ndim >= 2 and pt.size == B * s.nposture * self.nq and B > 1)
+        it = np.zeros(B, dtype=np.int32); cv = np.zeros(B, dtype=np.int32); st = np.zeros(B, dtype=np.int32)
+        i32 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        rc = lib().iko_converge(self.blob, self.tasks, self.ntasks, self.limits, self.nlimits, B, _d(q), _d(ft), _d(pt), batched, _d(ct),
+                                C.c_double(dt), C.c_double(damping), int(max_iters), C.c_double(pos_threshold), C.c_double(ori_threshold),
+                                i32(it), i32(cv), i32(st), int(nthreads))
+        assert rc == 0
+        return q, it, cv, st
+
     def integrate(self, q, dq):
         q = _f64(q).copy()
         assert lib().iko_integrate(self.blob, q.shape[0], _d(q), _d(_f64(dq))) == 0

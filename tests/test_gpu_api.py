@@ -203,3 +203,36 @@ def test_relative_frame_task_matches_reference_and_world_root_identity():
     np.testing.assert_allclose(a.compute_jacobian(one), -b.compute_jacobian(one), atol=2e-5)
     a.set_target_from_configuration(one)
     np.testing.assert_allclose(a.compute_error(one), np.zeros(6), atol=2e-6)
+
+
+def test_converge_ik_matches_the_explicit_loop():
+    """converge_ik == the examples' loop written with solve_ik + integrate_inplace (examples/arm_iiwa.py:63-70)."""
+    wl, fm, spec, g = load_case("ur5e")
+
+    def make(b):
+        cfg = mink.Configuration(fm, g["q"][b])
+        ee = mink.FrameTask("attachment_site", "site", position_cost=1.0, orientation_cost=1.0, lm_damping=1.0)
+        ee.set_target(SE3(wxyz_xyz=g["frame_targets"][b, 0]))
+        post = mink.PostureTask(fm, cost=1e-2)
+        post.set_target(g["posture_target"])
+        return cfg, [ee, post], ee, [mink.ConfigurationLimit(fm, gain=0.95)]
+
+    max_iters, pos, ori = int(g["conv_params"][0]), float(g["conv_params"][1]), float(g["conv_params"][2])
+    dt, damping = float(g["dt"]), float(g["damping"])
+    for b in range(4):
+        cfg, tasks, ee, limits = make(b)
+        it, ok = mink.converge_ik(cfg, tasks, dt, "quadprog", damping, limits=limits, max_iters=max_iters, pos_threshold=pos,
+                                  ori_threshold=ori)
+        assert it == int(g["conv_iters"][b]) and ok == bool(g["conv_ok"][b])
+        np.testing.assert_allclose(cfg.q, g["conv_q"][b], atol=1e-3)
+        cfg2, tasks2, ee2, limits2 = make(b)
+        steps = 0
+        for i in range(max_iters):
+            v = mink.solve_ik(cfg2, tasks2, dt, "quadprog", damping, limits=limits2)
+            cfg2.integrate_inplace(v, dt)
+            steps = i + 1
+            err = ee2.compute_error(cfg2)
+            if np.linalg.norm(err[:3]) <= pos and np.linalg.norm(err[3:]) <= ori:
+                break
+        assert steps == it
+        np.testing.assert_allclose(cfg.q, cfg2.q, atol=2e-5)

@@ -147,6 +147,46 @@ def test_rollout_matches_reference(name):
     np.testing.assert_allclose(_np(q), traj[-1], atol={"spot": 2e-2, "edge": 1e-2, "g1_rel": 2e-3}.get(name, 5e-4))
 
 
+@pytest.mark.parametrize("name", CASES)
+def test_converge_matches_reference(name):
+    """bik_converge against the reference's example loop (golden): steps taken, converged flag, final configuration."""
+    wl, fm, spec, g, model, prob = _engine(name)
+    CB = g["conv_q"].shape[0]
+    max_iters, pos, ori = int(g["conv_params"][0]), float(g["conv_params"][1]), float(g["conv_params"][2])
+    ct = g["com_target"][:CB] if "com_target" in g else None
+    q = torch.tensor(g["q"][:CB], dtype=torch.float32, device="cuda:0")
+    it, st = prob.converge(q, g["frame_targets"][:CB], g["posture_target"], ct, dt=float(g["dt"]), damping=float(g["damping"]),
+                           max_iters=max_iters, pos_threshold=pos, ori_threshold=ori)
+    sti = st.cpu().numpy().astype(np.int64)
+    np.testing.assert_array_equal(_np(it), g["conv_iters"])
+    np.testing.assert_array_equal((sti & 16) == 0, g["conv_ok"].astype(bool))
+    assert int((st & 15).max()) == 0
+    np.testing.assert_allclose(_np(q), g["conv_q"], atol={"spot": 4e-2, "edge": 2e-2, "g1_rel": 5e-3}.get(name, 1e-3))
+
+
+@pytest.mark.parametrize("check_every", [1, 3])
+def test_converge_batch_against_oracle(check_every):
+    """Per-instance early exit on a ragged UR5e batch: same steps and final q as the oracle's loop; instances that stop early
+    keep their configuration; the result does not depend on how often the host polls the device counter."""
+    wl, fm, spec, g, model, prob = _engine("ur5e")
+    orc = _oracle(fm, spec)
+    frames = task_frames(wl, fm)
+    B = 1500 + 13
+    inp = make_inputs(fm, wl, B, lambda qq: orc.fk(qq, frames), seed=5, sigma=0.05)
+    q = torch.tensor(inp["q"], dtype=torch.float32, device="cuda:0")
+    it, st = prob.converge(q, inp["frame_targets"], inp["posture_target"], None, dt=wl["dt"], damping=wl["damping"], max_iters=12,
+                           pos_threshold=2e-3, ori_threshold=2e-3, check_every=check_every)
+    q_ref, it_ref, ok_ref, st_ref = orc.converge(inp["q"], inp["frame_targets"], inp["posture_target"], None, dt=wl["dt"], damping=wl["damping"],
+                                                 max_iters=12, pos_threshold=2e-3, ori_threshold=2e-3)
+    it = _np(it).astype(np.int32)
+    same = it == it_ref
+    print(f"converge: iters histogram {np.bincount(it_ref).tolist()} converged {ok_ref.mean():.2f} mismatching iters {int((~same).sum())}/{B}")
+    assert same.mean() > 0.995     # an error within fp32 noise of a threshold may flip one decision
+    sti = st.cpu().numpy().astype(np.int64)
+    np.testing.assert_array_equal(((sti & 16) == 0)[same], ok_ref.astype(bool)[same])
+    np.testing.assert_allclose(_np(q)[same], q_ref[same], atol=1e-3)
+
+
 @pytest.mark.parametrize("group", [1, 2, 4, 8, 16, 32])
 def test_every_lane_group_size_against_oracle(group):
     """K1's lanes-per-instance mapping (BIK_K1_GROUP) must not change results; ragged batch (tail tile)."""

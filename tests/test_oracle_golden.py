@@ -89,3 +89,19 @@ def test_rollout(name):
     assert not st.any()
     tol = {"spot": 1e-5, "g1_rel": 1e-6}.get(name, 1e-8)
     np.testing.assert_allclose(q, traj[-1], atol=tol)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_converge_loop(name):
+    """The examples' solve+integrate-until-threshold loop (examples/arm_iiwa.py:63-70): iterations and final q per instance."""
+    wl, fm, spec, g, orc = _oracle(name)
+    CB = g["conv_q"].shape[0]
+    max_iters, pos, ori = int(g["conv_params"][0]), float(g["conv_params"][1]), float(g["conv_params"][2])
+    ct = g["com_target"][:CB] if "com_target" in g else None
+    q, it, ok, st = orc.converge(g["q"][:CB], g["frame_targets"][:CB], g["posture_target"], ct, dt=float(g["dt"]), damping=float(g["damping"]),
+                                 max_iters=max_iters, pos_threshold=pos, ori_threshold=ori)
+    assert not st.any()
+    np.testing.assert_array_equal(it, g["conv_iters"])
+    np.testing.assert_array_equal(ok, g["conv_ok"])
+    tol = {"spot": 1e-4, "g1_rel": 1e-5, "edge": 1e-6}.get(name, 1e-7)
+    np.testing.assert_allclose(q, g["conv_q"], atol=tol)
