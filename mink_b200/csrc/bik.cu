@@ -194,6 +194,44 @@ __global__ void integrate_masked_kernel(const uint32_t* __restrict__ gimage, int
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B && !done[b]) integrate_instance(P, q + (size_t)b * P.h().nq, dq + (size_t)b * P.h().nv);
 }
+// Coalesced variants: a CTA of 128 threads moves the q (and dq) rows of its 64 instances through a shared-memory tile with odd
+// row stride (flat, contiguous global traffic), then one thread per instance integrates / checks its row in the tile.
+enum { TILE_INST = 64, TILE_THREADS = 128 };
+__device__ __forceinline__ void tile_rows_in(float* tile, int S, const float* __restrict__ g, int n, int len) {
+  const int total = n * len;
+#pragma unroll 4
+  for (int k = threadIdx.x; k < total; k += TILE_THREADS) { int i = k / len; tile[i * S + (k - i * len)] = g[k]; }
+}
+__global__ void __launch_bounds__(TILE_THREADS) integrate_tiled_kernel(const uint32_t* __restrict__ gimage, int B, float* q, const float* __restrict__ dq, const int32_t* __restrict__ done) {
+  extern __shared__ __align__(16) float tile[];
+  PView P{gimage};
+  const int nq = P.h().nq, nv = P.h().nv, Sq = nq | 1, Sd = nv | 1;
+  const long long b0 = (long long)blockIdx.x * TILE_INST;
+  const int n = (B - b0) < TILE_INST ? (int)(B - b0) : TILE_INST;
+  float* tq = tile; float* td = tile + TILE_INST * Sq;
+  tile_rows_in(tq, Sq, q + b0 * nq, n, nq);
+  tile_rows_in(td, Sd, dq + b0 * nv, n, nv);
+  __syncthreads();
+  if ((int)threadIdx.x < n && !(done && done[b0 + threadIdx.x])) integrate_instance(P, tq + threadIdx.x * Sq, td + threadIdx.x * Sd);
+  __syncthreads();
+  float* gq = q + b0 * nq;
+  const int total = n * nq;
+#pragma unroll 4
+  for (int k = threadIdx.x; k < total; k += TILE_THREADS) { int i = k / nq; gq[k] = tq[i * Sq + (k - i * nq)]; }
+}
+__global__ void __launch_bounds__(TILE_THREADS) check_limits_tiled_kernel(const uint32_t* __restrict__ gimage, int B, const float* __restrict__ q, float tol, int32_t* status, int accumulate) {
+  extern __shared__ __align__(16) float tile[];
+  PView P{gimage};
+  const int nq = P.h().nq, Sq = nq | 1;
+  const long long b0 = (long long)blockIdx.x * TILE_INST;
+  const int n = (B - b0) < TILE_INST ? (int)(B - b0) : TILE_INST;
+  tile_rows_in(tile, Sq, q + b0 * nq, n, nq);
+  __syncthreads();
+  if ((int)threadIdx.x < n) {
+    int s = check_limits_instance(P, tile + threadIdx.x * Sq, tol);
+    status[b0 + threadIdx.x] = accumulate ? (status[b0 + threadIdx.x] | s) : s;
+  }
+}
 __global__ void converge_finish_kernel(int B, int max_iters, const int32_t* __restrict__ done, int32_t* iters, int32_t* status) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B && !done[b]) { iters[b] = max_iters; if (status) status[b] |= 16; }
@@ -271,6 +309,23 @@ struct bik_problem {
   int* conv_count = nullptr;
   int* conv_host = nullptr;
 };
+
+// integrate / check_limits launches: tiled (coalesced) when the tile fits the default 48 KB of dynamic shared memory
+static int launch_integrate(const uint32_t* d_image, const PHeader& h, int B, float* q, const float* dq, const int32_t* done, cudaStream_t st) {
+  const size_t smem = (size_t)TILE_INST * ((h.nq | 1) + (h.nv | 1)) * 4;
+  if (smem <= 48 * 1024) integrate_tiled_kernel<<<(B + TILE_INST - 1) / TILE_INST, TILE_THREADS, smem, st>>>(d_image, B, q, dq, done);
+  else if (done) integrate_masked_kernel<<<(B + 127) / 128, 128, 0, st>>>(d_image, B, q, dq, done);
+  else integrate_kernel<<<(B + 127) / 128, 128, 0, st>>>(d_image, B, q, dq);
+  CUDA_OK(cudaGetLastError());
+  return BIK_OK;
+}
+static int launch_check_limits(const uint32_t* d_image, const PHeader& h, int B, const float* q, float tol, int32_t* status, int accumulate, cudaStream_t st) {
+  const size_t smem = (size_t)TILE_INST * (h.nq | 1) * 4;
+  if (smem <= 48 * 1024) check_limits_tiled_kernel<<<(B + TILE_INST - 1) / TILE_INST, TILE_THREADS, smem, st>>>(d_image, B, q, tol, status, accumulate);
+  else check_limits_kernel<<<(B + 127) / 128, 128, 0, st>>>(d_image, B, q, tol, status, accumulate);
+  CUDA_OK(cudaGetLastError());
+  return BIK_OK;
+}
 
 static int valid_group(int G) { return G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32; }
 
@@ -666,17 +721,17 @@ extern "C" int bik_integrate(const bik_model* m, int B, float* q, const float* d
   if (!m || !q || !dq || B < 0) return fail(BIK_ERR_INVALID, "null argument");
   if (B == 0) return BIK_OK;
   DeviceGuard g(m->device);
-  integrate_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(m->d_image, B, q, dq);
-  CUDA_OK(cudaGetLastError());
-  return BIK_OK;
+  PHeader mh;
+  memcpy(&mh, m->image.data(), sizeof mh);
+  return launch_integrate(m->d_image, mh, B, q, dq, nullptr, static_cast<cudaStream_t>(stream));
 }
 extern "C" int bik_check_limits(const bik_model* m, int B, const float* q, float tol, int32_t* status, void* stream) {
   if (!m || !q || !status || B < 0) return fail(BIK_ERR_INVALID, "null argument");
   if (B == 0) return BIK_OK;
   DeviceGuard g(m->device);
-  check_limits_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(m->d_image, B, q, tol, status, 0);
-  CUDA_OK(cudaGetLastError());
-  return BIK_OK;
+  PHeader mh;
+  memcpy(&mh, m->image.data(), sizeof mh);
+  return launch_check_limits(m->d_image, mh, B, q, tol, status, 0, static_cast<cudaStream_t>(stream));
 }
 
 static int ensure_workspace(bik_problem* p, int B) {
@@ -708,8 +763,8 @@ static int step_core(bik_problem* p, int B, size_t ws_off, float* q, const bik_i
   if (warm) CUDA_OK(cudaMemsetAsync(warm_buf, 0, (size_t)B * Ud, st));
   for (int s = 0; s < nsteps; ++s) {
     if (status) {  // Configuration.check_limits(safety_break=False) of solve_ik.py:99
-      check_limits_kernel<<<(B + 127) / 128, 128, 0, st>>>(p->d_image, B, q, 1e-6f, status, s > 0);
-      CUDA_OK(cudaGetLastError());
+      int rcl = launch_check_limits(p->d_image, h, B, q, 1e-6f, status, s > 0, st);
+      if (rcl) return rcl;
     }
     K1Args a1{B, q, in->frame_targets, in->posture_targets, in->com_targets, in->posture_batched, dt, J, e, ep, Gc, hc};
     int rc = dispatch_k1(p, a1, st);
@@ -721,8 +776,8 @@ static int step_core(bik_problem* p, int B, size_t ws_off, float* q, const bik_i
     rc = dispatch_k2(p, a2, st);
     if (rc) return rc;
     if (integrate) {
-      integrate_kernel<<<(B + 127) / 128, 128, 0, st>>>(p->d_image, B, q, dq);
-      CUDA_OK(cudaGetLastError());
+      rc = launch_integrate(p->d_image, h, B, q, dq, nullptr, st);
+      if (rc) return rc;
     }
   }
   return BIK_OK;
@@ -794,8 +849,8 @@ extern "C" int bik_converge(const bik_problem* cp, int B, float* q, const bik_in
   bool all_done = false;
   for (int it = 0; it <= max_iters && !all_done; ++it) {
     if (status && it < max_iters) {
-      check_limits_kernel<<<blocks, 128, 0, st>>>(p->d_image, B, q, 1e-6f, status, it > 0);
-      CUDA_OK(cudaGetLastError());
+      rc = launch_check_limits(p->d_image, h, B, q, 1e-6f, status, it > 0, st);
+      if (rc) return rc;
     }
     K1Args a1{B, q, in->frame_targets, in->posture_targets, in->com_targets, in->posture_batched, dt, p->J, p->e, p->ep, p->Gc, p->hc};
     rc = dispatch_k1(p, a1, st);
@@ -817,8 +872,8 @@ extern "C" int bik_converge(const bik_problem* cp, int B, float* q, const bik_in
     a2.lockstep = p->k2_lockstep; a2.warm = warm ? p->warm : nullptr;
     rc = dispatch_k2(p, a2, st);
     if (rc) return rc;
-    integrate_masked_kernel<<<blocks, 128, 0, st>>>(p->d_image, B, q, p->conv_dq, p->conv_done);
-    CUDA_OK(cudaGetLastError());
+    rc = launch_integrate(p->d_image, h, B, q, p->conv_dq, p->conv_done, st);
+    if (rc) return rc;
   }
   // instances that never met the thresholds: iters = max_iters, status bit BIK_STATUS_NOT_CONVERGED
   converge_finish_kernel<<<blocks, 128, 0, st>>>(B, max_iters, p->conv_done, iters, status);
