@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(MAXT) k2t_kernel(const uint32_t* __restrict__ 
 
 // Fixed-size thread-per-problem K2 (bik_k2x.h): 32 problems per warp, factor in shared memory, H / c / box in a per-warp
 // global scratch (L2 resident), tables read straight from the global image; warps are independent.
-template <typename T, int N>
+template <typename TL, typename TH, int N>
 __global__ void __launch_bounds__(256) k2x_kernel(const uint32_t* __restrict__ gimage, int warp_smem, unsigned char* scratch, unsigned long long warp_scratch, K2Args a) {
   extern __shared__ __align__(16) uint32_t smem[];
   PView P{gimage};
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) k2x_kernel(const uint32_t* __restrict__ g
   unsigned char* wsc = scratch + ((size_t)blockIdx.x * nwarps + warp) * warp_scratch;
   const long long ntiles = ((long long)a.B + 31) / 32;
   for (long long tile = (long long)blockIdx.x * nwarps + warp; tile < ntiles; tile += (long long)gridDim.x * nwarps)
-    k2x_warp_tile<T, N, 32>(P, a, tile * 32, wsm, wsc, lane);
+    k2x_warp_tile<TL, TH, N, 32>(P, a, tile * 32, wsm, wsc, lane);
 }
 
 template <int SLOTS>
@@ -295,6 +295,7 @@ struct bik_problem {
   size_t ws_B = 0;
   float *J = nullptr, *e = nullptr, *ep = nullptr, *Gc = nullptr, *hc = nullptr;
   signed char* warm = nullptr;  // [B][nu] active-set guess carried between the steps of one bik_step call
+  int32_t* flags = nullptr;     // [B] instances the mixed-precision K2 hands to the fp64 kernel
   // bik_step_host staging
   size_t host_B = 0;
   float *hq = nullptr, *hft = nullptr, *hpt = nullptr, *hct = nullptr, *hdq = nullptr;
@@ -388,7 +389,7 @@ extern "C" int bik_problem_create(const bik_model* model, const bik_task_desc* t
 extern "C" void bik_problem_destroy(bik_problem* p) {
   if (!p) return;
   DeviceGuard g(p->device);
-  cudaFree(p->d_image); cudaFree(p->J); cudaFree(p->e); cudaFree(p->ep); cudaFree(p->Gc); cudaFree(p->hc); cudaFree(p->warm); cudaFree(p->k2x_scratch);
+  cudaFree(p->d_image); cudaFree(p->J); cudaFree(p->e); cudaFree(p->ep); cudaFree(p->Gc); cudaFree(p->hc); cudaFree(p->warm); cudaFree(p->flags); cudaFree(p->k2x_scratch);
   cudaFree(p->hq); cudaFree(p->hft); cudaFree(p->hpt); cudaFree(p->hct); cudaFree(p->hdq); cudaFree(p->hst);
   cudaFree(p->conv_done); cudaFree(p->conv_dq); cudaFree(p->conv_count);
   if (p->conv_host) cudaFreeHost(p->conv_host);
@@ -541,49 +542,52 @@ static int k2x_size(int nu) {
   for (int n : sizes) if (nu <= n) return n;
   return 0;
 }
-template <typename T, int N>
+template <typename TL, typename TH, int N>
 static int launch_k2x(const bik_problem* p, const K2Args& a, cudaStream_t st) {
   PView P{p->image.data()};
-  const size_t wb = (size_t)k2x_warp_smem_bytes(P, sizeof(T), N, 32);
+  const size_t wb = (size_t)k2x_warp_smem_bytes(P, sizeof(TL), sizeof(TH), N, 32);
   int NW = 8;
   while (NW > 1 && NW * wb > (size_t)p->model->max_smem) --NW;
   const size_t smem = NW * wb;
   int grid = 1;
   long long tiles = ((long long)a.B + 31) / 32;
-  int rc = launch_geometry(k2x_kernel<T, N>, p->model, smem, 32 * NW, (tiles + NW - 1) / NW, &grid);
+  int rc = launch_geometry(k2x_kernel<TL, TH, N>, p->model, smem, 32 * NW, (tiles + NW - 1) / NW, &grid);
   if (rc) return rc;
-  const size_t ws = k2x_warp_scratch_bytes(sizeof(T), N, 32), need = ws * NW * (size_t)grid;
+  const size_t ws = k2x_warp_scratch_bytes(sizeof(TH), N, 32), need = ws * NW * (size_t)grid;
   if (need > p->k2x_scratch_bytes) {
-    CUDA_OK(cudaStreamSynchronize(st));
+    CUDA_OK(cudaDeviceSynchronize());
     cudaFree(p->k2x_scratch); p->k2x_scratch = nullptr; p->k2x_scratch_bytes = 0;
     CUDA_OK(cudaMalloc(&p->k2x_scratch, need));
     p->k2x_scratch_bytes = need;
   }
-  k2x_kernel<T, N><<<grid, 32 * NW, smem, st>>>(p->d_image, (int)wb, p->k2x_scratch, (unsigned long long)ws, a);
+  k2x_kernel<TL, TH, N><<<grid, 32 * NW, smem, st>>>(p->d_image, (int)wb, p->k2x_scratch, (unsigned long long)ws, a);
   CUDA_OK(cudaGetLastError());
   return BIK_OK;
 }
-template <typename T>
+template <typename TL, typename TH>
 static int dispatch_k2x(const bik_problem* p, const K2Args& a, cudaStream_t st) {
   switch (k2x_size(p->h.nu)) {
-    case 6: return launch_k2x<T, 6>(p, a, st);
-    case 8: return launch_k2x<T, 8>(p, a, st);
-    case 12: return launch_k2x<T, 12>(p, a, st);
-    case 16: return launch_k2x<T, 16>(p, a, st);
-    case 18: return launch_k2x<T, 18>(p, a, st);
-    case 20: return launch_k2x<T, 20>(p, a, st);
-    default: return launch_k2x<T, 24>(p, a, st);
+    case 6: return launch_k2x<TL, TH, 6>(p, a, st);
+    case 8: return launch_k2x<TL, TH, 8>(p, a, st);
+    case 12: return launch_k2x<TL, TH, 12>(p, a, st);
+    case 16: return launch_k2x<TL, TH, 16>(p, a, st);
+    case 18: return launch_k2x<TL, TH, 18>(p, a, st);
+    case 20: return launch_k2x<TL, TH, 20>(p, a, st);
+    default: return launch_k2x<TL, TH, 24>(p, a, st);
   }
 }
-// Fixed-size path: box-only problems with at most 24 coupled dofs, fp32 solves only (BIK_SOLVE_PRECISION=f32): measured
-// on the G1 batch it is the fastest fp32 path (0.72 ms against 1.2 ms for the small-group path), while in fp64 its
-// register-resident rows spill and the small-group path wins (1.5 ms against 2.2 ms), so fp64 is not instantiated.
+// Fixed-size path: box-only problems with at most 24 coupled dofs.  Two instantiations: all fp32 (chosen for
+// BIK_SOLVE_PRECISION=f32: G1 0.72 ms against 1.2 ms for the small-group path in fp32) and mixed precision (fp32 factorisations
+// of the fp64 H, polished and re-judged in fp64, flagged instances handed to the fp64 small-group kernel; fp64-level results
+// but 1.94 ms on G1 against 1.29 ms for the small-group fp64 path -- its fp64 vectors spill -- so it only runs when forced
+// with BIK_K2_PATH=fixed).  An all-fp64 instantiation was slower still (2.2 ms) and is not built.
 static bool use_fixed(const bik_problem* p, const K2Args& a) {
   const PHeader& h = p->h;
-  if (p->solve_double || p->k2_path == 1 || p->k2_path == 2 || p->k2_path == 3 || !a.dq || a.Hout || a.lo_out) return false;
+  if (p->k2_path == 1 || p->k2_path == 2 || p->k2_path == 3 || !a.dq || a.Hout || a.lo_out) return false;
+  if (p->solve_double && p->k2_path != 4) return false;
   if (h.npairs != 0 || h.nu < 1 || k2x_size(h.nu) == 0) return false;
   PView P{p->image.data()};
-  return k2x_warp_smem_bytes(P, 4, k2x_size(h.nu), 32) <= p->model->max_smem;
+  return k2x_warp_smem_bytes(P, 4, p->solve_double ? 8 : 4, k2x_size(h.nu), 32) <= p->model->max_smem;
 }
 // Small-group path: box-only problems whose coupled block is small enough (at least one warp of them must fit in
 // an SM's shared memory).
@@ -595,7 +599,17 @@ static bool use_thread(const bik_problem* p, const K2Args& a) {
   return k2t_warp_bytes(P, p->solve_double ? 8 : 4, 32 / (p->k2_group == 8 ? 8 : 4)) <= p->model->max_smem;
 }
 static int dispatch_k2(const bik_problem* p, const K2Args& a, cudaStream_t st) {
-  if (use_fixed(p, a)) return dispatch_k2x<float>(p, a, st);
+  if (use_fixed(p, a)) {
+    if (!p->solve_double) return dispatch_k2x<float, float>(p, a, st);
+    // mixed precision, then the fp64 small-group kernel on the instances it flagged (normally none: the launch returns at once)
+    K2Args am = a;
+    am.flag_out = a.flag_out;   // caller passes the workspace slice (dispatch sites below)
+    int rc = dispatch_k2x<float, double>(p, am, st);
+    if (rc || !a.flag_out) return rc;
+    K2Args af = a;
+    af.flag_out = nullptr; af.only = a.flag_out;
+    return dispatch_k2t<double>(p, af, st);
+  }
   if (use_thread(p, a)) return p->solve_double ? dispatch_k2t<double>(p, a, st) : dispatch_k2t<float>(p, a, st);
   if (use_low_rank(p, a)) return (p->h.K + 1 <= 32) ? launch_k2lr<1>(p, a, st) : launch_k2lr<2>(p, a, st);
   return p->solve_double ? dispatch_k2_slots<double>(p, a, st) : dispatch_k2_slots<float>(p, a, st);
@@ -697,6 +711,7 @@ extern "C" int bik_limits_box(const bik_problem* p, int B, const float* q, float
   return dispatch_k2(p, a, static_cast<cudaStream_t>(stream));
 }
 
+static int ensure_workspace(bik_problem* p, int B);
 extern "C" int bik_solve_ex(const bik_problem* p, int B, const float* q, const float* J, const float* e, const float* e_posture, const float* G_coll,
                             const float* h_coll, float dt, double damping, float* dq, int32_t* status, int32_t* iters, void* stream);
 extern "C" int bik_solve(const bik_problem* p, int B, const float* q, const float* J, const float* e, const float* e_posture, const float* G_coll,
@@ -714,6 +729,14 @@ extern "C" int bik_solve_ex(const bik_problem* p, int B, const float* q, const f
   memset(&a, 0, sizeof a);
   a.B = B; a.q = q; a.J = J; a.e = e; a.ep = e_posture; a.Gc = G_coll; a.hc = h_coll; a.dt = dt; a.damping = damping; a.dq = dq; a.status = status; a.iters = iters; a.lockstep = p->k2_lockstep;
   if (status) CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, static_cast<cudaStream_t>(stream)));
+  if (use_fixed(p, a) && p->solve_double) {   // the mixed-precision path hands flagged instances over through the workspace
+    bik_problem* mp = const_cast<bik_problem*>(p);
+    std::lock_guard<std::mutex> lock(mp->mu);
+    int rc = ensure_workspace(mp, B);
+    if (rc) return rc;
+    a.flag_out = mp->flags;
+    return dispatch_k2(p, a, static_cast<cudaStream_t>(stream));
+  }
   return dispatch_k2(p, a, static_cast<cudaStream_t>(stream));
 }
 
@@ -737,8 +760,8 @@ extern "C" int bik_check_limits(const bik_model* m, int B, const float* q, float
 static int ensure_workspace(bik_problem* p, int B) {
   if ((size_t)B <= p->ws_B) return BIK_OK;
   const PHeader& h = p->h;
-  cudaFree(p->J); cudaFree(p->e); cudaFree(p->ep); cudaFree(p->Gc); cudaFree(p->hc); cudaFree(p->warm);
-  p->J = p->e = p->ep = p->Gc = p->hc = nullptr; p->warm = nullptr; p->ws_B = 0;
+  cudaFree(p->J); cudaFree(p->e); cudaFree(p->ep); cudaFree(p->Gc); cudaFree(p->hc); cudaFree(p->warm); cudaFree(p->flags);
+  p->J = p->e = p->ep = p->Gc = p->hc = nullptr; p->warm = nullptr; p->flags = nullptr; p->ws_B = 0;
   size_t b = (size_t)B;
   CUDA_OK(cudaMalloc(&p->J, sizeof(float) * b * (h.K > 0 ? h.K : 1) * h.nv));
   CUDA_OK(cudaMalloc(&p->e, sizeof(float) * b * (h.K > 0 ? h.K : 1)));
@@ -746,6 +769,7 @@ static int ensure_workspace(bik_problem* p, int B) {
   CUDA_OK(cudaMalloc(&p->Gc, sizeof(float) * b * (h.npairs > 0 ? h.npairs : 1) * h.nv));
   CUDA_OK(cudaMalloc(&p->hc, sizeof(float) * b * (h.npairs > 0 ? h.npairs : 1)));
   CUDA_OK(cudaMalloc(&p->warm, b * (size_t)(h.nu > 0 ? h.nu : 1)));
+  CUDA_OK(cudaMalloc(&p->flags, sizeof(int32_t) * b));
   p->ws_B = b;
   return BIK_OK;
 }
@@ -773,6 +797,7 @@ static int step_core(bik_problem* p, int B, size_t ws_off, float* q, const bik_i
     memset(&a2, 0, sizeof a2);
     a2.B = B; a2.q = q; a2.J = J; a2.e = e; a2.ep = ep; a2.Gc = Gc; a2.hc = hc; a2.dt = dt; a2.damping = damping; a2.dq = dq; a2.status = status; a2.lockstep = p->k2_lockstep;
     a2.warm = warm ? warm_buf : nullptr;
+    a2.flag_out = p->flags + ws_off;
     rc = dispatch_k2(p, a2, st);
     if (rc) return rc;
     if (integrate) {
@@ -869,7 +894,7 @@ extern "C" int bik_converge(const bik_problem* cp, int B, float* q, const bik_in
     K2Args a2;
     memset(&a2, 0, sizeof a2);
     a2.B = B; a2.q = q; a2.J = p->J; a2.e = p->e; a2.ep = p->ep; a2.Gc = p->Gc; a2.hc = p->hc; a2.dt = dt; a2.damping = damping; a2.dq = p->conv_dq; a2.status = status;
-    a2.lockstep = p->k2_lockstep; a2.warm = warm ? p->warm : nullptr;
+    a2.lockstep = p->k2_lockstep; a2.warm = warm ? p->warm : nullptr; a2.flag_out = p->flags;
     rc = dispatch_k2(p, a2, st);
     if (rc) return rc;
     rc = launch_integrate(p->d_image, h, B, q, p->conv_dq, p->conv_done, st);
@@ -930,7 +955,12 @@ extern "C" int bik_step_host(const bik_problem* cp, int B, float* q_host, const 
   if (rc) return rc;
   if (!p->hs[0]) { CUDA_OK(cudaStreamCreateWithFlags(&p->hs[0], cudaStreamNonBlocking)); CUDA_OK(cudaStreamCreateWithFlags(&p->hs[1], cudaStreamNonBlocking)); CUDA_OK(cudaEventCreateWithFlags(&p->hev, cudaEventDisableTiming)); }
   int NC = env_int("BIK_HOST_CHUNKS", 4);
-  if (NC < 1 || !p->solve_double) NC = 1;   // the fp32 fixed-size path shares one scratch per launch grid
+  {
+    K2Args ka;
+    memset(&ka, 0, sizeof ka);
+    ka.dq = reinterpret_cast<float*>(1); ka.damping = damping;
+    if (NC < 1 || use_fixed(p, ka)) NC = 1;   // the fixed-size path keeps one scratch per launch grid: one chunk in flight
+  }
   size_t chunk = (b + NC - 1) / NC;
   const long long wave = k2_wave_instances(p);
   if (wave > 0 && NC > 1) chunk = (size_t)(((long long)chunk + wave - 1) / wave * wave);

@@ -56,6 +56,8 @@ struct K2Args {
   int skip_box;        // bik_qp_objective: q is not read
   int lockstep;        // warps of a CTA advance through the pivoting iterations together (block barriers)
   signed char* warm;   // [B][nu] or null: active-set guess in (0 free, 1 lower, 2 upper), read at entry, updated at exit
+  int32_t* flag_out;   // [B] or null: mixed-precision path marks the instances it could not finish (bik_k2x.h)
+  const int32_t* only; // [B] or null: small-group path processes only the instances marked here (bik_k2t.h)
 };
 
 enum { K2_MAX_GEN = 16 };  // general (collision) rows that may be active at once

@@ -233,8 +233,9 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
   const int32_t* ucols = P.i(h.off_ucols);
   const int cnt = (a.B - b0) < NS ? (int)(a.B - b0) : NS;
   const int slot = lane / G, l = lane - slot * G;
-  const bool live = slot < cnt;
   const long long b = b0 + slot;
+  const bool live = slot < cnt && (!a.only || a.only[b] != 0);
+  if (a.only && !BIK_WARP_ANY(live)) return;   // fallback launch: nothing marked in this tile
   const int uw = k2t_union_words(P, sizeof(T));
   T* const Tb = reinterpret_cast<T*>(wsm);
   T* const Hp = Tb + slot;

@@ -62,7 +62,7 @@ class Emu:
         H = np.zeros((B, self.nv, self.nv)) if want_objective else None
         c = np.zeros((B, self.nv)) if want_objective else None
         lo = np.zeros((B, self.nv), np.float32); hi = np.zeros((B, self.nv), np.float32)
-        lib().emu_solve(self.h, B, _p(q), _p(_f32(J)), _p(_f32(pad(e, 1))), _p(_f32(pad(ep, 1))), _p(_f32(pad(Gc, 1))), _p(_f32(pad(hc, 1))),
+        self.last_rc = lib().emu_solve(self.h, B, _p(q), _p(_f32(J)), _p(_f32(pad(e, 1))), _p(_f32(pad(ep, 1))), _p(_f32(pad(Gc, 1))), _p(_f32(pad(hc, 1))),
                         C.c_float(dt), C.c_double(damping), int(use_double), _p(dq), _p(st, C.c_int32), _p(it, C.c_int32),
                         _p(H, C.c_double), _p(c, C.c_double), _p(lo), _p(hi))
         return dq, st, it, H, c, lo, hi

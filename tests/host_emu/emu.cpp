@@ -55,7 +55,7 @@ extern "C" int emu_solve(void* prob, int B, const float* q, const float* J, cons
                          float dt, double damping, int use_double, float* dq, int32_t* status, int32_t* iters, double* H, double* c, float* lo, float* hi) {
   EmuProblem* p = static_cast<EmuProblem*>(prob);
   PView P{p->image.data()};
-  K2Args a{B, q, J, e, ep, Gc, hc, dt, damping, dq, status, iters, H, c, lo, hi, 0, 0, 0, nullptr};
+  K2Args a{B, q, J, e, ep, Gc, hc, dt, damping, dq, status, iters, H, c, lo, hi, 0, 0, 0, nullptr, nullptr, nullptr};
   std::vector<double> wsm((k2_warp_bytes(P.h(), 8) + k2lr_warp_bytes(P.h())) / 8 + 16);
   if (use_double == 3 || use_double == 4) {   // small-group path (3: fp64, 4: fp32), one lane per problem on the host
     if (P.h().npairs != 0 || P.h().nu < 1 || P.h().nu > K2T_NMAX) { g_err = "thread path not applicable"; return -1; }
@@ -67,26 +67,32 @@ extern "C" int emu_solve(void* prob, int B, const float* q, const float* J, cons
     }
     return 0;
   }
-  if (use_double == 5 || use_double == 6) {   // fixed-size thread-per-problem path (5: fp64, 6: fp32)
-    const int nu = P.h().nu;
+  if (use_double == 5 || use_double == 6 || use_double == 7) {   // fixed-size thread-per-problem path (5: mixed fp32/fp64 without
+    const int nu = P.h().nu;                                      // hand-over, 6: fp32, 7: mixed with fp64 hand-over of flagged instances)
     if (P.h().npairs != 0 || nu < 1 || nu > 24) { g_err = "fixed-size path not applicable"; return -1; }
     const int N = nu <= 6 ? 6 : (nu <= 12 ? 12 : (nu <= 18 ? 18 : 24));
-    std::vector<double> tw(k2x_warp_smem_bytes(P, 8, N, 1) / 8 + 16), sc(k2x_warp_scratch_bytes(8, N, 1) / 8 + 16);
+    std::vector<double> tw(k2x_warp_smem_bytes(P, 8, 8, N, 1) / 8 + 16), sc(k2x_warp_scratch_bytes(8, N, 1) / 8 + 16);
+    std::vector<double> gw(k2t_warp_bytes(P, 8, 1) / 8 + 16);
+    int nflag = 0;
     for (int b = 0; b < B; ++b) {
       if (status) status[b] = 0;
-      if (use_double == 5) {
-        if (N == 6) k2x_warp_tile<double, 6, 1>(P, a, b, tw.data(), sc.data(), 0);
-        else if (N == 12) k2x_warp_tile<double, 12, 1>(P, a, b, tw.data(), sc.data(), 0);
-        else if (N == 18) k2x_warp_tile<double, 18, 1>(P, a, b, tw.data(), sc.data(), 0);
-        else k2x_warp_tile<double, 24, 1>(P, a, b, tw.data(), sc.data(), 0);
+      int32_t flag = 0;
+      K2Args ab = a;
+      ab.flag_out = use_double == 7 ? &flag - b : nullptr;   // indexed by instance
+      if (use_double != 6) {
+        if (N == 6) k2x_warp_tile<float, double, 6, 1>(P, ab, b, tw.data(), sc.data(), 0);
+        else if (N == 12) k2x_warp_tile<float, double, 12, 1>(P, ab, b, tw.data(), sc.data(), 0);
+        else if (N == 18) k2x_warp_tile<float, double, 18, 1>(P, ab, b, tw.data(), sc.data(), 0);
+        else k2x_warp_tile<float, double, 24, 1>(P, ab, b, tw.data(), sc.data(), 0);
+        if (flag) { ++nflag; ab.flag_out = nullptr; k2t_warp_tile<double, 1, 1>(P, ab, b, gw.data(), 0); }
       } else {
-        if (N == 6) k2x_warp_tile<float, 6, 1>(P, a, b, tw.data(), sc.data(), 0);
-        else if (N == 12) k2x_warp_tile<float, 12, 1>(P, a, b, tw.data(), sc.data(), 0);
-        else if (N == 18) k2x_warp_tile<float, 18, 1>(P, a, b, tw.data(), sc.data(), 0);
-        else k2x_warp_tile<float, 24, 1>(P, a, b, tw.data(), sc.data(), 0);
+        if (N == 6) k2x_warp_tile<float, float, 6, 1>(P, a, b, tw.data(), sc.data(), 0);
+        else if (N == 12) k2x_warp_tile<float, float, 12, 1>(P, a, b, tw.data(), sc.data(), 0);
+        else if (N == 18) k2x_warp_tile<float, float, 18, 1>(P, a, b, tw.data(), sc.data(), 0);
+        else k2x_warp_tile<float, float, 24, 1>(P, a, b, tw.data(), sc.data(), 0);
       }
     }
-    return 0;
+    return nflag;
   }
   for (int b = 0; b < B; ++b) {
     if (status) status[b] = 0;

@@ -205,7 +205,7 @@ def test_every_lane_group_size_against_oracle(group):
 @pytest.mark.parametrize("env", [{"BIK_USE_TMA": 0}, {"BIK_SOLVE_PRECISION": "f32", "BIK_K2_PATH": "dense"}, {"BIK_K2_PATH": "dense"},
                                  {"BIK_K2_PATH": "lowrank"}, {"BIK_K2_WARPS": 8}, {"BIK_K2_PATH": "group", "BIK_K2_GROUP": 4},
                                  {"BIK_K2_PATH": "group", "BIK_K2_GROUP": 8}, {"BIK_K2_PATH": "group", "BIK_SOLVE_PRECISION": "f32"},
-                                 {"BIK_K2_PATH": "fixed", "BIK_SOLVE_PRECISION": "f32"}])
+                                 {"BIK_K2_PATH": "fixed", "BIK_SOLVE_PRECISION": "f32"}, {"BIK_K2_PATH": "fixed"}])
 def test_alternate_paths(env):
     wl, fm, spec, g, model, prob = _engine("g1", env=env)
     q = torch.tensor(g["q"], dtype=torch.float32, device="cuda:0")
@@ -229,12 +229,13 @@ def test_k2_paths_on_relative_frame_golden(path):
 
 
 @pytest.mark.parametrize("name", ["g1", "shadow", "ur5e"])
-@pytest.mark.parametrize("path", ["dense", "group", "fixed"])
+@pytest.mark.parametrize("path", ["dense", "group", "fixed", "mixed"])
 def test_k2_paths_agree_on_a_ragged_batch(name, path):
-    """Every K2 path that applies to a box-only problem returns the same optimum (ragged batch: tail tiles of each path)."""
-    env = {"BIK_K2_PATH": path}
+    """Every K2 path that applies to a box-only problem returns the same optimum (ragged batch: tail tiles of each path).
+    "fixed" = fixed-size path in fp32, "mixed" = fixed-size path with fp32 factorisations polished in fp64."""
+    env = {"BIK_K2_PATH": "fixed" if path == "mixed" else path}
     if path == "fixed":
-        env["BIK_SOLVE_PRECISION"] = "f32"   # the fixed-size path is fp32 only
+        env["BIK_SOLVE_PRECISION"] = "f32"
     wl, fm, spec, g, model, prob = _engine(name, env=env)
     orc = _oracle(fm, spec)
     frames = task_frames(wl, fm)

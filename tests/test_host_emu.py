@@ -117,9 +117,10 @@ def test_low_rank_path_matches_reference(name):
 
 
 @pytest.mark.parametrize("name", ["g1", "ur5e", "ur5e_dls", "shadow", "g1_rel"])
-@pytest.mark.parametrize("code", [3, 4, 5, 6])
+@pytest.mark.parametrize("code", [3, 4, 5, 6, 7])
 def test_small_paths_match_reference(name, code):
-    """K2 small-group path (3/4) and fixed-size thread-per-problem path (5/6), fp64/fp32: same optimum as the warp path and the reference."""
+    """K2 small-group path (3 fp64, 4 fp32) and fixed-size thread-per-problem path (5 mixed precision, 6 fp32, 7 mixed with
+    hand-over of flagged instances to the fp64 kernel): same optimum as the warp path and the reference."""
     wl, fm, spec, g, emu = _emu(name)
     dt, damping = float(g["dt"]), float(g["damping"])
     J, e, ep, Gc, hc = emu.fk_jac(g["q"], g["frame_targets"], g["posture_target"], None, dt=dt)
@@ -128,11 +129,15 @@ def test_small_paths_match_reference(name, code):
     err = np.abs(dq - g["dq"]).max()
     print(name, "thread path max |dq - dq_ref| =", err, "iters mean/max", it.mean(), it.max())
     tol = 1e-4 * max(1.0, np.abs(g["dq"]).max())
-    assert err < (tol if code in (3, 5) else 20 * tol)
+    assert err < (tol if code in (3, 5, 7) else 20 * tol)
     dq_dense, _, it_dense, *_ = emu.solve(g["q"], J, e, ep, Gc, hc, dt, damping, use_double=1)
-    if code in (3, 5):
+    if code in (3, 5, 7):
         np.testing.assert_allclose(dq, dq_dense, atol=2e-6)
+    if code == 3:
         assert (it == it_dense).all()
+    if code == 7:
+        print("flagged for the fp64 kernel:", emu.last_rc, "of", len(dq))
+        assert emu.last_rc <= len(dq) // 8
 
 
 def test_check_limits():
