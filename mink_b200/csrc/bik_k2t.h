@@ -150,12 +150,13 @@ BIK_HD void k2t_task_accumulate(const T* tr, int nr, int nc, const int32_t* cols
 template <typename T, int NS>
 BIK_HD T k2t_row_dot(const T* __restrict__ Hp, const T* __restrict__ v, int i, int nu) {
   const T* row = Hp + tri(i) * NS;
+  const T* pv = v;
   T a0 = T(0), a1 = T(0);
-  int k = 0;
-  for (; k + 1 <= i; k += 2) { a0 += row[k * NS] * v[k * NS]; a1 += row[(k + 1) * NS] * v[(k + 1) * NS]; }
-  if (k <= i) a0 += row[k * NS] * v[k * NS];
+  int k = i + 1;
+  for (; k >= 2; k -= 2) { a0 += row[0] * pv[0]; a1 += row[NS] * pv[NS]; row += 2 * NS; pv += 2 * NS; }
+  if (k) { a0 += row[0] * pv[0]; pv += NS; }
   const T* col = Hp + (tri(i + 1) + i) * NS;   // entries (m, i), m > i, sit at tri(m) + i
-  for (int m = i + 1; m < nu; ++m) { a1 += col[0] * v[m * NS]; col += (m + 1) * NS; }
+  for (int m = i + 1; m < nu; ++m) { a1 += col[0] * pv[0]; col += (m + 1) * NS; pv += NS; }
   return a0 + a1;
 }
 // Masked factorisation of the coupled block, left-looking by blocks of G rows (lane l owns row i0 + l); rows
@@ -182,12 +183,13 @@ BIK_HD int k2t_factor(const T* __restrict__ Hp, T* __restrict__ Lp, int nu, uint
     auto step = [&](int k) {
       T s = T(0);
       if (!((msk >> k) & 1u)) {
-        const T* Lk = Lp + tri(k) * NS;
+        const T* pk = Lp + tri(k) * NS;   // row k (finished), walked together with my row
+        const T* pi = dst;
         T a0 = T(0), a1 = T(0);
-        int m = 0;
-        for (; m + 1 < k; m += 2) { a0 += dst[m * NS] * Lk[m * NS]; a1 += dst[(m + 1) * NS] * Lk[(m + 1) * NS]; }
-        if (m < k) a0 += dst[m * NS] * Lk[m * NS];
-        s = (src[k * NS] - (a0 + a1)) * Lk[k * NS];
+        int m = k;
+        for (; m >= 2; m -= 2) { a0 += pi[0] * pk[0]; a1 += pi[NS] * pk[NS]; pi += 2 * NS; pk += 2 * NS; }
+        if (m) { a0 += pi[0] * pk[0]; pk += NS; }
+        s = (src[k * NS] - (a0 + a1)) * pk[0];   // pk now points at 1 / L[k][k]
       }
       dst[k * NS] = s;
       ss += s * s;

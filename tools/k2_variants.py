@@ -57,8 +57,7 @@ def main():
     if build_only:
         return
     for name in VARIANTS:
-        for env in ({}, {"BIK_K2_PATH": "group"}, {"BIK_WL": "shadow"}, {"BIK_WL": "shadow", "BIK_K2_PATH": "group"}, {"BIK_WL": "ur5e_dls"},
-                    {"BIK_WL": "ur5e_dls", "BIK_K2_PATH": "group"}, {"BIK_WL": "g1_rel"}, {"BIK_WL": "g1_rel", "BIK_K2_PATH": "group"}):
+        for env in ({}, {"BIK_WL": "shadow"}, {"BIK_WL": "ur5e_dls"}, {"BIK_WL": "g1_rel"}):
             e = dict(os.environ, BIK_REPO=REPO, BIK_LIB=os.path.join(out, f"libbik_{name}.so"), **env)
             r = subprocess.run([sys.executable, "-c", CHILD], env=e, capture_output=True, text=True)
             line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:]
