@@ -346,6 +346,39 @@ def test_step_host_entry_point():
     assert up == 4 * (B * fm.nq + B * 3 * 7 + fm.nq) and down == 4 * (B * fm.nv + B * fm.nq + B)
 
 
+def test_step_host_chunking_does_not_change_results():
+    """bik_step_host cuts a large batch into chunks on two streams (copies overlap kernels): same dq, q and status as one chunk,
+    and as the device-buffer entry point; ragged batch so that the last chunk is partial."""
+    wl, fm, spec, g, model, prob = _engine("g1")
+    B = 40000 + 77
+    rng = np.random.default_rng(2)
+    idx = rng.integers(0, g["q"].shape[0], size=B)
+    q0 = g["q"][idx].astype(np.float32); ft = g["frame_targets"][idx].astype(np.float32)
+    outs = []
+    for chunks in (1, 4, 7):
+        os.environ["BIK_HOST_CHUNKS"] = str(chunks)
+        try:
+            dq, st, q, up, down = prob.step_host(q0.copy(), ft, g["posture_target"], None, dt=float(g["dt"]), damping=float(g["damping"]),
+                                                 nsteps=1, integrate=True)
+        finally:
+            os.environ.pop("BIK_HOST_CHUNKS", None)
+        assert not st.any()
+        outs.append((dq.copy(), q.copy()))
+        assert up == 4 * (B * fm.nq + B * 3 * 7 + fm.nq) and down == 4 * (B * fm.nv + B * fm.nq + B)
+    for dq, q in outs[1:]:
+        np.testing.assert_array_equal(dq, outs[0][0])
+        np.testing.assert_array_equal(q, outs[0][1])
+    assert np.abs(outs[0][0] - g["dq"][idx]).max() < 1e-4
+
+
+def test_describe_names_the_mapping():
+    wl, fm, spec, g, model, prob = _engine("g1")
+    d = prob.describe(float(g["damping"]))
+    assert "13/38 nodes visited" in d and "coupled=18" in d and "small-group G=8" in d and d.endswith("f64")
+    wl, fm, spec, g, model, prob = _engine("spot")
+    assert "dense warp-per-problem" in prob.describe(float(g["damping"]))
+
+
 def test_empty_batch_and_missing_target():
     wl, fm, spec, g, model, prob = _engine("g1")
     from mink_b200._lib import BikError
