@@ -119,8 +119,9 @@ __global__ void __launch_bounds__(MAXT) k2t_kernel(const uint32_t* __restrict__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   char* wsm = reinterpret_cast<char*>(smem) + (size_t)warp * warp_bytes;
   const long long ntiles = ((long long)a.B + NS - 1) / NS;
+  const int St = k2t_task_tile_words(P), uw = k2t_union_words(P, sizeof(T));
   for (long long tile = (long long)blockIdx.x * nwarps + warp; tile < ntiles; tile += (long long)gridDim.x * nwarps)
-    k2t_warp_tile<T, G, NS>(P, a, tile * NS, wsm, lane);
+    k2t_warp_tile<T, G, NS>(P, a, tile * NS, wsm, lane, St, uw);
 }
 
 // Fixed-size thread-per-problem K2 (bik_k2x.h): 32 problems per warp, factor in shared memory, H / c / box in a per-warp

@@ -226,7 +226,8 @@ BIK_HD void k2t_backsub(const T* __restrict__ Lp, int nu, int l, T* __restrict__
 
 // ---- one tile of NS instances per warp ----------------------------------------------------------------
 template <typename T, int G, int NS>
-BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* wsm, int lane) {
+BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* wsm, int lane, int St = 0, int uw = 0) {
+  if (St == 0) { St = k2t_task_tile_words(P); uw = k2t_union_words(P, sizeof(T)); }   // callers that loop over tiles pass them in
   constexpr int W = G * NS;
   const PHeader& h = P.h();
   const int nv = h.nv, nu = h.nu, K = h.K, nq = h.nq, NP = h.P;
@@ -238,14 +239,13 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
   const long long b = b0 + slot;
   const bool live = slot < cnt && (!a.only || a.only[b] != 0);
   if (a.only && !BIK_WARP_ANY(live)) return;   // fallback launch: nothing marked in this tile
-  const int uw = k2t_union_words(P, sizeof(T));
   T* const Tb = reinterpret_cast<T*>(wsm);
   T* const Hp = Tb + slot;
   T* const U = Tb + (size_t)tri(nu) * NS;   // warp-wide base of the union region
   T* const Lp = U + slot;
   T* const c = Tb + (size_t)(tri(nu) + uw) * NS + slot;
   T* const vs = c + (size_t)nu * NS;
-  float* const Fb = reinterpret_cast<float*>(Tb + (size_t)k2t_slot_T_words(P, sizeof(T)) * NS);
+  float* const Fb = reinterpret_cast<float*>(Tb + (size_t)(tri(nu) + uw + 2 * nu) * NS);
   float* const lo = Fb + slot;
   float* const hi = Fb + (size_t)nu * NS + slot;
 
@@ -253,7 +253,6 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
   for (int k = l; k < tri(nu); k += G) Hp[k * NS] = T(0);
   for (int k = l; k < nu; k += G) c[k * NS] = T(0);
   T mu = T(a.damping);
-  const int St = k2t_task_tile_words(P);
   for (int t = 0; t < h.F + h.C; ++t) {
     int row0, nr, nc, coff; const float* cost; float gain, lm;
     if (t < h.F) { const FrameRec& fr = P.frame(t); row0 = fr.row0; nr = 6; nc = fr.ncols; coff = fr.col_off; cost = fr.cost; gain = fr.gain; lm = fr.lm; }
