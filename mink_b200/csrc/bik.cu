@@ -835,7 +835,7 @@ extern "C" int bik_problem_describe(const bik_problem* p, double damping, char* 
   else if (use_low_rank(p, a)) k2 = "low-rank warp-per-problem";
   else k2 = "dense warp-per-problem";
   std::string d = "k1: " + std::to_string(h.G) + " lanes/instance, " + std::to_string(h.nneeded) + "/" + std::to_string(h.nnode) + " nodes visited; nv=" +
-                  std::to_string(h.nv) + " coupled=" + std::to_string(h.nu) + " rows=" + std::to_string(h.K) + " pairs=" + std::to_string(h.npairs) + "; k2: " + k2 +
+                  std::to_string(h.nv) + " coupled=" + std::to_string(h.nu) + " (unbounded, eliminated once: " + std::to_string(use_thread(p, a) && !use_fixed(p, a) ? h.nfree : 0) + ") rows=" + std::to_string(h.K) + " pairs=" + std::to_string(h.npairs) + "; k2: " + k2 +
                   (p->solve_double ? " f64" : " f32");
   if (buf && cap) { size_t n = d.size() < cap - 1 ? d.size() : cap - 1; memcpy(buf, d.c_str(), n); buf[n] = 0; }
   return (int)d.size();

@@ -320,6 +320,21 @@ inline bool build_image(const HostModel& m, const bik_task_desc* tasks, int ntas
     H.nu = (int)ucols.size();
     H.off_ucols = b.alloc(std::max(H.nu, 1));
     for (int k = 0; k < H.nu; ++k) b.i(H.off_ucols)[k] = ucols[k];
+    // Leading coupled dofs that no limit bounds (free-joint dofs, unlimited joints without a velocity limit): the QP is
+    // minimised over them in closed form once, the active-set iterations run on the rest (bik_k2t.h).  Only a prefix
+    // of the (ascending) coupled list qualifies, which is where MuJoCo's dof order puts a floating base.
+    H.nfree = 0;
+    if (H.npairs == 0) {
+      auto bounded = [&](int d) {
+        if (b.f(H.off_vmax)[d] < INF) return true;
+        for (int c = 0; c < ncfg; ++c) {
+          const float* p = b.f(H.off_cfg) + c * (2 + 2 * m.nv);
+          if (p[2 + d] > -INF || p[2 + m.nv + d] < INF) return true;
+        }
+        return false;
+      };
+      while (H.nfree < H.nu && !bounded(ucols[H.nfree])) ++H.nfree;
+    }
   }
   // Lane program over the nodes the outputs depend on: ancestors of task frames / roots, of collision geoms
   // and (CoM tasks) of every massive body.  mj_kinematics visits every body; nothing downstream of this
@@ -347,6 +362,24 @@ inline bool build_image(const HostModel& m, const bik_task_desc* tasks, int ntas
     H.off_prog = b.alloc((int)std::max<size_t>(prog.size(), 1));
     if (!prog.empty()) memcpy(b.i(H.off_prog), prog.data(), prog.size() * 4);
     H.nneeded = cnt;
+    // Rows of K1's per-instance pose state: only visited nodes get one (G1 headline config: 13 rows instead of 38, which
+    // is what bounds the resident warps of K1).  CoM tasks index first moments by node id and collision geoms are posed
+    // through node ids, so those problems keep the identity.
+    const bool compact = cnt < m.nnode && H.C == 0 && H.npairs == 0;
+    std::vector<int32_t> slot(m.nnode, -1);
+    int ns = 0;
+    for (int n = 0; n < m.nnode; ++n) slot[n] = compact ? (needed[n] ? ns++ : -1) : n;
+    H.nslots = compact ? ns : m.nnode;
+    for (int n = 0; n < m.nnode; ++n) {
+      NodeRec* r = reinterpret_cast<NodeRec*>(b.w.data() + H.off_nodes + NODE_WORDS * n);
+      r->slot = slot[n];
+      r->pslot = r->parent >= 0 ? slot[r->parent] : -1;
+    }
+    for (int f = 0; f < H.F; ++f) {
+      FrameRec* r = reinterpret_cast<FrameRec*>(b.w.data() + H.off_frames + FRAME_WORDS * f);
+      r->slot = r->node >= 0 ? slot[r->node] : -1;
+      r->rslot = (r->relative && r->rnode >= 0) ? slot[r->rnode] : -1;
+    }
   }
   H.words = (int)b.w.size();
   memcpy(b.w.data() + hoff, &H, sizeof H);

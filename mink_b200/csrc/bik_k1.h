@@ -72,7 +72,7 @@ struct K1Args {
 
 // ---- per-warp scratch layout (floats) ------------------------------------------------------
 BIK_HD int k1_state_stride(const PHeader& h) {  // pose (7) + CoM first moment (3) per node, odd stride
-  int s = 7 * h.nnode + (h.C > 0 ? 3 * h.nnode : 0);
+  int s = 7 * h.nslots + (h.C > 0 ? 3 * h.nnode : 0);
   return s | 1;
 }
 BIK_HD int k1_stage_rows(const PHeader& h) { return 6; }
@@ -98,8 +98,8 @@ BIK_HD void fk_node(const PView& P, int n, const float* q, float* xs) {
     quat = ld_q(q + r.qadr + 3);
   } else {
     if (r.parent >= 0) {
-      FQ pq = ld_q(xs + 7 * r.parent);
-      pos = ld_v(xs + 7 * r.parent + 4) + qrot(pq, ld_v(r.pos));
+      FQ pq = ld_q(xs + 7 * r.pslot);
+      pos = ld_v(xs + 7 * r.pslot + 4) + qrot(pq, ld_v(r.pos));
       quat = qmul(pq, ld_q(r.quat));
     } else {
       pos = ld_v(r.pos);
@@ -126,10 +126,11 @@ BIK_HD void fk_node(const PView& P, int n, const float* q, float* xs) {
     }
   }
   quat = qnormalize(quat);
-  float* o = xs + 7 * n;
+  float* o = xs + 7 * r.slot;
   o[0] = quat.w; o[1] = quat.x; o[2] = quat.y; o[3] = quat.z; o[4] = pos.x; o[5] = pos.y; o[6] = pos.z;
 }
 
+// `node` is the STATE ROW of the frame's node (FrameRec::slot; the node id itself where slots are the identity), -1 = world
 BIK_HD void frame_pose(int node, const float* lpos, const float* lquat, const float* xs, FQ* qf, F3* pf) {
   if (node < 0) { *qf = ld_q(lquat); *pf = ld_v(lpos); return; }
   FQ nq = ld_q(xs + 7 * node);
@@ -141,8 +142,8 @@ BIK_HD void frame_pose(int node, const float* lpos, const float* lquat, const fl
 // descendant of n: jp = linear part, jr = angular part (mj_jac restated per column).
 BIK_HD void jac_column(const PView& P, int d, int n, const float* xs, F3 p, F3* jp, F3* jr) {
   const NodeRec& r = P.node(n);
-  FQ nq = ld_q(xs + 7 * n);
-  F3 np = ld_v(xs + 7 * n + 4);
+  FQ nq = ld_q(xs + 7 * r.slot);
+  F3 np = ld_v(xs + 7 * r.slot + 4);
   int k = d - r.dadr;
   if (r.type == JNT_HINGE) {
     F3 ax = qrot(nq, ld_v(r.axis));
@@ -305,14 +306,14 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, float* wsm,
     for (int f = g; f < h.F; f += G) {
       const FrameRec& fr = P.frame(f);
       FQ qf; F3 pf, ev, ew; FM A1, A2;
-      frame_pose(fr.node, fr.lpos, fr.lquat, xs, &qf, &pf);
+      frame_pose(fr.slot, fr.lpos, fr.lquat, xs, &qf, &pf);
       float* sc = fsc + (li * h.F + f) * FS;
       if (!fr.relative) {
         frame_task(qf, pf, a.ftgt + ((long long)b * h.F + f) * 7, &ev, &ew, &A1, &A2);
         sc[0] = pf.x; sc[1] = pf.y; sc[2] = pf.z;
       } else {   // A1 = Ji, A2 = Mi of jlog(T_tf); plus both frames' poses for the column phase
         FQ qr; F3 pr;
-        frame_pose(fr.rnode, fr.rlpos, fr.rlquat, xs, &qr, &pr);
+        frame_pose(fr.rslot, fr.rlpos, fr.rlquat, xs, &qr, &pr);
         relative_frame_task(qf, pf, qr, pr, a.ftgt + ((long long)b * h.F + f) * 7, &ev, &ew, &A1, &A2);
         sc[0] = pf.x; sc[1] = pf.y; sc[2] = pf.z;
         sc[21] = qf.w; sc[22] = qf.x; sc[23] = qf.y; sc[24] = qf.z;
@@ -380,7 +381,7 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, float* wsm,
 
   // ---- centre-of-mass tasks (mj_comPos + mj_jacSubtreeCom for body 1) -------------------------
   if (h.C > 0) {
-    float* S = xs + 7 * h.nnode;  // first moments per node
+    float* S = xs + 7 * h.nslots;  // first moments per node (a CoM task keeps slots == node ids)
     if (valid && g == 0) {
       for (int n = 0; n < h.nnode; ++n) {
         const ComNodeRec& cn = P.comnode(n);

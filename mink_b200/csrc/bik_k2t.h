@@ -148,11 +148,11 @@ BIK_HD void k2t_task_accumulate(const T* tr, int nr, int nc, const int32_t* cols
 // instruction cache -- the fully unrolled variants of these routines were instruction-fetch bound) --------
 // Dot product of row i of the symmetric packed matrix with a vector (both slot-strided in shared memory).
 template <typename T, int NS>
-BIK_HD T k2t_row_dot(const T* __restrict__ Hp, const T* __restrict__ v, int i, int nu) {
-  const T* row = Hp + tri(i) * NS;
-  const T* pv = v;
+BIK_HD T k2t_row_dot(const T* __restrict__ Hp, const T* __restrict__ v, int i, int nu, int k0 = 0) {   // sum over m in [k0, nu), i >= k0
+  const T* row = Hp + (tri(i) + k0) * NS;
+  const T* pv = v + k0 * NS;
   T a0 = T(0), a1 = T(0);
-  int k = i + 1;
+  int k = i + 1 - k0;
   for (; k >= 2; k -= 2) { a0 += row[0] * pv[0]; a1 += row[NS] * pv[NS]; row += 2 * NS; pv += 2 * NS; }
   if (k) { a0 += row[0] * pv[0]; pv += NS; }
   const T* col = Hp + (tri(i + 1) + i) * NS;   // entries (m, i), m > i, sit at tri(m) + i
@@ -162,31 +162,37 @@ BIK_HD T k2t_row_dot(const T* __restrict__ Hp, const T* __restrict__ v, int i, i
 // Masked factorisation of the coupled block, left-looking by blocks of G rows (lane l owns row i0 + l); rows
 // 0..nu-1 are matrix rows, row nu is the right-hand side (already stored in Lp's row nu).  Active dofs (bit set in
 // `act`) become identity rows/columns.  On exit Lp row i holds L[i][0..i-1] and 1/L[i][i], row nu holds L^-1 rhs.
+// The column window [kb, ke) selects which part of the factor is produced:
+//   (0, nu)   the whole factor;
+//   (0, nf)   the columns of the nf leading dofs for EVERY row (rows >= nf keep only L[i][0..nf-1]): the one-off
+//             elimination of the dofs that have no finite bound (see k2t_warp_tile);
+//   (nf, nu)  the factor of the trailing block, whose source (in Hp / the right-hand-side row) must then be the Schur
+//             complement of the leading block; columns < nf of Lp are left alone.
 // Every lane of the warp must call it (it contains warp barriers).
 template <typename T, int G, int NS>
-BIK_HD int k2t_factor(const T* __restrict__ Hp, T* __restrict__ Lp, int nu, uint32_t act, int l) {
+BIK_HD int k2t_factor(const T* __restrict__ Hp, T* __restrict__ Lp, int nu, uint32_t act, int l, int kb, int ke) {
   int bad = 0;
   T* const rhsrow = Lp + tri(nu) * NS;
-  // Row blocks are aligned to the END of the (nu+1)-row system: the last rows are the expensive ones (cost ~ i^2),
+  // Row blocks are aligned to the END of the system (rows kb..nu): the last rows are the expensive ones (cost ~ i^2),
   // so the partial block, if any, is the first one and every lane has a row in the last block.
-  const int first = (nu + 1) % G;
-  for (int i0 = first ? first - G : 0; i0 <= nu; i0 += G) {
+  const int first = (nu + 1 - kb) % G;
+  for (int i0 = kb + (first ? first - G : 0); i0 <= nu; i0 += G) {
     const int i = i0 + l;
-    const bool has = i >= 0 && i <= nu, rhs = i == nu;
+    const bool has = i >= kb && i <= nu, rhs = i == nu;
     const bool ai = has && !rhs && ((act >> i) & 1u);
     const uint32_t msk = rhs ? 0u : (ai ? ~0u : act);
-    const int ir = has ? i : 0;
+    const int ir = has ? i : kb;
     const T* src = rhs ? rhsrow : Hp + tri(ir) * NS;
     T* dst = Lp + tri(ir) * NS;
     T ss = T(0);
-    // one entry of my row: L[i][k] = (A[i][k] - sum_m L[i][m] L[k][m]) / L[k][k]; a masked entry is exactly zero
+    // one entry of my row: L[i][k] = (A[i][k] - sum_{kb <= m < k} L[i][m] L[k][m]) / L[k][k]; a masked entry is exactly zero
     auto step = [&](int k) {
       T s = T(0);
       if (!((msk >> k) & 1u)) {
-        const T* pk = Lp + tri(k) * NS;   // row k (finished), walked together with my row
-        const T* pi = dst;
+        const T* pk = Lp + (tri(k) + kb) * NS;   // row k (finished), walked together with my row
+        const T* pi = dst + kb * NS;
         T a0 = T(0), a1 = T(0);
-        int m = k;
+        int m = k - kb;
         for (; m >= 2; m -= 2) { a0 += pi[0] * pk[0]; a1 += pi[NS] * pk[NS]; pi += 2 * NS; pk += 2 * NS; }
         if (m) { a0 += pi[0] * pk[0]; pk += NS; }
         s = (src[k * NS] - (a0 + a1)) * pk[0];   // pk now points at 1 / L[k][k]
@@ -194,10 +200,11 @@ BIK_HD int k2t_factor(const T* __restrict__ Hp, T* __restrict__ Lp, int nu, uint
       dst[k * NS] = s;
       ss += s * s;
     };
-    if (has) for (int k = 0; k < i0; ++k) step(k);   // rows above the block are complete
-    for (int j = 0; j < G; ++j) {                     // diagonal block: the owner of row k closes it, then the rows below use it
+    const int kfull = i0 < ke ? i0 : ke;
+    if (has) for (int k = kb; k < kfull; ++k) step(k);   // rows above the block are complete
+    for (int j = 0; j < G; ++j) {                         // diagonal block: the owner of row k closes it, then the rows below use it
       const int k = i0 + j;
-      if (k < 0) continue;
+      if (k < kb || k >= ke) continue;
       if (has && !rhs && l == j) {
         T d = (ai ? T(1) : src[k * NS]) - ss;
         if (!(d > T(0))) { bad = 1; d = T(1e-30); }
@@ -211,16 +218,35 @@ BIK_HD int k2t_factor(const T* __restrict__ Hp, T* __restrict__ Lp, int nu, uint
 }
 // x = L^-T y (y = row nu of Lp), dot-product form: x_k needs sum_{m>k} L[m][k] x_m; every lane sums the m it owns
 // (m = l mod G, kept in its own entries of xs), a butterfly adds the partial sums.  No barrier inside.
+// Produces x_k for k = khi-1 .. klo (x_m, m >= khi, must already be in xs).
 template <typename T, int G, int NS>
-BIK_HD void k2t_backsub(const T* __restrict__ Lp, int nu, int l, T* __restrict__ xs) {
+BIK_HD void k2t_backsub(const T* __restrict__ Lp, int nu, int l, T* __restrict__ xs, int khi, int klo) {
   const T* y = Lp + tri(nu) * NS;
-  for (int k = nu - 1; k >= 0; --k) {
+  for (int k = khi - 1; k >= klo; --k) {
     int m = (k + 1) + ((l - (k + 1)) & (G - 1));
     T p = T(0);
     for (; m < nu; m += G) p += Lp[(tri(m) + k) * NS] * xs[m * NS];
     p = grp_sum<T, G>(p);
     const T xk = (y[k * NS] - p) * Lp[(tri(k) + k) * NS];
     if ((k & (G - 1)) == l) xs[k * NS] = xk;
+  }
+}
+// Schur complement of the nf leading dofs, in place: after k2t_factor(.., 0, nf) every row i >= nf of Lp holds
+// L[i][0..nf-1] and the right-hand-side row holds y = L_bb^-1 (-c_b).  Then, for i, j >= nf,
+//   S[i][j] = H[i][j] - sum_{m<nf} L[i][m] L[j][m],   c~[i] = c[i] + sum_{m<nf} L[i][m] y[m]
+// is the QP that remains after minimising over the leading dofs exactly (they have no bounds).
+template <typename T, int G, int NS>
+BIK_HD void k2t_schur(T* __restrict__ Hp, const T* __restrict__ Lp, T* __restrict__ c, int nu, int nf, int l) {
+  const T* y = Lp + tri(nu) * NS;
+  for (int i = nf; i < nu; ++i) {
+    const T* pi = Lp + tri(i) * NS;
+    for (int j = nf + l; j <= i + 1; j += G) {       // j == i + 1 stands for the linear term
+      const T* pj = j <= i ? Lp + tri(j) * NS : y;
+      T a0 = T(0);
+      for (int m = 0; m < nf; ++m) a0 += pi[m * NS] * pj[m * NS];
+      if (j <= i) Hp[(tri(i) + j) * NS] -= a0;
+      else c[i * NS] += a0;
+    }
   }
 }
 
@@ -303,44 +329,64 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
   }
   BIK_SYNCWARP();   // the tile is dead; the union region becomes each slot's factor
 
+  // ---- dofs without any finite bound are minimised over once (the free joint has no limits) ----
+  // The image lists them first (nf = h.nfree leading coupled dofs).  Their columns of the factor do not depend on the
+  // active set, so they are produced once; the pivoting iterations then run on the Schur complement (nu - nf dofs:
+  // 12 instead of 18 for the G1 configuration), and the leading part of x is recovered by continuing the last back
+  // substitution.  With nf == 0 this block does nothing; with nf == nu (no bounded dof at all) it is the whole solve.
+#ifdef BIK_K2T_NO_ELIM   // A/B switch (tools/k2_variants.py): pivot on the whole coupled block as before
+  const int nf = 0;
+#else
+  const int nf = h.nfree;
+#endif
+  T* const rhsrow = Lp + tri(nu) * NS;
+  if (nf > 0) {
+    for (int k = l; k < nf; k += G) rhsrow[k * NS] = -c[k * NS];
+    BIK_SYNCWARP();
+    if (k2t_factor<T, G, NS>(Hp, Lp, nu, 0u, l, 0, nf)) st |= 4;
+    BIK_SYNCWARP();
+    k2t_schur<T, G, NS>(Hp, Lp, c, nu, nf, l);
+    BIK_SYNCWARP();
+  }
+
   // ---- block principal pivoting ----
   const int MAXIT = 60, PATIENCE = 3;
   const T tolx = K2Tol<T>::x(), tolg = K2Tol<T>::g();
   uint32_t lom = 0u, upm = 0u;
   if (a.warm && live) {
     const signed char* wm = a.warm + b * nu;
-    for (int i = 0; i < nu; ++i) {
+    for (int i = nf; i < nu; ++i) {
       int s0 = wm[i];
       if (s0 == 1 && lo[i * NS] > -1e30f) lom |= 1u << i;
       else if (s0 == 2 && hi[i * NS] < 1e30f) upm |= 1u << i;
     }
   }
-  int best = nu + 1, patience = PATIENCE, it = 0;
-  bool done = false;
-  T* const rhsrow = Lp + tri(nu) * NS;
+  int best = nu + 1, patience = PATIENCE;
+  bool done = nf == nu;     // no bounded dof at all: the elimination above was the whole solve (one factorisation)
+  int it = done ? 1 : 0;
   for (;;) {
     if (!BIK_WARP_ANY(!done && it < MAXIT)) break;
     const bool run = !done && it < MAXIT;   // a finished group keeps executing (idempotently) until its warp is done
     const uint32_t act = lom | upm;
     // x on the bounds
-    for (int k = l; k < nu; k += G) vs[k * NS] = ((lom >> k) & 1u) ? T(lo[k * NS]) : (((upm >> k) & 1u) ? T(hi[k * NS]) : T(0));
+    for (int k = nf + l; k < nu; k += G) vs[k * NS] = ((lom >> k) & 1u) ? T(lo[k * NS]) : (((upm >> k) & 1u) ? T(hi[k * NS]) : T(0));
     BIK_SYNCWARP();
     // right-hand side of the masked system: bound value on clamped dofs, -(c + H_FA x_A) on free ones
-    for (int k = l; k < nu; k += G) {
+    for (int k = nf + l; k < nu; k += G) {
       T rv;
       if ((act >> k) & 1u) rv = vs[k * NS];
-      else { rv = -c[k * NS]; if (act) rv -= k2t_row_dot<T, NS>(Hp, vs, k, nu); }
+      else { rv = -c[k * NS]; if (act) rv -= k2t_row_dot<T, NS>(Hp, vs, k, nu, nf); }
       rhsrow[k * NS] = rv;
     }
     BIK_SYNCWARP();
-    if (k2t_factor<T, G, NS>(Hp, Lp, nu, act, l)) st |= 4;
+    if (k2t_factor<T, G, NS>(Hp, Lp, nu, act, l, nf, nu)) st |= 4;
     BIK_SYNCWARP();
-    k2t_backsub<T, G, NS>(Lp, nu, l, vs);
+    k2t_backsub<T, G, NS>(Lp, nu, l, vs, nu, nf);
     BIK_SYNCWARP();
     // gradient on the clamped dofs, feasibility of the free ones
     int ninf = 0, last = -1;
     uint32_t nlo = 0u, nup = 0u;
-    for (int k = l; k < nu; k += G) {
+    for (int k = nf + l; k < nu; k += G) {
       const int cur = ((lom >> k) & 1u) ? 1 : (((upm >> k) & 1u) ? 2 : 0);
       int ns = cur;
       if (cur == 0) {
@@ -348,7 +394,7 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
         if (xi < bl - tolx * (T(1) + (bl < 0 ? -bl : bl))) ns = 1;
         else if (xi > bu + tolx * (T(1) + (bu < 0 ? -bu : bu))) ns = 2;
       } else {
-        const T gi = c[k * NS] + k2t_row_dot<T, NS>(Hp, vs, k, nu);
+        const T gi = c[k * NS] + k2t_row_dot<T, NS>(Hp, vs, k, nu, nf);
         if (cur == 1 && gi < -tolg) ns = 0;
         else if (cur == 2 && gi > tolg) ns = 0;
       }
@@ -370,6 +416,10 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
         else { const uint32_t bit = 1u << last; lom = (lom & ~bit) | (nlo & bit); upm = (upm & ~bit) | (nup & bit); }
       }
     }
+  }
+  if (nf > 0) {   // x_b = L_bb^-T (y_b - L_t^T x_t): the back substitution simply continues into the leading rows
+    k2t_backsub<T, G, NS>(Lp, nu, l, vs, nf, 0);
+    BIK_SYNCWARP();
   }
   if (!done) st |= 2;
   // ---- outputs: coupled dofs from vs (the last solve), status, warm-start state ----

@@ -21,7 +21,8 @@ struct NodeRec {  // 20 words, 16-byte aligned
   float quat[4];
   float axis[3];
   float jpos[3];
-  float pad[3];
+  int32_t slot, pslot;   // rows of the per-instance pose state (7 floats each) of this node and of its parent: the state only
+  float pad;             // holds the nodes the lane program visits (identity when there is a CoM task or a collision limit)
 };
 struct FrameRec {  // 32 words.  Column entries: dof | node << 16 | (belongs to the ROOT chain) << 31
   int32_t node;
@@ -34,7 +35,8 @@ struct FrameRec {  // 32 words.  Column entries: dof | node << 16 | (belongs to 
   int32_t rnode;
   float rlpos[3];
   float rlquat[4];
-  float pad[3];
+  int32_t slot, rslot;   // state rows of `node` / `rnode` (-1: world); filled by the image builder, equal to the node ids in
+  float pad;             // frames passed by value to bik_fk (model image: every node is visited)
 };
 struct ComNodeRec {  // 8 words: own mass of the node's weld group, its first moment in the node frame, subtree mass
   float own_m, own_c[3], sub_m, pad[3];
@@ -70,7 +72,9 @@ struct PHeader {  // all offsets in 32-bit words from the start of the image
   int32_t off_ucols;    // int[nu]: dof of each compact index
   int32_t nrel;         // number of RelativeFrameTasks among the F frame-like tasks
   int32_t nneeded;      // nodes visited by the lane program (ancestors of frames / masses / collision geoms)
-  int32_t reserved[3];
+  int32_t nfree;        // leading coupled dofs (compact indices 0..nfree-1) without any finite bound: eliminated once by K2
+  int32_t nslots;       // rows of the pose state = nodes visited by the lane program (nnode when slots are the identity)
+  int32_t reserved[1];
 };
 static_assert(sizeof(PHeader) % 16 == 0, "header must stay 16-byte aligned");
 

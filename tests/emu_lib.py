@@ -45,6 +45,12 @@ class Emu:
             raise RuntimeError(lib().emu_last_error().decode())
         self.h = C.c_void_p(self.h)
 
+    def header(self):
+        """nv, nu (coupled dofs), nfree (leading coupled dofs without bounds), nnode, nneeded, nslots, G, nsteps of the image."""
+        out = np.zeros(8, np.int32)
+        lib().emu_header(self.h, _p(out, C.c_int32))
+        return dict(zip(("nv", "nu", "nfree", "nnode", "nneeded", "nslots", "G", "nsteps"), (int(v) for v in out)))
+
     def fk_jac(self, q, ftgt=None, ptgt=None, ctgt=None, dt=1e-2):
         q = _f32(q); B = q.shape[0]; s = self.spec
         ftgt, ptgt, ctgt = _f32(ftgt), _f32(ptgt), _f32(ctgt)

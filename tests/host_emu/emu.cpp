@@ -29,6 +29,11 @@ extern "C" void* emu_problem_create(const void* blob, size_t nbytes, const bik_t
   if (!build_image(m, nullptr, 0, nullptr, 0, 1, &p->model_image, &g_err)) { delete p; return nullptr; }
   return p;
 }
+// header fields of the problem image the CPU tests pin: nv, nu, nfree, nnode, nneeded, nslots, G, nsteps
+extern "C" void emu_header(void* prob, int32_t* out) {
+  const PHeader& h = PView{static_cast<EmuProblem*>(prob)->image.data()}.h();
+  out[0] = h.nv; out[1] = h.nu; out[2] = h.nfree; out[3] = h.nnode; out[4] = h.nneeded; out[5] = h.nslots; out[6] = h.G; out[7] = h.nsteps;
+}
 extern "C" void emu_problem_destroy(void* p) { delete static_cast<EmuProblem*>(p); }
 
 extern "C" int emu_lane_program(const void* blob, size_t nbytes, int G, int32_t* out, int cap) {

@@ -147,3 +147,34 @@ def test_check_limits():
     q[3, 10] = 100.0
     st = emu.check_limits(q)
     assert st[3] == 1 and st.sum() == 1
+
+
+def test_image_marks_unbounded_leading_dofs_and_compact_state():
+    """K2 eliminates the leading coupled dofs that no limit bounds once (the free joint of G1: mink/limits/
+    configuration_limit.py:40-56 and velocity_limit.py:47-60 skip free joints); K1's pose state has one row per
+    VISITED node unless a CoM task / collision limit indexes by node id."""
+    h = _emu("g1")[4].header()
+    assert (h["nu"], h["nfree"]) == (18, 6)            # floating base + two legs coupled; the base has no bounds
+    assert h["nslots"] == h["nneeded"] == 13 and h["nnode"] == 38
+    h = _emu("ur5e_dls")[4].header()
+    assert h["nfree"] == h["nu"] == 6                  # limits=[]: the elimination is the whole solve
+    h = _emu("ur5e")[4].header()
+    assert h["nfree"] == 0 and h["nu"] == 6
+    h = _emu("shadow")[4].header()
+    assert h["nfree"] == 0
+    h = _emu("spot")[4].header()
+    assert h["nfree"] == 0 and h["nslots"] == h["nnode"]   # collision rows + CoM task: general path, identity slots
+
+
+def test_unbounded_elimination_matches_full_pivoting_with_active_bounds():
+    """The G1 golden has active velocity bounds: the reduced (Schur complement) pivoting must land on the reference's
+    optimum with the same number of pivoting iterations as the dense path on the whole coupled block."""
+    wl, fm, spec, g, emu = _emu("g1")
+    dt, damping = float(g["dt"]), float(g["damping"])
+    J, e, ep, Gc, hc = emu.fk_jac(g["q"], g["frame_targets"], g["posture_target"], None, dt=dt)
+    dq, st, it, *_ = emu.solve(g["q"], J, e, ep, Gc, hc, dt, damping, use_double=3)
+    dq_dense, _, it_dense, *_ = emu.solve(g["q"], J, e, ep, Gc, hc, dt, damping, use_double=1)
+    assert not st.any() and it.max() > 1
+    assert (it == it_dense).all()
+    np.testing.assert_allclose(dq, dq_dense, atol=1e-7)
+    np.testing.assert_allclose(dq, g["dq"], atol=1e-5)

@@ -8,6 +8,7 @@ import sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
     "base": [],
+    "noelim": ["-DBIK_K2T_NO_ELIM"],
 }
 
 CHILD = r'''
@@ -57,7 +58,7 @@ def main():
     if build_only:
         return
     for name in VARIANTS:
-        for env in ({}, {"BIK_WL": "shadow"}, {"BIK_WL": "ur5e_dls"}, {"BIK_WL": "g1_rel"}):
+        for env in ({}, {"BIK_K1_GROUP": "4"}, {"BIK_K1_GROUP": "2"}, {"BIK_WL": "shadow"}, {"BIK_WL": "ur5e_dls"}, {"BIK_WL": "g1_rel"}):
             e = dict(os.environ, BIK_REPO=REPO, BIK_LIB=os.path.join(out, f"libbik_{name}.so"), **env)
             r = subprocess.run([sys.executable, "-c", CHILD], env=e, capture_output=True, text=True)
             line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:]
