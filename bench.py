@@ -141,13 +141,12 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def measure_e2e(prob, inp, fm, B, dt_, damping, args, world, dev, barrier):
+def measure_e2e(prob, inp, fm, B, dt_, damping, args, world, allmax, barrier):
     """Same metric through the host-buffer C-ABI entry (bik_step_host): H2D + kernels + D2H inside the timing.
     Inputs live in PINNED host memory; every step copies q + targets up and dq + integrated q + status down.
     Every rank runs its own shard at the same time (they share the host's PCIe/memory system); the job time is
     the max over ranks of the summed host wall clock of the calls (bik_step_host synchronises before returning)."""
     import torch
-    import torch.distributed as dist
 
     def pinned(a, dtype=torch.float32):
         t = torch.empty(a.shape, dtype=dtype, pin_memory=True)
@@ -173,10 +172,7 @@ def measure_e2e(prob, inp, fm, B, dt_, damping, args, world, dev, barrier):
                                            out_status=hst)
         te += time.perf_counter() - t0
     assert not hst.any()
-    tt = torch.tensor([te], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    te = float(tt.item())
+    te = allmax(te)
     return {"value": world * B * n_e2e / te, "unit": UNIT, "h2d_bytes_per_step": up * world, "d2h_bytes_per_step": down * world,
             "note": "bik_step_host (C ABI, pinned host buffers), every rank on its shard at the same time; host wall clock "
                     "per call, max over ranks; bytes are whole-job"}
@@ -207,17 +203,32 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    # BIK_BENCH_BACKEND=gloo is a plumbing check for boxes with fewer GPUs than ranks (ranks share devices, timing
+    # reductions travel over gloo); the driver's runs use NCCL, one GPU per rank.
+    backend = os.environ.get("BIK_BENCH_BACKEND", "nccl")
+    dev_index = local_rank if backend == "nccl" else local_rank % torch.cuda.device_count()
+    torch.cuda.set_device(dev_index)
+    dev = torch.device("cuda", dev_index)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        if backend == "nccl":
+            dist.init_process_group("nccl", device_id=dev)
+        else:
+            dist.init_process_group(backend)
+
+    def allmax(x: float) -> float:
+        """max over ranks of a host scalar (device tensor over NCCL, host tensor over gloo)"""
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev if backend == "nccl" else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     from mink_b200.engine import DeviceModel, Problem
 
     wl = WORKLOADS[args.workload]
     fm = load_flat(wl["robot"])
     spec = spec_from_workload(fm, wl)
-    model = DeviceModel(fm, device=local_rank)
+    model = DeviceModel(fm, device=dev_index)
     prob = Problem(model, spec)
     frames = task_frames(wl, fm)
     B = args.batch_per_gpu
@@ -248,7 +259,7 @@ def main():
         q.copy_(q0)
         one_step()
     barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(dev_index)
     if rank == 0:
         sampler.start()
     # ---- timed region: exactly K steps, each from the same q0 with L2 flushed in between ----
@@ -263,10 +274,7 @@ def main():
     barrier()
     wall = time.perf_counter() - wall0
     ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = torch.tensor([sum(ms)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_s = float(total_ms.item()) * 1e-3
+    total_s = allmax(sum(ms)) * 1e-3
     clocks = sampler.stop() if rank == 0 else None
     assert int(status.max()) == 0, "status flags set during the bench"
     value = world * B * args.steps / total_s
@@ -277,7 +285,8 @@ def main():
     for s in range(max(5, min(args.steps, 10))):
         flush.fill_(1.0)
         a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        a.record()
+        torch.cuda._sleep(2_000_000)   # ~1 ms of device spin: the host enqueues both launches behind it, so the events
+        a.record()                     # bracket kernel time only (no host launch latency between them)
         J, e, ep, Gc, hc = prob.fk_jac(q0, ft, pt, ct, dt=dt_)
         b.record()
         prob.solve(q0, J, e, ep, Gc, hc, dt_, damping)
@@ -298,14 +307,12 @@ def main():
     prob.step(q, ft, pt, ct, dt=dt_, damping=damping, nsteps=T, integrate=True, dq=dq, status=status)
     r1.record()
     barrier()
-    roll_ms = torch.tensor([r0.elapsed_time(r1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(roll_ms, op=dist.ReduceOp.MAX)
-    rollout = {"timesteps": T, "value": world * B * T / (float(roll_ms.item()) * 1e-3), "unit": UNIT,
-               "ms_per_timestep": float(roll_ms.item()) / T,
+    roll_ms = allmax(r0.elapsed_time(r1))
+    rollout = {"timesteps": T, "value": world * B * T / (roll_ms * 1e-3), "unit": UNIT,
+               "ms_per_timestep": roll_ms / T,
                "note": "one bik_step call with nsteps=100 from q0, targets held: instances converge, bounds deactivate"}
 
-    e2e = measure_e2e(prob, inp, fm, B, dt_, damping, args, world, dev, barrier)
+    e2e = measure_e2e(prob, inp, fm, B, dt_, damping, args, world, allmax, barrier)
 
     if rank != 0:
         if world > 1:

@@ -78,8 +78,11 @@ __device__ __forceinline__ void stage_image(uint32_t* smem_image, const uint32_t
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
+#ifndef BIK_K1_MINBLOCKS
+#define BIK_K1_MINBLOCKS 4   // CTAs of 4 warps per SM the register allocation must allow (4 -> 128 registers per thread)
+#endif
 template <int G>
-__global__ void __launch_bounds__(128) k1_kernel(const uint32_t* __restrict__ gimage, int words, int use_tma, K1Args a) {
+__global__ void __launch_bounds__(128, BIK_K1_MINBLOCKS) k1_kernel(const uint32_t* __restrict__ gimage, int words, int use_tma, K1Args a) {
   extern __shared__ __align__(16) uint32_t smem[];
   __shared__ __align__(8) uint64_t bar;
   stage_image(smem, gimage, words, &bar, use_tma);
@@ -111,8 +114,12 @@ __global__ void __launch_bounds__(256) k2_kernel(const uint32_t* __restrict__ gi
 
 // Small-group K2 (bik_k2t.h): G lanes per problem, 32/G problems per warp, tables read straight from the (L1-resident)
 // global image so that all of shared memory goes to the per-problem triangles; warps are independent.
+// Tiles are handed out by an atomic counter (sched[0]) when the launcher has one for this stream: the pivoting count
+// differs between instances (G1: 91 % need one iteration, 1 in 10 000 needs six or more), and with a static round-robin
+// the warp that meets a slow instance also keeps its whole share of ordinary tiles, which set the kernel time.  The last
+// CTA to leave (sched[1] counts them) rewinds the counter for the next launch on the stream.
 template <typename T, int G, int MAXT>
-__global__ void __launch_bounds__(MAXT) k2t_kernel(const uint32_t* __restrict__ gimage, int warp_bytes, K2Args a) {
+__global__ void __launch_bounds__(MAXT, 512 / MAXT) k2t_kernel(const uint32_t* __restrict__ gimage, int warp_bytes, K2Args a, unsigned int* sched) {
   extern __shared__ __align__(16) uint32_t smem[];
   constexpr int NS = 32 / G;
   PView P{gimage};
@@ -120,6 +127,18 @@ __global__ void __launch_bounds__(MAXT) k2t_kernel(const uint32_t* __restrict__ 
   char* wsm = reinterpret_cast<char*>(smem) + (size_t)warp * warp_bytes;
   const long long ntiles = ((long long)a.B + NS - 1) / NS;
   const int St = k2t_task_tile_words(P), uw = k2t_union_words(P, sizeof(T));
+  if (sched) {
+    for (;;) {
+      unsigned int t = 0;
+      if (lane == 0) t = atomicAdd(&sched[0], 1u);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if ((long long)t >= ntiles) break;
+      k2t_warp_tile<T, G, NS>(P, a, (long long)t * NS, wsm, lane, St, uw);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicInc(&sched[1], gridDim.x - 1) == gridDim.x - 1) { __threadfence(); sched[0] = 0u; }
+    return;
+  }
   for (long long tile = (long long)blockIdx.x * nwarps + warp; tile < ntiles; tile += (long long)gridDim.x * nwarps)
     k2t_warp_tile<T, G, NS>(P, a, tile * NS, wsm, lane, St, uw);
 }
@@ -277,6 +296,7 @@ struct bik_model {
   uint32_t* d_image = nullptr;
 };
 
+enum { SCHED_SLOTS = 8 };
 struct bik_problem {
   const bik_model* model = nullptr;
   int device = 0;  // copy: the model may be destroyed first
@@ -297,6 +317,10 @@ struct bik_problem {
   float *J = nullptr, *e = nullptr, *ep = nullptr, *Gc = nullptr, *hc = nullptr;
   signed char* warm = nullptr;  // [B][nu] active-set guess carried between the steps of one bik_step call
   int32_t* flags = nullptr;     // [B] instances the mixed-precision K2 hands to the fp64 kernel
+  int k2_dynamic = 1;           // BIK_K2_DYNAMIC=0: static tile assignment in the small-group K2
+  unsigned int* d_sched = nullptr;   // SCHED_SLOTS x 32 words: {next tile, finished CTAs} per launching stream (own 128-byte line each)
+  cudaStream_t sched_stream[8];
+  int n_sched = 0;
   // bik_step_host staging
   size_t host_B = 0;
   float *hq = nullptr, *hft = nullptr, *hpt = nullptr, *hct = nullptr, *hdq = nullptr;
@@ -372,6 +396,11 @@ extern "C" int bik_problem_create(const bik_model* model, const bik_task_desc* t
   p->device = model->device;
   std::string err;
   if (!build_image(model->hm, tasks, ntasks, limits, nlimits, model->G, &p->image, &err)) { delete p; return fail(BIK_ERR_UNSUPPORTED, err); }
+  {  // launch-independent solver knob kept in the image header so that every K2 entry point sees it
+    PHeader* hh = reinterpret_cast<PHeader*>(p->image.data());
+    hh->k2_sweeps = std::max(0, std::min(16, env_int("BIK_K2_SWEEPS", hh->k2_sweeps)));
+    hh->k2_rule = env_int("BIK_K2_RULE", hh->k2_rule) != 0;
+  }
   memcpy(&p->h, p->image.data(), sizeof(PHeader));
   const char* prec = getenv("BIK_SOLVE_PRECISION");
   p->solve_double = !(prec && (std::string(prec) == "f32" || std::string(prec) == "float"));
@@ -380,6 +409,7 @@ extern "C" int bik_problem_create(const bik_model* model, const bik_task_desc* t
   p->k2_group = env_int("BIK_K2_GROUP", p->h.nu > 8 ? 8 : 4) == 8 ? 8 : 4;
   p->k2_warps = env_int("BIK_K2_WARPS", 8);
   p->k2_lockstep = env_int("BIK_K2_LOCKSTEP", 1);
+  p->k2_dynamic = env_int("BIK_K2_DYNAMIC", 1) != 0;
   if (p->k2_warps != 1 && p->k2_warps != 2 && p->k2_warps != 4 && p->k2_warps != 8) p->k2_warps = 8;
   DeviceGuard g(model->device);
   CUDA_OK(cudaMalloc(&p->d_image, p->image.size() * 4));
@@ -390,7 +420,7 @@ extern "C" int bik_problem_create(const bik_model* model, const bik_task_desc* t
 extern "C" void bik_problem_destroy(bik_problem* p) {
   if (!p) return;
   DeviceGuard g(p->device);
-  cudaFree(p->d_image); cudaFree(p->J); cudaFree(p->e); cudaFree(p->ep); cudaFree(p->Gc); cudaFree(p->hc); cudaFree(p->warm); cudaFree(p->flags); cudaFree(p->k2x_scratch);
+  cudaFree(p->d_sched); cudaFree(p->d_image); cudaFree(p->J); cudaFree(p->e); cudaFree(p->ep); cudaFree(p->Gc); cudaFree(p->hc); cudaFree(p->warm); cudaFree(p->flags); cudaFree(p->k2x_scratch);
   cudaFree(p->hq); cudaFree(p->hft); cudaFree(p->hpt); cudaFree(p->hct); cudaFree(p->hdq); cudaFree(p->hst);
   cudaFree(p->conv_done); cudaFree(p->conv_dq); cudaFree(p->conv_count);
   if (p->conv_host) cudaFreeHost(p->conv_host);
@@ -518,6 +548,21 @@ static bool use_low_rank_static(const bik_problem* p, double damping) {
   a.dq = reinterpret_cast<float*>(1); a.damping = damping;
   return use_low_rank(p, a);
 }
+// One (next tile, finished CTAs) pair per stream that launches the small-group K2 of this problem: launches on one stream
+// are ordered, launches on different streams (bik_step_host alternates two) must not share a counter.  More than
+// SCHED_SLOTS streams, or BIK_K2_DYNAMIC=0: static round-robin.
+static unsigned int* tile_counter(const bik_problem* cp, cudaStream_t st) {
+  bik_problem* p = const_cast<bik_problem*>(cp);
+  if (!p->k2_dynamic) return nullptr;
+  if (!p->d_sched) {
+    if (cudaMalloc(&p->d_sched, SCHED_SLOTS * 32 * sizeof(unsigned int)) != cudaSuccess) { cudaGetLastError(); p->k2_dynamic = 0; return nullptr; }
+    cudaMemset(p->d_sched, 0, SCHED_SLOTS * 32 * sizeof(unsigned int));
+  }
+  for (int i = 0; i < p->n_sched; ++i) if (p->sched_stream[i] == st) return p->d_sched + 32 * i;
+  if (p->n_sched == SCHED_SLOTS) return nullptr;
+  p->sched_stream[p->n_sched] = st;
+  return p->d_sched + 32 * p->n_sched++;
+}
 template <typename T, int G>
 static int launch_k2t(const bik_problem* p, const K2Args& a, cudaStream_t st) {
   constexpr int NS = 32 / G, MAXT = sizeof(T) == 8 ? 256 : 512;
@@ -530,7 +575,7 @@ static int launch_k2t(const bik_problem* p, const K2Args& a, cudaStream_t st) {
   long long tiles = ((long long)a.B + NS - 1) / NS;
   int rc = launch_geometry(k2t_kernel<T, G, MAXT>, p->model, smem, 32 * NW, (tiles + NW - 1) / NW, &grid);
   if (rc) return rc;
-  k2t_kernel<T, G, MAXT><<<grid, 32 * NW, smem, st>>>(p->d_image, (int)wb, a);
+  k2t_kernel<T, G, MAXT><<<grid, 32 * NW, smem, st>>>(p->d_image, (int)wb, a, tile_counter(p, st));
   CUDA_OK(cudaGetLastError());
   return BIK_OK;
 }

@@ -78,7 +78,19 @@ BIK_HD int k1_state_stride(const PHeader& h) {  // pose (7) + CoM first moment (
 BIK_HD int k1_stage_rows(const PHeader& h) { return 6; }
 BIK_HD int k1_state_words(const PHeader& h, int ipw) { return (ipw * k1_state_stride(h) + 3) & ~3; }  // keeps the stage 16-byte aligned
 BIK_HD int k1_fsc_stride(const PHeader& h) { return h.nrel > 0 ? 32 : 24; }
-BIK_HD int k1_stage_words(const PHeader& h, int ipw) { return (ipw * 6 * h.nv + 3) & ~3; }   // one frame's 6 rows per instance
+// Frame-task rows go straight to global memory when J holds nothing else (k1_frames_direct); the staging tile (6 rows
+// per instance) is only needed for CoM rows, collision rows, and frame rows that share J with CoM rows.
+BIK_HD bool k1_frames_direct(const PHeader& h) {
+#ifdef BIK_K1_STAGED   // A/B switch: every row through the staging tile, as before
+  return false;
+#else
+  return h.C == 0;
+#endif
+}
+BIK_HD int k1_stage_words(const PHeader& h, int ipw) {
+  if (k1_frames_direct(h) && h.npairs == 0) return 0;
+  return (ipw * 6 * h.nv + 3) & ~3;
+}
 BIK_HD int k1_warp_words(const PHeader& h, int ipw) {
   int w = k1_state_words(h, ipw) + k1_stage_words(h, ipw) + ipw * (h.K > 0 ? h.K : 1) + ipw * (h.F > 0 ? h.F : 1) * k1_fsc_stride(h) +
           ((ipw * h.nq + 3) & ~3);
@@ -330,16 +342,31 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, float* wsm,
   // (A whole-tile variant -- all K rows staged, one cp.async.bulk store per tile, no per-tile zero-fill --
   //  was measured slower: 0.198 vs 0.153 ms at G = 8, the 3x larger tile halves the resident warps;
   //  profiles/r1_kernels.md.)
+  // Direct variant (J holds frame rows only): the tile's K x nv blocks are one contiguous run of global memory; it is
+  // zero-filled with 16-byte stores straight from registers, then each lane scatters the columns it computes (a frame
+  // touches 12 of G1's 43 columns).  Zero-fill and scatter are ordered by the warp barrier; the partial sectors merge in
+  // L2.  No staging tile: 1 032 of the 1 932 shared-memory words a warp needed for G1, and the flush loop (12 % of the
+  // kernel's instructions) are gone.
+  const bool direct = k1_frames_direct(h);
+  if (direct && h.F > 0) {
+    float* Jt = a.J + (long long)inst0 * K * nv;
+    const int total = nvalid * K * nv;
+    if ((reinterpret_cast<size_t>(Jt) & 15) == 0) zero_words<W>(Jt, total, lane);
+    else for (int k = lane; k < total; k += W) Jt[k] = 0.f;
+    BIK_SYNCWARP();
+  }
   for (int f = 0; f < h.F; ++f) {
     const FrameRec& fr = P.frame(f);
-    zero_words<W>(stage, IPW * 6 * nv, lane);
-    BIK_SYNCWARP();
+    if (!direct) {
+      zero_words<W>(stage, IPW * 6 * nv, lane);
+      BIK_SYNCWARP();
+    }
     if (valid) {
       const float* sc = fsc + (li * h.F + f) * FS;
       F3 pf = ld_v(sc);
       FM A1, A2;
       for (int k = 0; k < 9; ++k) { A1.m[k] = sc[3 + k]; A2.m[k] = sc[12 + k]; }
-      float* st = stage + li * 6 * nv;
+      float* st = direct ? a.J + ((long long)b * K + fr.row0) * nv : stage + li * 6 * nv;
       if (!fr.relative) {
         for (int c = g; c < fr.ncols; c += G) {
           int ent = cols[fr.col_off + c], d = ent & 0xffff, n = (ent >> 16) & 0x7fff;
@@ -374,9 +401,11 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, float* wsm,
         }
       }
     }
-    BIK_SYNCWARP();
-    flush_rows<W>(stage, 6 * nv, nvalid, a.J + ((long long)inst0 * K + fr.row0) * nv, (long long)K * nv, lane);
-    BIK_SYNCWARP();
+    if (!direct) {
+      BIK_SYNCWARP();
+      flush_rows<W>(stage, 6 * nv, nvalid, a.J + ((long long)inst0 * K + fr.row0) * nv, (long long)K * nv, lane);
+      BIK_SYNCWARP();
+    }
   }
 
   // ---- centre-of-mass tasks (mj_comPos + mj_jacSubtreeCom for body 1) -------------------------

@@ -74,7 +74,9 @@ struct PHeader {  // all offsets in 32-bit words from the start of the image
   int32_t nneeded;      // nodes visited by the lane program (ancestors of frames / masses / collision geoms)
   int32_t nfree;        // leading coupled dofs (compact indices 0..nfree-1) without any finite bound: eliminated once by K2
   int32_t nslots;       // rows of the pose state = nodes visited by the lane program (nnode when slots are the identity)
-  int32_t reserved[1];
+  int32_t k2_sweeps;    // projected Gauss-Seidel sweeps that guess the active set before K2's pivoting (0: cold start)
+  int32_t k2_rule;      // pivoting rule after a guess: 1 = clamp all violated dofs, release one bound at a time; 0 = block flips
+  int32_t reserved[3];
 };
 static_assert(sizeof(PHeader) % 16 == 0, "header must stay 16-byte aligned");
 

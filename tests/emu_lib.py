@@ -51,6 +51,9 @@ class Emu:
         lib().emu_header(self.h, _p(out, C.c_int32))
         return dict(zip(("nv", "nu", "nfree", "nnode", "nneeded", "nslots", "G", "nsteps"), (int(v) for v in out)))
 
+    def set_knobs(self, sweeps: int, rule: int):
+        lib().emu_set_knobs(self.h, int(sweeps), int(rule))
+
     def fk_jac(self, q, ftgt=None, ptgt=None, ctgt=None, dt=1e-2):
         q = _f32(q); B = q.shape[0]; s = self.spec
         ftgt, ptgt, ctgt = _f32(ftgt), _f32(ptgt), _f32(ctgt)

@@ -34,6 +34,10 @@ extern "C" void emu_header(void* prob, int32_t* out) {
   const PHeader& h = PView{static_cast<EmuProblem*>(prob)->image.data()}.h();
   out[0] = h.nv; out[1] = h.nu; out[2] = h.nfree; out[3] = h.nnode; out[4] = h.nneeded; out[5] = h.nslots; out[6] = h.G; out[7] = h.nsteps;
 }
+extern "C" void emu_set_knobs(void* prob, int sweeps, int rule) {   // what BIK_K2_SWEEPS / BIK_K2_RULE do in bik_problem_create
+  PHeader* h = reinterpret_cast<PHeader*>(static_cast<EmuProblem*>(prob)->image.data());
+  h->k2_sweeps = sweeps; h->k2_rule = rule;
+}
 extern "C" void emu_problem_destroy(void* p) { delete static_cast<EmuProblem*>(p); }
 
 extern "C" int emu_lane_program(const void* blob, size_t nbytes, int G, int32_t* out, int cap) {

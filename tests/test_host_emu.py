@@ -133,8 +133,8 @@ def test_small_paths_match_reference(name, code):
     dq_dense, _, it_dense, *_ = emu.solve(g["q"], J, e, ep, Gc, hc, dt, damping, use_double=1)
     if code in (3, 5, 7):
         np.testing.assert_allclose(dq, dq_dense, atol=2e-6)
-    if code == 3:
-        assert (it == it_dense).all()
+    if code == 3:   # the projected Gauss-Seidel guess may only save pivoting iterations, never add any on these cases
+        assert it.sum() <= it_dense.sum() and it.max() <= it_dense.max()
     if code == 7:
         print("flagged for the fp64 kernel:", emu.last_rc, "of", len(dq))
         assert emu.last_rc <= len(dq) // 8
@@ -167,14 +167,15 @@ def test_image_marks_unbounded_leading_dofs_and_compact_state():
 
 
 def test_unbounded_elimination_matches_full_pivoting_with_active_bounds():
-    """The G1 golden has active velocity bounds: the reduced (Schur complement) pivoting must land on the reference's
-    optimum with the same number of pivoting iterations as the dense path on the whole coupled block."""
+    """The G1 golden has active velocity bounds: the reduced (Schur complement) pivoting, started from the projected
+    Gauss-Seidel guess, must land on the reference's optimum in fewer pivoting iterations than the dense path needs on
+    the whole coupled block from a cold start."""
     wl, fm, spec, g, emu = _emu("g1")
     dt, damping = float(g["dt"]), float(g["damping"])
     J, e, ep, Gc, hc = emu.fk_jac(g["q"], g["frame_targets"], g["posture_target"], None, dt=dt)
     dq, st, it, *_ = emu.solve(g["q"], J, e, ep, Gc, hc, dt, damping, use_double=3)
     dq_dense, _, it_dense, *_ = emu.solve(g["q"], J, e, ep, Gc, hc, dt, damping, use_double=1)
-    assert not st.any() and it.max() > 1
-    assert (it == it_dense).all()
+    assert not st.any() and it_dense.max() > 1
+    assert it.mean() < 0.5 * it_dense.mean()
     np.testing.assert_allclose(dq, dq_dense, atol=1e-7)
     np.testing.assert_allclose(dq, g["dq"], atol=1e-5)

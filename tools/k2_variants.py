@@ -8,7 +8,8 @@ import sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
     "base": [],
-    "noelim": ["-DBIK_K2T_NO_ELIM"],
+    "k1mb5": ["-DBIK_K1_MINBLOCKS=5"],
+    "k1mb6": ["-DBIK_K1_MINBLOCKS=6"],
 }
 
 CHILD = r'''
@@ -36,7 +37,7 @@ k1, k2 = [], []
 for s in range(8):
     flush.fill_(1.0)
     a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    a.record(); J, e, ep, Gc, hc = prob.fk_jac(q0, ft, pt, None, dt=wl["dt"]); b.record()
+    torch.cuda._sleep(2000000); a.record(); J, e, ep, Gc, hc = prob.fk_jac(q0, ft, pt, None, dt=wl["dt"]); b.record()
     dq, st = prob.solve(q0, J, e, ep, Gc, hc, wl["dt"], wl["damping"]); c.record()
     torch.cuda.synchronize()
     k1.append(a.elapsed_time(b)); k2.append(b.elapsed_time(c))
@@ -57,8 +58,11 @@ def main():
             subprocess.check_call(cmd)
     if build_only:
         return
+    ENVS = {"base": ({}, {"BIK_K2_SWEEPS": "2"}, {"BIK_K2_SWEEPS": "4"}, {"BIK_K1_GROUP": "8"}, {"BIK_K2_GROUP": "4"}, {"BIK_WL": "shadow"},
+                     {"BIK_WL": "shadow", "BIK_K1_GROUP": "4"}, {"BIK_WL": "shadow", "BIK_K2_SWEEPS": "0"}, {"BIK_WL": "ur5e_dls"}, {"BIK_WL": "g1_rel"}),
+            "k1mb5": ({}, {"BIK_WL": "shadow"}), "k1mb6": ({}, {"BIK_WL": "shadow"})}
     for name in VARIANTS:
-        for env in ({}, {"BIK_K1_GROUP": "4"}, {"BIK_K1_GROUP": "2"}, {"BIK_WL": "shadow"}, {"BIK_WL": "ur5e_dls"}, {"BIK_WL": "g1_rel"}):
+        for env in ENVS.get(name, ({},)):
             e = dict(os.environ, BIK_REPO=REPO, BIK_LIB=os.path.join(out, f"libbik_{name}.so"), **env)
             r = subprocess.run([sys.executable, "-c", CHILD], env=e, capture_output=True, text=True)
             line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:]
