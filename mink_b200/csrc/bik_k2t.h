@@ -250,19 +250,30 @@ BIK_HD int k2t_factor(const T* __restrict__ Hp, T* __restrict__ Lp, int nu, uint
   }
   return bad;
 }
-// x = L^-T y (y = row nu of Lp), dot-product form: x_k needs sum_{m>k} L[m][k] x_m; every lane sums the m it owns
-// (m = l mod G, kept in its own entries of xs), a butterfly adds the partial sums.  No barrier inside.
-// Produces x_k for k = khi-1 .. klo (x_m, m >= khi, must already be in xs).
+// x = L^-T y (y = row nu of Lp, consumed), column form: x_k = y_k / L_kk is computed by every lane from two broadcast reads,
+// then the G lanes subtract L[k][m] x_k from the y_m (mlo <= m < k) they own -- row k of the packed factor is contiguous.
+// One warp barrier per k, no shuffles, half the instructions of the dot-product form with its butterfly per k.
+// Produces x_k for k = khi-1 .. klo.  Every lane of the warp must call it.
 template <typename T, int G, int NS>
-BIK_HD void k2t_backsub(const T* __restrict__ Lp, int nu, int l, T* __restrict__ xs, int khi, int klo) {
-  const T* y = Lp + tri(nu) * NS;
+BIK_HD void k2t_backsub(T* __restrict__ Lp, int nu, int l, T* __restrict__ xs, int khi, int klo, int mlo) {
+  T* y = Lp + tri(nu) * NS;
   for (int k = khi - 1; k >= klo; --k) {
-    int m = (k + 1) + ((l - (k + 1)) & (G - 1));
-    T p = T(0);
-    for (; m < nu; m += G) p += Lp[(tri(m) + k) * NS] * xs[m * NS];
-    p = grp_sum<T, G>(p);
-    const T xk = (y[k * NS] - p) * Lp[(tri(k) + k) * NS];
-    if ((k & (G - 1)) == l) xs[k * NS] = xk;
+    const T* row = Lp + tri(k) * NS;
+    const T xk = y[k * NS] * row[k * NS];
+    for (int m = mlo + l; m < k; m += G) y[m * NS] -= row[m * NS] * xk;
+    if (l == 0) xs[k * NS] = xk;
+    if (G > 1) BIK_SYNCWARP();   // y_{k-1} is final
+  }
+}
+// y_m -= sum_{k in [klo, khi)} L[k][m] x_k for the m < mhi a lane owns: what the trailing dofs contribute to the leading
+// part of the right-hand side (each lane only touches its own m: no barrier inside).
+template <typename T, int G, int NS>
+BIK_HD void k2t_backsub_cross(T* __restrict__ Lp, int nu, int l, const T* __restrict__ xs, int khi, int klo, int mhi) {
+  T* y = Lp + tri(nu) * NS;
+  for (int m = l; m < mhi; m += G) {
+    T a = y[m * NS];
+    for (int k = klo; k < khi; ++k) a -= Lp[(tri(k) + m) * NS] * xs[k * NS];
+    y[m * NS] = a;
   }
 }
 // Active-set guess by projected Gauss-Seidel on  min 1/2 x^T S x + c^T x,  lo <= x <= hi  over the dofs [k0, nu):
@@ -463,7 +474,7 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
     BIK_SYNCWARP();
     if (k2t_factor<T, G, NS>(Hp, Lp, nu, act, l, nf, nu)) st |= 4;
     BIK_SYNCWARP();
-    k2t_backsub<T, G, NS>(Lp, nu, l, vs, nu, nf);
+    k2t_backsub<T, G, NS>(Lp, nu, l, vs, nu, nf, nf);
     BIK_SYNCWARP();
     // gradient on the clamped dofs, feasibility of the free ones
     uint32_t vlo = 0u, vup = 0u, rel = 0u;   // free dofs that violate a bound / clamped dofs whose multiplier has the wrong sign
@@ -510,7 +521,9 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
     }
   }
   if (nf > 0) {   // x_b = L_bb^-T (y_b - L_t^T x_t): the back substitution simply continues into the leading rows
-    k2t_backsub<T, G, NS>(Lp, nu, l, vs, nf, 0);
+    k2t_backsub_cross<T, G, NS>(Lp, nu, l, vs, nu, nf, nf);
+    BIK_SYNCWARP();
+    k2t_backsub<T, G, NS>(Lp, nu, l, vs, nf, 0, 0);
     BIK_SYNCWARP();
   }
   if (!done) st |= 2;
