@@ -355,7 +355,7 @@ inline bool build_image(const HostModel& m, const bik_task_desc* tasks, int ntas
     int cnt = 0; for (char c : needed) cnt += c;
     // G <= 0: pick the lanes per instance from the visited tree -- wide enough that the per-warp tile stays small
     // (occupancy), narrow enough that the program keeps the lanes busy (G1, 38 nodes: G=8 0.153 ms, 4: 0.168, 16: 0.239)
-    if (G <= 0) G = cnt > 16 ? 8 : (cnt > 4 ? 4 : 2);   // measured on G1 (13 visited nodes, rows written straight to global memory): 4 lanes 0.102 ms, 8 lanes 0.123 ms, 2 lanes 0.21 ms
+    if (G <= 0) G = cnt > 4 ? 4 : 2;   // measured (rows written straight to global memory): G1, 13 visited nodes: 4 lanes 0.101 ms, 8 lanes 0.123 ms, 2 lanes 0.21 ms; Shadow Hand, 25 nodes: 4 lanes 0.037 ms, 8 lanes 0.041 ms
     H.G = G;
     std::vector<int32_t> prog; int nsteps = 0;
     lane_program(m, G, &prog, &nsteps, &needed);

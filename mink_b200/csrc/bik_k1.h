@@ -137,7 +137,14 @@ BIK_HD void fk_node(const PView& P, int n, const float* q, float* xs) {
       if (off_centre) pos = anchor - qrot(quat, jp);
     }
   }
+  // mj_kinematics renormalises every body quaternion.  A product of unit quaternions leaves the unit sphere by ~1e-7
+  // per level in fp32 (1e-6 at the deepest node of the BASELINE robots, against a 1e-4 parity budget), so only
+  // quaternions that come straight from q (free / ball joints: callers may pass them unnormalised) are renormalised.
+#ifdef BIK_K1_NORMALIZE_ALL
   quat = qnormalize(quat);
+#else
+  if (r.type == JNT_FREE) quat = qnormalize(quat);
+#endif
   float* o = xs + 7 * r.slot;
   o[0] = quat.w; o[1] = quat.x; o[2] = quat.y; o[3] = quat.z; o[4] = pos.x; o[5] = pos.y; o[6] = pos.z;
 }

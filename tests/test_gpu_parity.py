@@ -251,6 +251,27 @@ def test_k2_paths_agree_on_a_ragged_batch(name, path):
     assert err < (1e-4 if path != "fixed" else 2e-3)
 
 
+@pytest.mark.parametrize("env", [{}, {"BIK_K2_SWEEPS": 0}, {"BIK_K2_SWEEPS": 6}, {"BIK_K2_RULE": 0}, {"BIK_K2_DYNAMIC": 0},
+                                 {"BIK_K2_SWEEPS": 0, "BIK_K2_DYNAMIC": 0, "BIK_K2_GROUP": 4}, {"BIK_K1_GROUP": 8}])
+def test_small_group_solver_knobs_against_oracle(env):
+    """Elimination of the unbounded dofs, Gauss-Seidel guess, release rule and tile hand-out only change HOW the optimum of
+    mink's QP (solve_ik.py:43-105) is reached: every setting must return the oracle's dq on a ragged G1 batch with active
+    bounds, and repeated launches on one stream must keep working (the tile counter rewinds itself)."""
+    wl, fm, spec, g, model, prob = _engine("g1", env=env)
+    orc = _oracle(fm, spec)
+    frames = task_frames(wl, fm)
+    B = 3 * 1024 + 5
+    inp = make_inputs(fm, wl, B, lambda qq: orc.fk(qq, frames), seed=23)
+    dq_ref, _, st_ref, nact = orc.step(inp["q"], inp["frame_targets"], inp["posture_target"], None, dt=wl["dt"], damping=wl["damping"],
+                                       nsteps=1, integrate=False)
+    assert not st_ref.any() and nact.mean() > 3
+    q = torch.tensor(inp["q"], dtype=torch.float32, device="cuda:0")
+    for rep in range(3):
+        dq, st = prob.step(q, inp["frame_targets"], inp["posture_target"], None, dt=wl["dt"], damping=wl["damping"])
+        assert int(st.max()) == 0
+        assert np.abs(_np(dq) - dq_ref).max() < 1e-4
+
+
 @pytest.mark.parametrize("name,B", [("g1", 4099), ("shadow", 2050), ("ur5e_dls", 4096), ("spot", 1031)])
 def test_batch_against_oracle(name, B):
     wl, fm, spec, g, model, prob = _engine(name)

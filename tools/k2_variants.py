@@ -8,8 +8,7 @@ import sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
     "base": [],
-    "k1mb5": ["-DBIK_K1_MINBLOCKS=5"],
-    "k1mb6": ["-DBIK_K1_MINBLOCKS=6"],
+    "k1old": ["-DBIK_K1_NORMALIZE_ALL", "-DBIK_K1_MINBLOCKS=4"],
 }
 
 CHILD = r'''
@@ -58,9 +57,7 @@ def main():
             subprocess.check_call(cmd)
     if build_only:
         return
-    ENVS = {"base": ({}, {"BIK_K2_SWEEPS": "2"}, {"BIK_K2_SWEEPS": "4"}, {"BIK_K1_GROUP": "8"}, {"BIK_K2_GROUP": "4"}, {"BIK_WL": "shadow"},
-                     {"BIK_WL": "shadow", "BIK_K1_GROUP": "4"}, {"BIK_WL": "shadow", "BIK_K2_SWEEPS": "0"}, {"BIK_WL": "ur5e_dls"}, {"BIK_WL": "g1_rel"}),
-            "k1mb5": ({}, {"BIK_WL": "shadow"}), "k1mb6": ({}, {"BIK_WL": "shadow"})}
+    ENVS = {"base": ({}, {"BIK_WL": "shadow"}, {"BIK_WL": "ur5e_dls"}, {"BIK_WL": "g1_rel"}), "k1old": ({}, {"BIK_WL": "shadow"})}
     for name in VARIANTS:
         for env in ENVS.get(name, ({},)):
             e = dict(os.environ, BIK_REPO=REPO, BIK_LIB=os.path.join(out, f"libbik_{name}.so"), **env)
