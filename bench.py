@@ -310,6 +310,7 @@ def main():
     roll_ms = allmax(r0.elapsed_time(r1))
     rollout = {"timesteps": T, "value": world * B * T / (roll_ms * 1e-3), "unit": UNIT,
                "ms_per_timestep": roll_ms / T,
+               "instances_flagged": int((status != 0).sum().item()),   # status bits OR-ed over the 100 steps (rank 0's shard)
                "note": "one bik_step call with nsteps=100 from q0, targets held: instances converge, bounds deactivate"}
 
     e2e = measure_e2e(prob, inp, fm, B, dt_, damping, args, world, allmax, barrier)

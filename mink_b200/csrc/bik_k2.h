@@ -55,7 +55,7 @@ struct K2Args {
   int skip_objective;  // bik_limits_box: J/e/ep are not read
   int skip_box;        // bik_qp_objective: q is not read
   int lockstep;        // warps of a CTA advance through the pivoting iterations together (block barriers)
-  signed char* warm;   // [B][nu] or null: active-set guess in (0 free, 1 lower, 2 upper), read at entry, updated at exit
+  signed char* warm;   // [B][nu] or null: active-set guess in (0 free, 1 lower, 2 upper; +4 = dq still holds the previous step's result), read at entry, updated at exit
   int32_t* flag_out;   // [B] or null: mixed-precision path marks the instances it could not finish (bik_k2x.h)
   const int32_t* only; // [B] or null: small-group path processes only the instances marked here (bik_k2t.h)
 };
@@ -365,7 +365,7 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
   const T tolx = K2Tol<T>::x(), tolg = K2Tol<T>::g();
   const float* Gb = np > 0 ? a.Gc + (long long)b * np * n : nullptr;
   for (int i = lane; i < n; i += W) {
-    int s0 = (a.warm && active) ? a.warm[(long long)b * n + i] : 0;   // warm start: last step's active set
+    int s0 = (a.warm && active) ? (a.warm[(long long)b * n + i] & 3) : 0;   // warm start: last step's active set (bit 2 is the small-group path's marker)
     if ((s0 == 1 && !(w.lo[i] > T(-1e30))) || (s0 == 2 && !(w.hi[i] < T(1e30)))) s0 = 0;
     w.st[i] = s0;
   }

@@ -89,7 +89,7 @@ template <typename T, int G> BIK_HD T grp_sum(T v) {
 }
 
 // ---- per-warp scratch ------------------------------------------------------------------------------
-// T words per slot:   Hp tri(nu) | U (factor incl. rhs row; aliased by the staging tiles) | c nu | vs nu
+// T words per slot:   Hp tri(nu) | U (factor incl. rhs row; aliased by the staging tiles) | c nu | vs nu | xf nu (feasible iterate)
 // float words / slot: lo nu | hi nu
 BIK_HD int k2t_task_tile_words(const PView& P) {  // widest task tile, in T words per instance (odd)
   const PHeader& h = P.h();
@@ -107,7 +107,7 @@ BIK_HD int k2t_union_words(const PView& P, int ts) {
   int fw = (sq + ts - 1) / ts;
   return fw > u ? fw : u;
 }
-BIK_HD int k2t_slot_T_words(const PView& P, int ts) { return tri(P.h().nu) + k2t_union_words(P, ts) + 2 * P.h().nu; }
+BIK_HD int k2t_slot_T_words(const PView& P, int ts) { return tri(P.h().nu) + k2t_union_words(P, ts) + 3 * P.h().nu; }
 BIK_HD int k2t_slot_bytes(const PView& P, int ts) { return k2t_slot_T_words(P, ts) * ts + 2 * P.h().nu * 4; }
 BIK_HD int k2t_warp_bytes(const PView& P, int ts, int NS) { return (NS * k2t_slot_bytes(P, ts) + 15) & ~15; }
 
@@ -287,11 +287,16 @@ BIK_HD void k2t_backsub_cross(T* __restrict__ Lp, int nu, int l, const T* __rest
 // clamped dofs of every group in the warp unchanged.  Every lane of the warp must call it.
 template <typename T, int G, int NS>
 BIK_HD void k2t_pgs_guess(const T* __restrict__ Hp, const T* __restrict__ c, const float* __restrict__ lo, const float* __restrict__ hi,
-                          T* __restrict__ xs, T* __restrict__ dinv, T* __restrict__ res, int nu, int k0, int l, int sweeps,
+                          T* __restrict__ xs, T* __restrict__ dinv, T* __restrict__ res, int nu, int k0, int l, int sweeps, bool from_xs,
                           uint32_t* lom_out, uint32_t* upm_out) {
   // Residual form: res = c + S x is kept up to date, so row i only needs res_i and x_i (broadcast reads, every lane
   // computes the new x_i), after which each lane adds S_mi (x_i' - x_i) to the residuals of the dofs m it owns.
-  for (int k = k0 + l; k < nu; k += G) { xs[k * NS] = T(0); res[k * NS] = c[k * NS]; dinv[k * NS] = T(1) / Hp[(tri(k) + k) * NS]; }
+  // from_xs (warp-uniform): xs already holds a feasible starting point (the previous step's dq, clipped), else start from 0
+  if (!from_xs) { for (int k = k0 + l; k < nu; k += G) xs[k * NS] = T(0); }
+  for (int k = k0 + l; k < nu; k += G) {
+    res[k * NS] = c[k * NS] + (from_xs ? k2t_row_dot<T, NS>(Hp, xs, k, nu, k0) : T(0));
+    dinv[k * NS] = T(1) / Hp[(tri(k) + k) * NS];
+  }
   BIK_SYNCWARP();
   uint32_t lom = 0u, upm = 0u;
   for (int s = 0; s < sweeps; ++s) {
@@ -357,7 +362,8 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
   T* const Lp = U + slot;
   T* const c = Tb + (size_t)(tri(nu) + uw) * NS + slot;
   T* const vs = c + (size_t)nu * NS;
-  float* const Fb = reinterpret_cast<float*>(Tb + (size_t)(tri(nu) + uw + 2 * nu) * NS);
+  T* const xf = vs + (size_t)nu * NS;
+  float* const Fb = reinterpret_cast<float*>(Tb + (size_t)(tri(nu) + uw + 3 * nu) * NS);
   float* const lo = Fb + slot;
   float* const hi = Fb + (size_t)nu * NS + slot;
 
@@ -440,19 +446,34 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
   const T tolx = K2Tol<T>::x(), tolg = K2Tol<T>::g();
   uint32_t lom = 0u, upm = 0u;
   bool guessed = false;
-  if (a.warm) {   // (warp-uniform branch: the guess below contains warp barriers)
+  const bool guess = sizeof(T) == 8 && h.k2_sweeps > 0 && nf < nu;   // fp64 only: fp32's gradient tolerance (1e-4) would accept a wrongly clamped dof
+  if (guess) {
+    // Starting point of the guess: zero, or -- inside a rollout, from its second step on -- the previous step's dq (still
+    // in a.dq; the warm-state bytes carry a marker once this kernel has written it), clipped to this step's box.
+    const bool have_prev = a.warm != nullptr;   // warp-uniform
+    if (have_prev) {
+      const bool valid = live && (a.warm[b * nu] & 4);
+      for (int k = nf + l; k < nu; k += G) {
+        T v = valid ? T(a.dq[b * nv + ucols[k]]) : T(0);
+        if (!(v == v)) v = T(0);
+        const T bl = T(lo[k * NS]), bu = T(hi[k * NS]);
+        vs[k * NS] = v < bl ? bl : (v > bu ? bu : v);
+      }
+      BIK_SYNCWARP();
+    }
+    k2t_pgs_guess<T, G, NS>(Hp, c, lo, hi, vs, rhsrow, Lp + tri(nu - 1) * NS, nu, nf, l, h.k2_sweeps, have_prev, &lom, &upm);   // scratch: free strips of the factor
+    guessed = h.k2_rule != 0;
+    for (int k = nf + l; k < nu; k += G) xf[k * NS] = vs[k * NS];   // the Gauss-Seidel iterate is feasible: it is where the active-set method starts
+    BIK_SYNCWARP();
+  } else if (a.warm) {   // (warp-uniform branch)
     if (live) {
       const signed char* wm = a.warm + b * nu;
       for (int i = nf; i < nu; ++i) {
-        int s0 = wm[i];
+        int s0 = wm[i] & 3;
         if (s0 == 1 && lo[i * NS] > -1e30f) lom |= 1u << i;
         else if (s0 == 2 && hi[i * NS] < 1e30f) upm |= 1u << i;
       }
     }
-  } else if (sizeof(T) == 8 && h.k2_sweeps > 0 && nf < nu) {   // fp64 only: fp32's gradient tolerance (1e-4) would accept a wrongly clamped dof   // no state from a previous step: guess the active set (see k2t_pgs_guess)
-    k2t_pgs_guess<T, G, NS>(Hp, c, lo, hi, vs, rhsrow, Lp + tri(nu - 1) * NS, nu, nf, l, h.k2_sweeps, &lom, &upm);   // scratch: free strips of the factor
-    guessed = h.k2_rule != 0;
-    BIK_SYNCWARP();
   }
   int best = nu + 1, patience = PATIENCE;
   bool done = nf == nu;     // no bounded dof at all: the elimination above was the whole solve (one factorisation)
@@ -479,12 +500,22 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
     // gradient on the clamped dofs, feasibility of the free ones
     uint32_t vlo = 0u, vup = 0u, rel = 0u;   // free dofs that violate a bound / clamped dofs whose multiplier has the wrong sign
     int worst = 0;                            // (float bits of the largest wrong-signed multiplier, low 5 bits = its index)
+    int blocking = 0x7fffffff;                // (float bits of the smallest step length to a violated bound, low 5 bits = its index)
     for (int k = nf + l; k < nu; k += G) {
       const uint32_t bit = 1u << k;
       if (!(act & bit)) {
         const T xi = vs[k * NS], bl = T(lo[k * NS]), bu = T(hi[k * NS]);
-        if (xi < bl - tolx * (T(1) + (bl < 0 ? -bl : bl))) vlo |= bit;
-        else if (xi > bu + tolx * (T(1) + (bu < 0 ? -bu : bu))) vup |= bit;
+        const bool below = xi < bl - tolx * (T(1) + (bl < 0 ? -bl : bl));
+        const bool above = !below && xi > bu + tolx * (T(1) + (bu < 0 ? -bu : bu));
+        if (below) vlo |= bit;
+        if (above) vup |= bit;
+        if (guessed && (below || above)) {   // how far the feasible iterate can move towards x before this bound stops it
+          const T xo = xf[k * NS], d = xi - xo;
+          T al = d != T(0) ? ((below ? bl : bu) - xo) / d : T(0);
+          al = al < T(0) ? T(0) : (al > T(1) ? T(1) : al);
+          const int key = (int)((bik_float_bits(float(al)) & 0x7fffffe0u) | (uint32_t)k);
+          blocking = key < blocking ? key : blocking;
+        }
       } else {
         T gi = c[k * NS] + k2t_row_dot<T, NS>(Hp, vs, k, nu, nf);
         if (upm & bit) gi = -gi;              // now: gi < 0 means the bound wants to let go
@@ -497,18 +528,42 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
     }
     vlo = (uint32_t)grp_or<G>((int)vlo); vup = (uint32_t)grp_or<G>((int)vup); rel = (uint32_t)grp_or<G>((int)rel);
     worst = grp_max<G>(worst);
-    BIK_SYNCWARP();   // every lane has read x before the next iteration overwrites vs
+    T alpha = T(0), bound = T(0);
+    int kb = 0;
+    if (guessed) {
+      blocking = -grp_max<G>(-blocking);
+      if (vlo | vup) {   // exact step length to the blocking bound (the key only ranked the candidates in fp32)
+        kb = blocking & 31;
+        const T xo = xf[kb * NS], d = vs[kb * NS] - xo;
+        bound = ((vlo >> kb) & 1u) ? T(lo[kb * NS]) : T(hi[kb * NS]);
+        alpha = d != T(0) ? (bound - xo) / d : T(0);
+        alpha = alpha < T(0) ? T(0) : (alpha > T(1) ? T(1) : alpha);
+      }
+    }
+    BIK_SYNCWARP();   // every lane has read x (and the feasible iterate) before anything below or the next iteration overwrites them
     if (run) {
       ++it;
       const uint32_t changed = vlo | vup | rel;
       const int ninf = bik_popc(changed);
       if (ninf == 0) done = true;
       else if (guessed) {
-        // Started from the Gauss-Seidel guess: few corrections are needed, and full block flips cycle on the rare
-        // near-degenerate instance (24 iterations on 1 of 65 536 G1 instances, which then sets the kernel's tail).
-        // Clamp every violated dof; let go of one bound (the worst multiplier) only when x is feasible.
-        if (vlo | vup) { lom |= vlo; upm |= vup; }
-        else { const uint32_t bit = 1u << (worst & 31); lom &= ~bit; upm &= ~bit; }
+        // Primal active-set step from the feasible iterate xf (started at the Gauss-Seidel guess): block flips cycle on a few
+        // instances per thousand once a rollout is under way (the single-pivot fallback then runs out of its 60 iterations),
+        // and flipping every violated dof at once gives up monotone descent.  Here the objective decreases at every step,
+        // so the method terminates: move towards the subspace minimiser x until the first bound stops the move and clamp
+        // that dof; at a feasible subspace minimiser let go of the bound with the worst multiplier, or stop if there is none.
+        if (vlo | vup) {
+          for (int k = nf + l; k < nu; k += G) {
+            if (k == kb) xf[k * NS] = bound;
+            else if (!((act >> k) & 1u)) xf[k * NS] += alpha * (vs[k * NS] - xf[k * NS]);
+          }
+          const uint32_t bit = 1u << kb;
+          if (vlo & bit) lom |= bit; else upm |= bit;
+        } else {
+          for (int k = nf + l; k < nu; k += G) xf[k * NS] = vs[k * NS];
+          const uint32_t bit = 1u << (worst & 31);
+          lom &= ~bit; upm &= ~bit;
+        }
       } else {
         bool block;
         if (ninf < best) { best = ninf; patience = PATIENCE; block = true; }
@@ -537,7 +592,7 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
   if (live && l == 0) {
     if (a.status) a.status[b] |= st;
     if (a.iters) a.iters[b] = it;
-    if (a.warm) { signed char* wm = a.warm + b * nu; for (int i = 0; i < nu; ++i) wm[i] = (signed char)(((lom >> i) & 1u) ? 1 : (((upm >> i) & 1u) ? 2 : 0)); }
+    if (a.warm) { signed char* wm = a.warm + b * nu; for (int i = 0; i < nu; ++i) wm[i] = (signed char)((((lom >> i) & 1u) ? 1 : (((upm >> i) & 1u) ? 2 : 0)) | 4); }   // +4: a.dq holds this step's result
   }
   BIK_SYNCWARP();
 }

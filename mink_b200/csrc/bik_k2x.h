@@ -331,7 +331,7 @@ BIK_HD void k2x_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       if (k < nu) {
-        const int s0 = wm[k];
+        const int s0 = wm[k] & 3;
         if (s0 == 1 && lo[k] > -1e30f) lom |= 1u << k;
         else if (s0 == 2 && hi[k] < 1e30f) upm |= 1u << k;
       }

@@ -78,6 +78,33 @@ WORKLOADS: Dict[str, dict] = {
         limits=[dict(kind="configuration", gain=0.95)],
         dt=5e-3, damping=1e-2, batch=4096,
     ),
+    # Not a BASELINE config: the reference's humanoid example as written (examples/humanoid_g1.py:20-50) -- pelvis
+    # orientation, posture, CoM, both feet AND both palms -- with the limits of the headline config.  The CoM task couples
+    # every dof (43 coupled: general warp-per-problem path).
+    "g1_full": dict(
+        robot="g1", scene="unitree_g1/scene.xml", key="stand",
+        frames=[dict(name="pelvis", type="body", position_cost=0.0, orientation_cost=10.0, lm_damping=0.0),
+                dict(name="right_foot", type="site", position_cost=200.0, orientation_cost=10.0, lm_damping=1.0),
+                dict(name="left_foot", type="site", position_cost=200.0, orientation_cost=10.0, lm_damping=1.0),
+                dict(name="right_palm", type="site", position_cost=200.0, orientation_cost=0.0, lm_damping=1.0),
+                dict(name="left_palm", type="site", position_cost=200.0, orientation_cost=0.0, lm_damping=1.0)],
+        posture=dict(cost=1.0), com=dict(cost=200.0),
+        limits=[dict(kind="configuration", gain=0.95), dict(kind="velocity", vmax=PI)],
+        dt=5e-3, damping=1e-1, batch=4096,
+    ),
+    # Same example without the CoM task: 31 coupled dofs (base 6 + legs 12 + waist 1 + arms 12), 6 of them unbounded --
+    # the largest block the small-group path takes (active sets are 32-bit masks), 25 dofs after the elimination.
+    "g1_hands": dict(
+        robot="g1", scene="unitree_g1/scene.xml", key="stand",
+        frames=[dict(name="pelvis", type="body", position_cost=0.0, orientation_cost=10.0, lm_damping=0.0),
+                dict(name="right_foot", type="site", position_cost=200.0, orientation_cost=10.0, lm_damping=1.0),
+                dict(name="left_foot", type="site", position_cost=200.0, orientation_cost=10.0, lm_damping=1.0),
+                dict(name="right_palm", type="site", position_cost=200.0, orientation_cost=0.0, lm_damping=1.0),
+                dict(name="left_palm", type="site", position_cost=200.0, orientation_cost=0.0, lm_damping=1.0)],
+        posture=dict(cost=1.0), com=None,
+        limits=[dict(kind="configuration", gain=0.95), dict(kind="velocity", vmax=PI)],
+        dt=5e-3, damping=1e-1, batch=4096,
+    ),
     # Not a BASELINE config: edge-case model authored for this repository (tests/golden/models/edge.xml):
     # ball joint with off-centre anchor, slide joint with ref, two joints on one body, a second floating
     # root, capsule/sphere/plane collision pairs, every task and limit kind at once.

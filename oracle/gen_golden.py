@@ -26,7 +26,7 @@ from mink_b200.flatten import flatten  # noqa: E402
 from mink_b200.workloads import WORKLOADS, make_inputs  # noqa: E402
 
 OUT = os.path.join(REPO, "tests", "golden")
-GOLDEN_B = {"ur5e": 8, "ur5e_dls": 16, "g1": 32, "shadow": 24, "spot": 24, "g1_rel": 16, "edge": 48}
+GOLDEN_B = {"ur5e": 8, "ur5e_dls": 16, "g1": 32, "shadow": 24, "spot": 24, "g1_rel": 16, "edge": 48, "g1_full": 16, "g1_hands": 24}
 ROLLOUT_T, ROLLOUT_B = 8, 4
 CONV_B, CONV_MAX_ITERS, CONV_POS, CONV_ORI = 8, 20, 2e-3, 2e-3
 
@@ -69,11 +69,14 @@ def build_reference_problem(model, wl):
 def main():
     os.makedirs(os.path.join(OUT, "models"), exist_ok=True)
     done_models = set()
+    only = set(sys.argv[1:])   # `python oracle/gen_golden.py g1_hands` regenerates just that case
     for name, wl in WORKLOADS.items():
+        if only and name not in only:
+            continue
         scene = os.path.join(REPO, wl["scene"][1:]) if wl["scene"].startswith("@") else os.path.join(REF, "examples", wl["scene"])
         model = mujoco.MjModel.from_xml_path(scene)
         fm = flatten(model)
-        if wl["robot"] not in done_models:
+        if wl["robot"] not in done_models and not only:
             with open(os.path.join(OUT, "models", wl["robot"] + ".bikm"), "wb") as f:
                 f.write(fm.to_blob())
             with open(os.path.join(OUT, "models", wl["robot"] + ".json"), "w") as f:

@@ -76,6 +76,17 @@ class Emu:
                         _p(H, C.c_double), _p(c, C.c_double), _p(lo), _p(hi))
         return dq, st, it, H, c, lo, hi
 
+    def solve_warm(self, q, J, e, ep, dt, damping, dq_prev, warm):
+        """One step of a rollout on the small-group fp64 path: `warm` ([B, nu] int8, zeros before the first step) and
+        `dq_prev` (the previous step's dq) are updated in place, as bik_step does between its steps."""
+        q = _f32(q); B = q.shape[0]
+        st = np.zeros(B, np.int32); it = np.zeros(B, np.int32)
+        assert dq_prev.dtype == np.float32 and warm.dtype == np.int8 and dq_prev.flags.c_contiguous and warm.flags.c_contiguous
+        rc = lib().emu_solve_warm(self.h, B, _p(q), _p(_f32(J)), _p(_f32(e)), _p(_f32(ep)), C.c_float(dt), C.c_double(damping),
+                                  _p(dq_prev), _p(st, C.c_int32), _p(it, C.c_int32), warm.ctypes.data_as(C.POINTER(C.c_byte)))
+        assert rc == 0, lib().emu_last_error()
+        return dq_prev, st, it
+
     def fk(self, q, frames, want_J=False):
         q = _f32(q); B = q.shape[0]
         poses = np.zeros((B, len(frames), 7), np.float32); com = np.zeros((B, 3), np.float32)

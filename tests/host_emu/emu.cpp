@@ -60,6 +60,22 @@ extern "C" int emu_fk_jac(void* prob, int B, const float* q, const float* ftgt, 
   return 0;
 }
 
+// Small-group fp64 path with the rollout state of bik_step (nsteps > 1): `warm` [B][nu] bytes and the dq of the previous
+// step in `dq` (in/out), as step_core passes them from its second step on.
+extern "C" int emu_solve_warm(void* prob, int B, const float* q, const float* J, const float* e, const float* ep, float dt, double damping,
+                              float* dq, int32_t* status, int32_t* iters, signed char* warm) {
+  EmuProblem* p = static_cast<EmuProblem*>(prob);
+  PView P{p->image.data()};
+  if (P.h().npairs != 0 || P.h().nu < 1 || P.h().nu > K2T_NMAX) { g_err = "thread path not applicable"; return -1; }
+  K2Args a{B, q, J, e, ep, nullptr, nullptr, dt, damping, dq, status, iters, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, warm, nullptr, nullptr};
+  std::vector<double> tw(k2t_warp_bytes(P, 8, 1) / 8 + 16);
+  for (int b = 0; b < B; ++b) {
+    if (status) status[b] = 0;
+    k2t_warp_tile<double, 1, 1>(P, a, b, tw.data(), 0);
+  }
+  return 0;
+}
+
 extern "C" int emu_solve(void* prob, int B, const float* q, const float* J, const float* e, const float* ep, const float* Gc, const float* hc,
                          float dt, double damping, int use_double, float* dq, int32_t* status, int32_t* iters, double* H, double* c, float* lo, float* hi) {
   EmuProblem* p = static_cast<EmuProblem*>(prob);

@@ -16,7 +16,7 @@ from mink_b200._abi import spec_from_workload  # noqa: E402
 from mink_b200.workloads import WORKLOADS, make_inputs  # noqa: E402
 from tests.helpers import load_case, load_flat, quat_align, task_frames  # noqa: E402
 
-CASES = ["ur5e", "ur5e_dls", "g1", "shadow", "spot", "g1_rel", "edge"]
+CASES = ["ur5e", "ur5e_dls", "g1", "shadow", "spot", "g1_rel", "edge", "g1_full", "g1_hands"]
 
 
 def _need_gpu():
@@ -270,6 +270,28 @@ def test_small_group_solver_knobs_against_oracle(env):
         dq, st = prob.step(q, inp["frame_targets"], inp["posture_target"], None, dt=wl["dt"], damping=wl["damping"])
         assert int(st.max()) == 0
         assert np.abs(_np(dq) - dq_ref).max() < 1e-4
+
+
+@pytest.mark.parametrize("name,B,T", [("g1", 4096 + 3, 8), ("g1_hands", 1024 + 1, 6), ("shadow", 2048, 6)])
+def test_rollout_batch_converges_and_matches_oracle(name, B, T):
+    """solve_ik + integrate with targets held (examples/humanoid_g1.py:81-94) on a batch: after the first step block
+    pivoting alone stalls on a few instances per thousand, so the small-group path carries the previous dq into a
+    Gauss-Seidel guess + primal active-set method.  No instance may be flagged, and the trajectory must follow the exact
+    oracle's (fp64 state; the device integrates q in fp32, hence the looser bound on q)."""
+    wl, fm, spec, g, model, prob = _engine(name)
+    orc = _oracle(fm, spec)
+    frames = task_frames(wl, fm)
+    inp = make_inputs(fm, wl, B, lambda qq: orc.fk(qq, frames), seed=29)
+    q = torch.tensor(inp["q"], dtype=torch.float32, device="cuda:0")
+    dq, st = prob.step(q, inp["frame_targets"], inp["posture_target"], None, dt=wl["dt"], damping=wl["damping"], nsteps=T, integrate=True)
+    assert int(st.max()) == 0, f"{int((st != 0).sum())} instances flagged in a {T}-step rollout"
+    dq_ref, q_end, st_ref, _ = orc.step(inp["q"], inp["frame_targets"], inp["posture_target"], None, dt=wl["dt"], damping=wl["damping"],
+                                        nsteps=T, integrate=True)
+    assert not st_ref.any()
+    err_q = np.abs(_np(q) - q_end).max()
+    err_dq = np.abs(_np(dq) - dq_ref).max()
+    print(f"{name}: {T}-step rollout of {B}: max|q - q_oracle| = {err_q:.2e}, last step max|dq - dq_oracle| = {err_dq:.2e}")
+    assert err_q < 5e-4 and err_dq < 2e-4
 
 
 @pytest.mark.parametrize("name,B", [("g1", 4099), ("shadow", 2050), ("ur5e_dls", 4096), ("spot", 1031)])
