@@ -361,7 +361,7 @@ template <typename T, int W, int SLOTS>
 BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane, int* iters_out, bool active = true) {
   const PHeader& h = P.h();
   const int n = h.nu, np = h.npairs;   // coupled dofs only (n == nv whenever there are general rows)
-  const int MAXIT = 60, PATIENCE = 3;
+  const int MAXIT = 400, PATIENCE = 3;   // the single-pivot fallback is finite but slow: stalled instances of a rollout need up to ~150 pivots (was 60: 1-5 per thousand flagged)
   const T tolx = K2Tol<T>::x(), tolg = K2Tol<T>::g();
   const float* Gb = np > 0 ? a.Gc + (long long)b * np * n : nullptr;
   for (int i = lane; i < n; i += W) {

@@ -173,7 +173,7 @@ BIK_HD void k2lr_warp(const PView& P, const K2Args& a, int b, void* wsm, const u
   }
   BIK_SYNCWARP();
 
-  const int MAXIT = 60, PATIENCE = 3;
+  const int MAXIT = 400, PATIENCE = 3;   // the single-pivot fallback is finite but slow: stalled instances of a rollout need up to ~150 pivots (was 60: 1-5 per thousand flagged)
   const T tolx = K2Tol<T>::x(), tolg = K2Tol<T>::g();
   int best = n + 1, patience = PATIENCE, it = 0, nactive = 0;
   for (; it < MAXIT; ++it) {

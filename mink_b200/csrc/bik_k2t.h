@@ -442,7 +442,7 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
   }
 
   // ---- block principal pivoting ----
-  const int MAXIT = 60, PATIENCE = 3;
+  const int MAXIT = 400, PATIENCE = 3;   // the primal active-set method needs ~20 at most; the block-pivoting branch (fp32, no guess) can need its slow fallback
   const T tolx = K2Tol<T>::x(), tolg = K2Tol<T>::g();
   uint32_t lom = 0u, upm = 0u;
   bool guessed = false;
