@@ -1,5 +1,5 @@
-// bik_k2t.h -- K2, small-group path: the same QP as bik_k2.h (same objective, same block principal
-// pivoting rule, same tolerances), laid out for coupled blocks of up to 24 dofs.
+// bik_k2t.h -- K2, small-group path: the same QP as bik_k2.h (same objective, same box, same tolerances, same optimum),
+// laid out for coupled blocks of up to 32 dofs.
 //
 // Why: with a whole warp per instance the 18-dof coupled block of the G1 configuration keeps half the
 // lanes idle and spends most instructions on run-time index arithmetic, shuffles and barriers
@@ -11,15 +11,20 @@
 //     (the G lanes of a group broadcast-read one address; the NS groups read one 8*NS-byte segment);
 //   * instance data from K1 (J, e, e_posture, q) is staged a task at a time through an instance-major
 //     tile with odd row stride: coalesced global reads by the whole warp, conflict-free private reads;
-//   * pivoting iterations refactor the FULL coupled block with clamped dofs turned into identity
-//     rows/columns (masked loads): every group executes the same instruction stream whatever its active
-//     set is, so groups never diverge; a group that has converged idles until its warp is done;
+//   * dofs without any finite bound (the free joint) are eliminated once; everything below runs on the Schur
+//     complement of that leading block (k2t_schur), and the leading part of dq is recovered at the end;
+//   * the active set is guessed by projected Gauss-Seidel sweeps (k2t_pgs_guess), inside a rollout from the
+//     previous step's dq; a primal active-set method then starts from that feasible point: every iteration
+//     refactors the pivoted block with clamped dofs turned into identity rows/columns (masked loads), so every
+//     group executes the same instruction stream whatever its active set is and groups never diverge; a group
+//     that has converged idles until its warp is done.  Without a guess (fp32 instantiation, BIK_K2_SWEEPS=0)
+//     the iterations are block principal pivoting as in bik_k2.h;
 //   * the factorisation is left-looking by blocks of G rows: lane l owns row i0+l, finished rows are
 //     broadcast-read from shared memory, the right-hand side rides along as the last row (forward
 //     substitution for free), diagonals are kept as reciprocal square roots, entries masked out by the
 //     active set are known to be zero and skipped; one warp barrier per row;
-//   * back substitution in dot-product form: every lane sums the columns it owns, a G-lane butterfly
-//     adds the partial sums (no barrier); multipliers are only evaluated on clamped dofs.
+//   * back substitution in column form (k2t_backsub): one barrier per row, no shuffles; multipliers are only
+//     evaluated on clamped dofs.
 //
 // Reference semantics: mink/solve_ik.py:13-65,101 (build_ik + qpsolvers), mink/tasks/task.py:105-138.
 // Device: G in {4, 8}, NS = 32 / G.  Host emulation (tests/host_emu): G = NS = 1.
