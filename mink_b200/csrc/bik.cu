@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) k2_kernel(const uint32_t* __restrict__ gi
 // differs between instances (G1: 91 % need one iteration, 1 in 10 000 needs six or more), and with a static round-robin
 // the warp that meets a slow instance also keeps its whole share of ordinary tiles, which set the kernel time.  The last
 // CTA to leave (sched[1] counts them) rewinds the counter for the next launch on the stream.
-template <typename T, int G, int MAXT>
+template <typename T, int G, int MAXT, typename M>
 __global__ void __launch_bounds__(MAXT, 512 / MAXT) k2t_kernel(const uint32_t* __restrict__ gimage, int warp_bytes, K2Args a, unsigned int* sched) {
   extern __shared__ __align__(16) uint32_t smem[];
   constexpr int NS = 32 / G;
@@ -134,14 +134,14 @@ __global__ void __launch_bounds__(MAXT, 512 / MAXT) k2t_kernel(const uint32_t* _
       if (lane == 0) t = atomicAdd(&sched[0], 1u);
       t = __shfl_sync(0xffffffffu, t, 0);
       if ((long long)t >= ntiles) break;
-      k2t_warp_tile<T, G, NS>(P, a, (long long)t * NS, wsm, lane, St, uw);
+      k2t_warp_tile<T, G, NS, M>(P, a, (long long)t * NS, wsm, lane, St, uw);
     }
     __syncthreads();
     if (threadIdx.x == 0 && atomicInc(&sched[1], gridDim.x - 1) == gridDim.x - 1) { __threadfence(); sched[0] = 0u; }
     return;
   }
   for (long long tile = (long long)blockIdx.x * nwarps + warp; tile < ntiles; tile += (long long)gridDim.x * nwarps)
-    k2t_warp_tile<T, G, NS>(P, a, tile * NS, wsm, lane, St, uw);
+    k2t_warp_tile<T, G, NS, M>(P, a, tile * NS, wsm, lane, St, uw);
 }
 
 // Fixed-size thread-per-problem K2 (bik_k2x.h): 32 problems per warp, factor in shared memory, H / c / box in a per-warp
@@ -319,6 +319,7 @@ struct bik_problem {
   signed char* warm = nullptr;  // [B][nu] active-set guess carried between the steps of one bik_step call
   int32_t* flags = nullptr;     // [B] instances the mixed-precision K2 hands to the fp64 kernel
   int k2_dynamic = 1;           // BIK_K2_DYNAMIC=0: static tile assignment in the small-group K2
+  int k2_wide = 0;              // BIK_K2_WIDE=1: box-only problems with 33..64 coupled dofs take the small-group path (64-bit masks)
   unsigned int* d_sched = nullptr;   // SCHED_SLOTS x 32 words: {next tile, finished CTAs} per launching stream (own 128-byte line each)
   cudaStream_t sched_stream[8];
   int n_sched = 0;
@@ -411,6 +412,7 @@ extern "C" int bik_problem_create(const bik_model* model, const bik_task_desc* t
   p->k2_warps = env_int("BIK_K2_WARPS", 8);
   p->k2_lockstep = env_int("BIK_K2_LOCKSTEP", 1);
   p->k2_dynamic = env_int("BIK_K2_DYNAMIC", 1) != 0;
+  p->k2_wide = env_int("BIK_K2_WIDE", 0) != 0;
   if (p->k2_warps != 1 && p->k2_warps != 2 && p->k2_warps != 4 && p->k2_warps != 8) p->k2_warps = 8;
   DeviceGuard g(model->device);
   CUDA_OK(cudaMalloc(&p->d_image, p->image.size() * 4));
@@ -564,7 +566,7 @@ static unsigned int* tile_counter(const bik_problem* cp, cudaStream_t st) {
   p->sched_stream[p->n_sched] = st;
   return p->d_sched + 32 * p->n_sched++;
 }
-template <typename T, int G>
+template <typename T, int G, typename M>
 static int launch_k2t(const bik_problem* p, const K2Args& a, cudaStream_t st) {
   constexpr int NS = 32 / G, MAXT = sizeof(T) == 8 ? 256 : 512;
   PView P{p->image.data()};
@@ -574,15 +576,16 @@ static int launch_k2t(const bik_problem* p, const K2Args& a, cudaStream_t st) {
   const size_t smem = NW * wb;
   int grid = 1;
   long long tiles = ((long long)a.B + NS - 1) / NS;
-  int rc = launch_geometry(k2t_kernel<T, G, MAXT>, p->model, smem, 32 * NW, (tiles + NW - 1) / NW, &grid);
+  int rc = launch_geometry(k2t_kernel<T, G, MAXT, M>, p->model, smem, 32 * NW, (tiles + NW - 1) / NW, &grid);
   if (rc) return rc;
-  k2t_kernel<T, G, MAXT><<<grid, 32 * NW, smem, st>>>(p->d_image, (int)wb, a, tile_counter(p, st));
+  k2t_kernel<T, G, MAXT, M><<<grid, 32 * NW, smem, st>>>(p->d_image, (int)wb, a, tile_counter(p, st));
   CUDA_OK(cudaGetLastError());
   return BIK_OK;
 }
 template <typename T>
 static int dispatch_k2t(const bik_problem* p, const K2Args& a, cudaStream_t st) {
-  return p->k2_group == 8 ? launch_k2t<T, 8>(p, a, st) : launch_k2t<T, 4>(p, a, st);
+  if (p->h.nu > K2T_NMAX) return launch_k2t<T, 8, uint64_t>(p, a, st);   // wide: 64-bit active-set masks (BIK_K2_WIDE=1)
+  return p->k2_group == 8 ? launch_k2t<T, 8, uint32_t>(p, a, st) : launch_k2t<T, 4, uint32_t>(p, a, st);
 }
 static int k2x_size(int nu) {
   const int sizes[] = {6, 8, 12, 16, 18, 20, 24};
@@ -641,7 +644,7 @@ static bool use_fixed(const bik_problem* p, const K2Args& a) {
 static bool use_thread(const bik_problem* p, const K2Args& a) {
   const PHeader& h = p->h;
   if (p->k2_path == 1 || p->k2_path == 2 || p->k2_path == 4 || !a.dq || a.Hout || a.lo_out) return false;
-  if (h.npairs != 0 || h.nu < 1 || h.nu > K2T_NMAX) return false;
+  if (h.npairs != 0 || h.nu < 1 || h.nu > (p->k2_wide ? K2T_NMAX_WIDE : K2T_NMAX)) return false;
   PView P{p->image.data()};
   return k2t_warp_bytes(P, p->solve_double ? 8 : 4, 32 / (p->k2_group == 8 ? 8 : 4)) <= p->model->max_smem;
 }

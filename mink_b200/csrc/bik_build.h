@@ -105,6 +105,13 @@ inline void put_frame(const bik_frame& fr, int32_t* node, float* lpos, float* lq
   for (int k = 0; k < 4; ++k) lquat[k] = (float)(fr.quat[k] / n);
 }
 
+inline void put_frame64(const bik_frame& fr, double* lpos, double* lquat) {
+  double n = sqrt(fr.quat[0] * fr.quat[0] + fr.quat[1] * fr.quat[1] + fr.quat[2] * fr.quat[2] + fr.quat[3] * fr.quat[3]);
+  if (!(n > 0)) n = 1;
+  for (int k = 0; k < 3; ++k) lpos[k] = fr.pos[k];
+  for (int k = 0; k < 4; ++k) lquat[k] = fr.quat[k] / n;
+}
+
 // Returns false and sets *err on unsupported input.
 inline bool build_image(const HostModel& m, const bik_task_desc* tasks, int ntasks, const bik_limit_desc* limits, int nlimits, int G,
                         std::vector<uint32_t>* image, std::string* err) {
@@ -148,6 +155,7 @@ inline bool build_image(const HostModel& m, const bik_task_desc* tasks, int ntas
   // frame tasks + ancestor-dof column lists
   H.off_frames = b.alloc(FRAME_WORDS * std::max(H.F, 1));
   std::vector<int32_t> cols;
+  int pk = 0;   // running offset in the packed K1 -> K2 record (frame tasks first, then CoM tasks, each in task order)
   {
     int fi = 0, ci = 0, row = 0;
     for (int t = 0; t < ntasks; ++t) {
@@ -178,6 +186,8 @@ inline bool build_image(const HostModel& m, const bik_task_desc* tasks, int ntas
           }
         std::sort(mine.begin(), mine.end(), [](int32_t a, int32_t b) { return (a & 0xffff) < (b & 0xffff); });
         r.ncols = (int)mine.size();
+        r.pk_off = pk;
+        pk += 6 * r.ncols + 6;
         cols.insert(cols.end(), mine.begin(), mine.end());
         memcpy(b.w.data() + H.off_frames + FRAME_WORDS * fi, &r, sizeof r);
         ++fi; row += 6;
@@ -233,11 +243,14 @@ inline bool build_image(const HostModel& m, const bik_task_desc* tasks, int ntas
         for (int k = 0; k < 3; ++k) { if (tasks[t].cost[k] < 0) { *err = "cost must be >= 0"; return false; } p[k] = (float)tasks[t].cost[k]; }
         p[3] = (float)tasks[t].gain; p[4] = (float)tasks[t].lm_damping;
         reinterpret_cast<int32_t*>(p)[5] = row;
+        reinterpret_cast<int32_t*>(p)[6] = pk;
+        pk += 3 * H.com_ncols + 3;
         ++ci; row += 3;
       }
     }
   }
 
+  H.pk_stride = (pk + 3) & ~3;
   // per-row (cost, gain, lm) table for the stacked rows
   H.off_rowinfo = b.alloc(3 * std::max(H.K, 1));
   {
@@ -381,6 +394,62 @@ inline bool build_image(const HostModel& m, const bik_task_desc* tasks, int ntas
       r->slot = r->node >= 0 ? slot[r->node] : -1;
       r->rslot = (r->relative && r->rnode >= 0) ? slot[r->rnode] : -1;
     }
+  }
+  // fp64 side tables: the kinematic constants at full precision for the fp64 instantiation of K1 (ill-conditioned problems:
+  // an fp32-rounded link offset moves e by ~1e-7, which cost / (2 sqrt(damping)) can amplify past the 1e-4 rad budget)
+  H.words32 = (int)b.w.size();
+  {
+    H.off_nodes64 = b.alloc(NODE64_WORDS * std::max(m.nnode, 1));
+    for (int n = 0; n < m.nnode; ++n) {
+      NodeRec64 r; memset(&r, 0, sizeof r);
+      for (int k = 0; k < 3; ++k) { r.pos[k] = m.node_pos[3 * n + k]; r.axis[k] = m.node_axis[3 * n + k]; r.jpos[k] = m.node_jpos[3 * n + k]; }
+      for (int k = 0; k < 4; ++k) r.quat[k] = m.node_quat[4 * n + k];
+      memcpy(b.w.data() + H.off_nodes64 + NODE64_WORDS * n, &r, sizeof r);
+    }
+    H.off_frames64 = b.alloc(FRAME64_WORDS * std::max(H.F, 1));
+    int fi = 0;
+    for (int t = 0; t < ntasks; ++t)
+      if (tasks[t].kind == BIK_TASK_FRAME || tasks[t].kind == BIK_TASK_RELATIVE_FRAME) {
+        FrameRec64 r; memset(&r, 0, sizeof r);
+        put_frame64(tasks[t].frame, r.lpos, r.lquat);
+        if (tasks[t].kind == BIK_TASK_RELATIVE_FRAME) put_frame64(tasks[t].root, r.rlpos, r.rlquat);
+        memcpy(b.w.data() + H.off_frames64 + FRAME64_WORDS * fi, &r, sizeof r);
+        ++fi;
+      }
+    H.off_qpos064 = b.alloc(2 * std::max(m.nq, 1));
+    memcpy(b.w.data() + H.off_qpos064, m.qpos0.data(), sizeof(double) * m.nq);
+    H.off_comnodes64 = b.alloc(COMNODE64_WORDS * std::max(m.nnode, 1));
+    H.off_com64 = b.alloc(16);   // { total mass, fixed first moment[3], collision gain, minimum / detection distance, relaxation }
+    {
+      std::vector<double> own_m(m.nnode, 0.0), sub_m(m.nnode, 0.0), own_c(3 * (size_t)m.nnode, 0.0);
+      double tot[4] = {0, 0, 0, 0};
+      for (int c = 0; c < m.ncom; ++c) {
+        int n = m.com_node[c]; double ms = m.com_mass[c]; tot[0] += ms;
+        if (n < 0) { for (int k = 0; k < 3; ++k) tot[1 + k] += ms * m.com_pos[3 * c + k]; continue; }
+        own_m[n] += ms; for (int k = 0; k < 3; ++k) own_c[3 * n + k] += ms * m.com_pos[3 * c + k];
+      }
+      for (int n = m.nnode - 1; n >= 0; --n) { sub_m[n] += own_m[n]; if (m.node_parent[n] >= 0) sub_m[m.node_parent[n]] += sub_m[n]; }
+      for (int n = 0; n < m.nnode; ++n) {
+        ComNodeRec64 r; memset(&r, 0, sizeof r);
+        r.own_m = own_m[n]; r.sub_m = sub_m[n];
+        for (int k = 0; k < 3; ++k) r.own_c[k] = own_c[3 * n + k];
+        memcpy(b.w.data() + H.off_comnodes64 + COMNODE64_WORDS * n, &r, sizeof r);
+      }
+      memcpy(b.w.data() + H.off_com64, tot, sizeof tot);
+      double coll[4] = {0, 0, 0, 0};
+      for (int l = 0; l < nlimits; ++l)
+        if (limits[l].kind == BIK_LIMIT_COLLISION) { coll[0] = limits[l].gain; coll[1] = limits[l].minimum_distance; coll[2] = limits[l].detection_distance; coll[3] = limits[l].bound_relaxation; }
+      memcpy(b.w.data() + H.off_com64 + 8, coll, sizeof coll);
+    }
+    H.off_geoms64 = b.alloc(GEOM64_WORDS * std::max(H.ngeoms, 1));
+    for (int l = 0; l < nlimits; ++l)
+      if (limits[l].kind == BIK_LIMIT_COLLISION)
+        for (int g = 0; g < limits[l].ngeoms; ++g) {
+          GeomRec64 r; memset(&r, 0, sizeof r);
+          put_frame64(limits[l].geoms[g].frame, r.lpos, r.lquat);
+          for (int k = 0; k < 3; ++k) r.size[k] = limits[l].geoms[g].size[k];
+          memcpy(b.w.data() + H.off_geoms64 + GEOM64_WORDS * g, &r, sizeof r);
+        }
   }
   H.words = (int)b.w.size();
   memcpy(b.w.data() + hoff, &H, sizeof H);

@@ -1,4 +1,5 @@
-// bik_k2.h -- K2: per-instance QP assembly and exact solve, one warp per problem.
+// bik_k2.h -- K2: per-instance QP assembly and exact solve, one warp per problem (the general path: collision rows,
+// any number of coupled dofs; box-only problems with at most 64 coupled dofs take the small-group path of bik_k2t.h).
 //
 //   H = damping I + sum_t (W_t J_t)^T (W_t J_t) + mu_t I,   c = sum_t -(W_t(-gain_t e_t))^T W_t J_t
 //       (reference mink/tasks/task.py:105-138, mink/solve_ik.py:13-22)
@@ -6,14 +7,24 @@
 //       (reference mink/solve_ik.py:43-65,101 -> qpsolvers)
 //
 // Structure exploited: frame-task Jacobians only have their ancestor-dof columns
-// non-zero, so each task adds a small dense block to H; the posture task is diagonal; configuration
+// non-zero, so each task adds a small dense block to H; the posture task is a diagonal; configuration
 // and velocity limits share their index set and collapse to one box per dof.
 //
-// Solver: block principal pivoting (Kunisch-Rendl infeasible active set with the Judice-Pires
-// single-pivot safeguard) -- every iteration guesses the active set, solves the reduced system with
-// a fresh packed Cholesky of the free block and flips every violated index at once.  It terminates
-// at the exact KKT point of the strictly convex QP, i.e. the same optimum quadprog/daqp return.
-// General rows (collision) join the same pivoting through a Schur complement on the factor.
+// Task rows arrive either packed (K1's hand-off inside bik_step: per task the non-zero columns, [ncols][6] + e[6], fp32
+// or fp64) or dense (bik_solve: what Task.compute_jacobian returns).
+//
+// Solver, two phases, same KKT point (the optimum quadprog / daqp return for the strictly convex QP):
+//   1. block principal pivoting (Kunisch-Rendl infeasible active set): guess the active set -- inside a rollout the
+//      previous step's --, solve the reduced system with a fresh packed Cholesky of the free block, flip every violated
+//      index at once.  Usually 2-4 iterations, 1-2 when warm-started; it has no descent property and stalls on a few
+//      instances per thousand once a rollout is under way.
+//   2. when the number of infeasibilities has not improved for PATIENCE iterations: a primal active-set method from the
+//      feasible point clip(0, lo, hi) (dq = 0 satisfies every limit of a configuration inside its limits: h >= 0 for the
+//      collision rows, collision_avoidance_limit.py:203).  Each iteration solves for the minimiser of the current working
+//      set, moves the feasible iterate towards it until the first bound or general row blocks (ratio test), adds that
+//      constraint; at a feasible subspace minimiser it drops the constraint with the most negative multiplier or stops.
+//      The objective decreases monotonically, so it terminates.
+// General rows (collision) enter both phases through a Schur complement on the factor.
 //
 // Lanes own rows (row i -> lane i % W); reductions over lanes use shuffles.  W = 1 on the host.
 #pragma once
@@ -25,64 +36,60 @@
 #define BIK_NOINLINE __attribute__((noinline))
 #endif
 
-// CTA-wide "does any warp still have work" vote (lock-step mode keeps the warps of a CTA in the same
-// solver phase so that they share instruction-cache lines); identity on the host.
-#if defined(__CUDA_ARCH__)
-#define BIK_BLOCK_ANY(x) __syncthreads_or(x)
-#else
-#define BIK_BLOCK_ANY(x) (x)
-#endif
-
 namespace bik {
 
 struct K2Args {
   int B;
-  const float* q;    // [B][nq]
-  const float* J;    // [B][K][nv]
-  const float* e;    // [B][K]
-  const float* ep;   // [B][P][nv]
-  const float* Gc;   // [B][npairs][nv]
-  const float* hc;   // [B][npairs]
-  float dt;
+  const void* q;       // [B][nq]; fp64 when io64
+  int io64;            // q, posture targets and dq are fp64 (else fp32)
+  // task rows, one of two forms
+  const void* pk;      // packed K1 hand-off [B][pk_stride] (fp64 when pk64), or null
+  int pk64;
+  const float* J;      // dense [B][K][nv]   (bik_solve / bik_qp_objective)
+  const float* e;      // dense [B][K]
+  const float* ep;     // dense [B][P][nv]; null: the posture error is computed from q and ptgt
+  const void* ptgt;    // [B or 1][P][nq] posture targets (dtype follows io64)
+  int pbatched;
+  const void* Gc;      // [B][npairs][nv], [B][npairs] collision rows (fp64 when gc64)
+  const void* hc;
+  int gc64;
+  double dt;
   double damping;
-  float* dq;         // [B][nv]
-  int32_t* status;   // [B] or null (OR-ed into)
-  int32_t* iters;    // [B] or null: active-set iterations (diagnostics)
-  double* Hout;      // [B][nv][nv] or null  (bik_qp_objective)
-  double* cout;      // [B][nv] or null
-  float* lo_out;     // [B][nv] or null      (bik_limits_box)
+  void* dq;            // [B][nv]
+  int integrate;       // q <- q (+) dq in place after the solve (Configuration.integrate_inplace, configuration.py:228-236)
+  int32_t* status;     // [B] or null (OR-ed into)
+  int32_t* iters;      // [B] or null: factorisations per instance (diagnostics)
+  double* Hout;        // [B][nv][nv] or null  (bik_qp_objective)
+  double* cout;        // [B][nv] or null
+  float* lo_out;       // [B][nv] or null      (bik_limits_box)
   float* hi_out;
-  int skip_objective;  // bik_limits_box: J/e/ep are not read
+  int skip_objective;  // bik_limits_box: task rows are not read
   int skip_box;        // bik_qp_objective: q is not read
-  int lockstep;        // warps of a CTA advance through the pivoting iterations together (block barriers)
   signed char* warm;   // [B][nu] or null: active-set guess in (0 free, 1 lower, 2 upper; +4 = dq still holds the previous step's result), read at entry, updated at exit
-  int32_t* flag_out;   // [B] or null: mixed-precision path marks the instances it could not finish (bik_k2x.h)
-  const int32_t* only; // [B] or null: small-group path processes only the instances marked here (bik_k2t.h)
+  const int32_t* skip; // [B] or null: instances marked here are neither solved nor integrated (bik_converge: already converged)
 };
 
-enum { K2_MAX_GEN = 16 };  // general (collision) rows that may be active at once
+enum { K2_MAX_GEN = 24 };  // general (collision) rows that may be active at once; more than that sets BIK_STATUS_QP_MAXITER
 
 BIK_HD int tri(int i) { return (i * (i + 1)) >> 1; }
 
+BIK_HD int k2_max_gen(const PHeader& h) { return h.npairs < K2_MAX_GEN ? h.npairs : K2_MAX_GEN; }
 // per-warp scratch, in bytes, for scalar type of size `ts`.
-// Layout: Hp | U | dinv c lo hi x | [general-row block] | ints.   U is a union: during assembly it
-// holds the weighted Jacobian rows (fp32), afterwards the packed factor augmented by the rhs row.
+// Layout: Hp | dinv c lo hi x xf xfull | [general-row block] | U | ints.   U is a union: during assembly it
+// holds the weighted task blocks (packed layout), afterwards the packed factor augmented by the rhs row.
 BIK_HD int k2_union_bytes(const PHeader& h, int ts) {
   int n = h.nu;
   int lp = tri(n + 1) * ts + 16;                       // (n+1) rows: factor + fused right-hand side
-  int wj = 4 * ((h.K > 0 ? h.K : 1) * (h.nv + 1)) + 16;  // wJ [K][nv] + we [K]
+  int wj = (h.pk_stride > 0 ? h.pk_stride : 4) * ts + 16;
   return ((lp > wj ? lp : wj) + 15) & ~15;
 }
 BIK_HD int k2_warp_bytes(const PHeader& h, int ts) {
-  int n = h.nu, np = h.npairs;
-  int words_T = tri(n) + 5 * n + h.nv + (np > 0 ? (K2_MAX_GEN * n + K2_MAX_GEN * K2_MAX_GEN + 3 * K2_MAX_GEN + np) : 0);
-  int bytes = ((words_T * ts + 15) & ~15) + k2_union_bytes(h, ts) + 4 * (2 * n + 3 * np + 12);
+  int n = h.nu, np = h.npairs, mg = k2_max_gen(h);
+  int words_T = tri(n) + 6 * n + h.nv + (np > 0 ? (mg * n + mg * mg + 3 * mg + 2 * np) : 0);
+  int bytes = ((words_T * ts + 15) & ~15) + k2_union_bytes(h, ts) + 4 * (2 * n + 3 * np + 16);
   return (bytes + 15) & ~15;
 }
 
-template <typename T> BIK_HD T bik_sqrt(T x);
-template <> BIK_HD float bik_sqrt<float>(float x) { return sqrtf(x); }
-template <> BIK_HD double bik_sqrt<double>(double x) { return sqrt(x); }
 template <typename T> BIK_HD T bik_rsqrt(T x);
 template <> BIK_HD float bik_rsqrt<float>(float x) {
 #if defined(__CUDA_ARCH__)
@@ -111,6 +118,13 @@ template <int W> BIK_HD int warp_max_i(int v) {
 #endif
   return v;
 }
+template <int W> BIK_HD int warp_min_i(int v) { return -warp_max_i<W>(-v); }
+template <int W, typename T> BIK_HD T warp_min_t(T v) {
+#if defined(__CUDA_ARCH__)
+  for (int o = W / 2; o > 0; o >>= 1) { T t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
+#endif
+  return v;
+}
 template <typename T> BIK_HD T warp_bcast(T v, int src) {
 #if defined(__CUDA_ARCH__)
   return __shfl_sync(0xffffffffu, v, src);
@@ -121,25 +135,24 @@ template <typename T> BIK_HD T warp_bcast(T v, int src) {
 }
 
 template <typename T> struct K2Ws {
-  T *Hp, *Lp, *dinv, *c, *lo, *hi, *x, *xfull;
-  T *Y, *S, *lam, *rg, *hg, *sg;  // general rows: Y = L^-1 G_F^T (K2_MAX_GEN x n), S Schur, lam, rhs, h, slack
+  T *Hp, *Lp, *dinv, *c, *lo, *hi, *x, *xf, *xfull;
+  T *Y, *S, *lam, *rg, *sg, *hg, *gp;  // general rows: Y = L^-1 G_F^T (maxg x n), S Schur, lam, rhs, slack, h [np], scratch [np]
   int *st, *idx, *gst, *gidx, *gnew;
-  float *wJ, *we;
+  T *wpk;                              // weighted task blocks in the packed layout (aliases Lp)
 };
 template <typename T> BIK_HD K2Ws<T> k2_carve(const PHeader& h, void* mem) {
   K2Ws<T> w;
-  int n = h.nu, np = h.npairs;
+  int n = h.nu, np = h.npairs, mg = k2_max_gen(h);
   char* base = reinterpret_cast<char*>(mem);
   T* p = reinterpret_cast<T*>(base);
   w.Hp = p; p += tri(n);
-  w.dinv = p; p += n; w.c = p; p += n; w.lo = p; p += n; w.hi = p; p += n; w.x = p; p += n; w.xfull = p; p += h.nv;
-  w.Y = w.S = w.lam = w.rg = w.hg = w.sg = nullptr;
-  if (np > 0) { w.Y = p; p += K2_MAX_GEN * n; w.S = p; p += K2_MAX_GEN * K2_MAX_GEN; w.lam = p; p += K2_MAX_GEN; w.rg = p; p += K2_MAX_GEN; w.sg = p; p += K2_MAX_GEN; w.hg = p; p += np; }
+  w.dinv = p; p += n; w.c = p; p += n; w.lo = p; p += n; w.hi = p; p += n; w.x = p; p += n; w.xf = p; p += n; w.xfull = p; p += h.nv;
+  w.Y = w.S = w.lam = w.rg = w.hg = w.sg = w.gp = nullptr;
+  if (np > 0) { w.Y = p; p += mg * n; w.S = p; p += mg * mg; w.lam = p; p += mg; w.rg = p; p += mg; w.sg = p; p += mg; w.hg = p; p += np; w.gp = p; p += np; }
   int words_T = (int)(p - reinterpret_cast<T*>(base));
   char* u = base + ((words_T * (int)sizeof(T) + 15) & ~15);
   w.Lp = reinterpret_cast<T*>(u);
-  w.wJ = reinterpret_cast<float*>(u);
-  w.we = w.wJ + (h.K > 0 ? h.K : 1) * h.nv;
+  w.wpk = reinterpret_cast<T*>(u);
   int* ip = reinterpret_cast<int*>(u + k2_union_bytes(h, sizeof(T)));
   w.st = ip; ip += n; w.idx = ip; ip += n; w.gst = ip; ip += np + 4; w.gidx = ip; ip += np + 4; w.gnew = ip; ip += np + 4;
   return w;
@@ -147,99 +160,120 @@ template <typename T> BIK_HD K2Ws<T> k2_carve(const PHeader& h, void* mem) {
 
 template <typename T> BIK_HD T Hsym(const T* Hp, int i, int j) { return i >= j ? Hp[tri(i) + j] : Hp[tri(j) + i]; }
 
+// One task of the stacked objective: rows, non-zero columns and where its block sits in the packed record.
+struct K2Task { int row0, nr, nc, coff, pk_off; const float* cost; float gain, lm; };
+BIK_HD K2Task k2_task(const PView& P, int t) {
+  const PHeader& h = P.h();
+  K2Task k;
+  if (t < h.F) { const FrameRec& fr = P.frame(t); k.row0 = fr.row0; k.nr = 6; k.nc = fr.ncols; k.coff = fr.col_off; k.pk_off = fr.pk_off; k.cost = fr.cost; k.gain = fr.gain; k.lm = fr.lm; }
+  else {
+    const float* cr = P.f(h.off_com) + 8 * (t - h.F);
+    k.row0 = reinterpret_cast<const int32_t*>(cr)[5]; k.pk_off = reinterpret_cast<const int32_t*>(cr)[6];
+    k.nr = 3; k.nc = h.com_ncols; k.coff = h.com_cols_off; k.cost = cr; k.gain = cr[3]; k.lm = cr[4];
+  }
+  return k;
+}
+
 // ---- assembly ------------------------------------------------------------------------------
 template <typename T, int W>
-BIK_HD void k2_assemble(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane) {
+BIK_HD int k2_assemble(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane) {
   const PHeader& h = P.h();
-  const int n = h.nv, nu = h.nu, K = h.K;
-  const float* Jb = a.J + (long long)b * K * n;
-  const float* eb = a.e + (long long)b * K;
+  const int n = h.nv, nu = h.nu, K = h.K, nq = h.nq;
   const int32_t* cols = P.i(h.off_cols);
   const int32_t* umap = P.i(h.off_umap);
+  const int32_t* dofqadr = P.i(h.off_dofqadr);
+  auto qv = [&](int i) { return ldin<T>(a.q, (long long)b * nq + i, a.io64); };
+  int status = 0;
   if (a.skip_objective) {  // bik_limits_box: only the box, for every dof
     for (int d = lane; d < n; d += W) {
-      float lo, hi;
-      box_dof(P, d, a.q + (long long)b * h.nq, a.dt, &lo, &hi);
-      a.lo_out[(long long)b * n + d] = lo; a.hi_out[(long long)b * n + d] = hi;
+      T lo, hi;
+      const int qa = dofqadr[d];
+      box_dof<T>(P, d, qa >= 0 ? qv(qa) : T(0), T(a.dt), &lo, &hi);
+      a.lo_out[(long long)b * n + d] = float(lo); a.hi_out[(long long)b * n + d] = float(hi);
     }
-    return;
+    return 0;
   }
   for (int k = lane; k < tri(nu); k += W) w.Hp[k] = T(0);
-  // weighted rows  W J  and  W(-gain e)
-  for (int f = 0; f < h.F; ++f) {
-    const FrameRec& fr = P.frame(f);
-    for (int k = lane; k < 6 * n; k += W) { int r = k / n; w.wJ[fr.row0 * n + k] = fr.cost[r] * Jb[fr.row0 * n + k]; }
-    for (int r = lane; r < 6; r += W) w.we[fr.row0 + r] = fr.cost[r] * (-fr.gain * eb[fr.row0 + r]);
-  }
-  for (int c = 0; c < h.C; ++c) {
-    const float* cr = P.f(h.off_com) + 8 * c;
-    int row0 = reinterpret_cast<const int32_t*>(cr)[5];
-    for (int k = lane; k < 3 * n; k += W) { int r = k / n; w.wJ[row0 * n + k] = cr[r] * Jb[row0 * n + k]; }
-    for (int r = lane; r < 3; r += W) w.we[row0 + r] = cr[r] * (-cr[3] * eb[row0 + r]);
+  for (int k = lane; k < nu; k += W) w.c[k] = T(0);
+  // weighted task blocks in the packed layout:  [ia][r] = cost_r J[row0+r][col_ia],  then  cost_r (-gain e[row0+r])
+  for (int t = 0; t < h.F + h.C; ++t) {
+    const K2Task tk = k2_task(P, t);
+    const int nj = tk.nr * tk.nc;
+    for (int k = lane; k < nj + tk.nr; k += W) {
+      const int ia = k / tk.nr, r = k - ia * tk.nr;
+      T v;
+      if (a.pk) v = ldin<T>(a.pk, (long long)b * h.pk_stride + tk.pk_off + k, a.pk64);
+      else if (k < nj) v = T(a.J[((long long)b * K + tk.row0 + r) * n + (cols[tk.coff + ia] & 0xffff)]);
+      else v = T(a.e[(long long)b * K + tk.row0 + r]);
+      w.wpk[tk.pk_off + k] = k < nj ? T(tk.cost[r]) * v : T(tk.cost[r]) * (T(-tk.gain) * v);
+    }
   }
   BIK_SYNCWARP();
-  // block contributions (W J)^T (W J), lower triangle of the COUPLED block, per task over its non-zero columns
+  // block contributions (W J)^T (W J) and the linear term, lower triangle of the COUPLED block, per task over its non-zero columns
   for (int t = 0; t < h.F + h.C; ++t) {
-    int row0, nr, nc, coff;
-    if (t < h.F) { const FrameRec& fr = P.frame(t); row0 = fr.row0; nr = 6; nc = fr.ncols; coff = fr.col_off; }
-    else { const float* cr = P.f(h.off_com) + 8 * (t - h.F); row0 = reinterpret_cast<const int32_t*>(cr)[5]; nr = 3; nc = h.com_ncols; coff = h.com_cols_off; }
-    for (int p = lane; p < nc * nc; p += W) {
-      int ia = p / nc, ib = p - ia * nc;
+    const K2Task tk = k2_task(P, t);
+    const T* blk = w.wpk + tk.pk_off;
+    const T* we = blk + tk.nr * tk.nc;
+    for (int p = lane; p < tk.nc * tk.nc; p += W) {
+      int ia = p / tk.nc, ib = p - ia * tk.nc;
       if (ib > ia) continue;
-      int ca = cols[coff + ia] & 0xffff, cb = cols[coff + ib] & 0xffff;
       T s = T(0);
-      for (int r = 0; r < nr; ++r) s += T(w.wJ[(row0 + r) * n + ca]) * T(w.wJ[(row0 + r) * n + cb]);
-      w.Hp[tri(umap[ca]) + umap[cb]] += s;   // column lists are ascending, so umap[ca] >= umap[cb]
+      for (int r = 0; r < tk.nr; ++r) s += blk[ia * tk.nr + r] * blk[ib * tk.nr + r];
+      const int ua = umap[cols[tk.coff + ia] & 0xffff], ub = umap[cols[tk.coff + ib] & 0xffff];   // column lists are ascending: ua >= ub
+      w.Hp[tri(ua) + ub] += s;
+      if (ib == ia) { T cs = T(0); for (int r = 0; r < tk.nr; ++r) cs += we[r] * blk[ia * tk.nr + r]; w.c[ua] -= cs; }
     }
     BIK_SYNCWARP();
   }
   // Levenberg-Marquardt terms mu_t = lm_t ||W(-gain e)||^2 (task.py:131) -- every lane, same order
   T mu = T(a.damping);
-  for (int f = 0; f < h.F; ++f) {
-    const FrameRec& fr = P.frame(f);
-    if (fr.lm != 0.f) { T s = T(0); for (int r = 0; r < 6; ++r) s += T(w.we[fr.row0 + r]) * T(w.we[fr.row0 + r]); mu += T(fr.lm) * s; }
+  for (int t = 0; t < h.F + h.C; ++t) {
+    const K2Task tk = k2_task(P, t);
+    if (tk.lm != 0.f) { const T* we = w.wpk + tk.pk_off + tk.nr * tk.nc; T s = T(0); for (int r = 0; r < tk.nr; ++r) s += we[r] * we[r]; mu += T(tk.lm) * s; }
   }
-  for (int c = 0; c < h.C; ++c) {
-    const float* cr = P.f(h.off_com) + 8 * c;
-    int row0 = reinterpret_cast<const int32_t*>(cr)[5];
-    if (cr[4] != 0.f) { T s = T(0); for (int r = 0; r < 3; ++r) s += T(w.we[row0 + r]) * T(w.we[row0 + r]); mu += T(cr[4]) * s; }
-  }
+  auto eperr = [&](int p, int d) -> T {
+    if (a.ep) return T(a.ep[((long long)b * h.P + p) * n + d]);
+    const long long t0 = ((long long)(a.pbatched ? b : 0) * h.P + p) * nq;
+    return posture_err_dof<T>(P, d, [&](int i) { return ldin<T>(a.ptgt, t0 + i, a.io64); }, qv);
+  };
   for (int p = 0; p < h.P; ++p) {
     const float* pr = P.f(h.off_posture) + p * (2 + n);
     if (pr[1] != 0.f) {
-      const float* epb = a.ep + ((long long)b * h.P + p) * n;
       T s = T(0);
-      for (int d = 0; d < n; ++d) { T v = T(pr[2 + d]) * T(pr[0]) * T(epb[d]); s += v * v; }
+      for (int d = lane; d < n; d += W) { T v = T(pr[2 + d]) * T(pr[0]) * eperr(p, d); s += v * v; }
+#if defined(__CUDA_ARCH__)
+      for (int o = W / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+#endif
       mu += T(pr[1]) * s;
     }
   }
-  // linear term, diagonal and box.  A DECOUPLED dof (zero column in every task Jacobian) only sees
+  // diagonal, posture part of the linear term and box.  A DECOUPLED dof (zero column in every task Jacobian) only sees
   // the diagonal: its optimum is the clamp of -c/h, written straight to xfull.
   for (int d = lane; d < n; d += W) {
     const int u = umap[d];
-    T cd = T(0);
-    if (u >= 0) for (int r = 0; r < K; ++r) cd -= T(w.we[r]) * T(w.wJ[r * n + d]);
-    T hd = mu;
+    T cd = T(0), hd = mu;
     for (int p = 0; p < h.P; ++p) {
       const float* pr = P.f(h.off_posture) + p * (2 + n);
       T wgt = T(pr[2 + d]);
-      hd += wgt * wgt;                                                        // (W J)^T (W J), J = -I
-      cd -= T(pr[0]) * wgt * wgt * T(a.ep[((long long)b * h.P + p) * n + d]);  // -(W(-g e))^T W (-I)
+      hd += wgt * wgt;                                  // (W J)^T (W J), J = -I
+      if (wgt != T(0)) cd -= T(pr[0]) * wgt * wgt * eperr(p, d);  // -(W(-g e))^T W (-I)
     }
-    float lo = -BIK_INF_F, hi = BIK_INF_F;
-    if (!a.skip_box) box_dof(P, d, a.q + (long long)b * h.nq, a.dt, &lo, &hi);
-    if (a.lo_out) { a.lo_out[(long long)b * n + d] = lo; a.hi_out[(long long)b * n + d] = hi; }
+    T lo = -T(BIK_INF_F), hi = T(BIK_INF_F);
+    if (!a.skip_box) { const int qa = dofqadr[d]; box_dof<T>(P, d, qa >= 0 ? qv(qa) : T(0), T(a.dt), &lo, &hi); }
+    if (a.lo_out) { a.lo_out[(long long)b * n + d] = float(lo); a.hi_out[(long long)b * n + d] = float(hi); }
+    if (lo > hi + T(1e-9) * (T(1) + (hi < 0 ? -hi : hi))) status |= 8;   // inconsistent limits (e.g. a configuration far outside its range with a velocity limit): the reference's QP has no solution (solve_ik.py:103)
     if (u >= 0) {
       w.Hp[tri(u) + u] += hd;
-      w.c[u] = cd; w.lo[u] = T(lo); w.hi[u] = T(hi);
+      w.c[u] += cd; w.lo[u] = lo; w.hi[u] = hi;
     } else {
       T v = -cd / hd;
-      v = v < T(lo) ? T(lo) : (v > T(hi) ? T(hi) : v);
+      v = v < lo ? lo : (v > hi ? hi : v);
       w.xfull[d] = v;
       if (a.Hout) { a.Hout[((long long)b * n + d) * n + d] = double(hd); a.cout[(long long)b * n + d] = double(cd); }
     }
   }
   BIK_SYNCWARP();
+  return status;
 }
 
 // ---- packed Cholesky of the free block, right-hand side fused as row nf -------------------------
@@ -321,92 +355,122 @@ BIK_NOINLINE void k2_forward(const T* Lp, const T* dinv, T* y, int nf, int lane)
   BIK_SYNCWARP();
 }
 
+// element j of collision row r of instance b
+template <typename T> BIK_HD T k2_grow(const K2Args& a, long long base, int r, int n, int j) { return ldin<T>(a.Gc, base + (long long)r * n + j, a.gc64); }
+
 // Active general rows R (collision): KKT  [H_FF G_RF^T; G_RF 0][x_F; lam] = [y; h_R - G_RA x_A] through the
 // factor:  Y_r = L^-1 G_rF^T,  S = Y Y^T,  lam = S^-1 (Y (L^-1 y) - rhs),  rhs row <- L^-1 y - Y^T lam.
 // Cold for box-only problems: kept out of line so it does not occupy the instruction cache.
 template <typename T, int W>
-BIK_NOINLINE void k2_general_rows(K2Ws<T>& w, const float* Gb, T* rhs, int n, int nf, int ng, int lane) {
+BIK_NOINLINE int k2_general_rows(K2Ws<T>& w, const K2Args& a, long long gbase, T* rhs, int n, int nf, int ng, int mg, int lane) {
+  int bad = 0;
   for (int r = 0; r < ng; ++r) {
-    const float* Gr = Gb + (long long)w.gidx[r] * n;
     T* Yr = w.Y + r * n;
-    for (int i = lane; i < nf; i += W) Yr[i] = T(Gr[w.idx[i]]);
-    if (lane == 0) { T sv = w.hg[w.gidx[r]]; for (int j = 0; j < n; ++j) if (w.st[j]) sv -= T(Gr[j]) * w.x[j]; w.rg[r] = sv; }
+    for (int i = lane; i < nf; i += W) Yr[i] = k2_grow<T>(a, gbase, w.gidx[r], n, w.idx[i]);
+    if (lane == 0) { T sv = w.hg[w.gidx[r]]; for (int j = 0; j < n; ++j) if (w.st[j]) sv -= k2_grow<T>(a, gbase, w.gidx[r], n, j) * w.x[j]; w.rg[r] = sv; }
     BIK_SYNCWARP();
     k2_forward<T, W>(w.Lp, w.dinv, Yr, nf, lane);
   }
   if (lane == 0) {  // tiny dense solve, serial
     for (int r = 0; r < ng; ++r) {
-      for (int q2 = 0; q2 <= r; ++q2) { T v = T(0); for (int i = 0; i < nf; ++i) v += w.Y[r * n + i] * w.Y[q2 * n + i]; w.S[r * K2_MAX_GEN + q2] = v; w.S[q2 * K2_MAX_GEN + r] = v; }
+      for (int q2 = 0; q2 <= r; ++q2) { T v = T(0); for (int i = 0; i < nf; ++i) v += w.Y[r * n + i] * w.Y[q2 * n + i]; w.S[r * mg + q2] = v; w.S[q2 * mg + r] = v; }
       T v = -w.rg[r]; for (int i = 0; i < nf; ++i) v += w.Y[r * n + i] * rhs[i]; w.lam[r] = v;
     }
     for (int j = 0; j < ng; ++j) {  // Cholesky of S in place + solve
-      T d = w.S[j * K2_MAX_GEN + j]; for (int k = 0; k < j; ++k) d -= w.S[j * K2_MAX_GEN + k] * w.S[j * K2_MAX_GEN + k];
-      d = bik_sqrt<T>(d > T(0) ? d : T(1e-30)); w.S[j * K2_MAX_GEN + j] = d;
-      for (int i = j + 1; i < ng; ++i) { T v = w.S[i * K2_MAX_GEN + j]; for (int k = 0; k < j; ++k) v -= w.S[i * K2_MAX_GEN + k] * w.S[j * K2_MAX_GEN + k]; w.S[i * K2_MAX_GEN + j] = v / d; }
+      const T sjj = w.S[j * mg + j];
+      T d = sjj; for (int k = 0; k < j; ++k) d -= w.S[j * mg + k] * w.S[j * mg + k];
+      if (!(d > T(1e-14) * sjj)) bad = 1;   // the active rows are (numerically) dependent
+      d = bik_sqrt<T>(d > T(0) ? d : T(1e-30)); w.S[j * mg + j] = d;
+      for (int i = j + 1; i < ng; ++i) { T v = w.S[i * mg + j]; for (int k = 0; k < j; ++k) v -= w.S[i * mg + k] * w.S[j * mg + k]; w.S[i * mg + j] = v / d; }
     }
-    for (int i = 0; i < ng; ++i) { T v = w.lam[i]; for (int k = 0; k < i; ++k) v -= w.S[i * K2_MAX_GEN + k] * w.lam[k]; w.lam[i] = v / w.S[i * K2_MAX_GEN + i]; }
-    for (int i = ng - 1; i >= 0; --i) { T v = w.lam[i]; for (int k = i + 1; k < ng; ++k) v -= w.S[k * K2_MAX_GEN + i] * w.lam[k]; w.lam[i] = v / w.S[i * K2_MAX_GEN + i]; }
+    for (int i = 0; i < ng; ++i) { T v = w.lam[i]; for (int k = 0; k < i; ++k) v -= w.S[i * mg + k] * w.lam[k]; w.lam[i] = v / w.S[i * mg + i]; }
+    for (int i = ng - 1; i >= 0; --i) { T v = w.lam[i]; for (int k = i + 1; k < ng; ++k) v -= w.S[k * mg + i] * w.lam[k]; w.lam[i] = v / w.S[i * mg + i]; }
   }
   BIK_SYNCWARP();
   for (int i = lane; i < nf; i += W) { T v = rhs[i]; for (int r = 0; r < ng; ++r) v -= w.Y[r * n + i] * w.lam[r]; rhs[i] = v; }
   BIK_SYNCWARP();
+  return warp_max_i<W>(bad);
 }
 
 template <typename T> struct K2Tol;
 template <> struct K2Tol<double> { static BIK_HD double x() { return 1e-12; } static BIK_HD double g() { return 1e-9; } };
 template <> struct K2Tol<float> { static BIK_HD float x() { return 1e-7f; } static BIK_HD float g() { return 1e-4f; } };
 
-// Returns status bits.  On exit w.x holds dq.
+// Minimiser of the QP on the working set (w.st: 0 free / 1 at lower / 2 at upper; w.gst: active general rows) into w.x,
+// multipliers of the active general rows into w.lam.  Returns status bits (4: factorisation broke down, 2: more than
+// k2_max_gen rows active, 32 (internal): the active general rows are linearly dependent, the multipliers are not
+// trustworthy); *ng_out = number of active general rows (their indices in w.gidx).
 template <typename T, int W, int SLOTS>
-BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane, int* iters_out, bool active = true) {
+BIK_HD int k2_solve_working_set(const PHeader& h, const K2Args& a, long long gbase, K2Ws<T>& w, int lane, int* ng_out) {
+  const int n = h.nu, np = h.npairs, mg = k2_max_gen(h);
+  int status = 0;
+  // compact free list / active general rows (every lane writes the same values)
+  int nf = 0, ng = 0;
+  for (int i = 0; i < n; ++i) if (w.st[i] == 0) { w.idx[nf] = i; ++nf; }
+  for (int r = 0; r < np; ++r) if (w.gst[r]) { if (ng < mg) { w.gidx[ng] = r; ++ng; } else status |= 2; }
+  BIK_SYNCWARP();
+  // x on the bounds, rhs of the reduced system, copy of H_FF
+  for (int i = lane; i < n; i += W) w.x[i] = w.st[i] == 1 ? w.lo[i] : (w.st[i] == 2 ? w.hi[i] : T(0));
+  BIK_SYNCWARP();
+  T* rhs = w.Lp + tri(nf);
+  for (int i = lane; i < nf; i += W) {
+    int ii = w.idx[i];
+    const T* Hrow = w.Hp + tri(ii);
+    T r = -w.c[ii];
+    for (int j = 0; j < ii; ++j) if (w.st[j]) r -= Hrow[j] * w.x[j];
+    for (int j = ii + 1; j < n; ++j) if (w.st[j]) r -= w.Hp[tri(j) + ii] * w.x[j];
+    rhs[i] = r;
+    T* Li = w.Lp + tri(i);
+    for (int j = 0; j <= i; ++j) Li[j] = Hrow[w.idx[j]];
+  }
+  BIK_SYNCWARP();
+  if (k2_factor<T, W, SLOTS>(w.Lp, w.dinv, nf, lane)) status |= 4;
+  status = warp_max_i<W>(status & 4) | (status & 2);
+  if (ng > 0 && k2_general_rows<T, W>(w, a, gbase, rhs, n, nf, ng, mg, lane)) status |= 32;   // internal: active rows dependent
+  // x_F = L^-T (.), overwriting the rhs row in place
+  k2_backsub<T, W, SLOTS>(w.Lp, w.dinv, nf, rhs, lane);
+  for (int i = lane; i < nf; i += W) w.x[w.idx[i]] = rhs[i];
+  BIK_SYNCWARP();
+  *ng_out = ng;
+  return status;
+}
+// gradient of the Lagrangian on dof i at w.x:  c_i + (H x)_i + sum_r G_ri lam_r
+template <typename T>
+BIK_HD T k2_grad(const K2Args& a, long long gbase, const K2Ws<T>& w, int n, int ng, int i) {
+  T gi = w.c[i];
+  const T* Hrow = w.Hp + tri(i);
+  for (int j = 0; j <= i; ++j) gi += Hrow[j] * w.x[j];
+  for (int j = i + 1; j < n; ++j) gi += w.Hp[tri(j) + i] * w.x[j];
+  for (int r = 0; r < ng; ++r) gi += k2_grow<T>(a, gbase, w.gidx[r], n, i) * w.lam[r];
+  return gi;
+}
+
+// Returns status bits.  On exit w.x holds dq (coupled dofs).
+template <typename T, int W, int SLOTS>
+BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane, int* iters_out) {
   const PHeader& h = P.h();
   const int n = h.nu, np = h.npairs;   // coupled dofs only (n == nv whenever there are general rows)
-  const int MAXIT = 400, PATIENCE = 3;   // the single-pivot fallback is finite but slow: stalled instances of a rollout need up to ~150 pivots (was 60: 1-5 per thousand flagged)
+  const int MAXIT = 60 + 2 * (n + np), PATIENCE = 2;
   const T tolx = K2Tol<T>::x(), tolg = K2Tol<T>::g();
-  const float* Gb = np > 0 ? a.Gc + (long long)b * np * n : nullptr;
+  const long long gbase = (long long)b * np * n;
   for (int i = lane; i < n; i += W) {
-    int s0 = (a.warm && active) ? (a.warm[(long long)b * n + i] & 3) : 0;   // warm start: last step's active set (bit 2 is the small-group path's marker)
+    int s0 = a.warm ? (a.warm[(long long)b * n + i] & 3) : 0;   // warm start: last step's active set (bit 2 is the small-group path's marker)
     if ((s0 == 1 && !(w.lo[i] > T(-1e30))) || (s0 == 2 && !(w.hi[i] < T(1e30)))) s0 = 0;
     w.st[i] = s0;
   }
-  for (int r = lane; r < np; r += W) { w.gst[r] = 0; w.hg[r] = T(a.hc[(long long)b * np + r]); }
+  for (int r = lane; r < np; r += W) { w.gst[r] = 0; w.hg[r] = ldin<T>(a.hc, (long long)b * np + r, a.gc64); }
   BIK_SYNCWARP();
-  int status = 0, best = n + np + 1, patience = PATIENCE, it = 0;
-  bool done = !active || n == 0;
-  for (;; ++it) {
-    if (a.lockstep) { if (!BIK_BLOCK_ANY(!done && it < MAXIT)) break; }
-    else if (done || it >= MAXIT) break;
-    if (done || it >= MAXIT) continue;
-    // compact free list / active general rows (every lane writes the same values)
-    int nf = 0, ng = 0;
-    for (int i = 0; i < n; ++i) if (w.st[i] == 0) { w.idx[nf] = i; ++nf; }
-    for (int r = 0; r < np; ++r) if (w.gst[r]) { if (ng < K2_MAX_GEN) { w.gidx[ng] = r; ++ng; } }
-    BIK_SYNCWARP();
-    // x on the bounds, rhs of the reduced system, copy of H_FF
-    for (int i = lane; i < n; i += W) w.x[i] = w.st[i] == 1 ? w.lo[i] : (w.st[i] == 2 ? w.hi[i] : T(0));
-    BIK_SYNCWARP();
-    T* rhs = w.Lp + tri(nf);
-    for (int i = lane; i < nf; i += W) {
-      int ii = w.idx[i];
-      const T* Hrow = w.Hp + tri(ii);
-      T r = -w.c[ii];
-      for (int j = 0; j < ii; ++j) if (w.st[j]) r -= Hrow[j] * w.x[j];
-      for (int j = ii + 1; j < n; ++j) if (w.st[j]) r -= w.Hp[tri(j) + ii] * w.x[j];
-      rhs[i] = r;
-      T* Li = w.Lp + tri(i);
-      for (int j = 0; j <= i; ++j) Li[j] = Hrow[w.idx[j]];
-    }
-    BIK_SYNCWARP();
-    if (k2_factor<T, W, SLOTS>(w.Lp, w.dinv, nf, lane)) status |= 4;
-    status = warp_max_i<W>(status);
-    if (ng > 0) k2_general_rows<T, W>(w, Gb, rhs, n, nf, ng, lane);
-    // x_F = L^-T (.), overwriting the rhs row in place
-    k2_backsub<T, W, SLOTS>(w.Lp, w.dinv, nf, rhs, lane);
-    for (int i = lane; i < nf; i += W) w.x[w.idx[i]] = rhs[i];
-    BIK_SYNCWARP();
+  int status = 0, best = n + np + 1, patience = PATIENCE, it = 0, ng = 0;
+  bool done = n == 0, primal = false;
+  // ---- phase 1: block principal pivoting ----
+  while (!done && !primal && it < MAXIT) {
+    const int ws = k2_solve_working_set<T, W, SLOTS>(h, a, gbase, w, lane, &ng);
+    status |= ws & ~32;
+    ++it;
+    if (ws & 32) { primal = true; break; }   // block flips activated dependent rows (the primal method never does)
     // gradient on the active bounds, feasibility of free variables and of general rows.
-    // Proposed new states go to w.idx (free after the scatter above) and w.gnew.
-    int ninf = 0, last = -1;
+    // Proposed new states go to w.idx (free after the scatter in the solve) and w.gnew.
+    int ninf = 0;
     for (int i = lane; i < n; i += W) {
       int cur = w.st[i], ns = cur;
       if (cur == 0) {
@@ -414,16 +478,12 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
         if (xi < w.lo[i] - tolx * (T(1) + (w.lo[i] < 0 ? -w.lo[i] : w.lo[i]))) ns = 1;
         else if (xi > w.hi[i] + tolx * (T(1) + (w.hi[i] < 0 ? -w.hi[i] : w.hi[i]))) ns = 2;
       } else {
-        T gi = w.c[i];
-        const T* Hrow = w.Hp + tri(i);
-        for (int j = 0; j <= i; ++j) gi += Hrow[j] * w.x[j];
-        for (int j = i + 1; j < n; ++j) gi += w.Hp[tri(j) + i] * w.x[j];
-        for (int r = 0; r < ng; ++r) gi += T(Gb[(long long)w.gidx[r] * n + i]) * w.lam[r];
+        T gi = k2_grad<T>(a, gbase, w, n, ng, i);
         if (cur == 1 && gi < -tolg) ns = 0;
         else if (cur == 2 && gi > tolg) ns = 0;
       }
       w.idx[i] = ns;
-      if (ns != cur) { ++ninf; last = i > last ? i : last; }
+      if (ns != cur) ++ninf;
     }
     for (int r = lane; r < np; r += W) {
       int cur = w.gst[r], ns = cur;
@@ -431,7 +491,7 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
       if (!(hr < T(1e30))) ns = 0;  // inactive row: h = +inf (collision_avoidance_limit.py:192-199)
       else if (cur == 0) {
         T sv = -hr;
-        for (int j = 0; j < n; ++j) sv += T(Gb[(long long)r * n + j]) * w.x[j];
+        for (int j = 0; j < n; ++j) sv += k2_grow<T>(a, gbase, r, n, j) * w.x[j];
         if (sv > tolx * (T(1) + (hr < 0 ? -hr : hr))) ns = 1;
       } else {
         int k = 0;
@@ -439,38 +499,118 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
         if (k < ng && w.lam[k] < -tolg) ns = 0;
       }
       w.gnew[r] = ns;
-      if (ns != cur) { ++ninf; last = n + r > last ? n + r : last; }
+      if (ns != cur) ++ninf;
     }
     ninf = warp_sum_i<W>(ninf);
-    last = warp_max_i<W>(last);
-    if (ninf == 0) { done = true; continue; }
-    bool block;
-    if (ninf < best) { best = ninf; patience = PATIENCE; block = true; }
-    else if (patience > 0) { --patience; block = true; }
-    else block = false;
+    if (ninf == 0) { done = true; break; }
+    if (ninf < best) { best = ninf; patience = PATIENCE; }
+    else if (patience > 0) --patience;
+    else { primal = true; break; }
     BIK_SYNCWARP();
-    for (int i = lane; i < n; i += W) if (block || i == last) w.st[i] = w.idx[i];
-    for (int r = lane; r < np; r += W) if (block || n + r == last) w.gst[r] = w.gnew[r];
+    for (int i = lane; i < n; i += W) w.st[i] = w.idx[i];
+    for (int r = lane; r < np; r += W) w.gst[r] = w.gnew[r];
     BIK_SYNCWARP();
   }
+  // ---- phase 2: primal active-set method from a feasible point ----
+  if (primal) {
+    BIK_SYNCWARP();
+    for (int i = lane; i < n; i += W) {   // clip(0, lo, hi); a bound that holds the iterate is in the working set
+      T v = T(0);
+      int s0 = 0;
+      if (w.lo[i] > v) { v = w.lo[i]; s0 = 1; }
+      if (w.hi[i] < v) { v = w.hi[i]; s0 = 2; }
+      w.xf[i] = v; w.st[i] = s0;
+    }
+    BIK_SYNCWARP();
+    int infeas = 0;
+    for (int r = lane; r < np; r += W) {
+      w.gst[r] = 0;
+      T hr = w.hg[r];
+      if (hr < T(1e30)) {
+        T sv = -hr;
+        for (int j = 0; j < n; ++j) sv += k2_grow<T>(a, gbase, r, n, j) * w.xf[j];
+        if (sv > tolx * (T(1) + (hr < 0 ? -hr : hr))) infeas = 1;
+      }
+    }
+    if (warp_max_i<W>(infeas)) status |= 8;   // no feasible starting point: limits inconsistent with the collision rows
+    BIK_SYNCWARP();
+    while (!done && it < MAXIT && !(status & 8)) {
+      status |= k2_solve_working_set<T, W, SLOTS>(h, a, gbase, w, lane, &ng) & ~32;
+      ++it;
+      // ratio test: how far can xf move towards x before a bound of a free dof or an inactive general row stops it
+      T alpha = T(2);
+      int blk = 0x7fffffff;
+      for (int i = lane; i < n; i += W) {
+        if (w.st[i] != 0) continue;
+        const T xi = w.x[i], xo = w.xf[i], lo = w.lo[i], hi = w.hi[i];
+        const bool below = xi < lo - tolx * (T(1) + (lo < 0 ? -lo : lo));
+        const bool above = !below && xi > hi + tolx * (T(1) + (hi < 0 ? -hi : hi));
+        if (below || above) {
+          const T d = xi - xo;
+          T al = d != T(0) ? ((below ? lo : hi) - xo) / d : T(0);
+          al = al < T(0) ? T(0) : al;
+          if (al < alpha) { alpha = al; blk = i; }
+        }
+      }
+      for (int r = lane; r < np; r += W) {
+        const T hr = w.hg[r];
+        if (w.gst[r] || !(hr < T(1e30))) continue;
+        T gx = T(0), gf = T(0);
+        for (int j = 0; j < n; ++j) { const T gj = k2_grow<T>(a, gbase, r, n, j); gx += gj * w.x[j]; gf += gj * w.xf[j]; }
+        if (gx > hr + tolx * (T(1) + (hr < 0 ? -hr : hr))) {
+          const T d = gx - gf;
+          T al = d > T(0) ? (hr - gf) / d : T(0);
+          al = al < T(0) ? T(0) : al;
+          if (al < alpha) { alpha = al; blk = n + r; }
+        }
+      }
+      const T amin = warp_min_t<W, T>(alpha);
+      blk = warp_min_i<W>(alpha == amin ? blk : 0x7fffffff);   // ties: smallest index
+      if (amin < T(1.5)) {   // blocked: partial step, the blocking constraint joins the working set
+        const T al = amin > T(1) ? T(1) : amin;
+        for (int i = lane; i < n; i += W) if (w.st[i] == 0) w.xf[i] += al * (w.x[i] - w.xf[i]);
+        BIK_SYNCWARP();
+        if (blk < n) {
+          if (lane == 0) { const bool lower = w.x[blk] < w.lo[blk]; w.st[blk] = lower ? 1 : 2; w.xf[blk] = lower ? w.lo[blk] : w.hi[blk]; }
+        } else if (lane == 0) w.gst[blk - n] = 1;
+        BIK_SYNCWARP();
+        continue;
+      }
+      // feasible subspace minimiser: it becomes the iterate; let go of the constraint with the most negative multiplier
+      for (int i = lane; i < n; i += W) w.xf[i] = w.x[i];
+      T worst = -tolg;
+      int rel = 0x7fffffff;
+      for (int i = lane; i < n; i += W) {
+        const int cur = w.st[i];
+        if (cur == 0) continue;
+        T gi = k2_grad<T>(a, gbase, w, n, ng, i);
+        if (cur == 2) gi = -gi;   // now: gi < 0 means the bound wants to let go
+        if (gi < worst) { worst = gi; rel = i; }
+      }
+      for (int k = lane; k < ng; k += W) if (w.lam[k] < worst) { worst = w.lam[k]; rel = n + w.gidx[k]; }
+      const T wmin = warp_min_t<W, T>(worst);
+      rel = warp_min_i<W>(worst == wmin ? rel : 0x7fffffff);
+      if (rel == 0x7fffffff) { done = true; break; }
+      BIK_SYNCWARP();
+      if (lane == 0) { if (rel < n) w.st[rel] = 0; else w.gst[rel - n] = 0; }
+      BIK_SYNCWARP();
+    }
+  }
   if (!done) status |= 2;
-  if (a.warm && active) for (int i = lane; i < n; i += W) a.warm[(long long)b * n + i] = (signed char)w.st[i];
+  if (a.warm) for (int i = lane; i < n; i += W) a.warm[(long long)b * n + i] = (signed char)w.st[i];
   if (iters_out) *iters_out = it;
   return status;
 }
 
-// One instance per warp: assemble, optionally dump (H, c) / (lo, hi), solve, write dq.
+// One instance per warp: assemble, optionally dump (H, c) / (lo, hi), solve, write dq, optionally integrate q.
 template <typename T, int W, int SLOTS>
-BIK_HD void k2_warp(const PView& P, const K2Args& a, int b, void* wsm, int lane, bool active = true) {
+BIK_HD void k2_warp(const PView& P, const K2Args& a, int b, void* wsm, int lane) {
   const PHeader& h = P.h();
-  const int n = h.nv, nu = h.nu;
+  const int n = h.nv, nu = h.nu, nq = h.nq;
   const int32_t* umap = P.i(h.off_umap);
+  if (a.skip && a.skip[b]) return;
   K2Ws<T> w = k2_carve<T>(h, wsm);
-  if (!active) {  // lock-step tail: no instance for this warp, but it must take part in the CTA votes
-    if (a.dq && nu > 0) { int it = 0; k2_solve<T, W, SLOTS>(P, a, b, w, lane, &it, false); }
-    return;
-  }
-  k2_assemble<T, W>(P, a, b, w, lane);
+  int st = k2_assemble<T, W>(P, a, b, w, lane);
   if (a.skip_objective) return;
   if (a.Hout) {
     for (int k = lane; k < n * n; k += W) {
@@ -481,12 +621,13 @@ BIK_HD void k2_warp(const PView& P, const K2Args& a, int b, void* wsm, int lane,
     for (int d = lane; d < n; d += W) if (umap[d] >= 0) a.cout[(long long)b * n + d] = double(w.c[umap[d]]);
   }
   if (!a.dq) return;
-  int iters = 0, st = 0;
-  if (nu > 0) st = k2_solve<T, W, SLOTS>(P, a, b, w, lane, &iters);
+  int iters = 0;
+  if (nu > 0) st |= k2_solve<T, W, SLOTS>(P, a, b, w, lane, &iters);
   for (int d = lane; d < n; d += W) {
     T v = umap[d] >= 0 ? w.x[umap[d]] : w.xfull[d];
     if (!(v == v)) st |= 4;
-    a.dq[(long long)b * n + d] = float(v);
+    w.xfull[d] = v;
+    stout<T>(a.dq, (long long)b * n + d, a.io64, v);
   }
   st = warp_max_i<W>(st & 2) | warp_max_i<W>(st & 4) | warp_max_i<W>(st & 8);
   if (lane == 0) {
@@ -494,6 +635,17 @@ BIK_HD void k2_warp(const PView& P, const K2Args& a, int b, void* wsm, int lane,
     if (a.iters) a.iters[b] = iters;
   }
   BIK_SYNCWARP();
+  if (a.integrate) {   // q <- q (+) dq, node by node (mj_integratePos); fp32 callers: the sum is rounded once
+    for (int nn = lane; nn < h.nnode; nn += W) {
+      const NodeRec& r = P.node(nn);
+      const int nqn = r.type == JNT_FREE ? 7 : (r.type == JNT_BALL ? 4 : 1);
+      T qn[7];
+      for (int k = 0; k < nqn; ++k) qn[k] = ldin<T>(a.q, (long long)b * nq + r.qadr + k, a.io64);
+      integrate_node<T>(r, qn - r.qadr, w.xfull);
+      for (int k = 0; k < nqn; ++k) stout<T>(const_cast<void*>(a.q), (long long)b * nq + r.qadr + k, a.io64, qn[k]);
+    }
+    BIK_SYNCWARP();
+  }
 }
 
 }  // namespace bik

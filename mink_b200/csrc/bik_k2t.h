@@ -9,8 +9,9 @@
 //
 //   * per-instance vectors and packed triangles live in shared memory, word w of slot s at [w*NS + s]
 //     (the G lanes of a group broadcast-read one address; the NS groups read one 8*NS-byte segment);
-//   * instance data from K1 (J, e, e_posture, q) is staged a task at a time through an instance-major
-//     tile with odd row stride: coalesced global reads by the whole warp, conflict-free private reads;
+//   * instance data from K1 (the packed task blocks -- or, for bik_solve, dense J / e / e_posture -- and q) is staged a task
+//     at a time through an instance-major tile with odd row stride: coalesced global reads by the whole warp,
+//     conflict-free private reads;
 //   * dofs without any finite bound (the free joint) are eliminated once; everything below runs on the Schur
 //     complement of that leading block (k2t_schur), and the leading part of dq is recovered at the end;
 //   * the active set is guessed by projected Gauss-Seidel sweeps (k2t_pgs_guess), inside a rollout from the
@@ -61,7 +62,9 @@ BIK_HD int bik_clz(uint32_t v) {   // v != 0
 #endif
 }
 
-enum { K2T_NMAX = 32 };  // largest coupled block this path takes (active sets are 32-bit masks)
+enum { K2T_NMAX = 32, K2T_NMAX_WIDE = 64 };   // 32-bit active-set masks by default, 64-bit in the wide instantiation
+BIK_HD int bik_popc(uint64_t v) { return bik_popc((uint32_t)v) + bik_popc((uint32_t)(v >> 32)); }
+BIK_HD int bik_clz(uint64_t v) { return (uint32_t)(v >> 32) ? bik_clz((uint32_t)(v >> 32)) : 32 + bik_clz((uint32_t)v); }   // v != 0  // largest coupled block this path takes (active sets are 32-bit masks)
 
 // ---- group reductions over G adjacent lanes (every lane of the warp must call them) --------------------
 template <int G> BIK_HD int grp_or(int v) {
@@ -70,6 +73,10 @@ template <int G> BIK_HD int grp_or(int v) {
   for (int o = G / 2; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
 #endif
   return v;
+}
+template <int G> BIK_HD uint32_t grp_or_m(uint32_t v) { return (uint32_t)grp_or<G>((int)v); }
+template <int G> BIK_HD uint64_t grp_or_m(uint64_t v) {
+  return (uint64_t)(uint32_t)grp_or<G>((int)(uint32_t)v) | ((uint64_t)(uint32_t)grp_or<G>((int)(uint32_t)(v >> 32)) << 32);
 }
 template <int G> BIK_HD int grp_add(int v) {
 #if defined(__CUDA_ARCH__)
@@ -108,8 +115,8 @@ BIK_HD int k2t_union_words(const PView& P, int ts) {
   int u = tri(h.nu + 1);
   int t = k2t_task_tile_words(P);
   u = t > u ? t : u;
-  int sq = ((h.nq + h.P * h.nv) | 1) * 4;
-  int fw = (sq + ts - 1) / ts;
+  int fw = (h.nq + h.P * h.nv) | 1;   // q (+ dense posture errors) of one instance, as T
+  (void)ts;
   return fw > u ? fw : u;
 }
 BIK_HD int k2t_slot_T_words(const PView& P, int ts) { return tri(P.h().nu) + k2t_union_words(P, ts) + 3 * P.h().nu; }
@@ -117,34 +124,42 @@ BIK_HD int k2t_slot_bytes(const PView& P, int ts) { return k2t_slot_T_words(P, t
 BIK_HD int k2t_warp_bytes(const PView& P, int ts, int NS) { return (NS * k2t_slot_bytes(P, ts) + 15) & ~15; }
 
 // ---- staging (warp-cooperative, W lanes, NS instances) -------------------------------------------------
-// One task's weighted rows:  tile[i][r*nc + ia] = cost_r J[row0+r][col_ia],  tile[i][nr*nc + r] = cost_r (-gain e[row0+r]);
-// fp32 products as in the warp path, converted to T once.
+// One task's weighted block, column-major like K1's packed record:
+//   tile[i][ia*nr + r] = cost_r J[row0+r][col_ia],   tile[i][nr*nc + r] = cost_r (-gain e[row0+r]).
+// Source: the packed hand-off (one contiguous run per instance: coalesced without any index arithmetic) or, for bik_solve,
+// the dense rows (gather through the task's column list).
 template <typename T, int W, int NS>
-BIK_HD void k2t_stage_task(T* tile, int S, int lane, int cnt, long long b0, const K2Args& a, int K, int nv, const int32_t* cols,
-                           int row0, int nr, int nc, const float* cost, float gain) {
-  const int ne = nr * nc + nr;
+BIK_HD void k2t_stage_task(T* tile, int S, int lane, int cnt, long long b0, const K2Args& a, int K, int nv, int pks, const int32_t* cols,
+                           const K2Task& tk) {
+  const int nj = tk.nr * tk.nc, ne = nj + tk.nr;
   for (int k = lane; k < ne; k += W) {
-    const bool isj = k < nr * nc;
-    int r, gofs;
-    long long stride;
-    const float* src;
-    if (isj) { r = k / nc; int ia = k - r * nc; gofs = (row0 + r) * nv + (cols[ia] & 0xffff); src = a.J; stride = (long long)K * nv; }
-    else { r = k - nr * nc; gofs = row0 + r; src = a.e; stride = K; }
-    const float cr = cost[r];
-    const float* s0 = src + b0 * stride + gofs;
+    const int ia = k / tk.nr, r = k - ia * tk.nr;
+    const bool isj = k < nj;
+    const T cr = isj ? T(tk.cost[r]) : T(tk.cost[r]) * T(-tk.gain);
+    if (a.pk) {
+      const long long o = b0 * pks + tk.pk_off + k;
 #pragma unroll
-    for (int i = 0; i < NS; ++i) {
-      float v = 0.f;
-      if (i < cnt) { float g = s0[i * stride]; v = isj ? cr * g : cr * (-gain * g); }
-      tile[i * S + k] = T(v);
+      for (int i = 0; i < NS; ++i) tile[i * S + k] = i < cnt ? cr * ldin<T>(a.pk, o + (long long)i * pks, a.pk64) : T(0);
+    } else {
+      const float* src = isj ? a.J + b0 * K * nv + (tk.row0 + r) * nv + (cols[ia] & 0xffff) : a.e + b0 * K + tk.row0 + r;
+      const long long stride = isj ? (long long)K * nv : K;
+#pragma unroll
+      for (int i = 0; i < NS; ++i) tile[i * S + k] = i < cnt ? cr * T(src[i * stride]) : T(0);
     }
   }
 }
-template <int W, int NS>
-BIK_HD void k2t_stage_rows(float* tile, int S, int off, int lane, int cnt, const float* src, long long stride, int n) {
+template <typename T, int W, int NS>
+BIK_HD void k2t_stage_q(T* tile, int S, int lane, int cnt, const void* src, int is64, long long b0, int n) {
   for (int k = lane; k < n; k += W) {
 #pragma unroll
-    for (int i = 0; i < NS; ++i) tile[i * S + off + k] = i < cnt ? src[i * stride + k] : 0.f;
+    for (int i = 0; i < NS; ++i) tile[i * S + k] = i < cnt ? ldin<T>(src, (b0 + i) * n + k, is64) : T(0);
+  }
+}
+template <typename T, int W, int NS>
+BIK_HD void k2t_stage_rows(T* tile, int S, int off, int lane, int cnt, const float* src, long long stride, int n) {
+  for (int k = lane; k < n; k += W) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) tile[i * S + off + k] = i < cnt ? T(src[i * stride + k]) : T(0);
   }
 }
 
@@ -162,13 +177,14 @@ BIK_HD void k2t_task_accumulate_nr(const T* tr, int nc, const int32_t* cols, con
     T col[NR];
     T cs = T(0);
 #pragma unroll
-    for (int r = 0; r < NR; ++r) { col[r] = tr[r * nc + ia]; cs += wev[r] * col[r]; }
+    for (int r = 0; r < NR; ++r) { col[r] = tr[ia * NR + r]; cs += wev[r] * col[r]; }
     const int ua = umap[cols[ia] & 0xffff];
     c[ua * NS] -= cs;
     for (int ib = 0; ib <= ia; ++ib) {
+      const T* cb = tr + ib * NR;
       T s = T(0);
 #pragma unroll
-      for (int r = 0; r < NR; ++r) s += col[r] * tr[r * nc + ib];
+      for (int r = 0; r < NR; ++r) s += col[r] * cb[r];
       const int ub = umap[cols[ib] & 0xffff];
       const int hi = ua > ub ? ua : ub, lo = ua > ub ? ub : ua;
       Hp[(tri(hi) + lo) * NS] += s;
@@ -208,8 +224,8 @@ BIK_HD T k2t_row_dot(const T* __restrict__ Hp, const T* __restrict__ v, int i, i
 //   (nf, nu)  the factor of the trailing block, whose source (in Hp / the right-hand-side row) must then be the Schur
 //             complement of the leading block; columns < nf of Lp are left alone.
 // Every lane of the warp must call it (it contains warp barriers).
-template <typename T, int G, int NS>
-BIK_HD int k2t_factor(const T* __restrict__ Hp, T* __restrict__ Lp, int nu, uint32_t act, int l, int kb, int ke) {
+template <typename T, int G, int NS, typename M>
+BIK_HD int k2t_factor(const T* __restrict__ Hp, T* __restrict__ Lp, int nu, M act, int l, int kb, int ke) {
   int bad = 0;
   T* const rhsrow = Lp + tri(nu) * NS;
   // Row blocks are aligned to the END of the system (rows kb..nu): the last rows are the expensive ones (cost ~ i^2),
@@ -218,8 +234,8 @@ BIK_HD int k2t_factor(const T* __restrict__ Hp, T* __restrict__ Lp, int nu, uint
   for (int i0 = kb + (first ? first - G : 0); i0 <= nu; i0 += G) {
     const int i = i0 + l;
     const bool has = i >= kb && i <= nu, rhs = i == nu;
-    const bool ai = has && !rhs && ((act >> i) & 1u);
-    const uint32_t msk = rhs ? 0u : (ai ? ~0u : act);
+    const bool ai = has && !rhs && ((act >> i) & M(1));
+    const M msk = rhs ? M(0) : (ai ? ~M(0) : act);
     const int ir = has ? i : kb;
     const T* src = rhs ? rhsrow : Hp + tri(ir) * NS;
     T* dst = Lp + tri(ir) * NS;
@@ -227,7 +243,7 @@ BIK_HD int k2t_factor(const T* __restrict__ Hp, T* __restrict__ Lp, int nu, uint
     // one entry of my row: L[i][k] = (A[i][k] - sum_{kb <= m < k} L[i][m] L[k][m]) / L[k][k]; a masked entry is exactly zero
     auto step = [&](int k) {
       T s = T(0);
-      if (!((msk >> k) & 1u)) {
+      if (!((msk >> k) & M(1))) {
         const T* pk = Lp + (tri(k) + kb) * NS;   // row k (finished), walked together with my row
         const T* pi = dst + kb * NS;
         T a0 = T(0), a1 = T(0);
@@ -290,10 +306,10 @@ BIK_HD void k2t_backsub_cross(T* __restrict__ Lp, int nu, int l, const T* __rest
 // pivoting iterations of the G1 workload from 3.6 (4.5 for the slowest of the 4 problems in a warp) to 1.1 (1.4).
 // dinv and res (nu words each, slot-strided, entries [k0, nu) used) are scratch: 1 / S_ii and the residual c + S x.  At most `sweeps` sweeps; they stop as soon as a sweep leaves the set of
 // clamped dofs of every group in the warp unchanged.  Every lane of the warp must call it.
-template <typename T, int G, int NS>
+template <typename T, int G, int NS, typename M>
 BIK_HD void k2t_pgs_guess(const T* __restrict__ Hp, const T* __restrict__ c, const float* __restrict__ lo, const float* __restrict__ hi,
                           T* __restrict__ xs, T* __restrict__ dinv, T* __restrict__ res, int nu, int k0, int l, int sweeps, bool from_xs,
-                          uint32_t* lom_out, uint32_t* upm_out) {
+                          M* lom_out, M* upm_out) {
   // Residual form: res = c + S x is kept up to date, so row i only needs res_i and x_i (broadcast reads, every lane
   // computes the new x_i), after which each lane adds S_mi (x_i' - x_i) to the residuals of the dofs m it owns.
   // from_xs (warp-uniform): xs already holds a feasible starting point (the previous step's dq, clipped), else start from 0
@@ -303,16 +319,16 @@ BIK_HD void k2t_pgs_guess(const T* __restrict__ Hp, const T* __restrict__ c, con
     dinv[k * NS] = T(1) / Hp[(tri(k) + k) * NS];
   }
   BIK_SYNCWARP();
-  uint32_t lom = 0u, upm = 0u;
+  M lom = M(0), upm = M(0);
   for (int s = 0; s < sweeps; ++s) {
-    const uint32_t plo = lom, pup = upm;
-    lom = 0u; upm = 0u;
+    const M plo = lom, pup = upm;
+    lom = M(0); upm = M(0);
     for (int i = k0; i < nu; ++i) {
       const T xo = xs[i * NS];
       T xi = xo - res[i * NS] * dinv[i * NS];
       const T bl = T(lo[i * NS]), bu = T(hi[i * NS]);
-      if (xi <= bl) { xi = bl; lom |= 1u << i; }
-      else if (xi >= bu) { xi = bu; upm |= 1u << i; }
+      if (xi <= bl) { xi = bl; lom |= M(1) << i; }
+      else if (xi >= bu) { xi = bu; upm |= M(1) << i; }
       const T dx = xi - xo;
       if (G > 1) BIK_SYNCWARP();   // every lane has read res_i and x_i
       for (int m = k0 + l; m < nu; m += G) {
@@ -347,7 +363,7 @@ BIK_HD void k2t_schur(T* __restrict__ Hp, const T* __restrict__ Lp, T* __restric
 }
 
 // ---- one tile of NS instances per warp ----------------------------------------------------------------
-template <typename T, int G, int NS>
+template <typename T, int G, int NS, typename M = uint32_t>
 BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* wsm, int lane, int St = 0, int uw = 0) {
   if (St == 0) { St = k2t_task_tile_words(P); uw = k2t_union_words(P, sizeof(T)); }   // callers that loop over tiles pass them in
   constexpr int W = G * NS;
@@ -359,8 +375,8 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
   const int cnt = (a.B - b0) < NS ? (int)(a.B - b0) : NS;
   const int slot = lane / G, l = lane - slot * G;
   const long long b = b0 + slot;
-  const bool live = slot < cnt && (!a.only || a.only[b] != 0);
-  if (a.only && !BIK_WARP_ANY(live)) return;   // fallback launch: nothing marked in this tile
+  const bool live = slot < cnt && !(a.skip && a.skip[b]);
+  if (a.skip && !BIK_WARP_ANY(live)) return;   // bik_converge: every instance of this tile has converged
   T* const Tb = reinterpret_cast<T*>(wsm);
   T* const Hp = Tb + slot;
   T* const U = Tb + (size_t)tri(nu) * NS;   // warp-wide base of the union region
@@ -377,30 +393,38 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
   for (int k = l; k < nu; k += G) c[k * NS] = T(0);
   T mu = T(a.damping);
   for (int t = 0; t < h.F + h.C; ++t) {
-    int row0, nr, nc, coff; const float* cost; float gain, lm;
-    if (t < h.F) { const FrameRec& fr = P.frame(t); row0 = fr.row0; nr = 6; nc = fr.ncols; coff = fr.col_off; cost = fr.cost; gain = fr.gain; lm = fr.lm; }
-    else { const float* cr = P.f(h.off_com) + 8 * (t - h.F); row0 = reinterpret_cast<const int32_t*>(cr)[5]; nr = 3; nc = h.com_ncols; coff = h.com_cols_off; cost = cr; gain = cr[3]; lm = cr[4]; }
+    const K2Task tk = k2_task(P, t);
     BIK_SYNCWARP();
-    k2t_stage_task<T, W, NS>(U, St, lane, cnt, b0, a, K, nv, cols + coff, row0, nr, nc, cost, gain);
+    k2t_stage_task<T, W, NS>(U, St, lane, cnt, b0, a, K, nv, h.pk_stride, cols + tk.coff, tk);
     BIK_SYNCWARP();
-    k2t_task_accumulate<T, G, NS>(U + (size_t)slot * St, nr, nc, cols + coff, umap, Hp, c, lm, &mu, l);
+    k2t_task_accumulate<T, G, NS>(U + (size_t)slot * St, tk.nr, tk.nc, cols + tk.coff, umap, Hp, c, tk.lm, &mu, l);
   }
   // q and posture errors: stage, then diagonal / linear term / box; decoupled dofs are finished on the spot
   BIK_SYNCWARP();
-  float* const ft = reinterpret_cast<float*>(U);
   const int Sq = (nq + NP * nv) | 1;
-  k2t_stage_rows<W, NS>(ft, Sq, 0, lane, cnt, a.q + b0 * nq, nq, nq);
-  if (NP > 0) k2t_stage_rows<W, NS>(ft, Sq, nq, lane, cnt, a.ep + b0 * NP * nv, (long long)NP * nv, NP * nv);
+  k2t_stage_q<T, W, NS>(U, Sq, lane, cnt, a.q, a.io64, b0, nq);
+  if (NP > 0 && a.ep) k2t_stage_rows<T, W, NS>(U, Sq, nq, lane, cnt, a.ep + b0 * NP * nv, (long long)NP * nv, NP * nv);
   BIK_SYNCWARP();
+  if (NP > 0 && !a.ep) {   // inside bik_step K1 hands no posture error over: e = q* (-) q from the staged q (posture_task.py:107-118)
+    const int per = NP * nv;
+    for (int k = lane; k < NS * per; k += W) {
+      const int i = k / per, r = k - i * per, p = r / nv, d = r - p * nv;
+      const T* qq = U + (size_t)i * Sq;
+      const long long t0 = ((long long)(a.pbatched ? (b0 + (i < cnt ? i : 0)) : 0) * NP + p) * nq;
+      U[(size_t)i * Sq + nq + r] = posture_err_dof<T>(P, d, [&](int j) { return ldin<T>(a.ptgt, t0 + j, a.io64); }, [&](int j) { return qq[j]; });
+    }
+    BIK_SYNCWARP();
+  }
   int st = 0;
   {
-    const float* qrow = ft + (size_t)slot * Sq;
-    const float* eprow = qrow + nq;
+    const T* qrow = U + (size_t)slot * Sq;
+    const T* eprow = qrow + nq;
+    const int32_t* dofqadr = P.i(h.off_dofqadr);
     for (int p = 0; p < NP; ++p) {
       const float* pr = P.f(h.off_posture) + p * (2 + nv);
       if (pr[1] != 0.f) {
         T s = T(0);
-        for (int d = 0; d < nv; ++d) { T v = T(pr[2 + d]) * T(pr[0]) * T(eprow[p * nv + d]); s += v * v; }
+        for (int d = 0; d < nv; ++d) { T v = T(pr[2 + d]) * T(pr[0]) * eprow[p * nv + d]; s += v * v; }
         mu += T(pr[1]) * s;
       }
     }
@@ -411,16 +435,18 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
         const float* pr = P.f(h.off_posture) + p * (2 + nv);
         const T wgt = T(pr[2 + d]);
         hd += wgt * wgt;
-        cd -= T(pr[0]) * wgt * wgt * T(eprow[p * nv + d]);
+        cd -= T(pr[0]) * wgt * wgt * eprow[p * nv + d];
       }
-      float bl, bu;
-      box_dof(P, d, qrow, a.dt, &bl, &bu);
-      if (u >= 0) { Hp[(tri(u) + u) * NS] += hd; c[u * NS] += cd; lo[u * NS] = bl; hi[u * NS] = bu; }
+      T bl, bu;
+      const int qa = dofqadr[d];
+      box_dof<T>(P, d, qa >= 0 ? qrow[qa] : T(0), T(a.dt), &bl, &bu);
+      if (bl > bu + T(1e-9) * (T(1) + (bu < 0 ? -bu : bu))) st |= 8;   // inconsistent limits: the reference's QP has no solution (solve_ik.py:103)
+      if (u >= 0) { Hp[(tri(u) + u) * NS] += hd; c[u * NS] += cd; lo[u * NS] = float(bl); hi[u * NS] = float(bu); }
       else {
         T v = -cd / hd;
-        v = v < T(bl) ? T(bl) : (v > T(bu) ? T(bu) : v);
+        v = v < bl ? bl : (v > bu ? bu : v);
         if (!(v == v)) st |= 4;
-        if (live) a.dq[b * nv + d] = float(v);
+        if (live) stout<T>(a.dq, b * nv + d, a.io64, v);
       }
     }
   }
@@ -440,7 +466,7 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
   if (nf > 0) {
     for (int k = l; k < nf; k += G) rhsrow[k * NS] = -c[k * NS];
     BIK_SYNCWARP();
-    if (k2t_factor<T, G, NS>(Hp, Lp, nu, 0u, l, 0, nf)) st |= 4;
+    if (k2t_factor<T, G, NS, M>(Hp, Lp, nu, M(0), l, 0, nf)) st |= 4;
     BIK_SYNCWARP();
     k2t_schur<T, G, NS>(Hp, Lp, c, nu, nf, l);
     BIK_SYNCWARP();
@@ -449,7 +475,9 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
   // ---- block principal pivoting ----
   const int MAXIT = 400, PATIENCE = 3;   // the primal active-set method needs ~20 at most; the block-pivoting branch (fp32, no guess) can need its slow fallback
   const T tolx = K2Tol<T>::x(), tolg = K2Tol<T>::g();
-  uint32_t lom = 0u, upm = 0u;
+  constexpr int IB = sizeof(M) == 8 ? 6 : 5;                       // index bits in the packed (value, index) keys
+  constexpr uint32_t KEYV = 0x7fffffffu & ~((1u << IB) - 1u), KEYI = (1u << IB) - 1u;
+  M lom = M(0), upm = M(0);
   bool guessed = false;
   const bool guess = sizeof(T) == 8 && h.k2_sweeps > 0 && nf < nu;   // fp64 only: fp32's gradient tolerance (1e-4) would accept a wrongly clamped dof
   if (guess) {
@@ -459,14 +487,14 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
     if (have_prev) {
       const bool valid = live && (a.warm[b * nu] & 4);
       for (int k = nf + l; k < nu; k += G) {
-        T v = valid ? T(a.dq[b * nv + ucols[k]]) : T(0);
+        T v = valid ? ldin<T>(a.dq, b * nv + ucols[k], a.io64) : T(0);
         if (!(v == v)) v = T(0);
         const T bl = T(lo[k * NS]), bu = T(hi[k * NS]);
         vs[k * NS] = v < bl ? bl : (v > bu ? bu : v);
       }
       BIK_SYNCWARP();
     }
-    k2t_pgs_guess<T, G, NS>(Hp, c, lo, hi, vs, rhsrow, Lp + tri(nu - 1) * NS, nu, nf, l, h.k2_sweeps, have_prev, &lom, &upm);   // scratch: free strips of the factor
+    k2t_pgs_guess<T, G, NS, M>(Hp, c, lo, hi, vs, rhsrow, Lp + tri(nu - 1) * NS, nu, nf, l, h.k2_sweeps, have_prev, &lom, &upm);   // scratch: free strips of the factor
     guessed = h.k2_rule != 0;
     for (int k = nf + l; k < nu; k += G) xf[k * NS] = vs[k * NS];   // the Gauss-Seidel iterate is feasible: it is where the active-set method starts
     BIK_SYNCWARP();
@@ -475,8 +503,8 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
       const signed char* wm = a.warm + b * nu;
       for (int i = nf; i < nu; ++i) {
         int s0 = wm[i] & 3;
-        if (s0 == 1 && lo[i * NS] > -1e30f) lom |= 1u << i;
-        else if (s0 == 2 && hi[i * NS] < 1e30f) upm |= 1u << i;
+        if (s0 == 1 && lo[i * NS] > -1e30f) lom |= M(1) << i;
+        else if (s0 == 2 && hi[i * NS] < 1e30f) upm |= M(1) << i;
       }
     }
   }
@@ -486,28 +514,28 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
   for (;;) {
     if (!BIK_WARP_ANY(!done && it < MAXIT)) break;
     const bool run = !done && it < MAXIT;   // a finished group keeps executing (idempotently) until its warp is done
-    const uint32_t act = lom | upm;
+    const M act = lom | upm;
     // x on the bounds
-    for (int k = nf + l; k < nu; k += G) vs[k * NS] = ((lom >> k) & 1u) ? T(lo[k * NS]) : (((upm >> k) & 1u) ? T(hi[k * NS]) : T(0));
+    for (int k = nf + l; k < nu; k += G) vs[k * NS] = ((lom >> k) & M(1)) ? T(lo[k * NS]) : (((upm >> k) & M(1)) ? T(hi[k * NS]) : T(0));
     BIK_SYNCWARP();
     // right-hand side of the masked system: bound value on clamped dofs, -(c + H_FA x_A) on free ones
     for (int k = nf + l; k < nu; k += G) {
       T rv;
-      if ((act >> k) & 1u) rv = vs[k * NS];
+      if ((act >> k) & M(1)) rv = vs[k * NS];
       else { rv = -c[k * NS]; if (act) rv -= k2t_row_dot<T, NS>(Hp, vs, k, nu, nf); }
       rhsrow[k * NS] = rv;
     }
     BIK_SYNCWARP();
-    if (k2t_factor<T, G, NS>(Hp, Lp, nu, act, l, nf, nu)) st |= 4;
+    if (k2t_factor<T, G, NS, M>(Hp, Lp, nu, act, l, nf, nu)) st |= 4;
     BIK_SYNCWARP();
     k2t_backsub<T, G, NS>(Lp, nu, l, vs, nu, nf, nf);
     BIK_SYNCWARP();
     // gradient on the clamped dofs, feasibility of the free ones
-    uint32_t vlo = 0u, vup = 0u, rel = 0u;   // free dofs that violate a bound / clamped dofs whose multiplier has the wrong sign
+    M vlo = M(0), vup = M(0), rel = M(0);   // free dofs that violate a bound / clamped dofs whose multiplier has the wrong sign
     int worst = 0;                            // (float bits of the largest wrong-signed multiplier, low 5 bits = its index)
     int blocking = 0x7fffffff;                // (float bits of the smallest step length to a violated bound, low 5 bits = its index)
     for (int k = nf + l; k < nu; k += G) {
-      const uint32_t bit = 1u << k;
+      const M bit = M(1) << k;
       if (!(act & bit)) {
         const T xi = vs[k * NS], bl = T(lo[k * NS]), bu = T(hi[k * NS]);
         const bool below = xi < bl - tolx * (T(1) + (bl < 0 ? -bl : bl));
@@ -518,7 +546,7 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
           const T xo = xf[k * NS], d = xi - xo;
           T al = d != T(0) ? ((below ? bl : bu) - xo) / d : T(0);
           al = al < T(0) ? T(0) : (al > T(1) ? T(1) : al);
-          const int key = (int)((bik_float_bits(float(al)) & 0x7fffffe0u) | (uint32_t)k);
+          const int key = (int)((bik_float_bits(float(al)) & KEYV) | (uint32_t)k);
           blocking = key < blocking ? key : blocking;
         }
       } else {
@@ -526,21 +554,21 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
         if (upm & bit) gi = -gi;              // now: gi < 0 means the bound wants to let go
         if (gi < -tolg) {
           rel |= bit;
-          const int key = (int)((bik_float_bits(float(-gi)) & 0x7fffffe0u) | (uint32_t)k);
+          const int key = (int)((bik_float_bits(float(-gi)) & KEYV) | (uint32_t)k);
           worst = key > worst ? key : worst;
         }
       }
     }
-    vlo = (uint32_t)grp_or<G>((int)vlo); vup = (uint32_t)grp_or<G>((int)vup); rel = (uint32_t)grp_or<G>((int)rel);
+    vlo = grp_or_m<G>(vlo); vup = grp_or_m<G>(vup); rel = grp_or_m<G>(rel);
     worst = grp_max<G>(worst);
     T alpha = T(0), bound = T(0);
     int kb = 0;
     if (guessed) {
       blocking = -grp_max<G>(-blocking);
       if (vlo | vup) {   // exact step length to the blocking bound (the key only ranked the candidates in fp32)
-        kb = blocking & 31;
+        kb = blocking & (int)KEYI;
         const T xo = xf[kb * NS], d = vs[kb * NS] - xo;
-        bound = ((vlo >> kb) & 1u) ? T(lo[kb * NS]) : T(hi[kb * NS]);
+        bound = ((vlo >> kb) & M(1)) ? T(lo[kb * NS]) : T(hi[kb * NS]);
         alpha = d != T(0) ? (bound - xo) / d : T(0);
         alpha = alpha < T(0) ? T(0) : (alpha > T(1) ? T(1) : alpha);
       }
@@ -548,7 +576,7 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
     BIK_SYNCWARP();   // every lane has read x (and the feasible iterate) before anything below or the next iteration overwrites them
     if (run) {
       ++it;
-      const uint32_t changed = vlo | vup | rel;
+      const M changed = vlo | vup | rel;
       const int ninf = bik_popc(changed);
       if (ninf == 0) done = true;
       else if (guessed) {
@@ -560,13 +588,13 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
         if (vlo | vup) {
           for (int k = nf + l; k < nu; k += G) {
             if (k == kb) xf[k * NS] = bound;
-            else if (!((act >> k) & 1u)) xf[k * NS] += alpha * (vs[k * NS] - xf[k * NS]);
+            else if (!((act >> k) & M(1))) xf[k * NS] += alpha * (vs[k * NS] - xf[k * NS]);
           }
-          const uint32_t bit = 1u << kb;
+          const M bit = M(1) << kb;
           if (vlo & bit) lom |= bit; else upm |= bit;
         } else {
           for (int k = nf + l; k < nu; k += G) xf[k * NS] = vs[k * NS];
-          const uint32_t bit = 1u << (worst & 31);
+          const M bit = M(1) << (worst & (int)KEYI);
           lom &= ~bit; upm &= ~bit;
         }
       } else {
@@ -574,9 +602,9 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
         if (ninf < best) { best = ninf; patience = PATIENCE; block = true; }
         else if (patience > 0) { --patience; block = true; }
         else block = false;
-        const uint32_t nlo = (lom & ~rel) | vlo, nup = (upm & ~rel) | vup;
+        const M nlo = (lom & ~rel) | vlo, nup = (upm & ~rel) | vup;
         if (block) { lom = nlo; upm = nup; }
-        else { const uint32_t bit = 1u << (31 - bik_clz(changed)); lom = (lom & ~bit) | (nlo & bit); upm = (upm & ~bit) | (nup & bit); }
+        else { const M bit = M(1) << ((int)(8 * sizeof(M)) - 1 - bik_clz(changed)); lom = (lom & ~bit) | (nlo & bit); upm = (upm & ~bit) | (nup & bit); }
       }
     }
   }
@@ -589,15 +617,28 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
   if (!done) st |= 2;
   // ---- outputs: coupled dofs from vs (the last solve), status, warm-start state ----
   for (int k = l; k < nu; k += G) {
-    const float v = float(vs[k * NS]);
+    const T v = vs[k * NS];
     if (!(v == v)) st |= 4;
-    if (live) a.dq[b * nv + ucols[k]] = v;
+    if (live) stout<T>(a.dq, b * nv + ucols[k], a.io64, v);
   }
   st = grp_or<G>(st);
   if (live && l == 0) {
     if (a.status) a.status[b] |= st;
     if (a.iters) a.iters[b] = it;
-    if (a.warm) { signed char* wm = a.warm + b * nu; for (int i = 0; i < nu; ++i) wm[i] = (signed char)((((lom >> i) & 1u) ? 1 : (((upm >> i) & 1u) ? 2 : 0)) | 4); }   // +4: a.dq holds this step's result
+    if (a.warm) { signed char* wm = a.warm + b * nu; for (int i = 0; i < nu; ++i) wm[i] = (signed char)((((lom >> i) & M(1)) ? 1 : (((upm >> i) & M(1)) ? 2 : 0)) | 4); }   // +4: a.dq holds this step's result
+  }
+  BIK_SYNCWARP();
+  // ---- q <- q (+) dq (Configuration.integrate_inplace, configuration.py:228-236): the lanes of a group take the nodes in turn ----
+  if (a.integrate && live) {
+    for (int nn = l; nn < h.nnode; nn += G) {
+      const NodeRec& r = P.node(nn);
+      const int nqn = r.type == JNT_FREE ? 7 : (r.type == JNT_BALL ? 4 : 1), ndn = r.type == JNT_FREE ? 6 : (r.type == JNT_BALL ? 3 : 1);
+      T qn[7], dn[6];
+      for (int k = 0; k < nqn; ++k) qn[k] = ldin<T>(a.q, b * nq + r.qadr + k, a.io64);
+      for (int k = 0; k < ndn; ++k) dn[k] = ldin<T>(a.dq, b * nv + r.dadr + k, a.io64);
+      integrate_node<T>(r, qn - r.qadr, dn - r.dadr);
+      for (int k = 0; k < nqn; ++k) stout<T>(const_cast<void*>(a.q), b * nq + r.qadr + k, a.io64, qn[k]);
+    }
   }
   BIK_SYNCWARP();
 }

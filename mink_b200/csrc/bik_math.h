@@ -41,7 +41,12 @@ template <typename T> BIK_HD Q4<T> qmul(Q4<T> a, Q4<T> b) {
                a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x, a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w);
 }
 template <typename T> BIK_HD Q4<T> qconj(Q4<T> a) { return q4<T>(a.w, -a.x, -a.y, -a.z); }
-template <typename T> BIK_HD T inv_sqrt(T x) { return T(1) / sqrt(x); }
+template <typename T> BIK_HD T bik_sqrt(T x);
+template <> BIK_HD float bik_sqrt<float>(float x) { return sqrtf(x); }
+template <> BIK_HD double bik_sqrt<double>(double x) { return sqrt(x); }
+template <typename T> BIK_HD T bik_min(T a, T b) { return a < b ? a : b; }
+template <typename T> BIK_HD T bik_max(T a, T b) { return a > b ? a : b; }
+template <typename T> BIK_HD T inv_sqrt(T x) { return T(1) / bik_sqrt<T>(x); }
 #if defined(__CUDA_ARCH__)
 template <> BIK_HD float inv_sqrt<float>(float x) {  // MUFU.RSQ + one Newton step: < 1 ulp, no division
   float r = rsqrtf(x);

@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE -- compiles the kernel headers (mink_b200/csrc/bik_k1.h, bik_k2.h) for the host
+// TEST INFRASTRUCTURE -- compiles the kernel headers (mink_b200/csrc/bik_k1.h, bik_k2.h, bik_k2t.h) for the host
 // with one lane per instance (G = W = 1) so the device math can be checked against the oracle on a
 // machine without a GPU.  Never shipped, never loaded by mink_b200/: the product path is CUDA only.
 #include <stdlib.h>
@@ -8,8 +8,7 @@
 #include <vector>
 
 #include "../../mink_b200/csrc/bik_build.h"
-#include "../../mink_b200/csrc/bik_k2lr.h"
-#include "../../mink_b200/csrc/bik_k2x.h"
+#include "../../mink_b200/csrc/bik_k2t.h"
 
 using namespace bik;
 
@@ -29,10 +28,11 @@ extern "C" void* emu_problem_create(const void* blob, size_t nbytes, const bik_t
   if (!build_image(m, nullptr, 0, nullptr, 0, 1, &p->model_image, &g_err)) { delete p; return nullptr; }
   return p;
 }
-// header fields of the problem image the CPU tests pin: nv, nu, nfree, nnode, nneeded, nslots, G, nsteps
+// header fields of the problem image the CPU tests pin: nv, nu, nfree, nnode, nneeded, nslots, G, nsteps, pk_stride, words32, words
 extern "C" void emu_header(void* prob, int32_t* out) {
   const PHeader& h = PView{static_cast<EmuProblem*>(prob)->image.data()}.h();
   out[0] = h.nv; out[1] = h.nu; out[2] = h.nfree; out[3] = h.nnode; out[4] = h.nneeded; out[5] = h.nslots; out[6] = h.G; out[7] = h.nsteps;
+  out[8] = h.pk_stride; out[9] = h.words32; out[10] = h.words;
 }
 extern "C" void emu_set_knobs(void* prob, int sweeps, int rule) {   // what BIK_K2_SWEEPS / BIK_K2_RULE do in bik_problem_create
   PHeader* h = reinterpret_cast<PHeader*>(static_cast<EmuProblem*>(prob)->image.data());
@@ -50,109 +50,81 @@ extern "C" int emu_lane_program(const void* blob, size_t nbytes, int G, int32_t*
   return nsteps;
 }
 
-extern "C" int emu_fk_jac(void* prob, int B, const float* q, const float* ftgt, const float* ptgt, int pbatched, const float* ctgt, float dt,
-                          float* J, float* e, float* ep, float* Gc, float* hc) {
+// K1.  f64 = 0: fp32 instantiation, fp32 buffers.  f64 = 1: fp64 instantiation, fp64 inputs and outputs.
+// f64 = 2: fp64 instantiation on fp32 inputs (what bik_step runs for ill-conditioned problems of fp32 callers), fp64 outputs.
+// pk != null: packed hand-off instead of dense J / e / ep.  status != null: fused check_limits.
+extern "C" int emu_fk_jac(void* prob, int B, int f64, const void* q, const void* ftgt, const void* ptgt, int pbatched, const void* ctgt, double dt,
+                          void* J, void* e, void* ep, void* Gc, void* hc, void* pk, int32_t* status) {
   EmuProblem* p = static_cast<EmuProblem*>(prob);
   PView P{p->image.data()};
-  K1Args a{B, q, ftgt, ptgt, ctgt, pbatched, dt, J, e, ep, Gc, hc};
-  std::vector<float> wsm(k1_warp_words(P.h(), 1) + 16);
-  for (int b = 0; b < B; ++b) k1_warp_tile<1, 1>(P, a, b, wsm.data(), 0);
-  return 0;
-}
-
-// Small-group fp64 path with the rollout state of bik_step (nsteps > 1): `warm` [B][nu] bytes and the dq of the previous
-// step in `dq` (in/out), as step_core passes them from its second step on.
-extern "C" int emu_solve_warm(void* prob, int B, const float* q, const float* J, const float* e, const float* ep, float dt, double damping,
-                              float* dq, int32_t* status, int32_t* iters, signed char* warm) {
-  EmuProblem* p = static_cast<EmuProblem*>(prob);
-  PView P{p->image.data()};
-  if (P.h().npairs != 0 || P.h().nu < 1 || P.h().nu > K2T_NMAX) { g_err = "thread path not applicable"; return -1; }
-  K2Args a{B, q, J, e, ep, nullptr, nullptr, dt, damping, dq, status, iters, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, warm, nullptr, nullptr};
-  std::vector<double> tw(k2t_warp_bytes(P, 8, 1) / 8 + 16);
+  K1Args a;
+  memset(&a, 0, sizeof a);
+  a.B = B; a.q = q; a.ftgt = ftgt; a.ptgt = ptgt; a.ctgt = ctgt; a.in64 = f64 == 1; a.pbatched = pbatched; a.dt = dt;
+  a.J = J; a.e = e; a.ep = ep; a.Gc = Gc; a.hc = hc; a.pk = pk; a.status = status; a.tol = 1e-6f;
+  std::vector<double> wsm(k1_warp_words(P.h(), 1) + 16);
   for (int b = 0; b < B; ++b) {
-    if (status) status[b] = 0;
-    k2t_warp_tile<double, 1, 1>(P, a, b, tw.data(), 0);
+    if (f64) k1_warp_tile<double, 1, 1>(P, a, b, wsm.data(), 0);
+    else k1_warp_tile<float, 1, 1>(P, a, b, reinterpret_cast<float*>(wsm.data()), 0);
   }
   return 0;
 }
 
-extern "C" int emu_solve(void* prob, int B, const float* q, const float* J, const float* e, const float* ep, const float* Gc, const float* hc,
-                         float dt, double damping, int use_double, float* dq, int32_t* status, int32_t* iters, double* H, double* c, float* lo, float* hi) {
+// K2.  path: 0 general fp32, 1 general fp64, 3 small-group fp64, 4 small-group fp32, 8 small-group fp64 with 64-bit masks.
+// Task rows: packed (pk, pk64) or dense (J, e, ep fp32; ep may be null with ptgt set).  io64: q / ptgt / dq are fp64.
+extern "C" int emu_solve(void* prob, int B, int path, int io64, const void* q, const void* pk, int pk64, const float* J, const float* e, const float* ep,
+                         const void* ptgt, int pbatched, const void* Gc, const void* hc, int gc64, double dt, double damping, void* dq,
+                         int integrate, int32_t* status, int32_t* iters, double* H, double* c, float* lo, float* hi, signed char* warm,
+                         const int32_t* skip) {
   EmuProblem* p = static_cast<EmuProblem*>(prob);
   PView P{p->image.data()};
-  K2Args a{B, q, J, e, ep, Gc, hc, dt, damping, dq, status, iters, H, c, lo, hi, 0, 0, 0, nullptr, nullptr, nullptr};
-  std::vector<double> wsm((k2_warp_bytes(P.h(), 8) + k2lr_warp_bytes(P.h())) / 8 + 16);
-  if (use_double == 3 || use_double == 4) {   // small-group path (3: fp64, 4: fp32), one lane per problem on the host
-    if (P.h().npairs != 0 || P.h().nu < 1 || P.h().nu > K2T_NMAX) { g_err = "thread path not applicable"; return -1; }
+  K2Args a;
+  memset(&a, 0, sizeof a);
+  a.B = B; a.q = q; a.io64 = io64; a.pk = pk; a.pk64 = pk64; a.J = J; a.e = e; a.ep = ep; a.ptgt = ptgt; a.pbatched = pbatched;
+  a.Gc = Gc; a.hc = hc; a.gc64 = gc64; a.dt = dt; a.damping = damping; a.dq = dq; a.integrate = integrate; a.status = status; a.iters = iters;
+  a.Hout = H; a.cout = c; a.lo_out = lo; a.hi_out = hi; a.warm = warm; a.skip = skip;
+  if (path == 3 || path == 4 || path == 8) {
+    const int nmax = path == 8 ? K2T_NMAX_WIDE : K2T_NMAX;
+    if (P.h().npairs != 0 || P.h().nu < 1 || P.h().nu > nmax) { g_err = "small-group path not applicable"; return -1; }
     std::vector<double> tw(k2t_warp_bytes(P, 8, 1) / 8 + 16);
     for (int b = 0; b < B; ++b) {
-      if (status) status[b] = 0;
-      if (use_double == 3) k2t_warp_tile<double, 1, 1>(P, a, b, tw.data(), 0);
-      else k2t_warp_tile<float, 1, 1>(P, a, b, tw.data(), 0);
+      if (path == 3) k2t_warp_tile<double, 1, 1>(P, a, b, tw.data(), 0);
+      else if (path == 4) k2t_warp_tile<float, 1, 1>(P, a, b, tw.data(), 0);
+      else k2t_warp_tile<double, 1, 1, uint64_t>(P, a, b, tw.data(), 0);
     }
     return 0;
   }
-  if (use_double == 5 || use_double == 6 || use_double == 7) {   // fixed-size thread-per-problem path (5: mixed fp32/fp64 without
-    const int nu = P.h().nu;                                      // hand-over, 6: fp32, 7: mixed with fp64 hand-over of flagged instances)
-    if (P.h().npairs != 0 || nu < 1 || nu > 24) { g_err = "fixed-size path not applicable"; return -1; }
-    const int N = nu <= 6 ? 6 : (nu <= 12 ? 12 : (nu <= 18 ? 18 : 24));
-    std::vector<double> tw(k2x_warp_smem_bytes(P, 8, 8, N, 1) / 8 + 16), sc(k2x_warp_scratch_bytes(8, N, 1) / 8 + 16);
-    std::vector<double> gw(k2t_warp_bytes(P, 8, 1) / 8 + 16);
-    int nflag = 0;
-    for (int b = 0; b < B; ++b) {
-      if (status) status[b] = 0;
-      int32_t flag = 0;
-      K2Args ab = a;
-      ab.flag_out = use_double == 7 ? &flag - b : nullptr;   // indexed by instance
-      if (use_double != 6) {
-        if (N == 6) k2x_warp_tile<float, double, 6, 1>(P, ab, b, tw.data(), sc.data(), 0);
-        else if (N == 12) k2x_warp_tile<float, double, 12, 1>(P, ab, b, tw.data(), sc.data(), 0);
-        else if (N == 18) k2x_warp_tile<float, double, 18, 1>(P, ab, b, tw.data(), sc.data(), 0);
-        else k2x_warp_tile<float, double, 24, 1>(P, ab, b, tw.data(), sc.data(), 0);
-        if (flag) { ++nflag; ab.flag_out = nullptr; k2t_warp_tile<double, 1, 1>(P, ab, b, gw.data(), 0); }
-      } else {
-        if (N == 6) k2x_warp_tile<float, float, 6, 1>(P, a, b, tw.data(), sc.data(), 0);
-        else if (N == 12) k2x_warp_tile<float, float, 12, 1>(P, a, b, tw.data(), sc.data(), 0);
-        else if (N == 18) k2x_warp_tile<float, float, 18, 1>(P, a, b, tw.data(), sc.data(), 0);
-        else k2x_warp_tile<float, float, 24, 1>(P, a, b, tw.data(), sc.data(), 0);
-      }
-    }
-    return nflag;
-  }
+  std::vector<double> wsm(k2_warp_bytes(P.h(), 8) / 8 + 16);
   for (int b = 0; b < B; ++b) {
-    if (status) status[b] = 0;
-    if (use_double == 2) {   // low-rank (Woodbury) path
-      std::vector<uint16_t> pairtab(tri(P.h().K) + 1);
-      for (int p = 0; p < tri(P.h().K); ++p) { int r, s; tri_unflatten(p, &r, &s); pairtab[p] = (uint16_t)((r << 8) | s); }
-      k2lr_warp<1, 65>(P, a, b, wsm.data(), pairtab.data(), 0);
-    }
-    else if (use_double) k2_warp<double, 1, 65>(P, a, b, wsm.data(), 0);
+    if (path) k2_warp<double, 1, 65>(P, a, b, wsm.data(), 0);
     else k2_warp<float, 1, 65>(P, a, b, wsm.data(), 0);
   }
   return 0;
 }
 
-extern "C" int emu_fk(void* prob, int B, const float* q, const bik_frame* frames, int nframes, float* poses, float* com, float* J) {
+extern "C" int emu_fk(void* prob, int B, int f64, const void* q, const bik_frame* frames, int nframes, void* poses, void* com, void* J) {
   EmuProblem* p = static_cast<EmuProblem*>(prob);
   PView P{p->model_image.data()};
   if (nframes > 16) return -1;
   FkArgs a; memset(&a, 0, sizeof a);
-  a.B = B; a.nframes = nframes; a.q = q; a.poses = poses; a.com = com; a.J = J;
-  for (int f = 0; f < nframes; ++f) put_frame(frames[f], &a.frames[f].node, a.frames[f].lpos, a.frames[f].lquat);
-  std::vector<float> wsm(7 * P.h().nnode + 16);
-  for (int b = 0; b < B; ++b) fk_warp_tile<1, 1>(P, a, b, wsm.data(), 0);
+  a.B = B; a.nframes = nframes; a.q = q; a.poses = poses; a.com = com; a.J = J; a.io64 = f64;
+  for (int f = 0; f < nframes; ++f) { a.frames[f].node = frames[f].node; put_frame64(frames[f], a.frames[f].lpos, a.frames[f].lquat); }
+  std::vector<double> wsm(fk_warp_words(P.h(), 1) + 16);
+  for (int b = 0; b < B; ++b) {
+    if (f64) fk_warp_tile<double, 1, 1>(P, a, b, wsm.data(), 0);
+    else fk_warp_tile<float, 1, 1>(P, a, b, reinterpret_cast<float*>(wsm.data()), 0);
+  }
   return 0;
 }
 
 extern "C" int emu_integrate(void* prob, int B, float* q, const float* dq) {
   EmuProblem* p = static_cast<EmuProblem*>(prob);
   PView P{p->image.data()};
-  for (int b = 0; b < B; ++b) integrate_instance(P, q + (size_t)b * P.h().nq, dq + (size_t)b * P.h().nv);
+  for (int b = 0; b < B; ++b) integrate_instance<float>(P, q + (size_t)b * P.h().nq, dq + (size_t)b * P.h().nv);
   return 0;
 }
 extern "C" int emu_check_limits(void* prob, int B, const float* q, float tol, int32_t* status) {
   EmuProblem* p = static_cast<EmuProblem*>(prob);
   PView P{p->image.data()};
-  for (int b = 0; b < B; ++b) status[b] = check_limits_instance(P, q + (size_t)b * P.h().nq, tol);
+  for (int b = 0; b < B; ++b) status[b] = check_limits_instance<float>(P, q + (size_t)b * P.h().nq, tol);
   return 0;
 }
