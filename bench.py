@@ -386,7 +386,7 @@ def main():
                        "batch_per_gpu": B, "global_batch": world * B, "dt": dt_, "damping": damping,
                        "step": "check_limits + FK/Jacobian (K1) + QP assemble/solve (K2) + integrate, every step from the same q0",
                        "l2": "256 MB flush between timed steps", "parallelism": f"dp{world} (independent instances, no collective)"},
-            "gpu_launches": 4 * args.steps, "clocks": clocks, "roofline": roofline, "roofline_k2": roofline_k2,
+            "gpu_launches": 2 * args.steps, "clocks": clocks, "roofline": roofline, "roofline_k2": roofline_k2,
             "cpu_baseline": cpu, "e2e": e2e, "rollout_T100": rollout, "wall_s_timed_region": wall}
     print(json.dumps(line), flush=True)
     if world > 1:

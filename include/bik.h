@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BIK_VERSION 100
+#define BIK_VERSION 200
 
 typedef enum bik_status {
   BIK_OK = 0,
@@ -43,7 +43,8 @@ typedef enum bik_status {
 #define BIK_STATUS_OUT_OF_LIMITS 1u  /* q outside [range - tol, range + tol] */
 #define BIK_STATUS_QP_MAXITER    2u  /* active-set iteration cap reached; dq is the last iterate */
 #define BIK_STATUS_NONFINITE     4u  /* NaN/Inf met in q, targets or the factorisation */
-#define BIK_STATUS_QP_INFEASIBLE 8u  /* inequality set inconsistent */
+#define BIK_STATUS_QP_INFEASIBLE 8u  /* inequality set inconsistent (lower > upper for a dof, or no feasible start): the
+                                      * reference's solver returns None there and solve_ik asserts (solve_ik.py:103) */
 #define BIK_STATUS_NOT_CONVERGED 16u /* bik_converge: thresholds not met within max_iters */
 
 typedef struct bik_model bik_model;     /* flattened kinematic tree resident on one device */
@@ -120,12 +121,12 @@ typedef struct bik_limit_desc {
  * PostureTask.set_target / ComTask.set_target store (frame_task.py:83, posture_task.py:77,
  * com_task.py:61), one per instance. */
 typedef struct bik_inputs {
-  const float* q;               /* [B][nq] */
-  const float* frame_targets;   /* [B][F][7]  F = number of FRAME + RELATIVE_FRAME tasks, in task-list order */
-  const float* posture_targets; /* [B or 1][P][nq]  P = number of POSTURE tasks */
-  const float* com_targets;     /* [B][C][3]  C = number of COM tasks */
-  int32_t posture_batched;      /* 0: one posture target shared by the batch, 1: per instance */
-  int32_t reserved;
+  const void* q;               /* [B][nq] */
+  const void* frame_targets;   /* [B][F][7]  F = number of FRAME + RELATIVE_FRAME tasks, in task-list order */
+  const void* posture_targets; /* [B or 1][P][nq]  P = number of POSTURE tasks */
+  const void* com_targets;     /* [B][C][3]  C = number of COM tasks */
+  int32_t posture_batched;     /* 0: one posture target shared by the batch, 1: per instance */
+  int32_t f64;                 /* element type of the four buffers: 0 float (fp32 entry points), 1 double (the ...64 ones) */
 } bik_inputs;
 
 typedef struct bik_dims {
@@ -203,8 +204,8 @@ int bik_integrate(const bik_model* model, int B, float* q, const float* dq, void
 int bik_check_limits(const bik_model* model, int B, const float* q, float tol, int32_t* status,
                      void* stream);
 
-/* The whole solve_ik step (solve_ik.py:68-105) `nsteps` times:
- *   check_limits -> K1 -> K2 -> (integrate if `integrate` != 0).
+/* The whole solve_ik step (solve_ik.py:68-105) `nsteps` times, two launches per step:
+ *   K1 (check_limits + FK + task rows, packed: only the non-zero Jacobian columns) -> K2 (QP + integrate if `integrate` != 0).
  * `in->q` is ignored; q [B][nq] is read and, when integrating, updated in place.
  * dq [B][nv] receives the last step's displacement. */
 int bik_step(const bik_problem* problem, int B, float* q, const bik_inputs* in, float dt,
@@ -229,7 +230,33 @@ int bik_converge(const bik_problem* problem, int B, float* q, const bik_inputs* 
                  double damping, int max_iters, float pos_threshold, float ori_threshold,
                  int check_every, int32_t* iters, int32_t* status, void* stream);
 
-/* Bytes of device scratch a problem needs for a batch of B (J, e, ... between K1 and K2). */
+/* ---- fp64 entry points --------------------------------------------------------------------------------------------
+ * The reference is fp64 end to end (numpy; mink/solve_ik.py:13-22).  These mirror the fp32 entry points above with
+ * double buffers (bik_inputs.f64 = 1): the fp64 instantiations of the kernels run, on the kinematic constants at full
+ * precision, and reproduce the reference to solver tolerance (~1e-8 rad) also where cost / sqrt(damping) would amplify
+ * fp32 rounding past 1e-4 rad (BASELINE config 5).  A single (numpy, B = 1) Configuration of the Python front end
+ * always takes them.  The fp32 entry points pick the fp64 K1 by themselves for ill-conditioned problems
+ * (bik_problem_describe says which; BIK_K1_PRECISION=f32|f64 overrides). */
+int bik_fk64(const bik_model* model, int B, const double* q, const bik_frame* frames, int nframes,
+             double* poses, double* com, void* stream);
+int bik_frame_jacobian64(const bik_model* model, int B, const double* q, const bik_frame* frames,
+                         int nframes, double* J, void* stream);
+int bik_fk_jac64(const bik_problem* problem, int B, const bik_inputs* in, double dt, double* J, double* e,
+                 double* e_posture, double* G_coll, double* h_coll, void* stream);
+int bik_qp_objective64(const bik_problem* problem, int B, const double* J, const double* e,
+                       const double* e_posture, double damping, double* H, double* c, void* stream);
+int bik_limits_box64(const bik_problem* problem, int B, const double* q, double dt, double* lo, double* hi,
+                     void* stream);
+int bik_solve64(const bik_problem* problem, int B, const double* q, const double* J, const double* e,
+                const double* e_posture, const double* G_coll, const double* h_coll, double dt,
+                double damping, double* dq, int32_t* status, int32_t* iters, void* stream);
+int bik_integrate64(const bik_model* model, int B, double* q, const double* dq, void* stream);
+int bik_check_limits64(const bik_model* model, int B, const double* q, double tol, int32_t* status,
+                       void* stream);
+int bik_step64(const bik_problem* problem, int B, double* q, const bik_inputs* in, double dt,
+               double damping, int nsteps, int integrate, double* dq, int32_t* status, void* stream);
+
+/* Bytes of device scratch a problem needs for a batch of B (K1's packed task rows, collision rows, ... between K1 and K2). */
 size_t bik_workspace_bytes(const bik_problem* problem, int B);
 
 /* One-line description of how a problem is mapped onto the device (lanes per instance and visited

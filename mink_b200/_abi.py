@@ -48,7 +48,7 @@ class BikLimitDesc(C.Structure):
 
 class BikInputs(C.Structure):
     _fields_ = [("q", C.c_void_p), ("frame_targets", C.c_void_p), ("posture_targets", C.c_void_p),
-                ("com_targets", C.c_void_p), ("posture_batched", C.c_int32), ("reserved", C.c_int32)]
+                ("com_targets", C.c_void_p), ("posture_batched", C.c_int32), ("f64", C.c_int32)]
 
 
 class BikDims(C.Structure):
@@ -239,6 +239,10 @@ def spec_from_workload(fm: FlatModel, wl: dict) -> ProblemSpec:
         p = wl["posture"]
         tasks.append(TaskSpec(TASK_POSTURE, dof_cost=np.broadcast_to(np.atleast_1d(p["cost"]).astype(float), fm.nv).copy(),
                               gain=p.get("gain", 1.0), lm_damping=p.get("lm_damping", 0.0)))
+    if wl.get("damping_task") is not None:   # DampingTask = PostureTask(gain 0, target qpos0), damping_task.py:19-20
+        p = wl["damping_task"]
+        tasks.append(TaskSpec(TASK_POSTURE, dof_cost=np.broadcast_to(np.atleast_1d(p["cost"]).astype(float), fm.nv).copy(),
+                              gain=0.0, lm_damping=0.0))
     if wl.get("com") is not None:
         c = wl["com"]
         cost = np.zeros(6)

@@ -55,7 +55,8 @@ class Configuration:
         self._device = device
         self._dm = None
         self.batched = False
-        self._q = None          # torch [B, nq] fp32 on the device
+        self._q = None          # torch [B, nq] on the device: fp64 for a single (numpy) configuration and for float64
+                                # tensors -- the reference's precision, fp64 kernels -- fp32 for every other batch
         self._q64 = None        # float64 host copy for the single-instance case (exact `.q` round trip)
         self.data = SimpleNamespace(qpos=None)   # minimal stand-in for the reference's `configuration.data`
         self.update(q=q if q is not None else self.flat.qpos0)
@@ -71,14 +72,17 @@ class Configuration:
         import torch
 
         if isinstance(q, torch.Tensor):
-            t = q.to(device=f"cuda:{self.dm.device}", dtype=torch.float32)
-            batched = t.ndim == 2
-            return t.reshape(-1, self.nq).contiguous().clone(), batched, None
+            if q.shape[-1] != self.nq:
+                raise ValueError(f"Expected q with trailing dimension {self.nq}, got {tuple(q.shape)}")
+            batched = q.ndim == 2
+            dtype = torch.float64 if (q.dtype == torch.float64 or not batched) else torch.float32
+            t = q.to(device=f"cuda:{self.dm.device}", dtype=dtype).reshape(-1, self.nq).contiguous().clone()
+            return t, batched, (None if batched else t[0].cpu().numpy().astype(np.float64))
         a = np.asarray(q, dtype=np.float64)
         if a.shape[-1] != self.nq:
             raise ValueError(f"Expected q with trailing dimension {self.nq}, got {a.shape}")
         batched = a.ndim == 2
-        t = torch.tensor(a.reshape(-1, self.nq), dtype=torch.float32, device=f"cuda:{self.dm.device}")
+        t = torch.tensor(a.reshape(-1, self.nq), dtype=torch.float32 if batched else torch.float64, device=f"cuda:{self.dm.device}")
         return t, batched, (None if batched else a.copy())
 
     def update(self, q=None) -> None:
@@ -158,7 +162,12 @@ class Configuration:
         import torch
 
         v = velocity if isinstance(velocity, torch.Tensor) else torch.tensor(np.asarray(velocity, dtype=np.float64))
-        return (v.to(device=self._q.device, dtype=torch.float32).reshape(-1, self.nv) * float(dt)).contiguous()
+        v = v.to(device=self._q.device, dtype=self._q.dtype).reshape(-1, self.nv) * float(dt)
+        if v.shape[0] != self._q.shape[0]:
+            if v.shape[0] != 1:
+                raise ValueError(f"velocity batch {v.shape[0]} does not match the configuration batch {self._q.shape[0]}")
+            v = v.expand(self._q.shape[0], -1)   # one velocity for the whole batch
+        return v.contiguous()
 
     def integrate(self, velocity, dt: float):
         """q (+) v dt without changing the configuration (reference configuration.py:214-226)."""
@@ -187,7 +196,7 @@ class Configuration:
 
     @property
     def q_device(self):
-        """[B, nq] fp32 CUDA tensor used by the kernels (no copy)."""
+        """[B, nq] CUDA tensor used by the kernels (no copy; fp64 for a single configuration, else the batch's dtype)."""
         return self._q
 
     @property

@@ -1,0 +1,142 @@
+// bik_dev.cuh -- what the translation units of libbik share: PTX helpers (mbarrier + 1-D bulk async copy), the handle
+// structs behind the C ABI and the launcher entry points each .cu exports to bik_api.cu.
+//
+//   bik_k1.cu   k1_kernel<T,G> (FK + task rows + collision rows + check_limits), fk_kernel<T,G> (Configuration API)
+//   bik_k2.cu   k2_kernel<T,SLOTS>  (general QP path: one warp per problem)
+//   bik_k2t.cu  k2t_kernel<T,G,M>   (small-group QP path: G lanes per problem, 32- or 64-bit active-set masks)
+//   bik_api.cu  C ABI (include/bik.h), workspace, bik_step / bik_converge / bik_step_host, small tiled kernels
+//
+// There is no CPU fallback in this library: without a CUDA device every entry point fails.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "bik_build.h"
+#include "bik_k2t.h"
+
+namespace bik {
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk async copy (TMA engine; SASS: UBLKCP / SYNCS)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(phase)
+      : "memory");
+  return ok != 0;
+}
+
+// Stage the first `words` words of the problem image into shared memory: one elected thread issues a single bulk copy and
+// everybody waits on the mbarrier (bounded spin; traps instead of hanging the GPU).
+__device__ __forceinline__ void stage_image(uint32_t* smem_image, const uint32_t* gimage, int words, uint64_t* bar, int use_tma) {
+  if (use_tma) {
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, (uint32_t)words * 4u);
+      bulk_g2s(smem_image, gimage, (uint32_t)words * 4u, bar);
+    }
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, 0)) {
+      if (++spins > (1u << 24)) __trap();
+    }
+  } else {
+    const uint4* src = reinterpret_cast<const uint4*>(gimage);
+    uint4* dst = reinterpret_cast<uint4*>(smem_image);
+    for (int k = threadIdx.x; k < words / 4; k += blockDim.x) dst[k] = src[k];
+    __syncthreads();
+  }
+}
+
+}  // namespace bik
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+int bik_fail(int code, const std::string& msg);   // records the message for bik_last_error(), returns code
+#define CUDA_OK(expr)                                                                                       \
+  do {                                                                                                      \
+    cudaError_t _e = (expr);                                                                                \
+    if (_e != cudaSuccess) return bik_fail(BIK_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+struct bik_model {
+  int device = 0, nsm = 0, max_smem = 0;
+  int G = 4, use_tma = 1;
+  bik::HostModel hm;
+  std::vector<uint32_t> image;  // model-only image (no tasks)
+  uint32_t* d_image = nullptr;
+};
+
+enum { BIK_SCHED_SLOTS = 8 };
+struct bik_problem {
+  const bik_model* model = nullptr;
+  int device = 0;  // copy: the model may be destroyed first
+  std::vector<uint32_t> image;
+  uint32_t* d_image = nullptr;
+  bik::PHeader h;
+  int solve_double = 1;   // BIK_SOLVE_PRECISION=f32 selects the fp32 instantiations of K2
+  int k2_general = 0;     // BIK_K2_PATH=dense: every problem takes the general warp-per-problem path
+  int k2_group = 8;       // lanes per problem on the small-group path (BIK_K2_GROUP = 4 | 8)
+  int k2_warps = 8;       // warps per CTA of the general K2 kernel (BIK_K2_WARPS)
+  int k2_dynamic = 1;     // BIK_K2_DYNAMIC=0: static tile assignment in the small-group K2
+  int k1_prec = 0;        // BIK_K1_PRECISION: 0 auto (by conditioning estimate), 1 f32, 2 f64
+  double max_cost2 = 0, min_post2 = 0;   // largest squared task cost / smallest squared posture cost over the coupled, bounded dofs
+  // K1 -> K2 hand-off (one caller at a time per problem)
+  std::mutex mu;
+  size_t ws_B = 0;
+  int ws_elem = 0;        // element size the hand-off buffers were sized for (4 or 8)
+  void *pk = nullptr, *Gc = nullptr, *hc = nullptr;
+  signed char* warm = nullptr;          // [B][nu] active-set guess carried between the steps of one bik_step call
+  unsigned int* d_sched = nullptr;      // BIK_SCHED_SLOTS x 32 words: {next tile, finished CTAs} per launching stream (own 128-byte line each)
+  cudaStream_t sched_stream[BIK_SCHED_SLOTS];
+  int n_sched = 0;
+  // bik_step_host staging
+  size_t host_B = 0;
+  float *hq = nullptr, *hft = nullptr, *hpt = nullptr, *hct = nullptr, *hdq = nullptr;
+  int32_t* hst = nullptr;
+  size_t host_pt_elems = 0;
+  cudaStream_t hs[3] = {nullptr, nullptr, nullptr};   // upload, compute, download
+  std::vector<cudaEvent_t> hev;
+  // bik_converge state
+  size_t conv_B = 0;
+  int32_t* conv_done = nullptr;
+  float* conv_dq = nullptr;
+  int* conv_count = nullptr;   // device: { steps taken so far, unconverged instances }
+  int* conv_host = nullptr;    // pinned mirror
+};
+
+// resident CTAs per SM for (kernel, dynamic smem, threads): attribute + occupancy queries run once per combination
+int bik_launch_geometry(const void* kern, const bik_model* m, size_t smem, int threads, long long work_ctas, int* grid);
+
+// launchers (each returns BIK_OK or records an error)
+int bik_launch_k1(const bik_problem* p, const bik::K1Args& a, bool use_double, cudaStream_t st);
+int bik_launch_fk(const bik_model* m, const bik::FkArgs& a, cudaStream_t st);
+int bik_launch_k2_general(const bik_problem* p, const bik::K2Args& a, cudaStream_t st);
+int bik_launch_k2_group(const bik_problem* p, const bik::K2Args& a, unsigned int* sched, cudaStream_t st);
+bool bik_k2_group_applies(const bik_problem* p);                  // box-only, at most 64 coupled dofs, fits in shared memory
+long long bik_k2_group_wave(const bik_problem* p);                // instances one resident wave of the small-group K2 covers
+const char* bik_k2_describe(const bik_problem* p, char* buf, size_t cap);

@@ -51,10 +51,14 @@ BIK_HD float bik_inf() {
 }
 
 // input element i of a caller buffer that holds fp32 or fp64 values (warp-uniform flag)
+// The fp32 instantiations only ever see fp32 buffers (the launchers refuse anything else), so for them the flag is ignored
+// at compile time: no branch, no fp64 load path in the fp32 kernels.
 template <typename T> BIK_HD T ldin(const void* p, long long i, int is64) {
+  if (sizeof(T) == 4) return T(reinterpret_cast<const float*>(p)[i]);
   return is64 ? T(reinterpret_cast<const double*>(p)[i]) : T(reinterpret_cast<const float*>(p)[i]);
 }
 template <typename T> BIK_HD void stout(void* p, long long i, int is64, T v) {
+  if (sizeof(T) == 4) { reinterpret_cast<float*>(p)[i] = float(v); return; }
   if (is64) reinterpret_cast<double*>(p)[i] = double(v); else reinterpret_cast<float*>(p)[i] = float(v);
 }
 
@@ -391,7 +395,9 @@ template <> BIK_HD void store6<double>(double* o, V3<double> top, V3<double> bot
 }
 
 // One warp tile: instances [inst0, inst0 + IPW) clipped to B.
-template <typename T, int G, int W>
+// PK (compile time): packed hand-off with the fused check_limits / convergence test (bik_step, bik_converge), else the dense
+// API form (bik_fk_jac) -- two instantiations so that neither carries the other's registers and code.
+template <typename T, int G, int W, bool PK>
 BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, T* wsm, int lane) {
   const PHeader& h = P.h();
   constexpr int IPW = W / G;
@@ -401,7 +407,7 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, T* wsm, int
   const int nvalid = (a.B - inst0) < IPW ? (a.B - inst0) : IPW;
   const bool valid = li < nvalid;
   const int SS = k1_state_stride(h);
-  const bool packed = a.pk != nullptr;
+  constexpr bool packed = PK;
   const long long PKS = h.pk_stride;
   T* const Jg = reinterpret_cast<T*>(a.J);
   T* const pkg = reinterpret_cast<T*>(a.pk);
@@ -416,13 +422,13 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, T* wsm, int
   {
     const long long q0 = (long long)inst0 * nq;
     for (int k = lane; k < nvalid * nq; k += W) qtile[k] = ldin<T>(a.q, q0 + k, a.in64);
-    if (a.status && lane < IPW) sflag[lane] = 0;
+    if (PK && a.status && lane < IPW) sflag[lane] = 0;
   }
   BIK_SYNCWARP();
   const T* qb = qtile + (valid ? li : 0) * nq;
 
   // ---- Configuration.check_limits (configuration.py:77-110), fused: every lane tests a few dofs of the tile ----
-  if (a.status) {
+  if (PK && a.status) {
     const int32_t* dofqadr = P.i(h.off_dofqadr);
     const float* rng = P.f(h.off_range);
     for (int i = 0; i < nvalid; ++i) {
@@ -613,7 +619,7 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, T* wsm, int
   }
 
   // ---- convergence test of the examples' inner loop (bik_converge), on the unweighted frame errors --------
-  if (a.done) {
+  if (PK && a.done) {
     BIK_SYNCWARP();
     const int it = *a.conv_it;
     if (it > 0 && lane < nvalid && !a.done[inst0 + lane]) {

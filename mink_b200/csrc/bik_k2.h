@@ -45,9 +45,10 @@ struct K2Args {
   // task rows, one of two forms
   const void* pk;      // packed K1 hand-off [B][pk_stride] (fp64 when pk64), or null
   int pk64;
-  const float* J;      // dense [B][K][nv]   (bik_solve / bik_qp_objective)
-  const float* e;      // dense [B][K]
-  const float* ep;     // dense [B][P][nv]; null: the posture error is computed from q and ptgt
+  const void* J;       // dense [B][K][nv]   (bik_solve / bik_qp_objective); fp64 when dense64
+  const void* e;       // dense [B][K]
+  const void* ep;      // dense [B][P][nv]; null: the posture error is computed from q and ptgt
+  int dense64;
   const void* ptgt;    // [B or 1][P][nq] posture targets (dtype follows io64)
   int pbatched;
   const void* Gc;      // [B][npairs][nv], [B][npairs] collision rows (fp64 when gc64)
@@ -61,8 +62,8 @@ struct K2Args {
   int32_t* iters;      // [B] or null: factorisations per instance (diagnostics)
   double* Hout;        // [B][nv][nv] or null  (bik_qp_objective)
   double* cout;        // [B][nv] or null
-  float* lo_out;       // [B][nv] or null      (bik_limits_box)
-  float* hi_out;
+  void* lo_out;        // [B][nv] or null      (bik_limits_box; dtype follows io64)
+  void* hi_out;
   int skip_objective;  // bik_limits_box: task rows are not read
   int skip_box;        // bik_qp_objective: q is not read
   signed char* warm;   // [B][nu] or null: active-set guess in (0 free, 1 lower, 2 upper; +4 = dq still holds the previous step's result), read at entry, updated at exit
@@ -189,7 +190,7 @@ BIK_HD int k2_assemble(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int l
       T lo, hi;
       const int qa = dofqadr[d];
       box_dof<T>(P, d, qa >= 0 ? qv(qa) : T(0), T(a.dt), &lo, &hi);
-      a.lo_out[(long long)b * n + d] = float(lo); a.hi_out[(long long)b * n + d] = float(hi);
+      stout<T>(a.lo_out, (long long)b * n + d, a.io64, lo); stout<T>(a.hi_out, (long long)b * n + d, a.io64, hi);
     }
     return 0;
   }
@@ -203,8 +204,8 @@ BIK_HD int k2_assemble(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int l
       const int ia = k / tk.nr, r = k - ia * tk.nr;
       T v;
       if (a.pk) v = ldin<T>(a.pk, (long long)b * h.pk_stride + tk.pk_off + k, a.pk64);
-      else if (k < nj) v = T(a.J[((long long)b * K + tk.row0 + r) * n + (cols[tk.coff + ia] & 0xffff)]);
-      else v = T(a.e[(long long)b * K + tk.row0 + r]);
+      else if (k < nj) v = ldin<T>(a.J, ((long long)b * K + tk.row0 + r) * n + (cols[tk.coff + ia] & 0xffff), a.dense64);
+      else v = ldin<T>(a.e, (long long)b * K + tk.row0 + r, a.dense64);
       w.wpk[tk.pk_off + k] = k < nj ? T(tk.cost[r]) * v : T(tk.cost[r]) * (T(-tk.gain) * v);
     }
   }
@@ -232,7 +233,7 @@ BIK_HD int k2_assemble(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int l
     if (tk.lm != 0.f) { const T* we = w.wpk + tk.pk_off + tk.nr * tk.nc; T s = T(0); for (int r = 0; r < tk.nr; ++r) s += we[r] * we[r]; mu += T(tk.lm) * s; }
   }
   auto eperr = [&](int p, int d) -> T {
-    if (a.ep) return T(a.ep[((long long)b * h.P + p) * n + d]);
+    if (a.ep) return ldin<T>(a.ep, ((long long)b * h.P + p) * n + d, a.dense64);
     const long long t0 = ((long long)(a.pbatched ? b : 0) * h.P + p) * nq;
     return posture_err_dof<T>(P, d, [&](int i) { return ldin<T>(a.ptgt, t0 + i, a.io64); }, qv);
   };
@@ -260,7 +261,7 @@ BIK_HD int k2_assemble(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int l
     }
     T lo = -T(BIK_INF_F), hi = T(BIK_INF_F);
     if (!a.skip_box) { const int qa = dofqadr[d]; box_dof<T>(P, d, qa >= 0 ? qv(qa) : T(0), T(a.dt), &lo, &hi); }
-    if (a.lo_out) { a.lo_out[(long long)b * n + d] = float(lo); a.hi_out[(long long)b * n + d] = float(hi); }
+    if (a.lo_out) { stout<T>(a.lo_out, (long long)b * n + d, a.io64, lo); stout<T>(a.hi_out, (long long)b * n + d, a.io64, hi); }
     if (lo > hi + T(1e-9) * (T(1) + (hi < 0 ? -hi : hi))) status |= 8;   // inconsistent limits (e.g. a configuration far outside its range with a velocity limit): the reference's QP has no solution (solve_ik.py:103)
     if (u >= 0) {
       w.Hp[tri(u) + u] += hd;

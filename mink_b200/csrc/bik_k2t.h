@@ -141,10 +141,10 @@ BIK_HD void k2t_stage_task(T* tile, int S, int lane, int cnt, long long b0, cons
 #pragma unroll
       for (int i = 0; i < NS; ++i) tile[i * S + k] = i < cnt ? cr * ldin<T>(a.pk, o + (long long)i * pks, a.pk64) : T(0);
     } else {
-      const float* src = isj ? a.J + b0 * K * nv + (tk.row0 + r) * nv + (cols[ia] & 0xffff) : a.e + b0 * K + tk.row0 + r;
-      const long long stride = isj ? (long long)K * nv : K;
+      const void* src = isj ? a.J : a.e;
+      const long long o = isj ? b0 * K * nv + (tk.row0 + r) * nv + (cols[ia] & 0xffff) : b0 * K + tk.row0 + r, stride = isj ? (long long)K * nv : K;
 #pragma unroll
-      for (int i = 0; i < NS; ++i) tile[i * S + k] = i < cnt ? cr * T(src[i * stride]) : T(0);
+      for (int i = 0; i < NS; ++i) tile[i * S + k] = i < cnt ? cr * ldin<T>(src, o + i * stride, a.dense64) : T(0);
     }
   }
 }
@@ -156,10 +156,10 @@ BIK_HD void k2t_stage_q(T* tile, int S, int lane, int cnt, const void* src, int 
   }
 }
 template <typename T, int W, int NS>
-BIK_HD void k2t_stage_rows(T* tile, int S, int off, int lane, int cnt, const float* src, long long stride, int n) {
+BIK_HD void k2t_stage_rows(T* tile, int S, int off, int lane, int cnt, const void* src, int is64, long long o, long long stride, int n) {
   for (int k = lane; k < n; k += W) {
 #pragma unroll
-    for (int i = 0; i < NS; ++i) tile[i * S + off + k] = i < cnt ? T(src[i * stride + k]) : T(0);
+    for (int i = 0; i < NS; ++i) tile[i * S + off + k] = i < cnt ? ldin<T>(src, o + i * stride + k, is64) : T(0);
   }
 }
 
@@ -403,7 +403,7 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
   BIK_SYNCWARP();
   const int Sq = (nq + NP * nv) | 1;
   k2t_stage_q<T, W, NS>(U, Sq, lane, cnt, a.q, a.io64, b0, nq);
-  if (NP > 0 && a.ep) k2t_stage_rows<T, W, NS>(U, Sq, nq, lane, cnt, a.ep + b0 * NP * nv, (long long)NP * nv, NP * nv);
+  if (NP > 0 && a.ep) k2t_stage_rows<T, W, NS>(U, Sq, nq, lane, cnt, a.ep, a.dense64, b0 * NP * nv, (long long)NP * nv, NP * nv);
   BIK_SYNCWARP();
   if (NP > 0 && !a.ep) {   // inside bik_step K1 hands no posture error over: e = q* (-) q from the staged q (posture_task.py:107-118)
     const int per = NP * nv;

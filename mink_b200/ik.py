@@ -68,8 +68,8 @@ def build_ik(configuration: Configuration, tasks: Sequence[Task], dt: float, dam
     if configuration.batched:
         import torch
 
-        G = torch.cat([g.float() for g in G_list], dim=1) if G_list else None
-        h = torch.cat([x.float() for x in h_list], dim=1) if h_list else None
+        G = torch.cat([g.to(h_list[0].dtype) for g in G_list], dim=1) if G_list else None
+        h = torch.cat(list(h_list), dim=1) if h_list else None
         return Problem(H, c, G, h)
     G = np.vstack(G_list) if G_list else None
     h = np.hstack(h_list) if h_list else None

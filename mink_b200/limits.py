@@ -55,7 +55,7 @@ def _box_constraint(limit: Limit, configuration: Configuration, dt: float, indic
 
         idx = torch.as_tensor(np.array(indices), device=lo.device, dtype=torch.long)
         h = torch.cat([hi[:, idx], -lo[:, idx]], dim=1)
-        return Constraint(torch.tensor(G, dtype=torch.float32, device=lo.device).expand(lo.shape[0], -1, -1), h)
+        return Constraint(torch.tensor(G, dtype=lo.dtype, device=lo.device).expand(lo.shape[0], -1, -1), h)
     ii = np.array(indices)
     h = np.concatenate([hi[0].cpu().numpy()[ii], -lo[0].cpu().numpy()[ii]]).astype(np.float64)
     return Constraint(G, h)
@@ -74,6 +74,11 @@ class ConfigurationLimit(Limit):
         index_list = []
         for d in range(flat.nv):
             a = int(flat.dof_qadr[d])
+            if a < 0 and flat.dof_limited[d] and int(flat.node_type[flat.dof_node[d]]) == 1:
+                # the reference adds the three dofs of a limited ball joint (configuration_limit.py:44-56); the device box
+                # has no cone limit, so refuse loudly instead of silently dropping the limit
+                raise LimitDefinitionError(f"{self.__class__.__name__}: limited ball joints are not supported on the device "
+                                           f"(joint {flat.names['joint'][int(flat.dof_node[d])]})")
             if a < 0 or not flat.dof_limited[d]:
                 continue
             lower[a] = flat.dof_lo[d] + min_distance_from_limits

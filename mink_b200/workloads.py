@@ -105,6 +105,15 @@ WORKLOADS: Dict[str, dict] = {
         limits=[dict(kind="configuration", gain=0.95), dict(kind="velocity", vmax=PI)],
         dt=5e-3, damping=1e-1, batch=4096,
     ),
+    # Not a BASELINE config: DampingTask (reference mink/tasks/damping_task.py:11-20 = PostureTask with gain 0
+    # and target qpos0, as examples/mobile_tidybot.py:60 uses it) next to a frame task, with both box limits.
+    "ur5e_damp": dict(
+        robot="ur5e", scene="universal_robots_ur5e/scene.xml", key="home",
+        frames=[dict(name="attachment_site", type="site", position_cost=1.0, orientation_cost=1.0, lm_damping=1.0)],
+        posture=None, damping_task=dict(cost=0.3), com=None,
+        limits=[dict(kind="configuration", gain=0.95), dict(kind="velocity", vmax=2 * PI)],
+        dt=2e-2, damping=1e-4, batch=1024,
+    ),
     # Not a BASELINE config: edge-case model authored for this repository (tests/golden/models/edge.xml):
     # ball joint with off-centre anchor, slide joint with ref, two joints on one body, a second floating
     # root, capsule/sphere/plane collision pairs, every task and limit kind at once.
@@ -186,7 +195,9 @@ def make_inputs(fm, wl: dict, B: int, fk: FkFn, seed: int = 0, sigma: float = 0.
     if n_al:
         idx = rng.choice(B, size=n_al, replace=False)
         targets[idx, :, :4] = poses_now[idx, :, :4]
-    out = dict(q=q, frame_targets=targets, posture_target=key_q.copy())
+    # a DampingTask's "target" is qpos0 (damping_task.py:20); it travels in the posture-target slot
+    ptgt = np.asarray(fm.qpos0, dtype=np.float64).copy() if (wl.get("damping_task") is not None and wl.get("posture") is None) else key_q.copy()
+    out = dict(q=q, frame_targets=targets, posture_target=ptgt)
     if wl.get("com") is not None:
         out["com_target"] = np.array(com_tgt, dtype=np.float64, copy=True)
     return out

@@ -26,7 +26,7 @@ from mink_b200.flatten import flatten  # noqa: E402
 from mink_b200.workloads import WORKLOADS, make_inputs  # noqa: E402
 
 OUT = os.path.join(REPO, "tests", "golden")
-GOLDEN_B = {"ur5e": 8, "ur5e_dls": 16, "g1": 32, "shadow": 24, "spot": 24, "g1_rel": 16, "edge": 48, "g1_full": 16, "g1_hands": 24}
+GOLDEN_B = {"ur5e_damp": 12, "ur5e": 8, "ur5e_dls": 16, "g1": 32, "shadow": 24, "spot": 24, "g1_rel": 16, "edge": 48, "g1_full": 16, "g1_hands": 24}
 ROLLOUT_T, ROLLOUT_B = 8, 4
 CONV_B, CONV_MAX_ITERS, CONV_POS, CONV_ORI = 8, 20, 2e-3, 2e-3
 
@@ -45,6 +45,10 @@ def build_reference_problem(model, wl):
     posture = com = None
     if wl["posture"] is not None:
         posture = mink.PostureTask(model, cost=wl["posture"]["cost"])
+        tasks.append(posture)
+    if wl.get("damping_task") is not None:   # takes the posture slot of the record (its target is qpos0)
+        assert posture is None
+        posture = mink.DampingTask(model, cost=wl["damping_task"]["cost"])
         tasks.append(posture)
     if wl["com"] is not None:
         com = mink.ComTask(cost=wl["com"]["cost"])
@@ -131,7 +135,8 @@ def main():
                     poses[b, k] = cfg.get_transform(f["name"], f["type"], f["root_name"], f["root_type"]).wxyz_xyz
             comp[b] = cfg.data.subtree_com[1]
             if posture is not None:
-                posture.set_target(inp["posture_target"])
+                if not isinstance(posture, mink.DampingTask):
+                    posture.set_target(inp["posture_target"])
                 eP[b] = posture.compute_error(cfg)
             if com is not None:
                 com.set_target(inp["com_target"][b])

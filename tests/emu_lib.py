@@ -99,7 +99,7 @@ class Emu:
         st = np.zeros(B, np.int32); it = np.zeros(B, np.int32)
         H = np.zeros((B, self.nv, self.nv)) if want_objective else None
         c = np.zeros((B, self.nv)) if want_objective else None
-        lo = np.zeros((B, self.nv), np.float32); hi = np.zeros((B, self.nv), np.float32)
+        lo = np.zeros((B, self.nv), tio); hi = np.zeros((B, self.nv), tio)
         gc64 = int(Gc is not None and Gc.dtype == np.float64 and pk is not None)
         Gc = pad(_as(Gc, np.float64 if gc64 else np.float32)); hc = pad(_as(hc, np.float64 if gc64 else np.float32))
         pk64 = int(pk is not None and pk.dtype == np.float64)
@@ -116,7 +116,7 @@ class Emu:
         skip = _as(skip, np.int32)
         self.last_rc = lib().emu_solve(self.h, B, path, int(io64), _vp(q), _vp(pk), pk64, _p(Jd), _p(ed), _p(epd), _vp(ptgt), batched,
                                        _vp(Gc), _vp(hc), gc64, C.c_double(dt), C.c_double(damping), _vp(dq), int(integrate),
-                                       _p(st, C.c_int32), _p(it, C.c_int32), _p(H, C.c_double), _p(c, C.c_double), _p(lo), _p(hi),
+                                       _p(st, C.c_int32), _p(it, C.c_int32), _p(H, C.c_double), _p(c, C.c_double), _vp(lo), _vp(hi),
                                        None if warm is None else warm.ctypes.data_as(C.POINTER(C.c_byte)), _p(skip, C.c_int32))
         assert self.last_rc == 0, lib().emu_last_error()
         out = (dq, st, it, H, c, lo, hi)

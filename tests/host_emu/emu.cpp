@@ -63,8 +63,9 @@ extern "C" int emu_fk_jac(void* prob, int B, int f64, const void* q, const void*
   a.J = J; a.e = e; a.ep = ep; a.Gc = Gc; a.hc = hc; a.pk = pk; a.status = status; a.tol = 1e-6f;
   std::vector<double> wsm(k1_warp_words(P.h(), 1) + 16);
   for (int b = 0; b < B; ++b) {
-    if (f64) k1_warp_tile<double, 1, 1>(P, a, b, wsm.data(), 0);
-    else k1_warp_tile<float, 1, 1>(P, a, b, reinterpret_cast<float*>(wsm.data()), 0);
+    if (f64) { if (pk) k1_warp_tile<double, 1, 1, true>(P, a, b, wsm.data(), 0); else k1_warp_tile<double, 1, 1, false>(P, a, b, wsm.data(), 0); }
+    else if (pk) k1_warp_tile<float, 1, 1, true>(P, a, b, reinterpret_cast<float*>(wsm.data()), 0);
+    else k1_warp_tile<float, 1, 1, false>(P, a, b, reinterpret_cast<float*>(wsm.data()), 0);
   }
   return 0;
 }
@@ -73,13 +74,13 @@ extern "C" int emu_fk_jac(void* prob, int B, int f64, const void* q, const void*
 // Task rows: packed (pk, pk64) or dense (J, e, ep fp32; ep may be null with ptgt set).  io64: q / ptgt / dq are fp64.
 extern "C" int emu_solve(void* prob, int B, int path, int io64, const void* q, const void* pk, int pk64, const float* J, const float* e, const float* ep,
                          const void* ptgt, int pbatched, const void* Gc, const void* hc, int gc64, double dt, double damping, void* dq,
-                         int integrate, int32_t* status, int32_t* iters, double* H, double* c, float* lo, float* hi, signed char* warm,
+                         int integrate, int32_t* status, int32_t* iters, double* H, double* c, void* lo, void* hi, signed char* warm,
                          const int32_t* skip) {
   EmuProblem* p = static_cast<EmuProblem*>(prob);
   PView P{p->image.data()};
   K2Args a;
   memset(&a, 0, sizeof a);
-  a.B = B; a.q = q; a.io64 = io64; a.pk = pk; a.pk64 = pk64; a.J = J; a.e = e; a.ep = ep; a.ptgt = ptgt; a.pbatched = pbatched;
+  a.B = B; a.q = q; a.io64 = io64; a.pk = pk; a.pk64 = pk64; a.J = J; a.e = e; a.ep = ep; a.dense64 = 0; a.ptgt = ptgt; a.pbatched = pbatched;
   a.Gc = Gc; a.hc = hc; a.gc64 = gc64; a.dt = dt; a.damping = damping; a.dq = dq; a.integrate = integrate; a.status = status; a.iters = iters;
   a.Hout = H; a.cout = c; a.lo_out = lo; a.hi_out = hi; a.warm = warm; a.skip = skip;
   if (path == 3 || path == 4 || path == 8) {

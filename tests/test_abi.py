@@ -12,12 +12,12 @@ def test_library_exports_every_declared_symbol():
     build.build()
     lib = _lib.load()
     header = open(os.path.join(REPO, "include", "bik.h")).read()
-    declared = set(re.findall(r"\b(bik_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(bik_[a-z_0-9]+)\s*\(", header))
     assert declared, "no declarations found"
     for name in sorted(declared):
         assert hasattr(lib, name), f"libbik.so does not export {name}"
     assert declared == set(_lib.EXPORTS)
-    assert lib.bik_version() == 100
+    assert lib.bik_version() == 200
 
 
 def test_no_cpu_fallback():
@@ -39,6 +39,6 @@ def test_product_never_imports_oracle():
     pkg = os.path.join(REPO, "mink_b200")
     for root, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(root, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "ikoracle" not in src, f

@@ -236,3 +236,44 @@ def test_converge_ik_matches_the_explicit_loop():
                 break
         assert steps == it
         np.testing.assert_allclose(cfg.q, cfg2.q, atol=2e-5)
+
+
+def test_damping_task_objective_matches_reference_test():
+    """reference tests/test_damping_task.py:21-26: DampingTask(cost=1) on UR5e gives H = I, c = 0 -- single configuration
+    (fp64 kernels) and a batch (fp32 kernels)."""
+    fm = load_flat("ur5e")
+    task = mink.DampingTask(fm, cost=1.0)
+    cfg = mink.Configuration(fm)
+    H, c = task.compute_qp_objective(cfg)
+    np.testing.assert_allclose(H, np.eye(cfg.nv))
+    np.testing.assert_allclose(c, np.zeros(cfg.nv))
+    q = np.tile(fm.key("home"), (7, 1)) + np.linspace(0, 0.3, 7)[:, None]
+    cfgb = mink.Configuration(fm, q)
+    Hb, cb = task.compute_qp_objective(cfgb)
+    np.testing.assert_allclose(_np(Hb), np.tile(np.eye(cfg.nv), (7, 1, 1)))
+    np.testing.assert_allclose(_np(cb), 0.0)
+    # the error is q0 - q whatever the configuration, and the gain is 0: it never enters c
+    np.testing.assert_allclose(task.compute_error(mink.Configuration(fm, q[3])), fm.qpos0 - q[3], atol=1e-12)
+
+
+def test_damping_task_in_solve_ik_matches_reference_golden():
+    """FrameTask + DampingTask + Configuration/Velocity limits through solve_ik against the golden made by running the
+    reference's DampingTask (oracle/gen_golden.py, case ur5e_damp)."""
+    wl, fm, spec, g = load_case("ur5e_damp")
+    f = wl["frames"][0]
+    frame = mink.FrameTask(f["name"], f["type"], f["position_cost"], f["orientation_cost"], lm_damping=f["lm_damping"])
+    damp = mink.DampingTask(fm, cost=wl["damping_task"]["cost"])
+    limits = [mink.ConfigurationLimit(fm), mink.VelocityLimit(fm, {n: 2 * np.pi for n, t in zip(fm.names["joint"], fm.node_type) if t >= 2})]
+    dt, damping = float(g["dt"]), float(g["damping"])
+    for b in range(4):
+        cfg = mink.Configuration(fm, g["q"][b])
+        frame.set_target(SE3(g["frame_targets"][b, 0]))
+        v = mink.solve_ik(cfg, [frame, damp], dt, "quadprog", damping, limits=limits)
+        np.testing.assert_allclose(v * dt, g["dq"][b], atol=2e-7)
+        prob = mink.build_ik(cfg, [frame, damp], dt, damping, limits)
+        np.testing.assert_allclose(prob.P, g["H"][b], atol=1e-10 * np.abs(g["H"][b]).max())
+        np.testing.assert_allclose(prob.q, g["c"][b], atol=1e-10 * max(1.0, np.abs(g["c"][b]).max()))
+    cfgb = mink.Configuration(fm, g["q"])
+    frame.set_target(SE3(g["frame_targets"][:, 0]))
+    vb = mink.solve_ik(cfgb, [frame, damp], dt, "quadprog", damping, limits=limits)
+    np.testing.assert_allclose(_np(vb) * dt, g["dq"], atol=1e-4)

@@ -1,7 +1,13 @@
 """GPU parity: the CUDA path (through the C ABI) against the golden vectors and the C oracle.
 
-Tolerance: BASELINE.json north_star -- dq within 1e-4 rad of the fp64 reference (fp32 device I/O).
-Tighter bounds are used where the quantity allows.  Property tests cover BASELINE's full sizes.
+Tolerance: BASELINE.json north_star -- dq within 1e-4 rad of the fp64 reference on identical inputs.
+  * fp64 entry points (double buffers, what a single numpy Configuration takes): every configuration, the
+    ill-conditioned ones included, against the goldens at 1e-6 or tighter;
+  * fp32 entry points (the batched fast path): against the goldens at 1e-4, except Spot / edge whose goldens were
+    generated from fp64 inputs -- rounding q to fp32 alone moves Spot's optimum by up to ~3e-4 (cost / (2 sqrt(damping))
+    = 3e3 times 1e-7) -- so those two are held to 1e-4 against the oracle evaluated on the SAME fp32-rounded inputs
+    (test_fp32_entry_points_match_oracle_on_identical_inputs) and to 1e-3 against the fp64-input golden.
+Property tests cover BASELINE's full sizes.
 """
 
 import os
@@ -16,12 +22,17 @@ from mink_b200._abi import spec_from_workload  # noqa: E402
 from mink_b200.workloads import WORKLOADS, make_inputs  # noqa: E402
 from tests.helpers import load_case, load_flat, quat_align, task_frames  # noqa: E402
 
-CASES = ["ur5e", "ur5e_dls", "g1", "shadow", "spot", "g1_rel", "edge", "g1_full", "g1_hands"]
+CASES = ["ur5e", "ur5e_dls", "g1", "shadow", "spot", "g1_rel", "edge", "g1_full", "g1_hands", "ur5e_damp"]
 
 
 def _need_gpu():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
+
+
+def _r32(a):
+    """fp32-representable copy of an fp64 array (None passes through)."""
+    return None if a is None else np.asarray(a, np.float32).astype(np.float64)
 
 
 def _engine(name, env=None):
@@ -114,7 +125,20 @@ def test_k2_objective_box_and_solve_from_reference_jacobians(name):
     np.testing.assert_allclose(_np(hi)[fin], g["box_hi"][fin], atol=1e-6)
     dq, st = prob.solve(g["q"], J, e, ep, Gc, hc, float(g["dt"]), float(g["damping"]))
     assert int(st.max()) == 0
-    np.testing.assert_allclose(_np(dq), g["dq"], atol={"spot": 2e-3, "g1_rel": 5e-5}.get(name, 1e-5))
+    np.testing.assert_allclose(_np(dq), g["dq"], atol={"spot": 2e-3, "g1_rel": 5e-5}.get(name, 1e-5))   # spot: the fp32 cast of J alone
+    # same through the fp64 entry points: the reference's own (J, e) in, the reference's dq out
+    f64 = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda:0")
+    J8 = f64(np.concatenate([g["J_frame"].reshape(B, 6 * F, fm.nv)] + ([g["J_com"]] if spec.ncom else []), axis=1))
+    e8 = f64(np.concatenate([g["e_frame"].reshape(B, 6 * F)] + ([g["e_com"]] if spec.ncom else []), axis=1))
+    ep8 = f64(g["e_posture"][:, None, :]) if spec.nposture else torch.zeros((B, 0, fm.nv), device="cuda:0", dtype=torch.float64)
+    Gc8 = f64(g["G"][:, -spec.npairs:]) if spec.npairs else torch.zeros((B, 0, fm.nv), device="cuda:0", dtype=torch.float64)
+    hc8 = f64(g["h"][:, -spec.npairs:]) if spec.npairs else torch.zeros((B, 0), device="cuda:0", dtype=torch.float64)
+    H8, c8 = prob.objective(J8, e8, ep8, float(g["damping"]))
+    np.testing.assert_allclose(_np(H8), g["H"], atol=1e-12 * scale)
+    np.testing.assert_allclose(_np(c8), g["c"], atol=1e-12 * max(1.0, np.abs(g["c"]).max()))
+    dq8, st8 = prob.solve(f64(g["q"]), J8, e8, ep8, Gc8, hc8, float(g["dt"]), float(g["damping"]))
+    assert int(st8.max()) == 0
+    np.testing.assert_allclose(_np(dq8), g["dq"], atol=2e-7 * max(1.0, np.abs(g["dq"]).max()))
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -125,9 +149,9 @@ def test_solve_ik_step_matches_reference(name):
     dq, st = prob.step(q, g["frame_targets"], g["posture_target"], g.get("com_target"), dt=float(g["dt"]),
                        damping=float(g["damping"]), nsteps=1, integrate=True)
     assert int(st.max()) == 0
-    # spot: cond(H) ~ 4e7, fp32 J alone moves the optimum; g1_rel: |dq| up to 2.3 rad (no velocity limit) -> relative 1e-4
-    tol = {"spot": 5e-3, "g1_rel": 1e-4 * max(1.0, np.abs(g["dq"]).max()),
-           "edge": 2e-3}.get(name, 1e-4)   # edge: an active near-parallel capsule pair (ill-conditioned contact point)
+    # spot / edge: fp32 rounding of the golden's fp64 inputs (see the module docstring; the fp64 K1 runs for both);
+    # g1_rel: |dq| up to 2.3 rad (no velocity limit) -> relative 1e-4
+    tol = {"spot": 1e-3, "g1_rel": 1e-4 * max(1.0, np.abs(g["dq"]).max()), "edge": 1e-3}.get(name, 1e-4)
     err = np.abs(_np(dq) - g["dq"]).max()
     print(f"{name}: max|dq - dq_ref| = {err:.3e}")
     assert err < tol
@@ -144,7 +168,7 @@ def test_rollout_matches_reference(name):
     dq, st = prob.step(q, g["frame_targets"][:RB], g["posture_target"], ct, dt=float(g["dt"]), damping=float(g["damping"]),
                        nsteps=T, integrate=True)
     assert int(st.max()) == 0
-    np.testing.assert_allclose(_np(q), traj[-1], atol={"spot": 2e-2, "edge": 1e-2, "g1_rel": 2e-3}.get(name, 5e-4))
+    np.testing.assert_allclose(_np(q), traj[-1], atol={"spot": 5e-3, "edge": 5e-3, "g1_rel": 2e-3}.get(name, 5e-4))
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -161,7 +185,7 @@ def test_converge_matches_reference(name):
     np.testing.assert_array_equal(_np(it), g["conv_iters"])
     np.testing.assert_array_equal((sti & 16) == 0, g["conv_ok"].astype(bool))
     assert int((st & 15).max()) == 0
-    np.testing.assert_allclose(_np(q), g["conv_q"], atol={"spot": 4e-2, "edge": 2e-2, "g1_rel": 5e-3}.get(name, 1e-3))
+    np.testing.assert_allclose(_np(q), g["conv_q"], atol={"spot": 1e-2, "edge": 1e-2, "g1_rel": 5e-3}.get(name, 1e-3))
 
 
 @pytest.mark.parametrize("check_every", [1, 3])
@@ -203,9 +227,8 @@ def test_every_lane_group_size_against_oracle(group):
 
 
 @pytest.mark.parametrize("env", [{"BIK_USE_TMA": 0}, {"BIK_SOLVE_PRECISION": "f32", "BIK_K2_PATH": "dense"}, {"BIK_K2_PATH": "dense"},
-                                 {"BIK_K2_PATH": "lowrank"}, {"BIK_K2_WARPS": 8}, {"BIK_K2_PATH": "group", "BIK_K2_GROUP": 4},
-                                 {"BIK_K2_PATH": "group", "BIK_K2_GROUP": 8}, {"BIK_K2_PATH": "group", "BIK_SOLVE_PRECISION": "f32"},
-                                 {"BIK_K2_PATH": "fixed", "BIK_SOLVE_PRECISION": "f32"}, {"BIK_K2_PATH": "fixed"}])
+                                 {"BIK_K2_PATH": "dense", "BIK_K2_WARPS": 4}, {"BIK_K2_GROUP": 4}, {"BIK_K2_GROUP": 8},
+                                 {"BIK_SOLVE_PRECISION": "f32"}, {"BIK_K1_PRECISION": "f64"}, {"BIK_K1_PRECISION": "f64", "BIK_K2_PATH": "dense"}])
 def test_alternate_paths(env):
     wl, fm, spec, g, model, prob = _engine("g1", env=env)
     q = torch.tensor(g["q"], dtype=torch.float32, device="cuda:0")
@@ -214,28 +237,24 @@ def test_alternate_paths(env):
     assert np.abs(_np(dq) - g["dq"]).max() < 1e-4
 
 
-@pytest.mark.parametrize("path", ["dense", "group", "fixed"])
+@pytest.mark.parametrize("path", ["dense", "group"])
 def test_k2_paths_on_relative_frame_golden(path):
     env = {"BIK_K2_PATH": path}
-    if path == "fixed":
-        env["BIK_SOLVE_PRECISION"] = "f32"
     wl, fm, spec, g, model, prob = _engine("g1_rel", env=env)
     rep = 5   # 80 instances: more than one tile of every path, ragged tail
     q = torch.tensor(np.tile(g["q"], (rep, 1)), dtype=torch.float32, device="cuda:0")
     dq, st = prob.step(q, np.tile(g["frame_targets"], (rep, 1, 1)), g["posture_target"], None, dt=float(g["dt"]), damping=float(g["damping"]))
     assert int(st.max()) == 0
     tol = 1e-4 * max(1.0, np.abs(g["dq"]).max())
-    assert np.abs(_np(dq) - np.tile(g["dq"], (rep, 1))).max() < (tol if path != "fixed" else 20 * tol)
+    assert np.abs(_np(dq) - np.tile(g["dq"], (rep, 1))).max() < tol
 
 
 @pytest.mark.parametrize("name", ["g1", "shadow", "ur5e"])
-@pytest.mark.parametrize("path", ["dense", "group", "fixed", "mixed"])
+@pytest.mark.parametrize("path", ["dense", "group", "group4", "k1f64"])
 def test_k2_paths_agree_on_a_ragged_batch(name, path):
-    """Every K2 path that applies to a box-only problem returns the same optimum (ragged batch: tail tiles of each path).
-    "fixed" = fixed-size path in fp32, "mixed" = fixed-size path with fp32 factorisations polished in fp64."""
-    env = {"BIK_K2_PATH": "fixed" if path == "mixed" else path}
-    if path == "fixed":
-        env["BIK_SOLVE_PRECISION"] = "f32"
+    """Every K2 path that applies to a box-only problem returns the same optimum (ragged batch: tail tiles of each path);
+    "k1f64": the fp64 K1 with its fp64 packed hand-off in front of the default K2."""
+    env = {"dense": {"BIK_K2_PATH": "dense"}, "group": {}, "group4": {"BIK_K2_GROUP": 4}, "k1f64": {"BIK_K1_PRECISION": "f64"}}[path]
     wl, fm, spec, g, model, prob = _engine(name, env=env)
     orc = _oracle(fm, spec)
     frames = task_frames(wl, fm)
@@ -248,7 +267,7 @@ def test_k2_paths_agree_on_a_ragged_batch(name, path):
     assert int(st.max()) == 0 and not st_ref.any()
     err = np.abs(_np(dq) - dq_ref).max()
     print(f"{name}/{path}: max|dq-dq_oracle|={err:.3e}")
-    assert err < (1e-4 if path != "fixed" else 2e-3)
+    assert err < 1e-4
 
 
 @pytest.mark.parametrize("env", [{}, {"BIK_K2_SWEEPS": 0}, {"BIK_K2_SWEEPS": 6}, {"BIK_K2_RULE": 0}, {"BIK_K2_DYNAMIC": 0},
@@ -308,8 +327,8 @@ def test_batch_against_oracle(name, B):
     assert int(st.max()) == 0 and not st_ref.any()
     err = np.abs(_np(dq) - dq_ref).max(axis=1)
     print(f"{name}: B={B} max|dq-dq_oracle|={err.max():.3e} median={np.median(err):.3e} active mean={nact.mean():.1f} max={nact.max()}")
-    assert err.max() < (1e-4 if name != "spot" else 2e-2)
-    np.testing.assert_allclose(_np(q), q_ref, atol=2e-4 if name != "spot" else 4e-2)
+    assert err.max() < (1e-4 if name != "spot" else 1e-3)   # spot: the oracle sees the fp64 inputs, the device their fp32 rounding
+    np.testing.assert_allclose(_np(q), q_ref, atol=2e-4 if name != "spot" else 2e-3)
 
 
 def test_full_size_properties_g1():
@@ -417,9 +436,12 @@ def test_step_host_chunking_does_not_change_results():
 def test_describe_names_the_mapping():
     wl, fm, spec, g, model, prob = _engine("g1")
     d = prob.describe(float(g["damping"]))
-    assert "13/38 nodes visited" in d and "coupled=18" in d and "small-group G=8" in d and d.endswith("f64")
+    assert "13/38 nodes visited, f32" in d and "coupled=18" in d and "small-group G=8" in d and d.endswith("f64")
     wl, fm, spec, g, model, prob = _engine("spot")
-    assert "dense warp-per-problem" in prob.describe(float(g["damping"]))
+    d = prob.describe(float(g["damping"]))
+    assert "general warp-per-problem" in d and "nodes visited, f64" in d     # ill-conditioned / collision rows: fp64 K1
+    wl, fm, spec, g, model, prob = _engine("g1_full")
+    assert "small-group G=8 (64-bit masks)" in prob.describe(float(g["damping"]))
 
 
 def test_empty_batch_and_missing_target():
@@ -431,3 +453,104 @@ def test_empty_batch_and_missing_target():
     assert dq.shape == (0, fm.nv)
     with pytest.raises((BikError, ValueError)):
         prob.step(torch.zeros((2, fm.nq), device="cuda:0"), None, g["posture_target"], None)
+
+
+# ---- fp64 entry points: the reference's precision ---------------------------------------------------------------------
+@pytest.mark.parametrize("name", CASES)
+def test_fp64_entry_points_reproduce_the_reference(name):
+    """bik_fk_jac64 / bik_step64 (fp64 kernels on the fp64 kinematic constants) against the goldens: FK-derived quantities
+    to 1e-9, dq to 2e-7 rad (bounds are kept in fp32), the integrated q and the 8-step rollout -- every BASELINE
+    configuration, Spot (cost 200 against damping 1e-3, collision rows) included."""
+    wl, fm, spec, g, model, prob = _engine(name)
+    f64 = lambda a: None if a is None else torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda:0")
+    q, ft, pt, ct = f64(g["q"]), f64(g["frame_targets"]), f64(g["posture_target"]), f64(g.get("com_target"))
+    J, e, ep, Gc, hc = map(_np, prob.fk_jac(q, ft, pt, ct, dt=float(g["dt"])))
+    F = spec.nframe
+    np.testing.assert_allclose(e[:, :6 * F].reshape(-1, F, 6), g["e_frame"], atol=1e-10)
+    np.testing.assert_allclose(J[:, :6 * F].reshape(-1, F, 6, fm.nv), g["J_frame"], atol=1e-9)
+    if spec.nposture:
+        np.testing.assert_allclose(ep[:, 0], g["e_posture"], atol=1e-12)
+    if spec.ncom:
+        np.testing.assert_allclose(e[:, 6 * F:], g["e_com"], atol=1e-12)
+        np.testing.assert_allclose(J[:, 6 * F:], g["J_com"], atol=1e-12)
+    if spec.npairs:
+        Gr, hr = g["G"][:, -spec.npairs:], g["h"][:, -spec.npairs:]
+        fin = np.isfinite(hr)
+        assert np.array_equal(np.isfinite(hc), fin)
+        np.testing.assert_allclose(hc[fin], hr[fin], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(Gc, Gr, atol=1e-9)
+    qs = q.clone()
+    dq, st = prob.step(qs, ft, pt, ct, dt=float(g["dt"]), damping=float(g["damping"]), nsteps=1, integrate=True)
+    assert int(st.max()) == 0 and dq.dtype == torch.float64
+    err = np.abs(_np(dq) - g["dq"]).max()
+    print(f"{name}: fp64 max|dq - dq_ref| = {err:.3e}")
+    assert err < 2e-7 * max(1.0, np.abs(g["dq"]).max())
+    np.testing.assert_allclose(_np(qs), g["q_next"], atol=1e-6)
+    traj = g["rollout_q"]
+    T, RB = traj.shape[0] - 1, traj.shape[1]
+    qr = f64(traj[0])
+    dq, st = prob.step(qr, ft[:RB], pt, None if ct is None else ct[:RB], dt=float(g["dt"]), damping=float(g["damping"]), nsteps=T, integrate=True)
+    assert int(st.max()) == 0
+    np.testing.assert_allclose(_np(qr), traj[-1], atol=1e-5)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_fp32_entry_points_match_oracle_on_identical_inputs(name):
+    """The batched fp32 fast path against the oracle evaluated on the SAME fp32-representable inputs (north_star:
+    identical inputs): every configuration within 1e-4 rad -- the ill-conditioned ones because bik_step switches K1
+    and the hand-off to fp64 by itself (bik_problem_describe says so)."""
+    wl, fm, spec, g, model, prob = _engine(name)
+    orc = _oracle(fm, spec)
+    q, ft, pt, ct = _r32(g["q"]), _r32(g["frame_targets"]), _r32(g["posture_target"]), _r32(g.get("com_target"))
+    dq_ref, q_ref, st_ref, _ = orc.step(q, ft, pt, ct, dt=float(g["dt"]), damping=float(g["damping"]), nsteps=1, integrate=True)
+    qd = torch.tensor(q, dtype=torch.float32, device="cuda:0")
+    dq, st = prob.step(qd, ft, pt, ct, dt=float(g["dt"]), damping=float(g["damping"]), nsteps=1, integrate=True)
+    assert int(st.max()) == 0 and not st_ref.any()
+    err = np.abs(_np(dq) - dq_ref).max()
+    print(f"{name}: fp32 entry, identical inputs: max|dq - dq_oracle| = {err:.3e}")
+    assert err < 1e-4 * max(1.0, np.abs(dq_ref).max())
+    np.testing.assert_allclose(_np(qd), q_ref, atol=2e-4 * max(1.0, np.abs(dq_ref).max()))
+
+
+def test_inconsistent_limits_set_the_infeasible_flag():
+    """A dof 1 rad past its limit under a velocity limit: the reference's QP is infeasible (qpsolvers returns None,
+    solve_ik.py:103 asserts).  Device: BIK_STATUS_QP_INFEASIBLE on that instance only, on both K2 paths."""
+    for env in ({}, {"BIK_K2_PATH": "dense"}):
+        wl, fm, spec, g, model, prob = _engine("g1", env=env)
+        orc = _oracle(fm, spec)
+        q = g["q"][:5].copy()
+        d = 20
+        q[3, int(fm.dof_qadr[d])] = fm.dof_hi[d] + 1.0
+        qd = torch.tensor(q, dtype=torch.float32, device="cuda:0")
+        dq, st = prob.step(qd, g["frame_targets"][:5], g["posture_target"], None, dt=float(g["dt"]), damping=float(g["damping"]))
+        st = st.cpu().numpy()
+        _, _, st_ref, _ = orc.step(q, g["frame_targets"][:5], g["posture_target"], None, dt=float(g["dt"]), damping=float(g["damping"]))
+        assert st[3] & 8 and st[3] & 1 and not (np.delete(st, 3) & 8).any()
+        assert st_ref[3] != 0 and not np.delete(st_ref, 3).any()
+
+
+@pytest.mark.parametrize("name,B,T", [("spot", 1024 + 7, 12), ("edge", 512 + 3, 10), ("g1_full", 1024 + 5, 10)])
+def test_general_and_wide_paths_in_rollouts(name, B, T):
+    """Rollouts (targets held, q integrated on the device) on the problems that used to need 10-100 factorisations per
+    instance: collision rows (general path: block pivoting with the primal active-set fallback) and the 43 coupled dofs of
+    the reference's humanoid example (small-group path with 64-bit masks).  No instance may be flagged; the trajectory
+    follows the oracle's."""
+    wl, fm, spec, g, model, prob = _engine(name)
+    orc = _oracle(fm, spec)
+    frames = task_frames(wl, fm)
+    inp = make_inputs(fm, wl, B, lambda qq: orc.fk(qq, frames), seed=41, sigma=0.05)
+    q0, ft, pt, ct = _r32(inp["q"]), _r32(inp["frame_targets"]), _r32(inp["posture_target"]), _r32(inp.get("com_target"))
+    q = torch.tensor(q0, dtype=torch.float32, device="cuda:0")
+    dq, st = prob.step(q, ft, pt, ct, dt=wl["dt"], damping=wl["damping"], nsteps=T, integrate=True)
+    assert int(st.max()) == 0, f"{int((st != 0).sum())} instances flagged (bits {np.unique(st.cpu().numpy())})"
+    dq_ref, q_end, st_ref, _ = orc.step(q0, ft, pt, ct, dt=wl["dt"], damping=wl["damping"], nsteps=T, integrate=True)
+    ok = st_ref == 0
+    err_q = np.abs(_np(q) - q_end)[ok].max()
+    print(f"{name}: {T}-step rollout of {B}: max|q - q_oracle| = {err_q:.2e} (oracle flagged {int((~ok).sum())})")
+    assert err_q < 2e-3
+    # iteration statistics of one more step from the reached configuration
+    J, e, ep, Gc, hc = prob.fk_jac(q, ft, pt, ct, dt=wl["dt"])
+    _, st2, it = prob.solve(q, J, e, ep, Gc, hc, wl["dt"], wl["damping"], return_iters=True)
+    it = it.cpu().numpy()
+    print(f"{name}: cold-start factorisations at the reached configuration: mean {it.mean():.2f} max {it.max()}")
+    assert int(st2.max()) == 0 and it.max() <= 60
