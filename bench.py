@@ -27,8 +27,7 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 from mink_b200._abi import spec_from_workload  # noqa: E402
-from mink_b200.workloads import WORKLOADS, make_inputs  # noqa: E402
-from tests.helpers import load_flat, task_frames  # noqa: E402
+from mink_b200.workloads import WORKLOADS, load_flat, make_inputs, task_frames  # noqa: E402
 
 METRIC = "ik_steps_per_s"
 UNIT = "IK steps/s"

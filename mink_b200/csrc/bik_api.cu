@@ -460,6 +460,7 @@ static int step_core(bik_problem* p, int B, void* q, const bik_inputs* in, doubl
                      void* dq, int32_t* status, int io64, bool k1d, cudaStream_t st) {
   const PHeader& h = p->h;
   const bool warm = nsteps > 1;   // rollouts: carry the active set (and the previous dq) from step to step
+  const int phase = env_int("BIK_STEP_PHASE", 0);   // measurement aid: 1 = only K1, 2 = only K2 (on the rows the last K1 left)
   if (warm) CUDA_OK(cudaMemsetAsync(p->warm, 0, (size_t)B * (size_t)(h.nu > 0 ? h.nu : 1), st));
   for (int s = 0; s < nsteps; ++s) {
     K1Args a1;
@@ -467,8 +468,9 @@ static int step_core(bik_problem* p, int B, void* q, const bik_inputs* in, doubl
     a1.B = B; a1.q = q; a1.ftgt = in->frame_targets; a1.ptgt = in->posture_targets; a1.ctgt = in->com_targets; a1.in64 = io64; a1.pbatched = in->posture_batched;
     a1.dt = dt; a1.pk = p->pk; a1.Gc = p->Gc; a1.hc = p->hc;
     a1.status = status; a1.accumulate = s > 0; a1.tol = 1e-6f;   // Configuration.check_limits(safety_break=False) of solve_ik.py:99
-    int rc = bik_launch_k1(p, a1, k1d, st);
+    int rc = phase == 2 ? BIK_OK : bik_launch_k1(p, a1, k1d, st);
     if (rc) return rc;
+    if (phase == 1) continue;
     K2Args a2;
     memset(&a2, 0, sizeof a2);
     a2.B = B; a2.q = q; a2.io64 = io64; a2.pk = p->pk; a2.pk64 = k1d; a2.ptgt = in->posture_targets; a2.pbatched = in->posture_batched;

@@ -650,6 +650,16 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, T* wsm, int
   // (the packed hand-off carries none: K2 recomputes them from q and the target it reads anyway)
   if (h.P > 0 && !packed) {
     T* epg = reinterpret_cast<T*>(a.ep);
+#ifdef BIK_K1_POSTURE_NESTED   // A/B: one instance and posture task at a time (nv = 43 leaves 21 of 64 lane slots idle per row)
+    for (int l2 = 0; l2 < nvalid; ++l2) {
+      const T* qq = qtile + l2 * nq;
+      for (int p = 0; p < h.P; ++p) {
+        const long long t0 = ((long long)(a.pbatched ? (inst0 + l2) : 0) * h.P + p) * nq;
+        T* o = epg + ((long long)(inst0 + l2) * h.P + p) * nv;
+        for (int d = lane; d < nv; d += W) o[d] = posture_err_dof<T>(P, d, [&](int i) { return ldin<T>(a.ptgt, t0 + i, a.in64); }, [&](int i) { return qq[i]; });
+      }
+    }
+#else
     const int per = h.P * nv;
     for (int k = lane; k < nvalid * per; k += W) {
       const int l2 = k / per, r = k - l2 * per, p = r / nv, d = r - p * nv;
@@ -657,6 +667,7 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, T* wsm, int
       const long long t0 = ((long long)(a.pbatched ? (inst0 + l2) : 0) * h.P + p) * nq;
       epg[(long long)inst0 * per + k] = posture_err_dof<T>(P, d, [&](int i) { return ldin<T>(a.ptgt, t0 + i, a.in64); }, [&](int i) { return qq[i]; });
     }
+#endif
   }
 
   // ---- collision rows (collision_avoidance_limit.py:187-210), 6 pairs per staging pass -----------

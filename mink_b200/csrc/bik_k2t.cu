@@ -8,7 +8,7 @@
 
 using namespace bik;
 
-template <typename T, int G, int MAXT, typename M>
+template <typename T, int G, int MAXT, typename M, bool F32IO>
 __global__ void __launch_bounds__(MAXT, 512 / MAXT) k2t_kernel(const uint32_t* __restrict__ gimage, int warp_bytes, K2Args a, unsigned int* sched) {
   extern __shared__ __align__(16) uint32_t smem[];
   constexpr int NS = 32 / G;
@@ -23,18 +23,18 @@ __global__ void __launch_bounds__(MAXT, 512 / MAXT) k2t_kernel(const uint32_t* _
       if (lane == 0) t = atomicAdd(&sched[0], 1u);
       t = __shfl_sync(0xffffffffu, t, 0);
       if ((long long)t >= ntiles) break;
-      k2t_warp_tile<T, G, NS, M>(P, a, (long long)t * NS, wsm, lane, St, uw);
+      k2t_warp_tile<T, G, NS, M, F32IO>(P, a, (long long)t * NS, wsm, lane, St, uw);
     }
     __syncthreads();
     if (threadIdx.x == 0 && atomicInc(&sched[1], gridDim.x - 1) == gridDim.x - 1) { __threadfence(); sched[0] = 0u; }
     return;
   }
   for (long long tile = (long long)blockIdx.x * nwarps + warp; tile < ntiles; tile += (long long)gridDim.x * nwarps)
-    k2t_warp_tile<T, G, NS, M>(P, a, tile * NS, wsm, lane, St, uw);
+    k2t_warp_tile<T, G, NS, M, F32IO>(P, a, tile * NS, wsm, lane, St, uw);
 }
 
-template <typename T, int G, typename M>
-static int launch_k2t(const bik_problem* p, const K2Args& a, unsigned int* sched, cudaStream_t st) {
+template <typename T, int G, typename M, bool F32IO>
+static int launch_k2t_io(const bik_problem* p, const K2Args& a, unsigned int* sched, cudaStream_t st) {
   constexpr int NS = 32 / G, MAXT = sizeof(T) == 8 ? 256 : 512;
   PView P{p->image.data()};
   const size_t wb = (size_t)k2t_warp_bytes(P, sizeof(T), NS);
@@ -43,11 +43,16 @@ static int launch_k2t(const bik_problem* p, const K2Args& a, unsigned int* sched
   const size_t smem = NW * wb;
   int grid = 1;
   long long tiles = ((long long)a.B + NS - 1) / NS;
-  int rc = bik_launch_geometry((const void*)k2t_kernel<T, G, MAXT, M>, p->model, smem, 32 * NW, (tiles + NW - 1) / NW, &grid);
+  int rc = bik_launch_geometry((const void*)k2t_kernel<T, G, MAXT, M, F32IO>, p->model, smem, 32 * NW, (tiles + NW - 1) / NW, &grid);
   if (rc) return rc;
-  k2t_kernel<T, G, MAXT, M><<<grid, 32 * NW, smem, st>>>(p->d_image, (int)wb, a, sched);
+  k2t_kernel<T, G, MAXT, M, F32IO><<<grid, 32 * NW, smem, st>>>(p->d_image, (int)wb, a, sched);
   CUDA_OK(cudaGetLastError());
   return BIK_OK;
+}
+template <typename T, int G, typename M>
+static int launch_k2t(const bik_problem* p, const K2Args& a, unsigned int* sched, cudaStream_t st) {
+  if (sizeof(T) == 4 || !(a.io64 || a.pk64 || a.dense64)) return launch_k2t_io<T, G, M, true>(p, a, sched, st);   // fp32 buffers everywhere
+  return launch_k2t_io<T, G, M, sizeof(T) == 4>(p, a, sched, st);
 }
 static int group_of(const bik_problem* p) { return (p->h.nu > K2T_NMAX || p->k2_group == 8) ? 8 : 4; }
 static bool use_double(const bik_problem* p, const K2Args& a) { return p->solve_double || a.io64 || a.pk64 || a.dense64 || p->h.nu > K2T_NMAX; }

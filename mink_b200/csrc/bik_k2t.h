@@ -38,6 +38,12 @@
 #define BIK_WARP_ANY(x) (x)
 #endif
 
+#ifdef BIK_K2T_UNROLL1
+#define BIK_K2T_LOOP _Pragma("unroll 1")
+#else
+#define BIK_K2T_LOOP
+#endif
+
 namespace bik {
 
 BIK_HD uint32_t bik_float_bits(float f) {
@@ -129,8 +135,8 @@ BIK_HD int k2t_warp_bytes(const PView& P, int ts, int NS) { return (NS * k2t_slo
 // Source: the packed hand-off (one contiguous run per instance: coalesced without any index arithmetic) or, for bik_solve,
 // the dense rows (gather through the task's column list).
 template <typename T, int W, int NS>
-BIK_HD void k2t_stage_task(T* tile, int S, int lane, int cnt, long long b0, const K2Args& a, int K, int nv, int pks, const int32_t* cols,
-                           const K2Task& tk) {
+BIK_HD void k2t_stage_task(T* tile, int S, int lane, int cnt, long long b0, const K2Args& a, int pk64, int dense64, int K, int nv, int pks,
+                           const int32_t* cols, const K2Task& tk) {
   const int nj = tk.nr * tk.nc, ne = nj + tk.nr;
   for (int k = lane; k < ne; k += W) {
     const int ia = k / tk.nr, r = k - ia * tk.nr;
@@ -139,12 +145,12 @@ BIK_HD void k2t_stage_task(T* tile, int S, int lane, int cnt, long long b0, cons
     if (a.pk) {
       const long long o = b0 * pks + tk.pk_off + k;
 #pragma unroll
-      for (int i = 0; i < NS; ++i) tile[i * S + k] = i < cnt ? cr * ldin<T>(a.pk, o + (long long)i * pks, a.pk64) : T(0);
+      for (int i = 0; i < NS; ++i) tile[i * S + k] = i < cnt ? cr * ldin<T>(a.pk, o + (long long)i * pks, pk64) : T(0);
     } else {
       const void* src = isj ? a.J : a.e;
       const long long o = isj ? b0 * K * nv + (tk.row0 + r) * nv + (cols[ia] & 0xffff) : b0 * K + tk.row0 + r, stride = isj ? (long long)K * nv : K;
 #pragma unroll
-      for (int i = 0; i < NS; ++i) tile[i * S + k] = i < cnt ? cr * ldin<T>(src, o + i * stride, a.dense64) : T(0);
+      for (int i = 0; i < NS; ++i) tile[i * S + k] = i < cnt ? cr * ldin<T>(src, o + i * stride, dense64) : T(0);
     }
   }
 }
@@ -180,6 +186,7 @@ BIK_HD void k2t_task_accumulate_nr(const T* tr, int nc, const int32_t* cols, con
     for (int r = 0; r < NR; ++r) { col[r] = tr[ia * NR + r]; cs += wev[r] * col[r]; }
     const int ua = umap[cols[ia] & 0xffff];
     c[ua * NS] -= cs;
+    BIK_K2T_LOOP
     for (int ib = 0; ib <= ia; ++ib) {
       const T* cb = tr + ib * NR;
       T s = T(0);
@@ -202,15 +209,27 @@ BIK_HD void k2t_task_accumulate(const T* tr, int nr, int nc, const int32_t* cols
 // ---- solver pieces: compact run-time loops (the whole pivoting iteration must stay resident in the
 // instruction cache -- the fully unrolled variants of these routines were instruction-fetch bound) --------
 // Dot product of row i of the symmetric packed matrix with a vector (both slot-strided in shared memory).
+#ifdef BIK_K2T_NOINLINE_ROWDOT
+#define BIK_K2T_ROWDOT_ATTR BIK_NOINLINE
+#else
+#define BIK_K2T_ROWDOT_ATTR BIK_HD
+#endif
+#ifdef BIK_K2T_INLINE_FACTOR
+#define BIK_K2T_FACTOR_ATTR BIK_HD
+#else
+#define BIK_K2T_FACTOR_ATTR BIK_NOINLINE
+#endif
 template <typename T, int NS>
-BIK_HD T k2t_row_dot(const T* __restrict__ Hp, const T* __restrict__ v, int i, int nu, int k0 = 0) {   // sum over m in [k0, nu), i >= k0
+BIK_K2T_ROWDOT_ATTR T k2t_row_dot(const T* __restrict__ Hp, const T* __restrict__ v, int i, int nu, int k0 = 0) {   // sum over m in [k0, nu), i >= k0
   const T* row = Hp + (tri(i) + k0) * NS;
   const T* pv = v + k0 * NS;
   T a0 = T(0), a1 = T(0);
   int k = i + 1 - k0;
+  BIK_K2T_LOOP
   for (; k >= 2; k -= 2) { a0 += row[0] * pv[0]; a1 += row[NS] * pv[NS]; row += 2 * NS; pv += 2 * NS; }
   if (k) { a0 += row[0] * pv[0]; pv += NS; }
   const T* col = Hp + (tri(i + 1) + i) * NS;   // entries (m, i), m > i, sit at tri(m) + i
+  BIK_K2T_LOOP
   for (int m = i + 1; m < nu; ++m) { a1 += col[0] * pv[0]; col += (m + 1) * NS; pv += NS; }
   return a0 + a1;
 }
@@ -225,7 +244,7 @@ BIK_HD T k2t_row_dot(const T* __restrict__ Hp, const T* __restrict__ v, int i, i
 //             complement of the leading block; columns < nf of Lp are left alone.
 // Every lane of the warp must call it (it contains warp barriers).
 template <typename T, int G, int NS, typename M>
-BIK_HD int k2t_factor(const T* __restrict__ Hp, T* __restrict__ Lp, int nu, M act, int l, int kb, int ke) {
+BIK_K2T_FACTOR_ATTR int k2t_factor(const T* __restrict__ Hp, T* __restrict__ Lp, int nu, M act, int l, int kb, int ke) {
   int bad = 0;
   T* const rhsrow = Lp + tri(nu) * NS;
   // Row blocks are aligned to the END of the system (rows kb..nu): the last rows are the expensive ones (cost ~ i^2),
@@ -248,6 +267,7 @@ BIK_HD int k2t_factor(const T* __restrict__ Hp, T* __restrict__ Lp, int nu, M ac
         const T* pi = dst + kb * NS;
         T a0 = T(0), a1 = T(0);
         int m = k - kb;
+        BIK_K2T_LOOP
         for (; m >= 2; m -= 2) { a0 += pi[0] * pk[0]; a1 += pi[NS] * pk[NS]; pi += 2 * NS; pk += 2 * NS; }
         if (m) { a0 += pi[0] * pk[0]; pk += NS; }
         s = (src[k * NS] - (a0 + a1)) * pk[0];   // pk now points at 1 / L[k][k]
@@ -255,17 +275,19 @@ BIK_HD int k2t_factor(const T* __restrict__ Hp, T* __restrict__ Lp, int nu, M ac
       dst[k * NS] = s;
       ss += s * s;
     };
-    const int kfull = i0 < ke ? i0 : ke;
-    if (has) for (int k = kb; k < kfull; ++k) step(k);   // rows above the block are complete
-    for (int j = 0; j < G; ++j) {                         // diagonal block: the owner of row k closes it, then the rows below use it
-      const int k = i0 + j;
-      if (k < kb || k >= ke) continue;
-      if (has && !rhs && l == j) {
-        T d = (ai ? T(1) : src[k * NS]) - ss;
-        if (!(d > T(0))) { bad = 1; d = T(1e-30); }
-        dst[k * NS] = bik_rsqrt<T>(d);
+    // columns kb .. min(i0 + G, ke) - 1 in order: those above the block are complete; inside the diagonal block the owner of
+    // row k closes it first (one barrier), then the rows below use it.  One call site of step(): the kernel carries a single
+    // copy of the dot loop.
+    const int kend = (i0 + G) < ke ? (i0 + G) : ke;
+    for (int k = kb; k < kend; ++k) {
+      if (k >= i0) {
+        if (has && !rhs && l == k - i0) {
+          T d = (ai ? T(1) : src[k * NS]) - ss;
+          if (!(d > T(0))) { bad = 1; d = T(1e-30); }
+          dst[k * NS] = bik_rsqrt<T>(d);
+        }
+        if (G > 1) BIK_SYNCWARP();
       }
-      if (G > 1) BIK_SYNCWARP();
       if (has && k < i) step(k);
     }
   }
@@ -281,6 +303,7 @@ BIK_HD void k2t_backsub(T* __restrict__ Lp, int nu, int l, T* __restrict__ xs, i
   for (int k = khi - 1; k >= klo; --k) {
     const T* row = Lp + tri(k) * NS;
     const T xk = y[k * NS] * row[k * NS];
+    BIK_K2T_LOOP
     for (int m = mlo + l; m < k; m += G) y[m * NS] -= row[m * NS] * xk;
     if (l == 0) xs[k * NS] = xk;
     if (G > 1) BIK_SYNCWARP();   // y_{k-1} is final
@@ -331,6 +354,7 @@ BIK_HD void k2t_pgs_guess(const T* __restrict__ Hp, const T* __restrict__ c, con
       else if (xi >= bu) { xi = bu; upm |= M(1) << i; }
       const T dx = xi - xo;
       if (G > 1) BIK_SYNCWARP();   // every lane has read res_i and x_i
+      BIK_K2T_LOOP
       for (int m = k0 + l; m < nu; m += G) {
         const int hi_ = m > i ? m : i, lo_ = m > i ? i : m;
         res[m * NS] += Hp[(tri(hi_) + lo_) * NS] * dx;
@@ -355,6 +379,7 @@ BIK_HD void k2t_schur(T* __restrict__ Hp, const T* __restrict__ Lp, T* __restric
     for (int j = nf + l; j <= i + 1; j += G) {       // j == i + 1 stands for the linear term
       const T* pj = j <= i ? Lp + tri(j) * NS : y;
       T a0 = T(0);
+      BIK_K2T_LOOP
       for (int m = 0; m < nf; ++m) a0 += pi[m * NS] * pj[m * NS];
       if (j <= i) Hp[(tri(i) + j) * NS] -= a0;
       else c[i * NS] += a0;
@@ -363,9 +388,13 @@ BIK_HD void k2t_schur(T* __restrict__ Hp, const T* __restrict__ Lp, T* __restric
 }
 
 // ---- one tile of NS instances per warp ----------------------------------------------------------------
-template <typename T, int G, int NS, typename M = uint32_t>
+// F32IO (compile time): every caller buffer and the hand-off hold fp32 -- the batched fast path: the fp64 load / store /
+// integrate code is not even compiled in (it tripled the kernel's SASS and its instruction-fetch stalls).  Otherwise the
+// element types follow the run-time flags of K2Args.
+template <typename T, int G, int NS, typename M = uint32_t, bool F32IO = false>
 BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* wsm, int lane, int St = 0, int uw = 0) {
   if (St == 0) { St = k2t_task_tile_words(P); uw = k2t_union_words(P, sizeof(T)); }   // callers that loop over tiles pass them in
+  const int io64 = F32IO ? 0 : a.io64, pk64 = F32IO ? 0 : a.pk64, dense64 = F32IO ? 0 : a.dense64;
   constexpr int W = G * NS;
   const PHeader& h = P.h();
   const int nv = h.nv, nu = h.nu, K = h.K, nq = h.nq, NP = h.P;
@@ -395,15 +424,15 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
   for (int t = 0; t < h.F + h.C; ++t) {
     const K2Task tk = k2_task(P, t);
     BIK_SYNCWARP();
-    k2t_stage_task<T, W, NS>(U, St, lane, cnt, b0, a, K, nv, h.pk_stride, cols + tk.coff, tk);
+    k2t_stage_task<T, W, NS>(U, St, lane, cnt, b0, a, pk64, dense64, K, nv, h.pk_stride, cols + tk.coff, tk);
     BIK_SYNCWARP();
     k2t_task_accumulate<T, G, NS>(U + (size_t)slot * St, tk.nr, tk.nc, cols + tk.coff, umap, Hp, c, tk.lm, &mu, l);
   }
   // q and posture errors: stage, then diagonal / linear term / box; decoupled dofs are finished on the spot
   BIK_SYNCWARP();
   const int Sq = (nq + NP * nv) | 1;
-  k2t_stage_q<T, W, NS>(U, Sq, lane, cnt, a.q, a.io64, b0, nq);
-  if (NP > 0 && a.ep) k2t_stage_rows<T, W, NS>(U, Sq, nq, lane, cnt, a.ep, a.dense64, b0 * NP * nv, (long long)NP * nv, NP * nv);
+  k2t_stage_q<T, W, NS>(U, Sq, lane, cnt, a.q, io64, b0, nq);
+  if (NP > 0 && a.ep) k2t_stage_rows<T, W, NS>(U, Sq, nq, lane, cnt, a.ep, dense64, b0 * NP * nv, (long long)NP * nv, NP * nv);
   BIK_SYNCWARP();
   if (NP > 0 && !a.ep) {   // inside bik_step K1 hands no posture error over: e = q* (-) q from the staged q (posture_task.py:107-118)
     const int per = NP * nv;
@@ -411,7 +440,7 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
       const int i = k / per, r = k - i * per, p = r / nv, d = r - p * nv;
       const T* qq = U + (size_t)i * Sq;
       const long long t0 = ((long long)(a.pbatched ? (b0 + (i < cnt ? i : 0)) : 0) * NP + p) * nq;
-      U[(size_t)i * Sq + nq + r] = posture_err_dof<T>(P, d, [&](int j) { return ldin<T>(a.ptgt, t0 + j, a.io64); }, [&](int j) { return qq[j]; });
+      U[(size_t)i * Sq + nq + r] = posture_err_dof<T>(P, d, [&](int j) { return ldin<T>(a.ptgt, t0 + j, io64); }, [&](int j) { return qq[j]; });
     }
     BIK_SYNCWARP();
   }
@@ -446,7 +475,7 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
         T v = -cd / hd;
         v = v < bl ? bl : (v > bu ? bu : v);
         if (!(v == v)) st |= 4;
-        if (live) stout<T>(a.dq, b * nv + d, a.io64, v);
+        if (live) stout<T>(a.dq, b * nv + d, io64, v);
       }
     }
   }
@@ -487,7 +516,7 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
     if (have_prev) {
       const bool valid = live && (a.warm[b * nu] & 4);
       for (int k = nf + l; k < nu; k += G) {
-        T v = valid ? ldin<T>(a.dq, b * nv + ucols[k], a.io64) : T(0);
+        T v = valid ? ldin<T>(a.dq, b * nv + ucols[k], io64) : T(0);
         if (!(v == v)) v = T(0);
         const T bl = T(lo[k * NS]), bu = T(hi[k * NS]);
         vs[k * NS] = v < bl ? bl : (v > bu ? bu : v);
@@ -619,7 +648,7 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
   for (int k = l; k < nu; k += G) {
     const T v = vs[k * NS];
     if (!(v == v)) st |= 4;
-    if (live) stout<T>(a.dq, b * nv + ucols[k], a.io64, v);
+    if (live) stout<T>(a.dq, b * nv + ucols[k], io64, v);
   }
   st = grp_or<G>(st);
   if (live && l == 0) {
@@ -629,16 +658,19 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
   }
   BIK_SYNCWARP();
   // ---- q <- q (+) dq (Configuration.integrate_inplace, configuration.py:228-236): the lanes of a group take the nodes in turn ----
-  if (a.integrate && live) {
-    for (int nn = l; nn < h.nnode; nn += G) {
-      const NodeRec& r = P.node(nn);
-      const int nqn = r.type == JNT_FREE ? 7 : (r.type == JNT_BALL ? 4 : 1), ndn = r.type == JNT_FREE ? 6 : (r.type == JNT_BALL ? 3 : 1);
-      T qn[7], dn[6];
-      for (int k = 0; k < nqn; ++k) qn[k] = ldin<T>(a.q, b * nq + r.qadr + k, a.io64);
-      for (int k = 0; k < ndn; ++k) dn[k] = ldin<T>(a.dq, b * nv + r.dadr + k, a.io64);
-      integrate_node<T>(r, qn - r.qadr, dn - r.dadr);
-      for (int k = 0; k < nqn; ++k) stout<T>(const_cast<void*>(a.q), b * nq + r.qadr + k, a.io64, qn[k]);
-    }
+  if (a.integrate) {
+    // scalar joints (hinge / slide): the whole warp sweeps the tile's dofs flat -- coalesced, independent loads; free and ball
+    // joints (quaternion update) are left to one lane per joint
+    const int32_t* dofqadr = P.i(h.off_dofqadr);
+    auto sweep = [&](auto* qg, const auto* dg) {
+      for (int k = lane; k < cnt * nv; k += W) {
+        const int i = k / nv, d = k - i * nv, qa = dofqadr[d];
+        if (qa >= 0 && !(a.skip && a.skip[b0 + i])) qg[(b0 + i) * nq + qa] += dg[(b0 + i) * nv + d];
+      }
+      if (live) for (int nn = l; nn < h.nnode; nn += G) { const NodeRec& r = P.node(nn); if (r.type == JNT_FREE || r.type == JNT_BALL) integrate_node(r, qg + b * nq, dg + b * nv); }
+    };
+    if (F32IO || !io64) sweep(reinterpret_cast<float*>(const_cast<void*>(a.q)), reinterpret_cast<const float*>(a.dq));   // fp32 buffers: fp32 arithmetic, as bik_integrate
+    else sweep(reinterpret_cast<double*>(const_cast<void*>(a.q)), reinterpret_cast<const double*>(a.dq));
   }
   BIK_SYNCWARP();
 }

@@ -8,6 +8,7 @@ drive (a) the golden-vector generator, which instantiates the *reference's* task
 
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, Optional, Tuple
 
 import numpy as np
@@ -114,11 +115,11 @@ WORKLOADS: Dict[str, dict] = {
         limits=[dict(kind="configuration", gain=0.95), dict(kind="velocity", vmax=2 * PI)],
         dt=2e-2, damping=1e-4, batch=1024,
     ),
-    # Not a BASELINE config: edge-case model authored for this repository (tests/golden/models/edge.xml):
+    # Not a BASELINE config: edge-case model authored for this repository (mink_b200/models/edge.xml):
     # ball joint with off-centre anchor, slide joint with ref, two joints on one body, a second floating
     # root, capsule/sphere/plane collision pairs, every task and limit kind at once.
     "edge": dict(
-        robot="edge", scene="@tests/golden/models/edge.xml", key="home",
+        robot="edge", scene="@mink_b200/models/edge.xml", key="home",
         frames=[dict(name="tool", type="site", position_cost=[3.0, 2.0, 1.0], orientation_cost=0.7, lm_damping=0.3, gain=0.8),
                 dict(name="float_site", type="site", position_cost=1.0, orientation_cost=[0.5, 0.0, 0.2], lm_damping=0.0)],
         relative_frames=[dict(name="side_tip", type="site", root_name="tool", root_type="site",
@@ -171,6 +172,25 @@ def perturb_q(fm, q: np.ndarray, sigma: float, rng: np.random.Generator) -> np.n
 
 
 FkFn = Callable[[np.ndarray], Tuple[np.ndarray, Optional[np.ndarray]]]
+
+MODELS_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "models")
+
+
+def load_flat(robot: str):
+    """Flattened model of a BASELINE robot (mink_b200/models/*.bikm + *.json, written by oracle/gen_golden.py from the
+    reference's vendored MJCFs): what bench.py and the tests build their problems from on a box without /root/reference."""
+    from .flatten import FlatModel
+
+    with open(os.path.join(MODELS_DIR, robot + ".bikm"), "rb") as f:
+        blob = f.read()
+    with open(os.path.join(MODELS_DIR, robot + ".json")) as f:
+        meta = f.read()
+    return FlatModel.from_blob(blob, meta)
+
+
+def task_frames(wl: dict, fm):
+    """Frames of the workload's (absolute) frame tasks, in task order."""
+    return [fm.frame(f["name"], f["type"]) for f in wl["frames"]]
 
 
 def make_inputs(fm, wl: dict, B: int, fk: FkFn, seed: int = 0, sigma: float = 0.1,

@@ -4,7 +4,7 @@ Imports /root/reference/mink on top of the oracle shims (oracle/mujoco, oracle/q
 for every BASELINE workload, records per instance: inputs (q, targets), FK poses, task errors and
 Jacobians (Task.compute_error / compute_jacobian), the QP (build_ik -> P, q, G, h), the solution
 dq = solve_ik(...) * dt, the integrated configuration, and a short solve+integrate rollout.
-Also writes the flattened model blobs (tests/golden/models/*.bikm + *.json) so that the GPU box,
+Also writes the flattened model blobs (mink_b200/models/*.bikm + *.json) so that the GPU box,
 which has no /root/reference, can rebuild every problem from numbers alone.
 
 Run here (needs /root/reference):  python oracle/gen_golden.py
@@ -71,7 +71,8 @@ def build_reference_problem(model, wl):
 
 
 def main():
-    os.makedirs(os.path.join(OUT, "models"), exist_ok=True)
+    MODELS = os.path.join(REPO, "mink_b200", "models")
+    os.makedirs(MODELS, exist_ok=True)
     done_models = set()
     only = set(sys.argv[1:])   # `python oracle/gen_golden.py g1_hands` regenerates just that case
     for name, wl in WORKLOADS.items():
@@ -81,9 +82,9 @@ def main():
         model = mujoco.MjModel.from_xml_path(scene)
         fm = flatten(model)
         if wl["robot"] not in done_models and not only:
-            with open(os.path.join(OUT, "models", wl["robot"] + ".bikm"), "wb") as f:
+            with open(os.path.join(MODELS, wl["robot"] + ".bikm"), "wb") as f:
                 f.write(fm.to_blob())
-            with open(os.path.join(OUT, "models", wl["robot"] + ".json"), "w") as f:
+            with open(os.path.join(MODELS, wl["robot"] + ".json"), "w") as f:
                 f.write(fm.to_meta_json())
             done_models.add(wl["robot"])
         tasks, frame_tasks, posture, com, limits = build_reference_problem(model, wl)

@@ -29,7 +29,7 @@ def test_no_cpu_fallback():
     if torch.cuda.is_available():
         return
     lib = _lib.load()
-    blob = open(os.path.join(REPO, "tests", "golden", "models", "ur5e.bikm"), "rb").read()
+    blob = open(os.path.join(REPO, "mink_b200", "models", "ur5e.bikm"), "rb").read()
     h = C.c_void_p()
     rc = lib.bik_model_create(blob, len(blob), 0, C.byref(h))
     assert rc == -2 and b"no CUDA device" in lib.bik_last_error()

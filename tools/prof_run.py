@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mink_b200._abi import spec_from_workload
 from mink_b200.engine import DeviceModel, Problem
 from mink_b200.workloads import WORKLOADS, make_inputs
-from tests.helpers import load_flat, task_frames
+from mink_b200.workloads import load_flat, task_frames
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="g1")
