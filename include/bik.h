@@ -256,6 +256,10 @@ int bik_check_limits64(const bik_model* model, int B, const double* q, double to
 int bik_step64(const bik_problem* problem, int B, double* q, const bik_inputs* in, double dt,
                double damping, int nsteps, int integrate, double* dq, int32_t* status, void* stream);
 
+/* Measurement aid for the K2 roofline (bench.py): sustained fused-multiply-add throughput of the CUDA cores of `device`
+ * in TFLOP/s (fp32 or fp64; 16 independent chains per thread, every SM filled), best of `repeats` event-timed launches. */
+int bik_measure_fma_peak(int device, int use_double, int repeats, double* tflops);
+
 /* Bytes of device scratch a problem needs for a batch of B (K1's packed task rows, collision rows, ... between K1 and K2). */
 size_t bik_workspace_bytes(const bik_problem* problem, int B);
 

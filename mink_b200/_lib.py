@@ -15,7 +15,7 @@ EXPORTS = ["bik_version", "bik_last_error", "bik_model_create", "bik_model_destr
            "bik_qp_objective", "bik_limits_box", "bik_solve", "bik_solve_ex", "bik_integrate", "bik_check_limits", "bik_step",
            "bik_step_host", "bik_workspace_bytes", "bik_problem_describe", "bik_converge",
            "bik_fk64", "bik_frame_jacobian64", "bik_fk_jac64", "bik_qp_objective64", "bik_limits_box64", "bik_solve64",
-           "bik_integrate64", "bik_check_limits64", "bik_step64"]
+           "bik_integrate64", "bik_check_limits64", "bik_step64", "bik_measure_fma_peak"]
 
 
 class BikError(RuntimeError):
@@ -73,6 +73,7 @@ def load():
     lib.bik_integrate64.argtypes = lib.bik_integrate.argtypes
     lib.bik_check_limits64.argtypes = [vp, ci, vp, cd, vp, vp]
     lib.bik_step64.argtypes = [vp, ci, vp, C.POINTER(BikInputs), cd, cd, ci, ci, vp, vp, vp]
+    lib.bik_measure_fma_peak.argtypes = [ci, ci, ci, C.POINTER(cd)]
     _lib = lib
     return lib
 

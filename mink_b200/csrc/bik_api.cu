@@ -69,6 +69,24 @@ __global__ void converge_finish_kernel(int B, int max_iters, const int32_t* __re
   if (b < B && !done[b]) { iters[b] = max_iters; if (status) status[b] |= 16; }
 }
 
+// CUDA-core FMA peak, measured: 16 independent dependent-chains of fused multiply-adds per thread, enough CTAs to fill every SM.
+// This is the denominator of K2's roofline (bench.py): the QP solve runs on the FMA pipes, not on tensor cores.
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(int iters, T seed, T* sink) {
+  T a[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a[k] = seed + T(k + threadIdx.x) * T(1e-3);
+  const T m = T(0.999), c = T(1e-3);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = a[k] * m + c;
+  }
+  T s = T(0);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s += a[k];
+  if (s == T(-1)) sink[0] = s;   // never true: keeps the chains alive
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -667,5 +685,35 @@ extern "C" int bik_step_host(const bik_problem* cp, int B, float* q_host, const 
   CUDA_OK(cudaStreamSynchronize(s_up));
   if (h2d_bytes) *h2d_bytes = up;
   if (d2h_bytes) *d2h_bytes = down;
+  return BIK_OK;
+}
+
+// Measured FMA throughput of the CUDA cores (2 flops per FMA), best of `repeats` launches timed with CUDA events.
+extern "C" int bik_measure_fma_peak(int device, int use_double, int repeats, double* tflops) {
+  if (!tflops) return bik_fail(BIK_ERR_INVALID, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return bik_fail(BIK_ERR_CUDA, "no such CUDA device");
+  DeviceGuard g(device);
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  const int iters = use_double ? 4096 : 8192, grid = prop.multiProcessorCount * 8, threads = 256;
+  void* sink = nullptr;
+  CUDA_OK(cudaMalloc(&sink, 8));
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+  double best = 0;
+  for (int r = 0; r < (repeats > 0 ? repeats : 5) + 1; ++r) {
+    CUDA_OK(cudaEventRecord(e0));
+    if (use_double) fma_peak_kernel<double><<<grid, threads>>>(iters, 1.0, static_cast<double*>(sink));
+    else fma_peak_kernel<float><<<grid, threads>>>(iters, 1.0f, static_cast<float*>(sink));
+    CUDA_OK(cudaEventRecord(e1));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = 2.0 * 16.0 * iters * (double)grid * threads / (ms * 1e-3) / 1e12;
+    if (r > 0 && tf > best) best = tf;   // first launch is the warm-up
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+  *tflops = best;
   return BIK_OK;
 }

@@ -13,13 +13,35 @@ template <typename T, int G, bool PK>
 __global__ void __launch_bounds__(128, sizeof(T) == 4 ? BIK_K1_MINBLOCKS : 2) k1_kernel(const uint32_t* __restrict__ gimage, int words, int use_tma, K1Args a) {
   extern __shared__ __align__(16) uint32_t smem[];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t pbar[4];   // one input-pipeline barrier per warp
   stage_image(smem, gimage, words, &bar, use_tma);
   PView P{smem};
+  const PHeader& h = P.h();
   constexpr int IPW = 32 / G;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  T* wsm = reinterpret_cast<T*>(smem + words) + (size_t)warp * k1_warp_words(P.h(), IPW);
-  const int ntiles = (a.B + IPW - 1) / IPW;
-  for (int tile = blockIdx.x * nwarps + warp; tile < ntiles; tile += gridDim.x * nwarps) k1_warp_tile<T, G, 32, PK>(P, a, tile * IPW, wsm, lane);
+  T* wsm = reinterpret_cast<T*>(smem + words) + (size_t)warp * k1_warp_words(h, IPW);
+  const int ntiles = (a.B + IPW - 1) / IPW, stride = gridDim.x * nwarps;
+  int tile = blockIdx.x * nwarps + warp;
+  // Input pipeline: tile t computes its Jacobian columns while the q rows and targets of tile t + stride arrive by bulk async
+  // copy (BIK_USE_TMA=0 turns it off together with the staged image: plain loads at the top of every tile).
+  K1Pipe pipe{&pbar[warp], 0u, -1};
+  K1Pipe* pp = use_tma ? &pipe : nullptr;
+  if (pp) {
+    if (lane == 0) {
+      mbar_init(pipe.bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (tile < ntiles && k1_tile_bulk_ok<T>(h, a, tile * IPW, IPW)) {
+      T* qtile = wsm + k1_qtile_offset(h, IPW);
+      if (lane == 0) k1_pipe_arm<T>(h, a, tile * IPW, IPW, &pipe, qtile, qtile + ((IPW * h.nq + 3) & ~3));
+      pipe.armed = tile * IPW;
+    }
+  }
+  for (; tile < ntiles; tile += stride) {
+    const int next = tile + stride < ntiles ? (tile + stride) * IPW : -1;
+    k1_warp_tile<T, G, 32, PK>(P, a, tile * IPW, wsm, lane, pp, next);
+  }
 }
 
 template <typename T, int G>

@@ -26,6 +26,9 @@
 #pragma once
 #include "bik_layout.h"
 #include "bik_math.h"
+#if defined(__CUDACC__)
+#include "bik_ptx.cuh"
+#endif
 
 #if defined(__CUDA_ARCH__)
 #define BIK_SYNCWARP() __syncwarp()
@@ -164,11 +167,50 @@ BIK_HD int k1_stage_words(const PHeader& h, int ipw) {
   if (k1_frames_direct(h) && h.npairs == 0) return 0;
   return (ipw * 6 * h.nv + 3) & ~3;
 }
+BIK_HD int k1_tgt_words(const PHeader& h) { return 7 * h.F + 3 * h.C; }   // frame + CoM targets of one instance
+BIK_HD int k1_e_words(const PHeader& h, int ipw) { return (ipw * (h.K > 0 ? h.K : 1) + 3) & ~3; }
+BIK_HD int k1_qtile_offset(const PHeader& h, int ipw) {   // where the tile's inputs (q rows, then targets) sit in the warp's scratch (16-byte aligned)
+  return k1_state_words(h, ipw) + k1_stage_words(h, ipw) + k1_e_words(h, ipw) + ipw * (h.F > 0 ? h.F : 1) * k1_fsc_stride(h);
+}
 BIK_HD int k1_warp_words(const PHeader& h, int ipw) {
-  int w = k1_state_words(h, ipw) + k1_stage_words(h, ipw) + ipw * (h.K > 0 ? h.K : 1) + ipw * (h.F > 0 ? h.F : 1) * k1_fsc_stride(h) +
-          ((ipw * h.nq + 3) & ~3) + ((ipw + 3) & ~3);
+  int w = k1_qtile_offset(h, ipw) + ((ipw * h.nq + 3) & ~3) + ((ipw * k1_tgt_words(h) + 3) & ~3) + ((ipw + 3) & ~3);
   return (w + 3) & ~3;
 }
+
+// Per-warp input pipeline (device): the q rows and the targets of a tile are contiguous runs of global memory, so the NEXT
+// tile's travel into shared memory as 1-D bulk async copies (cp.async.bulk + mbarrier) while the current tile computes its
+// Jacobian columns -- the inputs are dead by then.  `armed` is the first instance of the tile whose copies are in flight or
+// have landed (-1: none; the tile then loads its inputs itself).
+struct K1Pipe {
+  uint64_t* bar;
+  uint32_t phase;
+  int armed;
+};
+// Bulk copies need 16-byte sizes and addresses, and the buffers must hold the kernel's scalar type (fp32 kernel, fp32 inputs).
+template <typename T>
+BIK_HD bool k1_tile_bulk_ok(const PHeader& h, const K1Args& a, int inst0, int ipw) {
+  if (sizeof(T) != 4 || a.in64 || inst0 < 0 || inst0 >= a.B) return false;
+  const int nvalid = (a.B - inst0) < ipw ? (a.B - inst0) : ipw;
+  const size_t qb = (size_t)nvalid * h.nq * 4, fb = (size_t)nvalid * h.F * 7 * 4, cb = (size_t)nvalid * h.C * 3 * 4;
+  const size_t qa = reinterpret_cast<size_t>(a.q) + (size_t)inst0 * h.nq * 4, fa = reinterpret_cast<size_t>(a.ftgt) + (size_t)inst0 * h.F * 7 * 4,
+               ca = reinterpret_cast<size_t>(a.ctgt) + (size_t)inst0 * h.C * 3 * 4;
+  if ((qb | qa) & 15) return false;
+  if (h.F > 0 && ((fb | fa | ((size_t)ipw * h.F * 7 * 4)) & 15)) return false;   // (the CoM targets sit behind a full tile of frame targets)
+  if (h.C > 0 && ((cb | ca) & 15)) return false;
+  return true;
+}
+#if defined(__CUDACC__)
+// lane 0 of the warp: arm the barrier with the byte count and issue the copies of the tile starting at inst0
+template <typename T>
+__device__ __forceinline__ void k1_pipe_arm(const PHeader& h, const K1Args& a, int inst0, int ipw, K1Pipe* pipe, T* qtile, T* ttile) {
+  const int nvalid = (a.B - inst0) < ipw ? (a.B - inst0) : ipw;
+  const uint32_t qb = (uint32_t)nvalid * h.nq * 4, fb = (uint32_t)nvalid * h.F * 7 * 4, cb = (uint32_t)nvalid * h.C * 3 * 4;
+  mbar_expect_tx(pipe->bar, qb + fb + cb);
+  bulk_g2s(qtile, reinterpret_cast<const float*>(a.q) + (size_t)inst0 * h.nq, qb, pipe->bar);
+  if (fb) bulk_g2s(ttile, reinterpret_cast<const float*>(a.ftgt) + (size_t)inst0 * h.F * 7, fb, pipe->bar);
+  if (cb) bulk_g2s(ttile + ipw * h.F * 7, reinterpret_cast<const float*>(a.ctgt) + (size_t)inst0 * h.C * 3, cb, pipe->bar);
+}
+#endif
 
 template <typename T> BIK_HD Q4<T> ld_q(const T* p) { return q4<T>(p[0], p[1], p[2], p[3]); }
 template <typename T> BIK_HD V3<T> ld_v(const T* p) { return v3<T>(p[0], p[1], p[2]); }
@@ -398,7 +440,7 @@ template <> BIK_HD void store6<double>(double* o, V3<double> top, V3<double> bot
 // PK (compile time): packed hand-off with the fused check_limits / convergence test (bik_step, bik_converge), else the dense
 // API form (bik_fk_jac) -- two instantiations so that neither carries the other's registers and code.
 template <typename T, int G, int W, bool PK>
-BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, T* wsm, int lane) {
+BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, T* wsm, int lane, K1Pipe* pipe = nullptr, int next_inst0 = -1) {
   const PHeader& h = P.h();
   constexpr int IPW = W / G;
   const int nv = h.nv, nq = h.nq, K = h.K;
@@ -414,14 +456,29 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, T* wsm, int
   T* state = wsm;
   T* stage = wsm + k1_state_words(h, IPW);
   T* estage = stage + k1_stage_words(h, IPW);
-  T* fsc = estage + IPW * (K > 0 ? K : 1);  // per (instance, frame): per-frame SE(3) results
+  T* fsc = estage + k1_e_words(h, IPW);     // per (instance, frame): per-frame SE(3) results
   const int FS = k1_fsc_stride(h);
-  T* qtile = fsc + IPW * (h.F > 0 ? h.F : 1) * FS;  // q of this tile: one contiguous, coalesced run of global memory
-  int32_t* sflag = reinterpret_cast<int32_t*>(qtile + ((IPW * nq + 3) & ~3));   // check_limits bits per instance
+  T* qtile = wsm + k1_qtile_offset(h, IPW);          // q of this tile: one contiguous, coalesced run of global memory
+  T* ttile = qtile + ((IPW * nq + 3) & ~3);         // targets of this tile: [IPW][F][7] frame targets, then [IPW][C][3] CoM targets
+  int32_t* sflag = reinterpret_cast<int32_t*>(ttile + ((IPW * k1_tgt_words(h) + 3) & ~3));   // check_limits bits per instance
   T* xs = state + li * SS;
+  const bool direct = !packed && k1_frames_direct(h);
   {
-    const long long q0 = (long long)inst0 * nq;
-    for (int k = lane; k < nvalid * nq; k += W) qtile[k] = ldin<T>(a.q, q0 + k, a.in64);
+    bool landed = false;
+#if defined(__CUDA_ARCH__)
+    if (pipe && pipe->armed == inst0) {   // this tile's inputs were sent ahead by the previous tile (or the kernel prologue)
+      mbar_wait(pipe->bar, pipe->phase);
+      pipe->phase ^= 1u;
+      pipe->armed = -1;
+      landed = true;
+    }
+#endif
+    if (!landed) {
+      const long long q0 = (long long)inst0 * nq, f0 = (long long)inst0 * h.F * 7, c0 = (long long)inst0 * h.C * 3;
+      for (int k = lane; k < nvalid * nq; k += W) qtile[k] = ldin<T>(a.q, q0 + k, a.in64);
+      for (int k = lane; k < nvalid * h.F * 7; k += W) ttile[k] = ldin<T>(a.ftgt, f0 + k, a.in64);
+      for (int k = lane; k < nvalid * h.C * 3; k += W) ttile[IPW * h.F * 7 + k] = ldin<T>(a.ctgt, c0 + k, a.in64);
+    }
     if (PK && a.status && lane < IPW) sflag[lane] = 0;
   }
   BIK_SYNCWARP();
@@ -469,9 +526,9 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, T* wsm, int
       Q4<T> qf; V3<T> pf, ev, ew; M3<T> A1, A2;
       frame_pose<T>(fr.slot, KC<T>::flpos(P, f), KC<T>::flquat(P, f), xs, &qf, &pf);
       T* sc = fsc + (li * h.F + f) * FS;
-      const long long t0 = ((long long)b * h.F + f) * 7;
-      Q4<T> tq = q4<T>(ldin<T>(a.ftgt, t0, a.in64), ldin<T>(a.ftgt, t0 + 1, a.in64), ldin<T>(a.ftgt, t0 + 2, a.in64), ldin<T>(a.ftgt, t0 + 3, a.in64));
-      V3<T> tp = v3<T>(ldin<T>(a.ftgt, t0 + 4, a.in64), ldin<T>(a.ftgt, t0 + 5, a.in64), ldin<T>(a.ftgt, t0 + 6, a.in64));
+      const T* tg = ttile + (li * h.F + f) * 7;
+      Q4<T> tq = q4<T>(tg[0], tg[1], tg[2], tg[3]);
+      V3<T> tp = v3<T>(tg[4], tg[5], tg[6]);
       if (!fr.relative) {
         frame_task<T>(qf, pf, tq, tp, &ev, &ew, &A1, &A2);
         sc[0] = pf.x; sc[1] = pf.y; sc[2] = pf.z;
@@ -493,19 +550,40 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, T* wsm, int
       for (int k = 0; k < 9; ++k) { sc[3 + k] = A1.m[k]; sc[12 + k] = A2.m[k]; }
     }
   }
-  BIK_SYNCWARP();
-  // (2) per frame: Jacobian columns.
-  // Packed form: each lane writes the six entries of every column it computes as one 24-byte (fp32) run of the task's
-  // block -- nothing else is written, nothing is zero-filled.
+  if (valid && g == 0)   // CoM targets wait in the error slots until the CoM phase turns them into e = com - target
+    for (int c = 0; c < h.C; ++c) {
+      const int row0 = reinterpret_cast<const int32_t*>(P.f(h.off_com) + 8 * c)[5];
+      for (int k = 0; k < 3; ++k) estage[li * K + row0 + k] = ttile[IPW * h.F * 7 + (li * h.C + c) * 3 + k];
+    }
+  // ---- posture errors: e = q* (-) q, free-joint dofs zeroed (posture_task.py:107-118) ------------
+  // (the packed hand-off carries none: K2 recomputes them from q and the target it reads anyway)
+  if (h.P > 0 && !packed) {
+    T* epg = reinterpret_cast<T*>(a.ep);
+    const int per = h.P * nv;
+    const uint32_t mper = ((1u << 20) + per - 1) / per, mnv = ((1u << 20) + nv - 1) / nv;   // k / per, r / nv by multiplication (exact below 2^20 / divisor)
+    for (int k = lane; k < nvalid * per; k += W) {   // the tile's posture rows are one contiguous run of global memory
+      const int l2 = (int)(((uint32_t)k * mper) >> 20), r = k - l2 * per, p = (int)(((uint32_t)r * mnv) >> 20), d = r - p * nv;
+      const T* qq = qtile + l2 * nq;
+      const long long t0 = ((long long)(a.pbatched ? (inst0 + l2) : 0) * h.P + p) * nq;
+      epg[(long long)inst0 * per + k] = posture_err_dof<T>(P, d, [&](int i) { return ldin<T>(a.ptgt, t0 + i, a.in64); }, [&](int i) { return qq[i]; });
+    }
+  }
   // Dense direct form (J holds frame rows only): the tile's K x nv blocks are one contiguous run of global memory; it is
   // zero-filled with 16-byte stores straight from registers, then each lane scatters the columns it computes (a frame
-  // touches 12 of G1's 43 columns).  Zero-fill and scatter are ordered by the warp barrier; the partial sectors merge in
-  // L2.  Dense staged form (CoM rows share J): per frame through the staging tile, flushed as contiguous runs.
-  const bool direct = !packed && k1_frames_direct(h);
-  if (direct && h.F > 0) {
-    zero_words<W, T>(Jg + (long long)inst0 * K * nv, nvalid * K * nv, lane);
-    BIK_SYNCWARP();
+  // touches 12 of G1's 43 columns).  Zero-fill and scatter are ordered by the warp barrier; the partial sectors merge in L2.
+  if (direct && h.F > 0) zero_words<W, T>(Jg + (long long)inst0 * K * nv, nvalid * K * nv, lane);
+  BIK_SYNCWARP();
+  // ---- the tile's inputs are dead from here on: send the next tile's ahead (bulk async copies into the same buffers) ----
+#if defined(__CUDA_ARCH__)
+  if (pipe && k1_tile_bulk_ok<T>(h, a, next_inst0, IPW)) {
+    if (lane == 0) k1_pipe_arm<T>(h, a, next_inst0, IPW, pipe, qtile, ttile);
+    pipe->armed = next_inst0;
   }
+#endif
+  // (2) per frame: Jacobian columns.
+  // Packed form: each lane writes the six entries of every column it computes as one 24-byte (fp32) run of the task's
+  // block -- nothing else is written, nothing is zero-filled.  Dense direct form: scatter into the zero-filled run (see
+  // the top of the tile).  Dense staged form (CoM rows share J): per frame through the staging tile, flushed as contiguous runs.
   for (int f = 0; f < h.F; ++f) {
     const FrameRec& fr = P.frame(f);
     const bool staged = !packed && !direct;
@@ -582,9 +660,8 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, T* wsm, int
         if (g == 0) {
           V3<T> tot = KC<T>::com_fixed(P);
           for (int n = 0; n < h.nnode; ++n) if (P.node(n).parent < 0) tot = tot + ld_v(S + 3 * n);
-          const long long t0 = ((long long)b * h.C + c) * 3;
-          T* eo = estage + li * K + row0;  // e = com - target (com_task.py:82)
-          eo[0] = tot.x * invM - ldin<T>(a.ctgt, t0, a.in64); eo[1] = tot.y * invM - ldin<T>(a.ctgt, t0 + 1, a.in64); eo[2] = tot.z * invM - ldin<T>(a.ctgt, t0 + 2, a.in64);
+          T* eo = estage + li * K + row0;  // e = com - target (com_task.py:82); the target was parked here
+          eo[0] = tot.x * invM - eo[0]; eo[1] = tot.y * invM - eo[1]; eo[2] = tot.z * invM - eo[2];
           if (packed) { T* po = pkg + (long long)b * PKS + pk_off + 3 * h.com_ncols; po[0] = eo[0]; po[1] = eo[1]; po[2] = eo[2]; }
         }
         T* st = packed ? pkg + (long long)b * PKS + pk_off : stage + li * 3 * nv;
@@ -644,30 +721,6 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, T* wsm, int
   if (K > 0 && !packed) {
     T* eg = reinterpret_cast<T*>(a.e);
     for (int k = lane; k < nvalid * K; k += W) eg[(long long)inst0 * K + k] = estage[k];
-  }
-
-  // ---- posture errors: e = q* (-) q, free-joint dofs zeroed (posture_task.py:107-118) ------------
-  // (the packed hand-off carries none: K2 recomputes them from q and the target it reads anyway)
-  if (h.P > 0 && !packed) {
-    T* epg = reinterpret_cast<T*>(a.ep);
-#ifdef BIK_K1_POSTURE_NESTED   // A/B: one instance and posture task at a time (nv = 43 leaves 21 of 64 lane slots idle per row)
-    for (int l2 = 0; l2 < nvalid; ++l2) {
-      const T* qq = qtile + l2 * nq;
-      for (int p = 0; p < h.P; ++p) {
-        const long long t0 = ((long long)(a.pbatched ? (inst0 + l2) : 0) * h.P + p) * nq;
-        T* o = epg + ((long long)(inst0 + l2) * h.P + p) * nv;
-        for (int d = lane; d < nv; d += W) o[d] = posture_err_dof<T>(P, d, [&](int i) { return ldin<T>(a.ptgt, t0 + i, a.in64); }, [&](int i) { return qq[i]; });
-      }
-    }
-#else
-    const int per = h.P * nv;
-    for (int k = lane; k < nvalid * per; k += W) {
-      const int l2 = k / per, r = k - l2 * per, p = r / nv, d = r - p * nv;
-      const T* qq = qtile + l2 * nq;
-      const long long t0 = ((long long)(a.pbatched ? (inst0 + l2) : 0) * h.P + p) * nq;
-      epg[(long long)inst0 * per + k] = posture_err_dof<T>(P, d, [&](int i) { return ldin<T>(a.ptgt, t0 + i, a.in64); }, [&](int i) { return qq[i]; });
-    }
-#endif
   }
 
   // ---- collision rows (collision_avoidance_limit.py:187-210), 6 pairs per staging pass -----------

@@ -436,8 +436,9 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
   BIK_SYNCWARP();
   if (NP > 0 && !a.ep) {   // inside bik_step K1 hands no posture error over: e = q* (-) q from the staged q (posture_task.py:107-118)
     const int per = NP * nv;
+    const uint32_t mper = ((1u << 20) + per - 1) / per, mnv = ((1u << 20) + nv - 1) / nv;   // k / per, r / nv by multiplication (exact below 2^20 / divisor)
     for (int k = lane; k < NS * per; k += W) {
-      const int i = k / per, r = k - i * per, p = r / nv, d = r - p * nv;
+      const int i = (int)(((uint32_t)k * mper) >> 20), r = k - i * per, p = (int)(((uint32_t)r * mnv) >> 20), d = r - p * nv;
       const T* qq = U + (size_t)i * Sq;
       const long long t0 = ((long long)(a.pbatched ? (b0 + (i < cnt ? i : 0)) : 0) * NP + p) * nq;
       U[(size_t)i * Sq + nq + r] = posture_err_dof<T>(P, d, [&](int j) { return ldin<T>(a.ptgt, t0 + j, io64); }, [&](int j) { return qq[j]; });
@@ -662,9 +663,10 @@ BIK_HD void k2t_warp_tile(const PView& P, const K2Args& a, long long b0, void* w
     // scalar joints (hinge / slide): the whole warp sweeps the tile's dofs flat -- coalesced, independent loads; free and ball
     // joints (quaternion update) are left to one lane per joint
     const int32_t* dofqadr = P.i(h.off_dofqadr);
+    const uint32_t mnv = ((1u << 20) + nv - 1) / nv;
     auto sweep = [&](auto* qg, const auto* dg) {
       for (int k = lane; k < cnt * nv; k += W) {
-        const int i = k / nv, d = k - i * nv, qa = dofqadr[d];
+        const int i = (int)(((uint32_t)k * mnv) >> 20), d = k - i * nv, qa = dofqadr[d];
         if (qa >= 0 && !(a.skip && a.skip[b0 + i])) qg[(b0 + i) * nq + qa] += dg[(b0 + i) * nv + d];
       }
       if (live) for (int nn = l; nn < h.nnode; nn += G) { const NodeRec& r = P.node(nn); if (r.type == JNT_FREE || r.type == JNT_BALL) integrate_node(r, qg + b * nq, dg + b * nv); }

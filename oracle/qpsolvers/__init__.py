@@ -62,6 +62,8 @@ def goldfarb_idnani(H, c, G=None, h=None, max_iter=None, tol=1e-11):
     idx_map = np.nonzero(keep)[0]
     G, h = G[keep], h[keep]
     m = h.shape[0]
+    if m == 0:   # every row inactive (all collision pairs beyond the detection distance): the unconstrained minimiser
+        return x, np.zeros(len(keep)), [], 0
     rown = np.maximum(np.linalg.norm(G, axis=1), 1e-300)
     active: list[int] = []
     u = np.zeros(0)
