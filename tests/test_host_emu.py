@@ -315,3 +315,29 @@ def test_inconsistent_limits_are_flagged():
     for path in (1, 3, 8, 0, 4):
         dq, st, *_ = emu.solve(q, J, e, ep, Gc, hc, dt, damping, use_double=path)
         assert st[1] & 8 and not (st[[0, 2, 3]] & 8).any(), (path, st)
+
+
+def test_more_active_collision_rows_than_the_solver_holds_are_flagged():
+    """K2 keeps at most K2_MAX_GEN (24) general rows active at once.  A problem that needs more -- here Spot's four foot/floor
+    pairs listed ten times over, all pushed into the floor -- must come back flagged (BIK_STATUS_QP_MAXITER), never as a
+    silently truncated "solution" (round-1 advisor finding)."""
+    from mink_b200._abi import spec_from_workload
+    from mink_b200.workloads import WORKLOADS
+
+    wl = dict(WORKLOADS["spot"])
+    wl["limits"] = [dict(WORKLOADS["spot"]["limits"][0], pairs=[(["FL", "FR", "HR", "HL"], ["floor"])] * 10)]
+    _, fm, _, g = load_case("spot")
+    spec = spec_from_workload(fm, wl)
+    assert spec.npairs == 40
+    emu = Emu(fm.to_blob(), spec, fm.nq, fm.nv)
+    B = 3
+    q = np.tile(fm.key("home"), (B, 1))   # feet 3.5 mm inside the floor (sphere radius 0.036 at height 0.0325): d <= d_min, h = relaxation = 0
+    frames = task_frames(wl, fm)
+    poses, com, _ = emu.fk(q, frames)
+    ft = poses.astype(np.float64).copy()
+    ft[:, :, 6] += 0.2         # at penetration the witness-point normal points INTO the floor (collision_avoidance_limit.py:49
+                               # normalises fromto as it comes), so it is the upward move that all 40 rows oppose
+    pk, Gc, hc = emu.fk_jac(q, ft, None, com, dt=wl["dt"], prec="mixed", packed=True)
+    assert np.isfinite(hc).sum() == 40 * B
+    dq, st, it, *_ = emu.solve(q, None, None, None, Gc, hc, wl["dt"], wl["damping"], use_double=1, pk=pk)
+    assert (st & 2).all(), st
