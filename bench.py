@@ -252,7 +252,7 @@ def measure_e2e(prob, inp, fm, B, dt_, damping, args, world, allmax, barrier):
     ms = 1e3 * te / n_e2e
     return {"value": world * B * n_e2e / te, "unit": UNIT, "h2d_bytes_per_step": up * world, "d2h_bytes_per_step": down * world,
             "ms_per_step": ms, "pcie_gbs_up_plus_down_per_gpu": (up + down) / (ms * 1e-3) / 1e9,
-            "note": "bik_step_host (C ABI, pinned host buffers; 6 chunks through upload / compute / download streams), every rank on its "
+            "note": "bik_step_host (C ABI, pinned host buffers; whole-K2-wave chunks through an upload stream, two compute streams in turn and a download stream), every rank on its "
                     "shard at the same time; host wall clock per call, max over ranks; bytes are whole-job"}, hdq.copy()
 
 

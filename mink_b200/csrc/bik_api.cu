@@ -248,7 +248,7 @@ extern "C" void bik_problem_destroy(bik_problem* p) {
   cudaFree(p->hq); cudaFree(p->hft); cudaFree(p->hpt); cudaFree(p->hct); cudaFree(p->hdq); cudaFree(p->hst);
   cudaFree(p->conv_done); cudaFree(p->conv_dq); cudaFree(p->conv_count);
   if (p->conv_host) cudaFreeHost(p->conv_host);
-  for (int i = 0; i < 3; ++i) if (p->hs[i]) cudaStreamDestroy(p->hs[i]);
+  for (int i = 0; i < 4; ++i) if (p->hs[i]) cudaStreamDestroy(p->hs[i]);
   for (cudaEvent_t e : p->hev) cudaEventDestroy(e);
   delete p;
 }
@@ -474,26 +474,32 @@ static int ensure_workspace(bik_problem* p, int B, int elem) {
 
 // One or more solve_ik steps on device buffers: per step K1 (check_limits + FK + packed task rows + collision rows) and
 // K2 (QP + integrate).  Caller holds p->mu and has sized the workspace for `k1d ? 8 : 4`-byte elements.
-static int step_core(bik_problem* p, int B, void* q, const bik_inputs* in, double dt, double damping, int nsteps, int integrate,
+static int step_core(bik_problem* p, int B, size_t ws_off, void* q, const bik_inputs* in, double dt, double damping, int nsteps, int integrate,
                      void* dq, int32_t* status, int io64, bool k1d, cudaStream_t st) {
   const PHeader& h = p->h;
+  // hand-off rows [ws_off, ws_off + B): chunks of one batch may be in flight on different streams (bik_step_host)
+  const size_t es = k1d ? 8 : 4;
+  char* const pk = static_cast<char*>(p->pk) + ws_off * (size_t)std::max(h.pk_stride, 4) * es;
+  char* const Gc = static_cast<char*>(p->Gc) + ws_off * (size_t)(h.npairs > 0 ? h.npairs : 1) * h.nv * es;
+  char* const hc = static_cast<char*>(p->hc) + ws_off * (size_t)(h.npairs > 0 ? h.npairs : 1) * es;
+  signed char* const warmb = p->warm + ws_off * (size_t)(h.nu > 0 ? h.nu : 1);
   const bool warm = nsteps > 1;   // rollouts: carry the active set (and the previous dq) from step to step
   const int phase = env_int("BIK_STEP_PHASE", 0);   // measurement aid: 1 = only K1, 2 = only K2 (on the rows the last K1 left)
-  if (warm) CUDA_OK(cudaMemsetAsync(p->warm, 0, (size_t)B * (size_t)(h.nu > 0 ? h.nu : 1), st));
+  if (warm) CUDA_OK(cudaMemsetAsync(warmb, 0, (size_t)B * (size_t)(h.nu > 0 ? h.nu : 1), st));
   for (int s = 0; s < nsteps; ++s) {
     K1Args a1;
     memset(&a1, 0, sizeof a1);
     a1.B = B; a1.q = q; a1.ftgt = in->frame_targets; a1.ptgt = in->posture_targets; a1.ctgt = in->com_targets; a1.in64 = io64; a1.pbatched = in->posture_batched;
-    a1.dt = dt; a1.pk = p->pk; a1.Gc = p->Gc; a1.hc = p->hc;
+    a1.dt = dt; a1.pk = pk; a1.Gc = Gc; a1.hc = hc;
     a1.status = status; a1.accumulate = s > 0; a1.tol = 1e-6f;   // Configuration.check_limits(safety_break=False) of solve_ik.py:99
     int rc = phase == 2 ? BIK_OK : bik_launch_k1(p, a1, k1d, st);
     if (rc) return rc;
     if (phase == 1) continue;
     K2Args a2;
     memset(&a2, 0, sizeof a2);
-    a2.B = B; a2.q = q; a2.io64 = io64; a2.pk = p->pk; a2.pk64 = k1d; a2.ptgt = in->posture_targets; a2.pbatched = in->posture_batched;
-    a2.Gc = p->Gc; a2.hc = p->hc; a2.gc64 = k1d; a2.dt = dt; a2.damping = damping; a2.dq = dq; a2.integrate = integrate; a2.status = status;
-    a2.warm = warm ? p->warm : nullptr;
+    a2.B = B; a2.q = q; a2.io64 = io64; a2.pk = pk; a2.pk64 = k1d; a2.ptgt = in->posture_targets; a2.pbatched = in->posture_batched;
+    a2.Gc = Gc; a2.hc = hc; a2.gc64 = k1d; a2.dt = dt; a2.damping = damping; a2.dq = dq; a2.integrate = integrate; a2.status = status;
+    a2.warm = warm ? warmb : nullptr;
     rc = dispatch_k2(p, a2, st);
     if (rc) return rc;
   }
@@ -514,7 +520,7 @@ static int step_common(const bik_problem* cp, int B, void* q, const bik_inputs* 
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // (status needs no clearing: K1's fused check_limits assigns it on the first step, everything later ORs into it)
-  return step_core(p, B, q, in, dt, damping, nsteps, integrate, dq, status, f64, k1d, st);
+  return step_core(p, B, 0, q, in, dt, damping, nsteps, integrate, dq, status, f64, k1d, st);
 }
 extern "C" int bik_step(const bik_problem* p, int B, float* q, const bik_inputs* in, float dt, double damping, int nsteps, int integrate, float* dq,
                         int32_t* status, void* stream) {
@@ -605,10 +611,10 @@ extern "C" int bik_converge(const bik_problem* cp, int B, float* q, const bik_in
 }
 
 // Host-buffer variant: device staging lives in the problem (separate allocations).  The batch is cut into chunks that flow
-// through three streams -- upload, compute, download -- chained by events, so that the copies of neighbouring chunks overlap
-// the kernels (PCIe is full duplex: chunk i+1 goes up while chunk i computes and chunk i-1 comes down).  The kernels of all
-// chunks run back to back on ONE stream and share the K1 -> K2 hand-off buffers.  Default plan: chunk sizes 1:3:4:4:3:1
-// (a short first chunk fills the pipeline quickly, a short last one drains it quickly); BIK_HOST_CHUNKS=n forces n equal chunks.
+// through an upload stream, two compute streams taken in turn and a download stream, chained by events, so that the copies of
+// neighbouring chunks overlap the kernels (PCIe is full duplex: chunk i+1 goes up while chunk i computes and chunk i-1 comes
+// down) and the kernels of chunk i+1 fill the SMs that chunk i's K2 frees while its last tiles finish.  Default plan: whole K2 waves per chunk
+// (see below), 1:3:4:4:3:1 where the wave size is unknown; BIK_HOST_CHUNKS=n forces n equal chunks.
 extern "C" int bik_step_host(const bik_problem* cp, int B, float* q_host, const bik_inputs* in, float dt, double damping, int nsteps, int integrate,
                              float* dq_host, int32_t* status_host, size_t* h2d_bytes, size_t* d2h_bytes) {
   int rc = check_inputs(cp, in, false, 0);
@@ -633,14 +639,25 @@ extern "C" int bik_step_host(const bik_problem* cp, int B, float* q_host, const 
     CUDA_OK(cudaMalloc(&p->hst, 4 * b));
     p->host_B = b; p->host_pt_elems = pt_elems;
   }
-  if (!p->hs[0]) for (int i = 0; i < 3; ++i) CUDA_OK(cudaStreamCreateWithFlags(&p->hs[i], cudaStreamNonBlocking));
+  if (!p->hs[0]) for (int i = 0; i < 4; ++i) CUDA_OK(cudaStreamCreateWithFlags(&p->hs[i], cudaStreamNonBlocking));
   // chunk plan
   std::vector<size_t> cuts;
   const int forced = env_int("BIK_HOST_CHUNKS", 0);
+  const long long wave = bik_k2_group_wave(p);   // instances one resident wave of the small-group K2 covers (0: other path)
   if (forced > 0 || b < 8192) {
     const int NC = forced > 0 ? forced : 1;
     const size_t chunk = (b + NC - 1) / NC;
     for (size_t o = 0; o < b; o += chunk) cuts.push_back(std::min(chunk, b - o));
+  } else if (wave > 0 && b > (size_t)(2 * wave)) {
+    // K2's time is quantised in waves (a tile takes ~80 us however few there are), so chunks are whole waves: one wave first
+    // (the pipeline fills after the shortest possible upload), two-wave chunks in the middle, the fractional wave last (the
+    // shortest possible download drains it).
+    const size_t w = (size_t)wave, rem = b % w;
+    size_t left = b - w - rem;
+    cuts.push_back(w);
+    while (left > 0) { const size_t n = std::min(left, 2 * w); cuts.push_back(n); left -= n; }
+    if (rem) cuts.push_back(rem);
+    else if (cuts.size() > 2 && cuts.back() == 2 * w) { cuts.back() = w; cuts.push_back(w); }
   } else {
     const int w[6] = {1, 3, 4, 4, 3, 1};
     size_t used = 0;
@@ -653,13 +670,18 @@ extern "C" int bik_step_host(const bik_problem* cp, int B, float* q_host, const 
   }
   while (p->hev.size() < 2 * cuts.size() + 1) { cudaEvent_t e; CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); p->hev.push_back(e); }
   const bool k1d = k1_double(p, damping, false);
-  size_t maxc = 0;
-  for (size_t n : cuts) maxc = std::max(maxc, n);
-  rc = ensure_workspace(p, (int)maxc, k1d ? 8 : 4);
+  rc = ensure_workspace(p, B, k1d ? 8 : 4);   // chunks keep disjoint hand-off rows: two of them compute at the same time
   if (rc) return rc;
-  cudaStream_t s_up = p->hs[0], s_cmp = p->hs[1], s_dn = p->hs[2];
+  cudaStream_t s_up = p->hs[0], s_dn = p->hs[3];
   size_t up = 0, down = 0;
+  // BIK_HOST_TRACE=1: timed events around every stage of every chunk, printed after the call (measurement aid)
+  const bool trace = env_int("BIK_HOST_TRACE", 0) != 0;
+  std::vector<cudaEvent_t> tev;
+  auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
+  mark(s_up);
   if (h.P) { CUDA_OK(cudaMemcpyAsync(p->hpt, in->posture_targets, 4 * pt_elems, cudaMemcpyHostToDevice, s_up)); up += 4 * pt_elems; }
+  // every upload is enqueued first: the copy engine then streams the chunks back to back, whatever the host spends on
+  // enqueuing kernels and downloads afterwards
   size_t o = 0;
   for (size_t ci = 0; ci < cuts.size(); ++ci) {
     const size_t n = cuts[ci];
@@ -667,22 +689,44 @@ extern "C" int bik_step_host(const bik_problem* cp, int B, float* q_host, const 
     if (h.F) { CUDA_OK(cudaMemcpyAsync(p->hft + o * h.F * 7, static_cast<const float*>(in->frame_targets) + o * h.F * 7, 4 * n * h.F * 7, cudaMemcpyHostToDevice, s_up)); up += 4 * n * h.F * 7; }
     if (h.C) { CUDA_OK(cudaMemcpyAsync(p->hct + o * h.C * 3, static_cast<const float*>(in->com_targets) + o * h.C * 3, 4 * n * h.C * 3, cudaMemcpyHostToDevice, s_up)); up += 4 * n * h.C * 3; }
     CUDA_OK(cudaEventRecord(p->hev[2 * ci], s_up));
-    CUDA_OK(cudaStreamWaitEvent(s_cmp, p->hev[2 * ci], 0));
+    mark(s_up);
+    o += n;
+  }
+  o = 0;
+  for (size_t ci = 0; ci < cuts.size(); ++ci) {
+    const size_t n = cuts[ci];
+    cudaStream_t s_cmp = p->hs[1 + (ci & 1)];   // two compute streams in turn: the tail of one chunk's K2 (CTAs waiting for their
+    CUDA_OK(cudaStreamWaitEvent(s_cmp, p->hev[2 * ci], 0));   // slowest tile) is filled by the next chunk's kernels
+    mark(s_cmp);
     bik_inputs din = *in;
     din.q = p->hq + o * nq; din.frame_targets = p->hft + o * h.F * 7; din.com_targets = p->hct + o * h.C * 3;
     din.posture_targets = in->posture_batched ? p->hpt + o * (size_t)h.P * nq : p->hpt;
-    rc = step_core(p, (int)n, p->hq + o * nq, &din, dt, damping, nsteps, integrate, p->hdq + o * nv, status_host ? p->hst + o : nullptr, 0, k1d, s_cmp);
+    rc = step_core(p, (int)n, o, p->hq + o * nq, &din, dt, damping, nsteps, integrate, p->hdq + o * nv, status_host ? p->hst + o : nullptr, 0, k1d, s_cmp);
     if (rc) return rc;
     CUDA_OK(cudaEventRecord(p->hev[2 * ci + 1], s_cmp));
+    mark(s_cmp);
     CUDA_OK(cudaStreamWaitEvent(s_dn, p->hev[2 * ci + 1], 0));
+    mark(s_dn);
     CUDA_OK(cudaMemcpyAsync(dq_host + o * nv, p->hdq + o * nv, 4 * n * nv, cudaMemcpyDeviceToHost, s_dn)); down += 4 * n * nv;
     if (integrate) { CUDA_OK(cudaMemcpyAsync(q_host + o * nq, p->hq + o * nq, 4 * n * nq, cudaMemcpyDeviceToHost, s_dn)); down += 4 * n * nq; }
     if (status_host) { CUDA_OK(cudaMemcpyAsync(status_host + o, p->hst + o, 4 * n, cudaMemcpyDeviceToHost, s_dn)); down += 4 * n; }
+    mark(s_dn);
     o += n;
   }
   CUDA_OK(cudaStreamSynchronize(s_dn));
-  CUDA_OK(cudaStreamSynchronize(s_cmp));
+  CUDA_OK(cudaStreamSynchronize(p->hs[1]));
+  CUDA_OK(cudaStreamSynchronize(p->hs[2]));
   CUDA_OK(cudaStreamSynchronize(s_up));
+  if (trace) {   // uploads done (one per chunk), then per chunk: compute start, end, download start, end  (ms since the call's first event)
+    std::string line = "bik_step_host trace (ms): up";
+    const size_t nc = cuts.size();
+    for (size_t k = 1; k < tev.size(); ++k) {
+      float ms = 0; cudaEventElapsedTime(&ms, tev[0], tev[k]);
+      char buf[32]; snprintf(buf, sizeof buf, "%s%.3f", (k > nc && (k - 1 - nc) % 4 == 0) ? " | " : " ", ms); line += buf;
+    }
+    fprintf(stderr, "%s\n", line.c_str());
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
+  }
   if (h2d_bytes) *h2d_bytes = up;
   if (d2h_bytes) *d2h_bytes = down;
   return BIK_OK;

@@ -95,7 +95,7 @@ struct bik_problem {
   float *hq = nullptr, *hft = nullptr, *hpt = nullptr, *hct = nullptr, *hdq = nullptr;
   int32_t* hst = nullptr;
   size_t host_pt_elems = 0;
-  cudaStream_t hs[3] = {nullptr, nullptr, nullptr};   // upload, compute, download
+  cudaStream_t hs[4] = {nullptr, nullptr, nullptr, nullptr};   // upload, compute A, compute B, download
   std::vector<cudaEvent_t> hev;
   // bik_converge state
   size_t conv_B = 0;

@@ -41,3 +41,14 @@ for chunks in ("0", "1", "2", "4", "8", "16"):
         ts.append(time.perf_counter() - t0)
     res[f"step_host_ms_chunks_{chunks}"] = 1e3 * statistics.median(ts[2:])
 print(json.dumps(res))
+os.environ["BIK_HOST_CHUNKS"] = "0"; os.environ["BIK_HOST_TRACE"] = "1"
+for i in range(2):
+    hq[:] = hq0
+    t0 = time.perf_counter()
+    prob.step_host(hq, hft, hpt, None, dt=wl["dt"], damping=wl["damping"], nsteps=1, integrate=True, out_dq=hdq, out_status=hst)
+    print("wall ms", 1e3 * (time.perf_counter() - t0))
+os.environ["BIK_HOST_CHUNKS"] = "1"
+hq[:] = hq0
+t0 = time.perf_counter()
+prob.step_host(hq, hft, hpt, None, dt=wl["dt"], damping=wl["damping"], nsteps=1, integrate=True, out_dq=hdq, out_status=hst)
+print("wall ms (1 chunk)", 1e3 * (time.perf_counter() - t0))
