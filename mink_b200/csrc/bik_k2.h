@@ -567,6 +567,7 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
       }
       const T amin = warp_min_t<W, T>(alpha);
       blk = warp_min_i<W>(alpha == amin ? blk : 0x7fffffff);   // ties: smallest index
+      BIK_SYNCWARP();   // every lane has read xf (the shuffles above already gather the lanes; this orders the memory accesses too)
       if (amin < T(1.5)) {   // blocked: partial step, the blocking constraint joins the working set
         const T al = amin > T(1) ? T(1) : amin;
         for (int i = lane; i < n; i += W) if (w.st[i] == 0) w.xf[i] += al * (w.x[i] - w.xf[i]);
