@@ -84,10 +84,11 @@ struct PView {
 // ---- kinematic constants at the precision of the instantiation -------------------------------------------
 template <typename T> struct KC;
 template <> struct KC<float> {
-  static BIK_HD V3<float> npos(const PView& P, int n) { const NodeRec& r = P.node(n); return v3<float>(r.pos[0], r.pos[1], r.pos[2]); }
-  static BIK_HD Q4<float> nquat(const PView& P, int n) { const NodeRec& r = P.node(n); return q4<float>(r.quat[0], r.quat[1], r.quat[2], r.quat[3]); }
-  static BIK_HD V3<float> naxis(const PView& P, int n) { const NodeRec& r = P.node(n); return v3<float>(r.axis[0], r.axis[1], r.axis[2]); }
-  static BIK_HD V3<float> njpos(const PView& P, int n) { const NodeRec& r = P.node(n); return v3<float>(r.jpos[0], r.jpos[1], r.jpos[2]); }
+  // (the caller's NodeRec reference is used as is: re-deriving it from the image header costs a dependent shared-memory load each time)
+  static BIK_HD V3<float> npos(const PView&, int, const NodeRec& r) { return v3<float>(r.pos[0], r.pos[1], r.pos[2]); }
+  static BIK_HD Q4<float> nquat(const PView&, int, const NodeRec& r) { return q4<float>(r.quat[0], r.quat[1], r.quat[2], r.quat[3]); }
+  static BIK_HD V3<float> naxis(const PView&, int, const NodeRec& r) { return v3<float>(r.axis[0], r.axis[1], r.axis[2]); }
+  static BIK_HD V3<float> njpos(const PView&, int, const NodeRec& r) { return v3<float>(r.jpos[0], r.jpos[1], r.jpos[2]); }
   static BIK_HD float qpos0(const PView& P, int k) { return P.f(P.h().off_qpos0)[k]; }
   static BIK_HD V3<float> flpos(const PView& P, int f) { const FrameRec& r = P.frame(f); return v3<float>(r.lpos[0], r.lpos[1], r.lpos[2]); }
   static BIK_HD Q4<float> flquat(const PView& P, int f) { const FrameRec& r = P.frame(f); return q4<float>(r.lquat[0], r.lquat[1], r.lquat[2], r.lquat[3]); }
@@ -104,10 +105,10 @@ template <> struct KC<float> {
   static BIK_HD float coll(const PView& P, int k) { const PHeader& h = P.h(); return k == 0 ? h.coll_gain : (k == 1 ? h.coll_dmin : (k == 2 ? h.coll_ddet : h.coll_relax)); }
 };
 template <> struct KC<double> {
-  static BIK_HD V3<double> npos(const PView& P, int n) { const NodeRec64& r = P.node64(n); return v3<double>(r.pos[0], r.pos[1], r.pos[2]); }
-  static BIK_HD Q4<double> nquat(const PView& P, int n) { const NodeRec64& r = P.node64(n); return q4<double>(r.quat[0], r.quat[1], r.quat[2], r.quat[3]); }
-  static BIK_HD V3<double> naxis(const PView& P, int n) { const NodeRec64& r = P.node64(n); return v3<double>(r.axis[0], r.axis[1], r.axis[2]); }
-  static BIK_HD V3<double> njpos(const PView& P, int n) { const NodeRec64& r = P.node64(n); return v3<double>(r.jpos[0], r.jpos[1], r.jpos[2]); }
+  static BIK_HD V3<double> npos(const PView& P, int n, const NodeRec&) { const NodeRec64& r = P.node64(n); return v3<double>(r.pos[0], r.pos[1], r.pos[2]); }
+  static BIK_HD Q4<double> nquat(const PView& P, int n, const NodeRec&) { const NodeRec64& r = P.node64(n); return q4<double>(r.quat[0], r.quat[1], r.quat[2], r.quat[3]); }
+  static BIK_HD V3<double> naxis(const PView& P, int n, const NodeRec&) { const NodeRec64& r = P.node64(n); return v3<double>(r.axis[0], r.axis[1], r.axis[2]); }
+  static BIK_HD V3<double> njpos(const PView& P, int n, const NodeRec&) { const NodeRec64& r = P.node64(n); return v3<double>(r.jpos[0], r.jpos[1], r.jpos[2]); }
   static BIK_HD double qpos0(const PView& P, int k) { return P.d(P.h().off_qpos064)[k]; }
   static BIK_HD V3<double> flpos(const PView& P, int f) { const FrameRec64& r = P.frame64(f); return v3<double>(r.lpos[0], r.lpos[1], r.lpos[2]); }
   static BIK_HD Q4<double> flquat(const PView& P, int f) { const FrameRec64& r = P.frame64(f); return q4<double>(r.lquat[0], r.lquat[1], r.lquat[2], r.lquat[3]); }
@@ -228,16 +229,16 @@ BIK_HD void fk_node(const PView& P, int n, const T* q, T* xs) {
   } else {
     if (r.parent >= 0) {
       Q4<T> pq = ld_q(xs + 7 * r.pslot);
-      pos = ld_v(xs + 7 * r.pslot + 4) + qrot(pq, KC<T>::npos(P, n));
-      quat = qmul(pq, KC<T>::nquat(P, n));
+      pos = ld_v(xs + 7 * r.pslot + 4) + qrot(pq, KC<T>::npos(P, n, r));
+      quat = qmul(pq, KC<T>::nquat(P, n, r));
     } else {
-      pos = KC<T>::npos(P, n);
-      quat = KC<T>::nquat(P, n);
+      pos = KC<T>::npos(P, n, r);
+      quat = KC<T>::nquat(P, n, r);
     }
     if (r.type == JNT_SLIDE) {
-      pos = pos + (q[r.qadr] - KC<T>::qpos0(P, r.qadr)) * qrot(quat, KC<T>::naxis(P, n));
+      pos = pos + (q[r.qadr] - KC<T>::qpos0(P, r.qadr)) * qrot(quat, KC<T>::naxis(P, n, r));
     } else {
-      V3<T> jp = KC<T>::njpos(P, n);
+      V3<T> jp = KC<T>::njpos(P, n, r);
       bool off_centre = (jp.x != T(0)) || (jp.y != T(0)) || (jp.z != T(0));
       V3<T> anchor = pos;
       if (off_centre) anchor = pos + qrot(quat, jp);
@@ -245,7 +246,7 @@ BIK_HD void fk_node(const PView& P, int n, const T* q, T* xs) {
       if (r.type == JNT_HINGE) {
         T s, c;
         bik_sincos<T>(T(0.5) * (q[r.qadr] - KC<T>::qpos0(P, r.qadr)), &s, &c);
-        V3<T> ax = KC<T>::naxis(P, n);
+        V3<T> ax = KC<T>::naxis(P, n, r);
         ql = q4<T>(c, s * ax.x, s * ax.y, s * ax.z);
       } else {
         ql = qnormalize(ld_q(q + r.qadr));
@@ -281,17 +282,17 @@ BIK_HD void jac_column(const PView& P, int d, int n, const T* xs, V3<T> p, V3<T>
   V3<T> np = ld_v(xs + 7 * r.slot + 4);
   int k = d - r.dadr;
   if (r.type == JNT_HINGE) {
-    V3<T> ax = qrot(nq, KC<T>::naxis(P, n));
-    V3<T> anchor = np + qrot(nq, KC<T>::njpos(P, n));
+    V3<T> ax = qrot(nq, KC<T>::naxis(P, n, r));
+    V3<T> anchor = np + qrot(nq, KC<T>::njpos(P, n, r));
     *jr = ax; *jp = cross(ax, p - anchor);
   } else if (r.type == JNT_SLIDE) {
-    *jr = v3<T>(T(0), T(0), T(0)); *jp = qrot(nq, KC<T>::naxis(P, n));
+    *jr = v3<T>(T(0), T(0), T(0)); *jp = qrot(nq, KC<T>::naxis(P, n, r));
   } else if (r.type == JNT_FREE && k < 3) {
     *jr = v3<T>(T(0), T(0), T(0)); *jp = unit_axis<T>(k);
   } else {  // rotational dof of a free or ball joint: body-frame axis k
     int c = (r.type == JNT_FREE) ? k - 3 : k;
     V3<T> ax = qrot(nq, unit_axis<T>(c));
-    V3<T> anchor = (r.type == JNT_FREE) ? np : np + qrot(nq, KC<T>::njpos(P, n));
+    V3<T> anchor = (r.type == JNT_FREE) ? np : np + qrot(nq, KC<T>::njpos(P, n, r));
     *jr = ax; *jp = cross(ax, p - anchor);
   }
 }
@@ -671,15 +672,15 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, T* wsm, int
           T Ms = KC<T>::sub_m(P, n);
           Q4<T> nq_ = ld_q(xs + 7 * n); V3<T> np = ld_v(xs + 7 * n + 4), Sn = ld_v(S + 3 * n), col;
           int k = d - r.dadr;
-          if (r.type == JNT_SLIDE) col = (Ms * invM) * qrot(nq_, KC<T>::naxis(P, n));
+          if (r.type == JNT_SLIDE) col = (Ms * invM) * qrot(nq_, KC<T>::naxis(P, n, r));
           else if (r.type == JNT_FREE && k < 3) col = (Ms * invM) * unit_axis<T>(k);
           else {
             V3<T> ax, anchor;
-            if (r.type == JNT_HINGE) { ax = qrot(nq_, KC<T>::naxis(P, n)); anchor = np + qrot(nq_, KC<T>::njpos(P, n)); }
+            if (r.type == JNT_HINGE) { ax = qrot(nq_, KC<T>::naxis(P, n, r)); anchor = np + qrot(nq_, KC<T>::njpos(P, n, r)); }
             else {
               int cc = (r.type == JNT_FREE) ? k - 3 : k;
               ax = qrot(nq_, unit_axis<T>(cc));
-              anchor = (r.type == JNT_FREE) ? np : np + qrot(nq_, KC<T>::njpos(P, n));
+              anchor = (r.type == JNT_FREE) ? np : np + qrot(nq_, KC<T>::njpos(P, n, r));
             }
             col = invM * cross(ax, Sn - Ms * anchor);
           }

@@ -95,6 +95,7 @@ class FlatModel:
     site_frames: List[Frame] = field(default_factory=list)
     geom_frames: List[Frame] = field(default_factory=list)
     key_qpos: np.ndarray = None
+    com_missing: list = None   # bodies of subtree(body 1) whose mass the MJCF compiler could not derive (no <inertial>)
     geom_type: np.ndarray = None
     geom_size: np.ndarray = None
     jnt_limited: np.ndarray = None
@@ -153,7 +154,8 @@ class FlatModel:
             names=self.names, body_frames=fr(self.body_frames), site_frames=fr(self.site_frames),
             geom_frames=fr(self.geom_frames), key_qpos=self.key_qpos.tolist(),
             geom_type=self.geom_type.tolist(), geom_size=self.geom_size.tolist(),
-            jnt_limited=[int(x) for x in self.jnt_limited], jnt_range=self.jnt_range.tolist()))
+            jnt_limited=[int(x) for x in self.jnt_limited], jnt_range=self.jnt_range.tolist(),
+            com_missing=list(self.com_missing or [])))
 
     @classmethod
     def from_blob(cls, blob: bytes, meta_json: str = None) -> "FlatModel":
@@ -178,6 +180,7 @@ class FlatModel:
             fm.site_frames = fr(meta["site_frames"])
             fm.geom_frames = fr(meta["geom_frames"])
             fm.key_qpos = np.array(meta["key_qpos"]).reshape(-1, nq)
+            fm.com_missing = list(meta.get("com_missing", []))
             fm.geom_type = np.array(meta["geom_type"], dtype=np.int32)
             fm.geom_size = np.array(meta["geom_size"]).reshape(-1, 3)
             fm.jnt_limited = np.array(meta["jnt_limited"], dtype=bool)
@@ -236,7 +239,9 @@ def flatten(model) -> FlatModel:
                 dof_lo[dadr[j]], dof_hi[dadr[j]] = rng[j]
 
     # CoM bookkeeping for mj_jacSubtreeCom(body=1) (reference com_task.py:69,82,96).
-    com_node, com_pos, com_mass = [], [], []
+    com_node, com_pos, com_mass, com_missing = [], [], [], []
+    missing = getattr(model, "body_mass_missing", None)   # only the MJCF-subset compiler sets it; a real MjModel has every mass
+    names_body = getattr(model, "body_names", None)
     mass = np.asarray(model.body_mass, dtype=np.float64)
     ipos = np.asarray(model.body_ipos, dtype=np.float64)
     if nb > 1:
@@ -244,6 +249,8 @@ def flatten(model) -> FlatModel:
             a = b
             while a > 1:
                 a = int(parentid[a])
+            if a == 1 and missing is not None and missing[b]:
+                com_missing.append(str(names_body[b]) if names_body is not None else str(b))
             if a != 1 or mass[b] <= 0.0:
                 continue
             f = body_frames[b]
@@ -285,6 +292,7 @@ def flatten(model) -> FlatModel:
                     geom=names_of("geom", int(model.ngeom)), site=names_of("site", int(model.nsite)),
                     key=names_of("key", int(model.nkey)))
     fm.key_qpos = np.asarray(model.key_qpos, dtype=np.float64).reshape(-1, nq).copy()
+    fm.com_missing = com_missing
     fm.geom_type = np.asarray(model.geom_type).astype(np.int32)
     fm.geom_size = np.asarray(model.geom_size, dtype=np.float64).reshape(-1, 3).copy()
     fm.jnt_limited = limited.copy()

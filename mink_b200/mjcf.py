@@ -300,12 +300,13 @@ def _walk_body(elem: ET.Element, parent_id: int, childclass: Optional[str], ctx:
         name=battr.get("name", ""), parent=parent_id,
         pos=_floats(battr.get("pos", "0 0 0")), quat=_orientation(battr, ctx),
         mocap=battr.get("mocap", "false") == "true",
-        ipos=np.zeros(3), mass=0.0, joints=[], geoms=[], sites=[],
+        ipos=np.zeros(3), mass=0.0, joints=[], geoms=[], sites=[], has_inertial=False,
     )
     ctx.bodies.append(body)
     for child in elem:
         tag = child.tag
         if tag == "inertial":
+            body["has_inertial"] = True
             body["ipos"] = _floats(child.attrib.get("pos", "0 0 0"))
             body["mass"] = float(child.attrib.get("mass", "0"))
         elif tag in ("joint", "freejoint"):
@@ -406,6 +407,10 @@ def _compile(root: ET.Element, base_dir: str) -> Model:
     m.body_quat = np.array([b["quat"] for b in ctx.bodies], dtype=np.float64).reshape(nb, 4)
     m.body_ipos = np.array([b["ipos"] for b in ctx.bodies], dtype=np.float64).reshape(nb, 3)
     m.body_mass = np.array([b["mass"] for b in ctx.bodies], dtype=np.float64)
+    # MuJoCo derives mass and inertia from the geoms of a body that has no <inertial>; this compiler does not (no meshes, no
+    # geom densities), so such bodies carry mass 0 here.  Remember them: a ComTask on such a model must be refused, not wrong.
+    m.body_mass_missing = np.array([(not b.get("has_inertial", False)) and len(b["geoms"]) > 0 and not b.get("mocap", False)
+                                    for b in ctx.bodies], dtype=bool)
     mocapid = np.full(nb, -1, dtype=np.int32)
     nmocap = 0
     for i, b in enumerate(ctx.bodies):

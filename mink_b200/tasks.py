@@ -293,6 +293,11 @@ class ComTask(Task):
         self.set_target(configuration.get_com())
 
     def _spec(self, flat) -> TaskSpec:
+        if getattr(flat, "com_missing", None):
+            raise TaskDefinitionError(
+                f"{self.__class__.__name__}: the model was compiled from MJCF without mesh/geom-derived inertia and "
+                f"{len(flat.com_missing)} bodies of the robot have no <inertial> (e.g. {flat.com_missing[:3]}): their mass would be "
+                "taken as 0 and the centre of mass would be wrong.  Pass a real mujoco.MjModel (its body_mass is complete).")
         cost = np.zeros(6)
         cost[:3] = self.cost
         return TaskSpec(TASK_COM, cost=cost, gain=self.gain, lm_damping=self.lm_damping)
