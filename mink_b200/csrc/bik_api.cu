@@ -64,6 +64,13 @@ __global__ void check_limits_kernel(const uint32_t* __restrict__ gimage, int B, 
 // bik_converge bookkeeping: one thread advances the step counter and rewinds the count of unconverged instances before K1's
 // fused test; the closing kernel marks the instances that never met the thresholds.
 __global__ void converge_tick_kernel(int* count) { count[0] += 1; count[1] = 0; }
+// count = { steps taken, unconverged instances, go }.  After K1's test of step `it`: go on iff it < max_iters and (nothing has
+// been tested yet or somebody is still unconverged); `go` gates this pass's K2 and, in graph mode, the WHILE node's next pass.
+__global__ void converge_cond_kernel(int* count, int max_iters, cudaGraphConditionalHandle handle, int use_handle) {
+  const int it = count[0], go = it < max_iters && (it == 0 || count[1] > 0);
+  count[2] = go;
+  if (use_handle) cudaGraphSetConditional(handle, go ? 1u : 0u);
+}
 __global__ void converge_finish_kernel(int B, int max_iters, const int32_t* __restrict__ done, int32_t* iters, int32_t* status) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B && !done[b]) { iters[b] = max_iters; if (status) status[b] |= 16; }
@@ -241,9 +248,11 @@ extern "C" int bik_problem_create(const bik_model* model, const bik_task_desc* t
   *out = p;
   return BIK_OK;
 }
+static void conv_graph_drop(bik_problem* p);
 extern "C" void bik_problem_destroy(bik_problem* p) {
   if (!p) return;
   DeviceGuard g(p->device);
+  conv_graph_drop(p);
   cudaFree(p->d_sched); cudaFree(p->d_image); cudaFree(p->pk); cudaFree(p->Gc); cudaFree(p->hc); cudaFree(p->warm);
   cudaFree(p->hq); cudaFree(p->hft); cudaFree(p->hpt); cudaFree(p->hct); cudaFree(p->hdq); cudaFree(p->hst);
   cudaFree(p->conv_done); cudaFree(p->conv_dq); cudaFree(p->conv_count);
@@ -547,10 +556,57 @@ extern "C" int bik_problem_describe(const bik_problem* p, double damping, char* 
 
 // solve_ik + integrate until every frame task of an instance is within (pos_threshold, ori_threshold) or max_iters steps were
 // taken -- the inner loop of the reference's examples (examples/quadruped_spot.py:89-104, examples/arm_aloha.py:146-169), per
-// instance.  Two launches per step plus a one-thread tick: K1 also tests the thresholds on the errors it has just computed
-// (instances that pass are marked done and keep their q), K2 skips the done instances and integrates the others.  The batch
-// loop ends as soon as the device counter of unconverged instances reads zero (read back every `check_every` steps: one
-// 4-byte D2H copy and a stream synchronisation).
+// instance.  One pass = a one-thread tick, K1 (which also tests the thresholds on the errors it has just computed: instances
+// that pass are marked done and keep their q), a one-thread condition, K2 (skips the done instances, integrates the others).
+// The loop itself runs ON THE DEVICE: the passes are the body of a CUDA-graph WHILE node whose condition the condition kernel
+// sets (cudaGraphSetConditional), so the host enqueues one graph launch and never polls.  The graph is kept and reused as long
+// as the call's arguments do not change (the usual control loop).  BIK_CONVERGE_GRAPH=0, or any failure to build the graph,
+// falls back to a host loop that reads the device counter back every `check_every` steps.
+struct ConvKey {
+  int B, max_iters, check_every; float dt, pos, ori; double damping; const void *q, *ft, *pt, *ct, *iters, *status; int pb; bool k1d;
+  bool operator==(const ConvKey& o) const { return memcmp(this, &o, sizeof *this) == 0; }
+};
+static int converge_pass(bik_problem* p, int B, float* q, const bik_inputs* in, float dt, double damping, int max_iters, float pos_threshold,
+                         float ori_threshold, int32_t* iters, int32_t* status, bool k1d, cudaGraphConditionalHandle handle, int use_handle, cudaStream_t st) {
+  converge_tick_kernel<<<1, 1, 0, st>>>(p->conv_count);
+  K1Args a1;
+  memset(&a1, 0, sizeof a1);
+  a1.B = B; a1.q = q; a1.ftgt = in->frame_targets; a1.ptgt = in->posture_targets; a1.ctgt = in->com_targets; a1.pbatched = in->posture_batched;
+  a1.dt = dt; a1.pk = p->pk; a1.Gc = p->Gc; a1.hc = p->hc;
+  a1.status = status; a1.tol = 1e-6f;
+  a1.done = p->conv_done; a1.iters = iters; a1.not_done = p->conv_count + 1; a1.conv_it = p->conv_count; a1.conv_max = max_iters;
+  a1.pos_thr = pos_threshold; a1.ori_thr = ori_threshold;
+  int rc = bik_launch_k1(p, a1, k1d, st);
+  if (rc) return rc;
+  converge_cond_kernel<<<1, 1, 0, st>>>(p->conv_count, max_iters, handle, use_handle);
+  K2Args a2;
+  memset(&a2, 0, sizeof a2);
+  a2.B = B; a2.q = q; a2.pk = p->pk; a2.pk64 = k1d; a2.ptgt = in->posture_targets; a2.pbatched = in->posture_batched;
+  a2.Gc = p->Gc; a2.hc = p->hc; a2.gc64 = k1d; a2.dt = dt; a2.damping = damping; a2.dq = p->conv_dq; a2.integrate = 1; a2.status = status;
+  a2.warm = p->warm; a2.skip = p->conv_done; a2.gate = p->conv_count + 2;
+  rc = dispatch_k2(p, a2, st);
+  if (rc) return rc;
+  CUDA_OK(cudaGetLastError());
+  return BIK_OK;
+}
+struct bik_conv_graph { ConvKey key; cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; cudaStream_t cap = nullptr; };
+static std::mutex g_conv_mu;
+static std::vector<std::pair<bik_problem*, bik_conv_graph*>> g_conv;   // one cached graph per problem (heap nodes: pointers stay valid)
+
+static void conv_graph_drop(bik_problem* p) {
+  std::lock_guard<std::mutex> lock(g_conv_mu);
+  for (size_t i = 0; i < g_conv.size(); ++i)
+    if (g_conv[i].first == p) {
+      bik_conv_graph* c = g_conv[i].second;
+      if (c->exec) cudaGraphExecDestroy(c->exec);
+      if (c->graph) cudaGraphDestroy(c->graph);
+      if (c->cap) cudaStreamDestroy(c->cap);
+      delete c;
+      g_conv.erase(g_conv.begin() + i);
+      return;
+    }
+}
+
 extern "C" int bik_converge(const bik_problem* cp, int B, float* q, const bik_inputs* in, float dt, double damping, int max_iters, float pos_threshold,
                             float ori_threshold, int check_every, int32_t* iters, int32_t* status, void* stream) {
   if (B == 0 && cp) return BIK_OK;
@@ -567,42 +623,86 @@ extern "C" int bik_converge(const bik_problem* cp, int B, float* q, const bik_in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const PHeader& h = p->h;
   if ((size_t)B > p->conv_B) {
+    conv_graph_drop(p);   // the cached graph captured the old buffers
     cudaFree(p->conv_done); cudaFree(p->conv_dq);
     p->conv_done = nullptr; p->conv_dq = nullptr; p->conv_B = 0;
     CUDA_OK(cudaMalloc(&p->conv_done, sizeof(int32_t) * (size_t)B));
     CUDA_OK(cudaMalloc(&p->conv_dq, sizeof(float) * (size_t)B * h.nv));
     p->conv_B = (size_t)B;
   }
-  if (!p->conv_count) CUDA_OK(cudaMalloc(&p->conv_count, 2 * sizeof(int)));
-  if (!p->conv_host) CUDA_OK(cudaMallocHost(&p->conv_host, 2 * sizeof(int)));
+  if (!p->conv_count) CUDA_OK(cudaMalloc(&p->conv_count, 4 * sizeof(int)));
+  if (!p->conv_host) CUDA_OK(cudaMallocHost(&p->conv_host, 4 * sizeof(int)));
+  const int blocks = (B + 127) / 128;
+  bool graph_ok = env_int("BIK_CONVERGE_GRAPH", 1) != 0;
+  bik_conv_graph* cg = nullptr;
+  if (graph_ok) {
+    ConvKey key;
+    memset(&key, 0, sizeof key);
+    key.B = B; key.max_iters = max_iters; key.check_every = 0; key.dt = dt; key.pos = pos_threshold; key.ori = ori_threshold; key.damping = damping;
+    key.q = q; key.ft = in->frame_targets; key.pt = in->posture_targets; key.ct = in->com_targets; key.iters = iters; key.status = status;
+    key.pb = in->posture_batched; key.k1d = k1d;
+    {
+      std::lock_guard<std::mutex> l2(g_conv_mu);
+      for (auto& e : g_conv) if (e.first == p) cg = e.second;
+    }
+    if (cg && !(cg->key == key)) { conv_graph_drop(p); cg = nullptr; }
+    if (!cg) {
+      // warm the launch-geometry cache and the tile counter outside the capture (those paths allocate / query attributes):
+      // one K1 + a K2 that skips every instance
+      bik_conv_graph ng;
+      ng.key = key;
+      bool built = false;
+      do {
+        if (cudaStreamCreateWithFlags(&ng.cap, cudaStreamNonBlocking) != cudaSuccess) break;
+        cudaMemsetAsync(p->conv_done, 1, sizeof(int32_t) * (size_t)B, ng.cap);
+        cudaMemsetAsync(p->conv_count, 0, 4 * sizeof(int), ng.cap);
+        cudaGraphConditionalHandle none{};
+        if (converge_pass(p, B, q, in, dt, damping, max_iters, pos_threshold, ori_threshold, iters, nullptr, k1d, none, 0, ng.cap) != BIK_OK) break;
+        if (cudaStreamSynchronize(ng.cap) != cudaSuccess) break;
+        if (cudaGraphCreate(&ng.graph, 0) != cudaSuccess) break;
+        cudaGraphConditionalHandle handle;
+        if (cudaGraphConditionalHandleCreate(&handle, ng.graph, 1, cudaGraphCondAssignDefault) != cudaSuccess) break;
+        cudaGraphNodeParams cp2 = {cudaGraphNodeTypeConditional};
+        cp2.conditional.handle = handle; cp2.conditional.type = cudaGraphCondTypeWhile; cp2.conditional.size = 1;
+        cudaGraphNode_t node;
+        if (cudaGraphAddNode(&node, ng.graph, nullptr, 0, &cp2) != cudaSuccess) break;
+        cudaGraph_t body = cp2.conditional.phGraph_out[0];
+        if (cudaStreamBeginCaptureToGraph(ng.cap, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) != cudaSuccess) break;
+        const int prc = converge_pass(p, B, q, in, dt, damping, max_iters, pos_threshold, ori_threshold, iters, status, k1d, handle, 1, ng.cap);
+        if (cudaStreamEndCapture(ng.cap, nullptr) != cudaSuccess || prc != BIK_OK) break;
+        if (cudaGraphInstantiate(&ng.exec, ng.graph, 0) != cudaSuccess) break;
+        built = true;
+      } while (false);
+      if (built) {
+        std::lock_guard<std::mutex> l2(g_conv_mu);
+        cg = new bik_conv_graph(ng);
+        g_conv.push_back({p, cg});
+      } else {
+        (void)cudaGetLastError();
+        if (ng.exec) cudaGraphExecDestroy(ng.exec);
+        if (ng.graph) cudaGraphDestroy(ng.graph);
+        if (ng.cap) cudaStreamDestroy(ng.cap);
+        graph_ok = false;
+      }
+    }
+  }
   CUDA_OK(cudaMemsetAsync(p->conv_done, 0, sizeof(int32_t) * (size_t)B, st));
   CUDA_OK(cudaMemsetAsync(p->conv_count, 0xff, sizeof(int), st));   // step counter = -1: the first tick makes it 0
   CUDA_OK(cudaMemsetAsync(p->warm, 0, (size_t)B * (size_t)(h.nu > 0 ? h.nu : 1), st));
-  const int blocks = (B + 127) / 128;
-  bool all_done = false;
-  for (int it = 0; it <= max_iters && !all_done; ++it) {
-    converge_tick_kernel<<<1, 1, 0, st>>>(p->conv_count);
-    K1Args a1;
-    memset(&a1, 0, sizeof a1);
-    a1.B = B; a1.q = q; a1.ftgt = in->frame_targets; a1.ptgt = in->posture_targets; a1.ctgt = in->com_targets; a1.pbatched = in->posture_batched;
-    a1.dt = dt; a1.pk = p->pk; a1.Gc = p->Gc; a1.hc = p->hc;
-    if (status && it < max_iters) { a1.status = status; a1.accumulate = it > 0; a1.tol = 1e-6f; }
-    a1.done = p->conv_done; a1.iters = iters; a1.not_done = p->conv_count + 1; a1.conv_it = p->conv_count; a1.pos_thr = pos_threshold; a1.ori_thr = ori_threshold;
-    rc = bik_launch_k1(p, a1, k1d, st);
-    if (rc) return rc;
-    if (it > 0 && (it == max_iters || it % check_every == 0)) {   // errors at the configuration reached after `it` steps
-      CUDA_OK(cudaMemcpyAsync(p->conv_host, p->conv_count, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-      CUDA_OK(cudaStreamSynchronize(st));
-      all_done = p->conv_host[1] == 0;
+  if (graph_ok && cg) {
+    CUDA_OK(cudaGraphLaunch(cg->exec, st));
+  } else {
+    bool all_done = false;
+    cudaGraphConditionalHandle none{};
+    for (int it = 0; it <= max_iters && !all_done; ++it) {
+      rc = converge_pass(p, B, q, in, dt, damping, max_iters, pos_threshold, ori_threshold, iters, status, k1d, none, 0, st);
+      if (rc) return rc;
+      if (it > 0 && (it == max_iters || it % check_every == 0)) {   // errors at the configuration reached after `it` steps
+        CUDA_OK(cudaMemcpyAsync(p->conv_host, p->conv_count, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        all_done = p->conv_host[1] == 0;
+      }
     }
-    if (it == max_iters || all_done) break;
-    K2Args a2;
-    memset(&a2, 0, sizeof a2);
-    a2.B = B; a2.q = q; a2.pk = p->pk; a2.pk64 = k1d; a2.ptgt = in->posture_targets; a2.pbatched = in->posture_batched;
-    a2.Gc = p->Gc; a2.hc = p->hc; a2.gc64 = k1d; a2.dt = dt; a2.damping = damping; a2.dq = p->conv_dq; a2.integrate = 1; a2.status = status;
-    a2.warm = p->warm; a2.skip = p->conv_done;
-    rc = dispatch_k2(p, a2, st);
-    if (rc) return rc;
   }
   // instances that never met the thresholds: iters = max_iters, status bit BIK_STATUS_NOT_CONVERGED
   converge_finish_kernel<<<blocks, 128, 0, st>>>(B, max_iters, p->conv_done, iters, status);

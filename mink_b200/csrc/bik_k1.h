@@ -151,6 +151,7 @@ struct K1Args {
   int32_t* iters;
   int* not_done;
   const int* conv_it;    // device counter: steps taken so far (0: nothing is tested yet)
+  int conv_max;          // max_iters: at step conv_max nothing is solved any more, so the limits are not checked either
   float pos_thr, ori_thr;
 };
 
@@ -486,7 +487,11 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, T* wsm, int
   const T* qb = qtile + (valid ? li : 0) * nq;
 
   // ---- Configuration.check_limits (configuration.py:77-110), fused: every lane tests a few dofs of the tile ----
-  if (PK && a.status) {
+  // inside bik_converge the step index lives on the device (the loop may be a CUDA-graph WHILE node: no host in between)
+  const int conv_step = (PK && a.done) ? *a.conv_it : 0;
+  const bool do_check = PK && a.status && !(a.done && conv_step >= a.conv_max);
+  const bool accumulate = a.done ? conv_step > 0 : a.accumulate != 0;
+  if (do_check) {
     const int32_t* dofqadr = P.i(h.off_dofqadr);
     const float* rng = P.f(h.off_range);
     for (int i = 0; i < nvalid; ++i) {
@@ -507,7 +512,7 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, T* wsm, int
       }
     }
     BIK_SYNCWARP();
-    if (lane < nvalid) a.status[inst0 + lane] = a.accumulate ? (a.status[inst0 + lane] | sflag[lane]) : sflag[lane];
+    if (lane < nvalid) a.status[inst0 + lane] = accumulate ? (a.status[inst0 + lane] | sflag[lane]) : sflag[lane];
   }
 
   // ---- forward kinematics over the lane program --------------------------------------------
@@ -699,7 +704,7 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, T* wsm, int
   // ---- convergence test of the examples' inner loop (bik_converge), on the unweighted frame errors --------
   if (PK && a.done) {
     BIK_SYNCWARP();
-    const int it = *a.conv_it;
+    const int it = conv_step;
     if (it > 0 && lane < nvalid && !a.done[inst0 + lane]) {
       bool ok = true;
       for (int f = 0; f < h.F; ++f) {

@@ -7,6 +7,7 @@ template <typename T, int SLOTS>
 __global__ void __launch_bounds__(256) k2_kernel(const uint32_t* __restrict__ gimage, int words, int use_tma, K2Args a) {
   extern __shared__ __align__(16) uint32_t smem[];
   __shared__ __align__(8) uint64_t bar;
+  if (a.gate && *a.gate == 0) return;
   stage_image(smem, gimage, words, &bar, use_tma);
   PView P{smem};
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;

@@ -68,6 +68,7 @@ struct K2Args {
   int skip_box;        // bik_qp_objective: q is not read
   signed char* warm;   // [B][nu] or null: active-set guess in (0 free, 1 lower, 2 upper; +4 = dq still holds the previous step's result), read at entry, updated at exit
   const int32_t* skip; // [B] or null: instances marked here are neither solved nor integrated (bik_converge: already converged)
+  const int* gate;     // device flag or null: the whole launch is a no-op when it reads 0 (bik_converge's last pass through the graph body)
 };
 
 enum { K2_MAX_GEN = 24 };  // general (collision) rows that may be active at once; more than that sets BIK_STATUS_QP_MAXITER

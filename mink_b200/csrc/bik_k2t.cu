@@ -12,6 +12,7 @@ template <typename T, int G, int MAXT, typename M, bool F32IO>
 __global__ void __launch_bounds__(MAXT, 512 / MAXT) k2t_kernel(const uint32_t* __restrict__ gimage, int warp_bytes, K2Args a, unsigned int* sched) {
   extern __shared__ __align__(16) uint32_t smem[];
   constexpr int NS = 32 / G;
+  if (a.gate && *a.gate == 0) return;   // (uniform over the grid: the tile counter is left untouched)
   PView P{gimage};
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   char* wsm = reinterpret_cast<char*>(smem) + (size_t)warp * warp_bytes;

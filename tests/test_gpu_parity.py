@@ -555,3 +555,35 @@ def test_general_and_wide_paths_in_rollouts(name, B, T):
     it = it.cpu().numpy()
     print(f"{name}: cold-start factorisations at the reached configuration: mean {it.mean():.2f} max {it.max()}")
     assert int(st2.max()) == 0 and it.max() <= 60
+
+
+def test_converge_device_loop_matches_host_polled_loop():
+    """bik_converge runs its loop as a CUDA-graph WHILE node (the condition is set on the device); BIK_CONVERGE_GRAPH=0 is the
+    host-polled loop.  Same steps, flags and configurations; a second call with the same buffers reuses the graph, a call with
+    other thresholds rebuilds it."""
+    wl, fm, spec, g, model, prob = _engine("ur5e")
+    orc = _oracle(fm, spec)
+    frames = task_frames(wl, fm)
+    B = 700 + 9
+    inp = make_inputs(fm, wl, B, lambda qq: orc.fk(qq, frames), seed=15, sigma=0.05)
+    ft = torch.tensor(inp["frame_targets"], dtype=torch.float32, device="cuda:0")
+    pt = torch.tensor(inp["posture_target"], dtype=torch.float32, device="cuda:0")
+    q = torch.empty((B, fm.nq), dtype=torch.float32, device="cuda:0")
+    out = {}
+    for mode, thr in (("1", 2e-3), ("1", 2e-3), ("1", 5e-3), ("0", 2e-3), ("0", 5e-3)):
+        os.environ["BIK_CONVERGE_GRAPH"] = mode
+        try:
+            q.copy_(torch.tensor(inp["q"], dtype=torch.float32))
+            it, st = prob.converge(q, ft, pt, None, dt=wl["dt"], damping=wl["damping"], max_iters=10, pos_threshold=thr, ori_threshold=thr,
+                                   check_every=2)
+        finally:
+            os.environ.pop("BIK_CONVERGE_GRAPH", None)
+        res = (it.cpu().numpy().copy(), st.cpu().numpy().copy(), q.cpu().numpy().copy())
+        if (mode, thr) in out:
+            for a, b in zip(out[(mode, thr)], res):
+                np.testing.assert_array_equal(a, b)       # replaying the cached graph is deterministic
+        out[(mode, thr)] = res
+    for thr in (2e-3, 5e-3):
+        for a, b in zip(out[("1", thr)], out[("0", thr)]):
+            np.testing.assert_array_equal(a, b)
+    assert (out[("1", 5e-3)][0] <= out[("1", 2e-3)][0]).all() and (out[("1", 5e-3)][0] < out[("1", 2e-3)][0]).any()
