@@ -82,7 +82,7 @@ typedef struct bik_task_desc {
 } bik_task_desc;
 
 enum { BIK_LIMIT_CONFIGURATION = 0, BIK_LIMIT_VELOCITY = 1, BIK_LIMIT_COLLISION = 2 };
-enum { BIK_GEOM_PLANE = 0, BIK_GEOM_SPHERE = 2, BIK_GEOM_CAPSULE = 3 };
+enum { BIK_GEOM_PLANE = 0, BIK_GEOM_SPHERE = 2, BIK_GEOM_CAPSULE = 3, BIK_GEOM_BOX = 6 };   /* mjtGeom codes */
 
 typedef struct bik_geom {
   int32_t type;
@@ -99,7 +99,7 @@ typedef struct bik_geom {
  *   COLLISION     (collision_avoidance_limit.py:187-210): one row per geom pair,
  *        -n^T (Jp2 - Jp1) dq <= gain*(dist - minimum_distance)/dt + bound_relaxation, rows whose
  *        distance is >= detection_distance are inactive.  Primitive pairs only (plane, sphere,
- *        capsule). */
+ *        capsule, box; no plane-plane and no box-box pair). */
 typedef struct bik_limit_desc {
   int32_t kind;
   int32_t n;             /* CONFIGURATION/VELOCITY: number of listed dofs; COLLISION: number of pairs */

@@ -17,7 +17,7 @@ from .flatten import FlatModel, Frame
 
 TASK_FRAME, TASK_POSTURE, TASK_COM, TASK_RELATIVE_FRAME = 0, 1, 2, 3
 LIMIT_CONFIGURATION, LIMIT_VELOCITY, LIMIT_COLLISION = 0, 1, 2
-GEOM_PLANE, GEOM_SPHERE, GEOM_CAPSULE = 0, 2, 3
+GEOM_PLANE, GEOM_SPHERE, GEOM_CAPSULE, GEOM_BOX = 0, 2, 3, 6
 
 STATUS_OUT_OF_LIMITS, STATUS_QP_MAXITER, STATUS_NONFINITE, STATUS_QP_INFEASIBLE = 1, 2, 4, 8
 

@@ -304,7 +304,7 @@ inline bool build_image(const HostModel& m, const bik_task_desc* tasks, int ntas
       for (int g = 0; g < L.ngeoms; ++g) {
         GeomRec r; memset(&r, 0, sizeof r);
         r.type = L.geoms[g].type;
-        if (r.type != BIK_GEOM_PLANE && r.type != BIK_GEOM_SPHERE && r.type != BIK_GEOM_CAPSULE) { *err = "collision geoms must be plane, sphere or capsule"; return false; }
+        if (r.type != BIK_GEOM_PLANE && r.type != BIK_GEOM_SPHERE && r.type != BIK_GEOM_CAPSULE && r.type != BIK_GEOM_BOX) { *err = "collision geoms must be plane, sphere, capsule or box"; return false; }
         put_frame(L.geoms[g].frame, &r.node, r.lpos, r.lquat);
         for (int k = 0; k < 3; ++k) r.size[k] = (float)L.geoms[g].size[k];
         memcpy(b.w.data() + H.off_geoms + GEOM_WORDS * g, &r, sizeof r);
@@ -313,7 +313,11 @@ inline bool build_image(const HostModel& m, const bik_task_desc* tasks, int ntas
         if (L.pairs[k] < 0 || L.pairs[k] >= L.ngeoms) { *err = "collision pair index out of range"; return false; }
         b.i(H.off_pairs)[k] = L.pairs[k];
       }
-      for (int k = 0; k < L.n; ++k) if (L.geoms[L.pairs[2 * k]].type == BIK_GEOM_PLANE && L.geoms[L.pairs[2 * k + 1]].type == BIK_GEOM_PLANE) { *err = "plane-plane pair"; return false; }
+      for (int k = 0; k < L.n; ++k) {
+        const int t1 = L.geoms[L.pairs[2 * k]].type, t2 = L.geoms[L.pairs[2 * k + 1]].type;
+        if (t1 == BIK_GEOM_PLANE && t2 == BIK_GEOM_PLANE) { *err = "plane-plane pair"; return false; }
+        if (t1 == BIK_GEOM_BOX && t2 == BIK_GEOM_BOX) { *err = "box-box pairs are not supported (no convex-convex distance on the device)"; return false; }
+      }
     } else { *err = "unknown limit kind"; return false; }
   }
   if (!H.off_geoms) { H.off_geoms = b.alloc(GEOM_WORDS); H.off_pairs = b.alloc(4); }

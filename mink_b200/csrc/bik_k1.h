@@ -342,7 +342,7 @@ BIK_HD T posture_err_dof(const PView& P, int d, FT tg, FQ qq) {
   return c == 0 ? w.x : (c == 1 ? w.y : w.z);
 }
 
-// ---- primitive geom distance (plane / sphere / capsule) ------------------------------------
+// ---- primitive geom distance (plane / sphere / capsule / box) ------------------------------
 template <typename T>
 BIK_HD void seg_closest(V3<T> p1, V3<T> d1, V3<T> p2, V3<T> d2, V3<T>* a, V3<T>* b) {
   V3<T> r = p1 - p2;
@@ -357,11 +357,50 @@ BIK_HD void seg_closest(V3<T> p1, V3<T> d1, V3<T> p2, V3<T> d2, V3<T>* a, V3<T>*
   }
   *a = p1 + s * d1; *b = p2 + t * d2;
 }
+// Parameter t in [-1, 1] of the point of the segment c + t d nearest to the box |x_k| <= s_k (everything in the box frame).
+// f(t) = sum_k max(|c_k + t d_k| - s_k, 0)^2 is convex and C1 with a piecewise-linear derivative: bisect f' and finish with
+// one secant step, which lands on the root of the linear piece the bracket has shrunk into.
+template <typename T>
+BIK_HD T seg_box_slope(V3<T> c, V3<T> d, V3<T> s, T t) {
+  const T px = c.x + t * d.x, py = c.y + t * d.y, pz = c.z + t * d.z;
+  const T ex = px > s.x ? px - s.x : (px < -s.x ? px + s.x : T(0));
+  const T ey = py > s.y ? py - s.y : (py < -s.y ? py + s.y : T(0));
+  const T ez = pz > s.z ? pz - s.z : (pz < -s.z ? pz + s.z : T(0));
+  return d.x * ex + d.y * ey + d.z * ez;
+}
+// If the segment passes through the box the distance is zero on a whole interval of t: take the middle of the part inside
+// (slab clipping), so that the penetrating branch of the caller sees one well-defined core point.
+template <typename T>
+BIK_HD bool seg_box_clip(T c, T d, T s, T* t0, T* t1) {
+  if (d == T(0)) return c >= -s && c <= s;
+  T a = (-s - c) / d, b = (s - c) / d;
+  if (a > b) { T x = a; a = b; b = x; }
+  *t0 = bik_max(*t0, a); *t1 = bik_min(*t1, b);
+  return *t0 <= *t1;
+}
+template <typename T>
+BIK_HD T seg_box_param(V3<T> c, V3<T> d, V3<T> s) {
+  T t0 = T(-1), t1 = T(1);
+  if (seg_box_clip<T>(c.x, d.x, s.x, &t0, &t1) && seg_box_clip<T>(c.y, d.y, s.y, &t0, &t1) && seg_box_clip<T>(c.z, d.z, s.z, &t0, &t1))
+    return T(0.5) * (t0 + t1);
+  T lo = T(-1), hi = T(1);
+  T flo = seg_box_slope<T>(c, d, s, lo), fhi = seg_box_slope<T>(c, d, s, hi);
+  if (flo >= T(0)) return lo;
+  if (fhi <= T(0)) return hi;
+  const int iters = sizeof(T) == 8 ? 48 : 22;
+  for (int it = 0; it < iters; ++it) {
+    T mid = T(0.5) * (lo + hi), fm = seg_box_slope<T>(c, d, s, mid);
+    if (fm == T(0)) return mid;
+    if (fm < T(0)) { lo = mid; flo = fm; } else { hi = mid; fhi = fm; }
+  }
+  return lo + (hi - lo) * (-flo / (fhi - flo));
+}
 template <typename T>
 BIK_HD T geom_distance(const PView& P, int i1, int i2, const T* xs, T distmax, V3<T>* on1, V3<T>* on2) {
   int ia = i1, ib = i2;
   bool swap = false;
-  if (P.geom(i2).type == 0) { ia = i2; ib = i1; swap = true; }
+  // canonical order: a plane first, else a box first (plane-plane and box-box pairs are refused when the problem is built)
+  if (P.geom(i2).type == 0 || (P.geom(i2).type == 6 && P.geom(i1).type != 0)) { ia = i2; ib = i1; swap = true; }
   const GeomRec& A = P.geom(ia); const GeomRec& Bg = P.geom(ib);
   Q4<T> qa, qb; V3<T> pa, pb;
   frame_pose<T>(A.node, KC<T>::glpos(P, ia), KC<T>::glquat(P, ia), xs, &qa, &pa);
@@ -369,7 +408,17 @@ BIK_HD T geom_distance(const PView& P, int i1, int i2, const T* xs, T distmax, V
   const T ra = KC<T>::gsize(P, ia, 0), rb = KC<T>::gsize(P, ib, 0), ha = KC<T>::gsize(P, ia, 1), hb = KC<T>::gsize(P, ib, 1);
   V3<T> oa, ob; T dist;
   V3<T> zb = qrot(qb, unit_axis<T>(2));
-  if (A.type == 0) {  // plane vs sphere/capsule
+  if (A.type == 0 && Bg.type == 6) {  // plane vs box: the lowest corner
+    V3<T> n = qrot(qa, unit_axis<T>(2));
+    V3<T> end = pb;
+    for (int k = 0; k < 3; ++k) {
+      V3<T> ax = KC<T>::gsize(P, ib, k) * qrot(qb, unit_axis<T>(k));
+      end = dot(ax, n) >= T(0) ? end - ax : end + ax;
+    }
+    T hgt = dot(end - pa, n);
+    dist = hgt;
+    ob = end; oa = end - hgt * n;
+  } else if (A.type == 0) {  // plane vs sphere/capsule
     V3<T> n = qrot(qa, unit_axis<T>(2));
     V3<T> end = pb;
     if (Bg.type == 3) {
@@ -379,6 +428,27 @@ BIK_HD T geom_distance(const PView& P, int i1, int i2, const T* xs, T distmax, V
     T hgt = dot(end - pa, n);
     dist = hgt - rb;
     ob = end - rb * n; oa = end - hgt * n;
+  } else if (A.type == 6) {  // box vs sphere/capsule: nearest point of the core segment, in the box frame
+    const V3<T> s = v3<T>(ra, ha, KC<T>::gsize(P, ia, 2));
+    const V3<T> c = qrot_inv(qa, pb - pa);
+    const V3<T> d = Bg.type == 3 ? hb * qrot_inv(qa, zb) : v3<T>(T(0), T(0), T(0));
+    const T t = Bg.type == 3 ? seg_box_param<T>(c, d, s) : T(0);
+    const V3<T> p = c + t * d;
+    V3<T> qc = v3<T>(bik_min(bik_max(p.x, -s.x), s.x), bik_min(bik_max(p.y, -s.y), s.y), bik_min(bik_max(p.z, -s.z), s.z));
+    V3<T> v = p - qc, nl;
+    T L = bik_sqrt<T>(dot(v, v));
+    if (L > T(1e-15)) {
+      nl = (T(1) / L) * v;
+    } else {  // the core point is inside the box: leave through the nearest face (depth is signed, L < 0)
+      const T gx = s.x - (p.x < T(0) ? -p.x : p.x), gy = s.y - (p.y < T(0) ? -p.y : p.y), gz = s.z - (p.z < T(0) ? -p.z : p.z);
+      nl = v3<T>(T(0), T(0), T(0));
+      if (gx <= gy && gx <= gz) { nl.x = p.x < T(0) ? T(-1) : T(1); L = -gx; }
+      else if (gy <= gz) { nl.y = p.y < T(0) ? T(-1) : T(1); L = -gy; }
+      else { nl.z = p.z < T(0) ? T(-1) : T(1); L = -gz; }
+      qc = p - L * nl;
+    }
+    dist = L - rb;
+    oa = pa + qrot(qa, qc); ob = pa + qrot(qa, p - rb * nl);
   } else {
     V3<T> d1 = v3<T>(T(0), T(0), T(0)), d2 = d1, a, b;
     if (A.type == 3) d1 = ha * qrot(qa, unit_axis<T>(2));

@@ -144,7 +144,7 @@ class VelocityLimit(Limit):
 
 class CollisionAvoidanceLimit(Limit):
     """Normal-velocity limit between geom pairs (reference limits/collision_avoidance_limit.py).
-    Supported geoms: plane, sphere, capsule (SURVEY.md 7 hard part 6)."""
+    Supported geoms: plane, sphere, capsule, box (box against plane/sphere/capsule; SURVEY.md 7 hard part 6)."""
 
     def __init__(self, model, geom_pairs, gain: float = 0.85, minimum_distance_from_collisions: float = 0.005,
                  collision_detection_distance: float = 0.01, bound_relaxation: float = 0.0):
@@ -187,8 +187,11 @@ class CollisionAvoidanceLimit(Limit):
         local = {g: i for i, g in enumerate(used)}
         geoms = [(int(flat.geom_type[g]), flat.geom_frames[g], flat.geom_size[g]) for g in used]
         for t, _, _ in geoms:
-            if t not in (0, 2, 3):
-                raise LimitDefinitionError("CollisionAvoidanceLimit: only plane, sphere and capsule geoms are supported on the device")
+            if t not in (0, 2, 3, 6):
+                raise LimitDefinitionError("CollisionAvoidanceLimit: only plane, sphere, capsule and box geoms are supported on the device")
+        for a, b in self.geom_id_pairs:
+            if flat.geom_type[a] == 6 and flat.geom_type[b] == 6:
+                raise LimitDefinitionError("CollisionAvoidanceLimit: box-box pairs are not supported on the device")
         pairs = np.array([[local[a], local[b]] for a, b in self.geom_id_pairs], dtype=np.int32).reshape(-1, 2)
         return LimitSpec(LIMIT_COLLISION, geoms=geoms, pairs=pairs, gain=self.gain,
                          minimum_distance=self.minimum_distance_from_collisions,

@@ -115,6 +115,17 @@ WORKLOADS: Dict[str, dict] = {
         limits=[dict(kind="configuration", gain=0.95), dict(kind="velocity", vmax=2 * PI)],
         dt=2e-2, damping=1e-4, batch=1024,
     ),
+    # Not a BASELINE config: the limit set of examples/arm_ur5e.py:29-47 (wrist capsule against the floor plane and the wall BOX,
+    # configuration and velocity limits); detection distance widened so that sampled configurations have active rows.
+    "ur5e_wall": dict(
+        robot="ur5e", scene="universal_robots_ur5e/scene.xml", key="home",
+        frames=[dict(name="attachment_site", type="site", position_cost=1.0, orientation_cost=1.0, lm_damping=1.0)],
+        posture=dict(cost=1e-2), com=None,
+        limits=[dict(kind="configuration", gain=0.95), dict(kind="velocity", vmax=PI),
+                dict(kind="collision", pairs=[(["wrist_3_link"], ["floor", "wall"])],
+                     gain=0.85, minimum_distance=0.005, detection_distance=0.5, bound_relaxation=0.0)],
+        dt=2e-3, damping=1e-3, batch=1024,
+    ),
     # Not a BASELINE config: edge-case model authored for this repository (mink_b200/models/edge.xml):
     # ball joint with off-centre anchor, slide joint with ref, two joints on one body, a second floating
     # root, capsule/sphere/plane collision pairs, every task and limit kind at once.

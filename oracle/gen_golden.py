@@ -26,7 +26,7 @@ from mink_b200.flatten import flatten  # noqa: E402
 from mink_b200.workloads import WORKLOADS, make_inputs  # noqa: E402
 
 OUT = os.path.join(REPO, "tests", "golden")
-GOLDEN_B = {"ur5e_damp": 12, "ur5e": 8, "ur5e_dls": 16, "g1": 32, "shadow": 24, "spot": 24, "g1_rel": 16, "edge": 48, "g1_full": 16, "g1_hands": 24}
+GOLDEN_B = {"ur5e_wall": 24, "ur5e_damp": 12, "ur5e": 8, "ur5e_dls": 16, "g1": 32, "shadow": 24, "spot": 24, "g1_rel": 16, "edge": 48, "g1_full": 16, "g1_hands": 24}
 ROLLOUT_T, ROLLOUT_B = 8, 4
 CONV_B, CONV_MAX_ITERS, CONV_POS, CONV_ORI = 8, 20, 2e-3, 2e-3
 

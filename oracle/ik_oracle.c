@@ -550,7 +550,7 @@ int iko_box(const void* blob, const bik_limit_desc* limits, int nlimits, int B, 
   return 0;
 }
 
-/* signed distance between primitive geoms (plane / sphere / capsule), fromto on (g1, g2) */
+/* signed distance between primitive geoms (plane / sphere / capsule / box), fromto on (g1, g2) */
 static void seg_closest(const double* p1, const double* d1, const double* p2, const double* d2, double* a, double* b) {
   double r[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
   double A = d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2], E = d2[0] * d2[0] + d2[1] * d2[1] + d2[2] * d2[2];
@@ -561,12 +561,74 @@ static void seg_closest(const double* p1, const double* d1, const double* p2, co
   if (t < -1 || t > 1) { t = t < -1 ? -1 : 1; if (A > 1e-14) { s = (Bq * t - C) / A; if (s < -1) s = -1; if (s > 1) s = 1; } else s = 0; }
   for (int i = 0; i < 3; ++i) { a[i] = p1[i] + s * d1[i]; b[i] = p2[i] + t * d2[i]; }
 }
+/* squared distance from c + t d to the box |x_k| <= s_k (box frame) */
+static double seg_box_f(const double* c, const double* d, const double* s, double t) {
+  double f = 0;
+  for (int k = 0; k < 3; ++k) { double e = fabs(c[k] + t * d[k]) - s[k]; if (e > 0) f += e * e; }
+  return f;
+}
+/* its minimiser over t in [-1, 1]: piecewise quadratic between the face-plane crossings, each piece minimised in closed form */
+static double seg_box_param(const double* c, const double* d, const double* s) {
+  double t0 = -1, t1 = 1; int hit = 1;   /* segment through the box: the middle of the part inside */
+  for (int k = 0; k < 3; ++k) {
+    if (d[k] == 0) { if (fabs(c[k]) > s[k]) hit = 0; continue; }
+    double a = (-s[k] - c[k]) / d[k], b = (s[k] - c[k]) / d[k];
+    if (a > b) { double x = a; a = b; b = x; }
+    if (a > t0) t0 = a;
+    if (b < t1) t1 = b;
+  }
+  if (hit && t0 <= t1) return 0.5 * (t0 + t1);
+  double cuts[8]; int nc = 0;
+  cuts[nc++] = -1; cuts[nc++] = 1;
+  for (int k = 0; k < 3; ++k) if (d[k] != 0) for (int sg = -1; sg <= 1; sg += 2) { double t = (sg * s[k] - c[k]) / d[k]; if (t > -1 && t < 1) cuts[nc++] = t; }
+  for (int i = 1; i < nc; ++i) { double v = cuts[i]; int j = i - 1; while (j >= 0 && cuts[j] > v) { cuts[j + 1] = cuts[j]; --j; } cuts[j + 1] = v; }
+  double bt = -1, bf = seg_box_f(c, d, s, -1);
+  for (int i = 0; i + 1 < nc; ++i) {
+    double a = cuts[i], b = cuts[i + 1], tm = 0.5 * (a + b), num = 0, den = 0;
+    for (int k = 0; k < 3; ++k) { double pm = c[k] + tm * d[k]; if (fabs(pm) > s[k]) { double sg = pm < 0 ? -1 : 1; num += sg * d[k] * (sg * c[k] - s[k]); den += d[k] * d[k]; } }
+    double t = tm; if (den > 0) { t = -num / den; if (t < a) t = a; if (t > b) t = b; }
+    double f = seg_box_f(c, d, s, t); if (f < bf) { bf = f; bt = t; }
+    f = seg_box_f(c, d, s, b); if (f < bf) { bf = f; bt = b; }
+  }
+  return bt;
+}
 static double geom_distance(const Kin* k, const bik_geom* g1, const bik_geom* g2, double distmax, double* fromto) {
   const bik_geom* G[2] = {g1, g2}; int swap = 0;
-  if (g2->type == BIK_GEOM_PLANE) { G[0] = g2; G[1] = g1; swap = 1; }
+  if (g2->type == BIK_GEOM_PLANE || (g2->type == BIK_GEOM_BOX && g1->type != BIK_GEOM_PLANE)) { G[0] = g2; G[1] = g1; swap = 1; }
   double p[2][3], R[2][9], on1[3], on2[3], dist;
   for (int i = 0; i < 2; ++i) frame_pose(k, &G[i]->frame, p[i], R[i]);
-  if (G[0]->type == BIK_GEOM_PLANE) {
+  if (G[0]->type == BIK_GEOM_PLANE && G[1]->type == BIK_GEOM_BOX) {   /* lowest corner */
+    double n[3] = {R[0][2], R[0][5], R[0][8]}, corner[3] = {p[1][0], p[1][1], p[1][2]};
+    for (int a = 0; a < 3; ++a) {
+      double ax[3] = {R[1][a] * G[1]->size[a], R[1][3 + a] * G[1]->size[a], R[1][6 + a] * G[1]->size[a]};
+      double sg = ax[0] * n[0] + ax[1] * n[1] + ax[2] * n[2] >= 0 ? 1 : -1;
+      for (int i = 0; i < 3; ++i) corner[i] -= sg * ax[i];
+    }
+    dist = 0; for (int i = 0; i < 3; ++i) dist += (corner[i] - p[0][i]) * n[i];
+    for (int i = 0; i < 3; ++i) { on2[i] = corner[i]; on1[i] = corner[i] - n[i] * dist; }
+  } else if (G[0]->type == BIK_GEOM_BOX) {   /* box vs sphere / capsule core, in the box frame */
+    const double* s = G[0]->size; double c[3], d[3] = {0, 0, 0}, rel[3] = {p[1][0] - p[0][0], p[1][1] - p[0][1], p[1][2] - p[0][2]};
+    for (int a = 0; a < 3; ++a) c[a] = R[0][a] * rel[0] + R[0][3 + a] * rel[1] + R[0][6 + a] * rel[2];
+    if (G[1]->type == BIK_GEOM_CAPSULE) {
+      double ax[3] = {R[1][2] * G[1]->size[1], R[1][5] * G[1]->size[1], R[1][8] * G[1]->size[1]};
+      for (int a = 0; a < 3; ++a) d[a] = R[0][a] * ax[0] + R[0][3 + a] * ax[1] + R[0][6 + a] * ax[2];
+    }
+    double t = G[1]->type == BIK_GEOM_CAPSULE ? seg_box_param(c, d, s) : 0, pt[3], qc[3], v[3], nl[3] = {0, 0, 0}, Ln = 0, rb = G[1]->size[0];
+    for (int a = 0; a < 3; ++a) { pt[a] = c[a] + t * d[a]; qc[a] = pt[a] < -s[a] ? -s[a] : (pt[a] > s[a] ? s[a] : pt[a]); v[a] = pt[a] - qc[a]; Ln += v[a] * v[a]; }
+    Ln = sqrt(Ln);
+    if (Ln > MJ_MINVAL) { for (int a = 0; a < 3; ++a) nl[a] = v[a] / Ln; }
+    else {
+      int kb = 0; double gb = s[0] - fabs(pt[0]);
+      for (int a = 1; a < 3; ++a) if (s[a] - fabs(pt[a]) < gb) { gb = s[a] - fabs(pt[a]); kb = a; }
+      nl[kb] = pt[kb] < 0 ? -1 : 1; Ln = -gb;
+      for (int a = 0; a < 3; ++a) qc[a] = pt[a] - Ln * nl[a];
+    }
+    dist = Ln - rb;
+    for (int i = 0; i < 3; ++i) {
+      on1[i] = p[0][i]; on2[i] = p[0][i];
+      for (int a = 0; a < 3; ++a) { on1[i] += R[0][3 * i + a] * qc[a]; on2[i] += R[0][3 * i + a] * (pt[a] - rb * nl[a]); }
+    }
+  } else if (G[0]->type == BIK_GEOM_PLANE) {
     double n[3] = {R[0][2], R[0][5], R[0][8]}, ends[2][3]; int ne = 1;
     memcpy(ends[0], p[1], sizeof p[1]);
     if (G[1]->type == BIK_GEOM_CAPSULE) {

@@ -492,18 +492,102 @@ def _primitive_core(m, d, g):
         return "seg", (pos, R[:, 2] * m.geom_size[g, 1]), m.geom_size[g, 0]
     if t == mjtGeom.mjGEOM_PLANE:
         return "plane", (pos, R[:, 2]), 0.0
+    if t == mjtGeom.mjGEOM_BOX:
+        return "box", (pos, R, np.array(m.geom_size[g], dtype=np.float64)), 0.0
     raise NotImplementedError(f"oracle mj_geomDistance: geom type {int(t)} not restated")
 
 
+def _seg_box_param(c, d, s):
+    """t in [-1, 1] minimising the squared distance from c + t d to the box |x_k| <= s_k (box frame).
+
+    The squared distance is piecewise quadratic in t with breakpoints where a coordinate crosses a face plane:
+    minimise each piece in closed form and keep the best (exact, no iteration)."""
+    def f(t):
+        p = c + t * d
+        e = np.maximum(np.abs(p) - s, 0.0)
+        return float(e @ e)
+
+    # segment through the box: the middle of the part inside (the distance is zero on that whole interval)
+    t0, t1, hit = -1.0, 1.0, True
+    for k in range(3):
+        if d[k] == 0.0:
+            hit = hit and abs(c[k]) <= s[k]
+        else:
+            a, b = sorted(((-s[k] - c[k]) / d[k], (s[k] - c[k]) / d[k]))
+            t0, t1 = max(t0, a), min(t1, b)
+    if hit and t0 <= t1:
+        return 0.5 * (t0 + t1)
+
+    cuts = [-1.0, 1.0]
+    for k in range(3):
+        if abs(d[k]) > 0.0:
+            for sg in (-1.0, 1.0):
+                t = (sg * s[k] - c[k]) / d[k]
+                if -1.0 < t < 1.0:
+                    cuts.append(float(t))
+    cuts = sorted(set(cuts))
+    best_t, best_f = -1.0, f(-1.0)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        pm = c + 0.5 * (a + b) * d
+        num = den = 0.0
+        for k in range(3):
+            if abs(pm[k]) > s[k]:   # coordinate k is outside on this piece: term (sg*(c_k + t d_k) - s_k)^2
+                sg = np.sign(pm[k])
+                num += sg * d[k] * (sg * c[k] - s[k])
+                den += d[k] * d[k]
+        t = float(np.clip(-num / den, a, b)) if den > 0.0 else 0.5 * (a + b)
+        for cand in (t, b):
+            fc = f(cand)
+            if fc < best_f:
+                best_t, best_f = cand, fc
+    return best_t
+
+
+def _box_distance(box, k2, c2, r2):
+    """Box against a sphere / capsule core (point or segment + radius): (dist, point on box, point on the other geom)."""
+    pos, R, s = box
+    c = R.T @ (c2[0] - pos)
+    dd = R.T @ c2[1]
+    t = _seg_box_param(c, dd, s) if k2 == "seg" else 0.0
+    p = c + t * dd
+    qc = np.clip(p, -s, s)
+    v = p - qc
+    L = float(np.sqrt(v @ v))
+    if L > mjMINVAL:
+        n = v / L
+    else:   # core point inside the box: leave through the nearest face
+        gap = s - np.abs(p)
+        k = int(np.argmin(gap))
+        n = np.zeros(3)
+        n[k] = -1.0 if p[k] < 0 else 1.0
+        L = -float(gap[k])
+        qc = p - L * n
+    return L - r2, pos + R @ qc, pos + R @ (p - r2 * n)
+
+
 def mj_geomDistance(m, d, geom1, geom2, distmax, fromto):
-    """Signed distance between two primitive geoms; `distmax` and zero fromto when farther."""
+    """Signed distance between two primitive geoms; `distmax` and zero fromto when farther.
+
+    Box pairs (box vs plane / sphere / capsule) restate what MuJoCo's convex-distance routine returns for non-penetrating
+    shapes (the witness points of the minimum distance); MuJoCo itself is not available to pin them against."""
     k1, c1, r1 = _primitive_core(m, d, geom1)
     k2, c2, r2 = _primitive_core(m, d, geom2)
     swap = False
-    if k2 == "plane":
+    if k2 == "plane" or (k2 == "box" and k1 != "plane"):
         k1, c1, r1, k2, c2, r2 = k2, c2, r2, k1, c1, r1
         swap = True
-    if k1 == "plane":
+    if k1 == "plane" and k2 == "box":
+        p0, n = c1
+        pos, R, s = c2
+        corner = pos - R @ (np.where(R.T @ n >= 0.0, 1.0, -1.0) * s)
+        dist = float((corner - p0) @ n)
+        on2 = corner
+        on1 = corner - n * dist
+    elif k1 == "box":
+        if k2 == "box":
+            raise NotImplementedError("box-box")
+        dist, on1, on2 = _box_distance(c1, k2, c2, r2)
+    elif k1 == "plane":
         if k2 == "plane":
             raise NotImplementedError("plane-plane")
         p0, n = c1

@@ -174,6 +174,35 @@ def test_com_task_and_collision_limit_spot():
     np.testing.assert_allclose(_np(v) * float(g["dt"]), g["dq"], atol=5e-3)
 
 
+def test_collision_limit_against_box_wall_ur5e():
+    """The limit set of the reference's examples/arm_ur5e.py:29-47: wrist capsule against the floor plane and the wall BOX."""
+    wl, fm, spec, g = load_case("ur5e_wall")
+    cfg = mink.Configuration(fm, g["q"])
+    l = wl["limits"][2]
+    lim = mink.CollisionAvoidanceLimit(fm, l["pairs"], gain=l["gain"], minimum_distance_from_collisions=l["minimum_distance"],
+                                       collision_detection_distance=l["detection_distance"], bound_relaxation=l["bound_relaxation"])
+    assert lim.max_num_contacts == 2
+    con = lim.compute_qp_inequalities(cfg, float(g["dt"]))
+    Gr, hr = g["G"][:, -2:], g["h"][:, -2:]
+    fin = np.isfinite(hr)
+    assert np.array_equal(np.isfinite(_np(con.h)), fin)
+    np.testing.assert_allclose(_np(con.h)[fin], hr[fin], rtol=2e-4, atol=2e-3)
+    np.testing.assert_allclose(_np(con.G), Gr, atol=2e-5)
+    task = mink.FrameTask("attachment_site", "site", 1.0, 1.0, lm_damping=1.0)
+    task.set_target(SE3(g["frame_targets"][:, 0]))
+    post = mink.PostureTask(fm, cost=1e-2)
+    post.set_target(g["posture_target"])
+    limits = [mink.ConfigurationLimit(fm, gain=0.95), mink.VelocityLimit(fm, {n: np.pi for n in
+              ("shoulder_pan", "shoulder_lift", "elbow", "wrist_1", "wrist_2", "wrist_3")}), lim]
+    v = mink.solve_ik(cfg, [task, post], float(g["dt"]), "quadprog", float(g["damping"]), limits=limits)
+    np.testing.assert_allclose(_np(v) * float(g["dt"]), g["dq"], atol=2e-5)
+    # box-box pairs have no device distance: refused when the limit is compiled into a problem
+    bad = mink.CollisionAvoidanceLimit(fm, [(["wall"], [fm.names["geom"].index("wall") - 1])])
+    if bad.geom_id_pairs:
+        with pytest.raises(mink.LimitDefinitionError):
+            bad.compute_qp_inequalities(cfg, 0.01)
+
+
 def test_relative_frame_task_matches_reference_and_world_root_identity():
     """RelativeFrameTask vs the reference golden (g1_rel), and the reference's own cross-check
     (tests/test_relative_frame_task.py:128-154): with root = world it equals minus the FrameTask."""

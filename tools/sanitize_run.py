@@ -14,7 +14,7 @@ from mink_b200.workloads import WORKLOADS, load_flat
 
 GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 for name, env in (("g1", {}), ("g1", {"BIK_K2_PATH": "dense"}), ("g1", {"BIK_USE_TMA": "0"}), ("shadow", {}), ("spot", {}), ("edge", {}),
-                  ("g1_full", {}), ("g1_rel", {}), ("ur5e_dls", {}), ("ur5e_damp", {})):
+                  ("g1_full", {}), ("g1_rel", {}), ("ur5e_dls", {}), ("ur5e_damp", {}), ("ur5e_wall", {})):
     os.environ.update(env)
     wl = WORKLOADS[name]
     fm = load_flat(wl["robot"])
