@@ -32,8 +32,16 @@
 
 #if defined(__CUDACC__)
 #define BIK_NOINLINE __host__ __device__ __noinline__
+// Out-of-line helpers receive generic pointers; telling the compiler they point into shared memory turns their LD.E/ST.E
+// (two R2UR descriptor moves each) into LDS/STS.
+#if defined(__CUDA_ARCH__)
+#define BIK_IN_SHARED(p) __builtin_assume(__isShared(p))
+#else
+#define BIK_IN_SHARED(p) ((void)0)
+#endif
 #else
 #define BIK_NOINLINE __attribute__((noinline))
+#define BIK_IN_SHARED(p) ((void)0)
 #endif
 
 namespace bik {
@@ -146,6 +154,7 @@ template <typename T> BIK_HD K2Ws<T> k2_carve(const PHeader& h, void* mem) {
   K2Ws<T> w;
   int n = h.nu, np = h.npairs, mg = k2_max_gen(h);
   char* base = reinterpret_cast<char*>(mem);
+  BIK_IN_SHARED(base);
   T* p = reinterpret_cast<T*>(base);
   w.Hp = p; p += tri(n);
   w.dinv = p; p += n; w.c = p; p += n; w.lo = p; p += n; w.hi = p; p += n; w.x = p; p += n; w.xf = p; p += n; w.xfull = p; p += h.nv;
@@ -216,14 +225,19 @@ BIK_HD int k2_assemble(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int l
     const K2Task tk = k2_task(P, t);
     const T* blk = w.wpk + tk.pk_off;
     const T* we = blk + tk.nr * tk.nc;
-    for (int p = lane; p < tk.nc * tk.nc; p += W) {
-      int ia = p / tk.nc, ib = p - ia * tk.nc;
-      if (ib > ia) continue;
+    for (int p = lane; p < tri(tk.nc); p += W) {   // p = tri(ia) + ib, ib <= ia
+      int ia = (int)((bik_sqrt<float>(8.f * (float)p + 1.f) - 1.f) * 0.5f);
+      if (tri(ia) > p) --ia; else if (tri(ia + 1) <= p) ++ia;
+      const int ib = p - tri(ia);
       T s = T(0);
       for (int r = 0; r < tk.nr; ++r) s += blk[ia * tk.nr + r] * blk[ib * tk.nr + r];
       const int ua = umap[cols[tk.coff + ia] & 0xffff], ub = umap[cols[tk.coff + ib] & 0xffff];   // column lists are ascending: ua >= ub
       w.Hp[tri(ua) + ub] += s;
-      if (ib == ia) { T cs = T(0); for (int r = 0; r < tk.nr; ++r) cs += we[r] * blk[ia * tk.nr + r]; w.c[ua] -= cs; }
+    }
+    for (int ia = lane; ia < tk.nc; ia += W) {
+      T cs = T(0);
+      for (int r = 0; r < tk.nr; ++r) cs += we[r] * blk[ia * tk.nr + r];
+      w.c[umap[cols[tk.coff + ia] & 0xffff]] -= cs;
     }
     BIK_SYNCWARP();
   }
@@ -286,6 +300,7 @@ BIK_HD int k2_assemble(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int l
 // path (rsqrt once per column, by the lane that owns the next diagonal, from a running sum of squares).
 template <typename T, int W, int SLOTS>
 BIK_NOINLINE int k2_factor(T* __restrict__ Lp, T* __restrict__ dinv, int nf, int lane) {
+  BIK_IN_SHARED(Lp); BIK_IN_SHARED(dinv);
   int bad = 0;
   T ss[SLOTS];
 #pragma unroll
@@ -328,6 +343,7 @@ BIK_NOINLINE int k2_factor(T* __restrict__ Lp, T* __restrict__ dinv, int nf, int
 // the pivot value travels by shuffle.  Writes x_k into out[k] (compact indices).
 template <typename T, int W, int SLOTS>
 BIK_NOINLINE void k2_backsub(const T* __restrict__ Lp, const T* __restrict__ dinv, int nf, T* out, int lane) {
+  BIK_IN_SHARED(Lp); BIK_IN_SHARED(dinv); BIK_IN_SHARED(out);
   T y[SLOTS];
   const T* rhs = Lp + tri(nf);
 #pragma unroll
@@ -348,6 +364,7 @@ BIK_NOINLINE void k2_backsub(const T* __restrict__ Lp, const T* __restrict__ din
 // y <- L^-1 y for a separate vector (general-row path only)
 template <typename T, int W>
 BIK_NOINLINE void k2_forward(const T* Lp, const T* dinv, T* y, int nf, int lane) {
+  BIK_IN_SHARED(Lp); BIK_IN_SHARED(dinv); BIK_IN_SHARED(y);
   for (int k = 0; k < nf; ++k) {
     if (k % W == lane) y[k] = y[k] * dinv[k];
     BIK_SYNCWARP();
@@ -364,32 +381,46 @@ template <typename T> BIK_HD T k2_grow(const K2Args& a, long long base, int r, i
 // factor:  Y_r = L^-1 G_rF^T,  S = Y Y^T,  lam = S^-1 (Y (L^-1 y) - rhs),  rhs row <- L^-1 y - Y^T lam.
 // Cold for box-only problems: kept out of line so it does not occupy the instruction cache.
 template <typename T, int W>
-BIK_NOINLINE int k2_general_rows(K2Ws<T>& w, const K2Args& a, long long gbase, T* rhs, int n, int nf, int ng, int mg, int lane) {
+BIK_NOINLINE int k2_general_rows(const K2Ws<T> w, const K2Args& a, long long gbase, T* rhs, int n, int nf, int ng, int mg, int lane) {
+  // local copies: the assumption has to sit on the very pointer values the loops use
+  T* const Y = w.Y; T* const S = w.S; T* const lam = w.lam; T* const rg = w.rg; const T* const hg = w.hg; const T* const x = w.x;
+  const int* const st = w.st; const int* const idx = w.idx; const int* const gidx = w.gidx;
+  BIK_IN_SHARED(Y); BIK_IN_SHARED(S); BIK_IN_SHARED(lam); BIK_IN_SHARED(rg); BIK_IN_SHARED(hg); BIK_IN_SHARED(x);
+  BIK_IN_SHARED(st); BIK_IN_SHARED(idx); BIK_IN_SHARED(gidx); BIK_IN_SHARED(rhs);
   int bad = 0;
   for (int r = 0; r < ng; ++r) {
-    T* Yr = w.Y + r * n;
-    for (int i = lane; i < nf; i += W) Yr[i] = k2_grow<T>(a, gbase, w.gidx[r], n, w.idx[i]);
-    if (lane == 0) { T sv = w.hg[w.gidx[r]]; for (int j = 0; j < n; ++j) if (w.st[j]) sv -= k2_grow<T>(a, gbase, w.gidx[r], n, j) * w.x[j]; w.rg[r] = sv; }
+    T* Yr = Y + r * n;
+    for (int i = lane; i < nf; i += W) Yr[i] = k2_grow<T>(a, gbase, gidx[r], n, idx[i]);
+    if (nf < n) {   // some dofs sit on their bounds: move their part of the row to the right-hand side
+      if (lane == 0) { T sv = hg[gidx[r]]; for (int j = 0; j < n; ++j) if (st[j]) sv -= k2_grow<T>(a, gbase, gidx[r], n, j) * x[j]; rg[r] = sv; }
+    } else if (lane == 0) rg[r] = hg[gidx[r]];
     BIK_SYNCWARP();
     k2_forward<T, W>(w.Lp, w.dinv, Yr, nf, lane);
   }
-  if (lane == 0) {  // tiny dense solve, serial
-    for (int r = 0; r < ng; ++r) {
-      for (int q2 = 0; q2 <= r; ++q2) { T v = T(0); for (int i = 0; i < nf; ++i) v += w.Y[r * n + i] * w.Y[q2 * n + i]; w.S[r * mg + q2] = v; w.S[q2 * mg + r] = v; }
-      T v = -w.rg[r]; for (int i = 0; i < nf; ++i) v += w.Y[r * n + i] * rhs[i]; w.lam[r] = v;
-    }
-    for (int j = 0; j < ng; ++j) {  // Cholesky of S in place + solve
-      const T sjj = w.S[j * mg + j];
-      T d = sjj; for (int k = 0; k < j; ++k) d -= w.S[j * mg + k] * w.S[j * mg + k];
-      if (!(d > T(1e-14) * sjj)) bad = 1;   // the active rows are (numerically) dependent
-      d = bik_sqrt<T>(d > T(0) ? d : T(1e-30)); w.S[j * mg + j] = d;
-      for (int i = j + 1; i < ng; ++i) { T v = w.S[i * mg + j]; for (int k = 0; k < j; ++k) v -= w.S[i * mg + k] * w.S[j * mg + k]; w.S[i * mg + j] = v / d; }
-    }
-    for (int i = 0; i < ng; ++i) { T v = w.lam[i]; for (int k = 0; k < i; ++k) v -= w.S[i * mg + k] * w.lam[k]; w.lam[i] = v / w.S[i * mg + i]; }
-    for (int i = ng - 1; i >= 0; --i) { T v = w.lam[i]; for (int k = i + 1; k < ng; ++k) v -= w.S[k * mg + i] * w.lam[k]; w.lam[i] = v / w.S[i * mg + i]; }
+  // S = Y Y^T and the right-hand side Y (L^-1 y) - rhs: one (r, q) entry per lane
+  for (int p = lane; p < ng * (ng + 1) / 2 + ng; p += W) {
+    int r = 0, q2 = p;
+    if (p < ng * (ng + 1) / 2) { while (q2 > r) { q2 -= r + 1; ++r; } } else { r = p - ng * (ng + 1) / 2; q2 = -1; }
+    const T* Yr = Y + r * n;
+    const T* Yq = q2 >= 0 ? Y + q2 * n : rhs;
+    T v = T(0);
+    for (int i = 0; i < nf; ++i) v += Yr[i] * Yq[i];
+    if (q2 >= 0) { S[r * mg + q2] = v; S[q2 * mg + r] = v; } else lam[r] = v - rg[r];
   }
   BIK_SYNCWARP();
-  for (int i = lane; i < nf; i += W) { T v = rhs[i]; for (int r = 0; r < ng; ++r) v -= w.Y[r * n + i] * w.lam[r]; rhs[i] = v; }
+  if (lane == 0) {  // tiny dense solve, serial
+    for (int j = 0; j < ng; ++j) {  // Cholesky of S in place + solve
+      const T sjj = S[j * mg + j];
+      T d = sjj; for (int k = 0; k < j; ++k) d -= S[j * mg + k] * S[j * mg + k];
+      if (!(d > T(1e-14) * sjj)) bad = 1;   // the active rows are (numerically) dependent
+      d = bik_sqrt<T>(d > T(0) ? d : T(1e-30)); S[j * mg + j] = d;
+      for (int i = j + 1; i < ng; ++i) { T v = S[i * mg + j]; for (int k = 0; k < j; ++k) v -= S[i * mg + k] * S[j * mg + k]; S[i * mg + j] = v / d; }
+    }
+    for (int i = 0; i < ng; ++i) { T v = lam[i]; for (int k = 0; k < i; ++k) v -= S[i * mg + k] * lam[k]; lam[i] = v / S[i * mg + i]; }
+    for (int i = ng - 1; i >= 0; --i) { T v = lam[i]; for (int k = i + 1; k < ng; ++k) v -= S[k * mg + i] * lam[k]; lam[i] = v / S[i * mg + i]; }
+  }
+  BIK_SYNCWARP();
+  for (int i = lane; i < nf; i += W) { T v = rhs[i]; for (int r = 0; r < ng; ++r) v -= Y[r * n + i] * lam[r]; rhs[i] = v; }
   BIK_SYNCWARP();
   return warp_max_i<W>(bad);
 }
@@ -402,13 +433,18 @@ template <> struct K2Tol<float> { static BIK_HD float x() { return 1e-7f; } stat
 // multipliers of the active general rows into w.lam.  Returns status bits (4: factorisation broke down, 2: more than
 // k2_max_gen rows active, 32 (internal): the active general rows are linearly dependent, the multipliers are not
 // trustworthy); *ng_out = number of active general rows (their indices in w.gidx).
+// *fkey remembers which free set the factor in w.Lp belongs to (bit 63 = valid, problems with at most 63 coupled dofs): when only
+// the general rows of the working set changed -- always, for a problem without box limits -- the factor is reused and only the
+// right-hand side is forward-substituted.
 template <typename T, int W, int SLOTS>
-BIK_HD int k2_solve_working_set(const PHeader& h, const K2Args& a, long long gbase, K2Ws<T>& w, int lane, int* ng_out) {
+BIK_HD int k2_solve_working_set(const PHeader& h, const K2Args& a, long long gbase, K2Ws<T>& w, int lane, int* ng_out, unsigned long long* fkey) {
   const int n = h.nu, np = h.npairs, mg = k2_max_gen(h);
   int status = 0;
   // compact free list / active general rows (every lane writes the same values)
   int nf = 0, ng = 0;
-  for (int i = 0; i < n; ++i) if (w.st[i] == 0) { w.idx[nf] = i; ++nf; }
+  unsigned long long key = n <= 63 ? 1ull << 63 : 0ull;
+  for (int i = 0; i < n; ++i) if (w.st[i] == 0) { w.idx[nf] = i; ++nf; if (i < 63) key |= 1ull << i; }
+  const bool reuse = key != 0ull && key == *fkey;
   for (int r = 0; r < np; ++r) if (w.gst[r]) { if (ng < mg) { w.gidx[ng] = r; ++ng; } else status |= 2; }
   BIK_SYNCWARP();
   // x on the bounds, rhs of the reduced system, copy of H_FF
@@ -422,11 +458,15 @@ BIK_HD int k2_solve_working_set(const PHeader& h, const K2Args& a, long long gba
     for (int j = 0; j < ii; ++j) if (w.st[j]) r -= Hrow[j] * w.x[j];
     for (int j = ii + 1; j < n; ++j) if (w.st[j]) r -= w.Hp[tri(j) + ii] * w.x[j];
     rhs[i] = r;
-    T* Li = w.Lp + tri(i);
-    for (int j = 0; j <= i; ++j) Li[j] = Hrow[w.idx[j]];
+    if (!reuse) {
+      T* Li = w.Lp + tri(i);
+      for (int j = 0; j <= i; ++j) Li[j] = Hrow[w.idx[j]];
+    }
   }
   BIK_SYNCWARP();
-  if (k2_factor<T, W, SLOTS>(w.Lp, w.dinv, nf, lane)) status |= 4;
+  if (reuse) k2_forward<T, W>(w.Lp, w.dinv, rhs, nf, lane);
+  else if (k2_factor<T, W, SLOTS>(w.Lp, w.dinv, nf, lane)) status |= 4;
+  *fkey = key;
   status = warp_max_i<W>(status & 4) | (status & 2);
   if (ng > 0 && k2_general_rows<T, W>(w, a, gbase, rhs, n, nf, ng, mg, lane)) status |= 32;   // internal: active rows dependent
   // x_F = L^-T (.), overwriting the rhs row in place
@@ -463,10 +503,11 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
   for (int r = lane; r < np; r += W) { w.gst[r] = 0; w.hg[r] = ldin<T>(a.hc, (long long)b * np + r, a.gc64); }
   BIK_SYNCWARP();
   int status = 0, best = n + np + 1, patience = PATIENCE, it = 0, ng = 0;
+  unsigned long long fkey = 0ull;
   bool done = n == 0, primal = false;
   // ---- phase 1: block principal pivoting ----
   while (!done && !primal && it < MAXIT) {
-    const int ws = k2_solve_working_set<T, W, SLOTS>(h, a, gbase, w, lane, &ng);
+    const int ws = k2_solve_working_set<T, W, SLOTS>(h, a, gbase, w, lane, &ng, &fkey);
     status |= ws & ~32;
     ++it;
     if (ws & 32) { primal = true; break; }   // block flips activated dependent rows (the primal method never does)
@@ -537,7 +578,7 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
     if (warp_max_i<W>(infeas)) status |= 8;   // no feasible starting point: limits inconsistent with the collision rows
     BIK_SYNCWARP();
     while (!done && it < MAXIT && !(status & 8)) {
-      status |= k2_solve_working_set<T, W, SLOTS>(h, a, gbase, w, lane, &ng) & ~32;
+      status |= k2_solve_working_set<T, W, SLOTS>(h, a, gbase, w, lane, &ng, &fkey) & ~32;
       ++it;
       // ratio test: how far can xf move towards x before a bound of a free dof or an inactive general row stops it
       T alpha = T(2);
