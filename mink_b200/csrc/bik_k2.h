@@ -504,141 +504,143 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
   BIK_SYNCWARP();
   int status = 0, best = n + np + 1, patience = PATIENCE, it = 0, ng = 0;
   unsigned long long fkey = 0ull;
-  bool done = n == 0, primal = false;
-  // ---- phase 1: block principal pivoting ----
-  while (!done && !primal && it < MAXIT) {
+  bool done = n == 0;
+  // One loop, one call site of the working-set solve (the kernel is instruction-cache bound):
+  //   mode 0  block principal pivoting;  mode 1  set up the primal method from clip(0);  mode 2  primal active-set method.
+  int mode = 0;
+  while (!done && it < MAXIT) {
+    if (mode == 1) {
+      BIK_SYNCWARP();
+      for (int i = lane; i < n; i += W) {   // clip(0, lo, hi); a bound that holds the iterate is in the working set
+        T v = T(0);
+        int s0 = 0;
+        if (w.lo[i] > v) { v = w.lo[i]; s0 = 1; }
+        if (w.hi[i] < v) { v = w.hi[i]; s0 = 2; }
+        w.xf[i] = v; w.st[i] = s0;
+      }
+      BIK_SYNCWARP();
+      int infeas = 0;
+      for (int r = lane; r < np; r += W) {
+        w.gst[r] = 0;
+        T hr = w.hg[r];
+        if (hr < T(1e30)) {
+          T sv = -hr;
+          for (int j = 0; j < n; ++j) sv += k2_grow<T>(a, gbase, r, n, j) * w.xf[j];
+          if (sv > tolx * (T(1) + (hr < 0 ? -hr : hr))) infeas = 1;
+        }
+      }
+      if (warp_max_i<W>(infeas)) status |= 8;   // no feasible starting point: limits inconsistent with the collision rows
+      BIK_SYNCWARP();
+      mode = 2;
+      if (status & 8) break;
+    }
     const int ws = k2_solve_working_set<T, W, SLOTS>(h, a, gbase, w, lane, &ng, &fkey);
     status |= ws & ~32;
     ++it;
-    if (ws & 32) { primal = true; break; }   // block flips activated dependent rows (the primal method never does)
-    // gradient on the active bounds, feasibility of free variables and of general rows.
-    // Proposed new states go to w.idx (free after the scatter in the solve) and w.gnew.
-    int ninf = 0;
-    for (int i = lane; i < n; i += W) {
-      int cur = w.st[i], ns = cur;
-      if (cur == 0) {
-        T xi = w.x[i];
-        if (xi < w.lo[i] - tolx * (T(1) + (w.lo[i] < 0 ? -w.lo[i] : w.lo[i]))) ns = 1;
-        else if (xi > w.hi[i] + tolx * (T(1) + (w.hi[i] < 0 ? -w.hi[i] : w.hi[i]))) ns = 2;
-      } else {
-        T gi = k2_grad<T>(a, gbase, w, n, ng, i);
-        if (cur == 1 && gi < -tolg) ns = 0;
-        else if (cur == 2 && gi > tolg) ns = 0;
-      }
-      w.idx[i] = ns;
-      if (ns != cur) ++ninf;
-    }
-    for (int r = lane; r < np; r += W) {
-      int cur = w.gst[r], ns = cur;
-      T hr = w.hg[r];
-      if (!(hr < T(1e30))) ns = 0;  // inactive row: h = +inf (collision_avoidance_limit.py:192-199)
-      else if (cur == 0) {
-        T sv = -hr;
-        for (int j = 0; j < n; ++j) sv += k2_grow<T>(a, gbase, r, n, j) * w.x[j];
-        if (sv > tolx * (T(1) + (hr < 0 ? -hr : hr))) ns = 1;
-      } else {
-        int k = 0;
-        while (k < ng && w.gidx[k] != r) ++k;
-        if (k < ng && w.lam[k] < -tolg) ns = 0;
-      }
-      w.gnew[r] = ns;
-      if (ns != cur) ++ninf;
-    }
-    ninf = warp_sum_i<W>(ninf);
-    if (ninf == 0) { done = true; break; }
-    if (ninf < best) { best = ninf; patience = PATIENCE; }
-    else if (patience > 0) --patience;
-    else { primal = true; break; }
-    BIK_SYNCWARP();
-    for (int i = lane; i < n; i += W) w.st[i] = w.idx[i];
-    for (int r = lane; r < np; r += W) w.gst[r] = w.gnew[r];
-    BIK_SYNCWARP();
-  }
-  // ---- phase 2: primal active-set method from a feasible point ----
-  if (primal) {
-    BIK_SYNCWARP();
-    for (int i = lane; i < n; i += W) {   // clip(0, lo, hi); a bound that holds the iterate is in the working set
-      T v = T(0);
-      int s0 = 0;
-      if (w.lo[i] > v) { v = w.lo[i]; s0 = 1; }
-      if (w.hi[i] < v) { v = w.hi[i]; s0 = 2; }
-      w.xf[i] = v; w.st[i] = s0;
-    }
-    BIK_SYNCWARP();
-    int infeas = 0;
-    for (int r = lane; r < np; r += W) {
-      w.gst[r] = 0;
-      T hr = w.hg[r];
-      if (hr < T(1e30)) {
-        T sv = -hr;
-        for (int j = 0; j < n; ++j) sv += k2_grow<T>(a, gbase, r, n, j) * w.xf[j];
-        if (sv > tolx * (T(1) + (hr < 0 ? -hr : hr))) infeas = 1;
-      }
-    }
-    if (warp_max_i<W>(infeas)) status |= 8;   // no feasible starting point: limits inconsistent with the collision rows
-    BIK_SYNCWARP();
-    while (!done && it < MAXIT && !(status & 8)) {
-      status |= k2_solve_working_set<T, W, SLOTS>(h, a, gbase, w, lane, &ng, &fkey) & ~32;
-      ++it;
-      // ratio test: how far can xf move towards x before a bound of a free dof or an inactive general row stops it
-      T alpha = T(2);
-      int blk = 0x7fffffff;
+    if (mode == 0) {
+      if (ws & 32) { mode = 1; continue; }   // block flips activated dependent rows (the primal method never does)
+      // gradient on the active bounds, feasibility of free variables and of general rows.
+      // Proposed new states go to w.idx (free after the scatter in the solve) and w.gnew.
+      int ninf = 0;
       for (int i = lane; i < n; i += W) {
-        if (w.st[i] != 0) continue;
-        const T xi = w.x[i], xo = w.xf[i], lo = w.lo[i], hi = w.hi[i];
-        const bool below = xi < lo - tolx * (T(1) + (lo < 0 ? -lo : lo));
-        const bool above = !below && xi > hi + tolx * (T(1) + (hi < 0 ? -hi : hi));
-        if (below || above) {
-          const T d = xi - xo;
-          T al = d != T(0) ? ((below ? lo : hi) - xo) / d : T(0);
-          al = al < T(0) ? T(0) : al;
-          if (al < alpha) { alpha = al; blk = i; }
+        int cur = w.st[i], ns = cur;
+        if (cur == 0) {
+          T xi = w.x[i];
+          if (xi < w.lo[i] - tolx * (T(1) + (w.lo[i] < 0 ? -w.lo[i] : w.lo[i]))) ns = 1;
+          else if (xi > w.hi[i] + tolx * (T(1) + (w.hi[i] < 0 ? -w.hi[i] : w.hi[i]))) ns = 2;
+        } else {
+          T gi = k2_grad<T>(a, gbase, w, n, ng, i);
+          if (cur == 1 && gi < -tolg) ns = 0;
+          else if (cur == 2 && gi > tolg) ns = 0;
         }
+        w.idx[i] = ns;
+        if (ns != cur) ++ninf;
       }
       for (int r = lane; r < np; r += W) {
-        const T hr = w.hg[r];
-        if (w.gst[r] || !(hr < T(1e30))) continue;
-        T gx = T(0), gf = T(0);
-        for (int j = 0; j < n; ++j) { const T gj = k2_grow<T>(a, gbase, r, n, j); gx += gj * w.x[j]; gf += gj * w.xf[j]; }
-        if (gx > hr + tolx * (T(1) + (hr < 0 ? -hr : hr))) {
-          const T d = gx - gf;
-          T al = d > T(0) ? (hr - gf) / d : T(0);
-          al = al < T(0) ? T(0) : al;
-          if (al < alpha) { alpha = al; blk = n + r; }
+        int cur = w.gst[r], ns = cur;
+        T hr = w.hg[r];
+        if (!(hr < T(1e30))) ns = 0;  // inactive row: h = +inf (collision_avoidance_limit.py:192-199)
+        else if (cur == 0) {
+          T sv = -hr;
+          for (int j = 0; j < n; ++j) sv += k2_grow<T>(a, gbase, r, n, j) * w.x[j];
+          if (sv > tolx * (T(1) + (hr < 0 ? -hr : hr))) ns = 1;
+        } else {
+          int k = 0;
+          while (k < ng && w.gidx[k] != r) ++k;
+          if (k < ng && w.lam[k] < -tolg) ns = 0;
         }
+        w.gnew[r] = ns;
+        if (ns != cur) ++ninf;
       }
-      const T amin = warp_min_t<W, T>(alpha);
-      blk = warp_min_i<W>(alpha == amin ? blk : 0x7fffffff);   // ties: smallest index
-      BIK_SYNCWARP();   // every lane has read xf (the shuffles above already gather the lanes; this orders the memory accesses too)
-      if (amin < T(1.5)) {   // blocked: partial step, the blocking constraint joins the working set
-        const T al = amin > T(1) ? T(1) : amin;
-        for (int i = lane; i < n; i += W) if (w.st[i] == 0) w.xf[i] += al * (w.x[i] - w.xf[i]);
-        BIK_SYNCWARP();
-        if (blk < n) {
-          if (lane == 0) { const bool lower = w.x[blk] < w.lo[blk]; w.st[blk] = lower ? 1 : 2; w.xf[blk] = lower ? w.lo[blk] : w.hi[blk]; }
-        } else if (lane == 0) w.gst[blk - n] = 1;
-        BIK_SYNCWARP();
-        continue;
-      }
-      // feasible subspace minimiser: it becomes the iterate; let go of the constraint with the most negative multiplier
-      for (int i = lane; i < n; i += W) w.xf[i] = w.x[i];
-      T worst = -tolg;
-      int rel = 0x7fffffff;
-      for (int i = lane; i < n; i += W) {
-        const int cur = w.st[i];
-        if (cur == 0) continue;
-        T gi = k2_grad<T>(a, gbase, w, n, ng, i);
-        if (cur == 2) gi = -gi;   // now: gi < 0 means the bound wants to let go
-        if (gi < worst) { worst = gi; rel = i; }
-      }
-      for (int k = lane; k < ng; k += W) if (w.lam[k] < worst) { worst = w.lam[k]; rel = n + w.gidx[k]; }
-      const T wmin = warp_min_t<W, T>(worst);
-      rel = warp_min_i<W>(worst == wmin ? rel : 0x7fffffff);
-      if (rel == 0x7fffffff) { done = true; break; }
+      ninf = warp_sum_i<W>(ninf);
+      if (ninf == 0) { done = true; break; }
+      if (ninf < best) { best = ninf; patience = PATIENCE; }
+      else if (patience > 0) --patience;
+      else { mode = 1; continue; }
       BIK_SYNCWARP();
-      if (lane == 0) { if (rel < n) w.st[rel] = 0; else w.gst[rel - n] = 0; }
+      for (int i = lane; i < n; i += W) w.st[i] = w.idx[i];
+      for (int r = lane; r < np; r += W) w.gst[r] = w.gnew[r];
       BIK_SYNCWARP();
+      continue;
     }
+    // mode 2 -- ratio test: how far can xf move towards x before a bound of a free dof or an inactive general row stops it
+    T alpha = T(2);
+    int blk = 0x7fffffff;
+    for (int i = lane; i < n; i += W) {
+      if (w.st[i] != 0) continue;
+      const T xi = w.x[i], xo = w.xf[i], lo = w.lo[i], hi = w.hi[i];
+      const bool below = xi < lo - tolx * (T(1) + (lo < 0 ? -lo : lo));
+      const bool above = !below && xi > hi + tolx * (T(1) + (hi < 0 ? -hi : hi));
+      if (below || above) {
+        const T d = xi - xo;
+        T al = d != T(0) ? ((below ? lo : hi) - xo) / d : T(0);
+        al = al < T(0) ? T(0) : al;
+        if (al < alpha) { alpha = al; blk = i; }
+      }
+    }
+    for (int r = lane; r < np; r += W) {
+      const T hr = w.hg[r];
+      if (w.gst[r] || !(hr < T(1e30))) continue;
+      T gx = T(0), gf = T(0);
+      for (int j = 0; j < n; ++j) { const T gj = k2_grow<T>(a, gbase, r, n, j); gx += gj * w.x[j]; gf += gj * w.xf[j]; }
+      if (gx > hr + tolx * (T(1) + (hr < 0 ? -hr : hr))) {
+        const T d = gx - gf;
+        T al = d > T(0) ? (hr - gf) / d : T(0);
+        al = al < T(0) ? T(0) : al;
+        if (al < alpha) { alpha = al; blk = n + r; }
+      }
+    }
+    const T amin = warp_min_t<W, T>(alpha);
+    blk = warp_min_i<W>(alpha == amin ? blk : 0x7fffffff);   // ties: smallest index
+    BIK_SYNCWARP();   // every lane has read xf (the shuffles above already gather the lanes; this orders the memory accesses too)
+    if (amin < T(1.5)) {   // blocked: partial step, the blocking constraint joins the working set
+      const T al = amin > T(1) ? T(1) : amin;
+      for (int i = lane; i < n; i += W) if (w.st[i] == 0) w.xf[i] += al * (w.x[i] - w.xf[i]);
+      BIK_SYNCWARP();
+      if (blk < n) {
+        if (lane == 0) { const bool lower = w.x[blk] < w.lo[blk]; w.st[blk] = lower ? 1 : 2; w.xf[blk] = lower ? w.lo[blk] : w.hi[blk]; }
+      } else if (lane == 0) w.gst[blk - n] = 1;
+      BIK_SYNCWARP();
+      continue;
+    }
+    // feasible subspace minimiser: it becomes the iterate; let go of the constraint with the most negative multiplier
+    for (int i = lane; i < n; i += W) w.xf[i] = w.x[i];
+    T worst = -tolg;
+    int rel = 0x7fffffff;
+    for (int i = lane; i < n; i += W) {
+      const int cur = w.st[i];
+      if (cur == 0) continue;
+      T gi = k2_grad<T>(a, gbase, w, n, ng, i);
+      if (cur == 2) gi = -gi;   // now: gi < 0 means the bound wants to let go
+      if (gi < worst) { worst = gi; rel = i; }
+    }
+    for (int k = lane; k < ng; k += W) if (w.lam[k] < worst) { worst = w.lam[k]; rel = n + w.gidx[k]; }
+    const T wmin = warp_min_t<W, T>(worst);
+    rel = warp_min_i<W>(worst == wmin ? rel : 0x7fffffff);
+    if (rel == 0x7fffffff) { done = true; break; }
+    BIK_SYNCWARP();
+    if (lane == 0) { if (rel < n) w.st[rel] = 0; else w.gst[rel - n] = 0; }
+    BIK_SYNCWARP();
   }
   if (!done) status |= 2;
   if (a.warm) for (int i = lane; i < n; i += W) a.warm[(long long)b * n + i] = (signed char)w.st[i];
