@@ -323,6 +323,54 @@ def config_row(torch, model_cache, name, B, sigma, flush, seed=SEED0, oracle_sam
     return row
 
 
+def latency_row(torch, model_cache, name, flush, T=200):
+    """BASELINE configs[0]: ONE instance (the reference's interactive use) -- per-step latency, the regime where launch overhead
+    and not throughput decides.  Device time per step inside one bik_step(nsteps=T) call, and host wall time of one-step calls."""
+    from mink_b200.engine import DeviceModel, Problem
+
+    wl = WORKLOADS[name]
+    fm = load_flat(wl["robot"])
+    spec = spec_from_workload(fm, wl)
+    dev = flush.device
+    if wl["robot"] not in model_cache:
+        model_cache[wl["robot"]] = DeviceModel(fm, device=dev.index)
+    model = model_cache[wl["robot"]]
+    prob = Problem(model, spec)
+    frames = task_frames(wl, fm)
+
+    def fk(qq):
+        poses, com = model.fk(qq, frames, want_com=spec.ncom > 0)
+        return poses.cpu().numpy().astype(np.float64), (com.cpu().numpy().astype(np.float64) if com is not None else None)
+
+    inp = make_inputs(fm, wl, 1, fk, seed=SEED0)
+    f32 = lambda a: None if a is None else torch.tensor(np.ascontiguousarray(a), dtype=torch.float32, device=dev)
+    q0, ft, pt, ct = f32(inp["q"]), f32(inp["frame_targets"]), f32(inp["posture_target"]), f32(inp.get("com_target"))
+    q = q0.clone()
+    dq = torch.empty((1, fm.nv), device=dev, dtype=torch.float32)
+    status = torch.empty(1, device=dev, dtype=torch.int32)
+    kw = dict(dt=wl["dt"], damping=wl["damping"], integrate=True, dq=dq, status=status)
+    dev_ms = []
+    for rep in range(5):
+        q.copy_(q0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        prob.step(q, ft, pt, ct, nsteps=T, **kw)
+        b.record()
+        torch.cuda.synchronize()
+        dev_ms.append(a.elapsed_time(b))
+    walls = []
+    for rep in range(300):
+        t0 = time.perf_counter()
+        prob.step(q, ft, pt, ct, nsteps=1, **kw)
+        torch.cuda.synchronize()
+        walls.append(time.perf_counter() - t0)
+    prob.close()
+    return {"batch": 1, "timesteps": T, "us_per_step_device": 1e3 * statistics.median(dev_ms[1:]) / T,
+            "us_per_call_host_wall": 1e6 * statistics.median(walls[50:]), "mapping": None,
+            "note": "device: T steps inside one bik_step call (2 launches per step, no host round trip); host wall: one-step calls "
+                    "through the Python engine including the synchronize"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -569,11 +617,15 @@ def main():
     if extras and world == 1:
         cache = {wl["robot"]: model}
         per_config = {}
-        for cname, cB, sg in (("ur5e_dls", 4096, 0.1), ("shadow", 16384, 0.1), ("spot", 32768, 0.1), ("g1_full", 4096, 0.1)):
+        for cname, cB, sg in (("ur5e_dls", 4096, 0.1), ("shadow", 16384, 0.1), ("spot", 32768, 0.1), ("g1_full", 4096, 0.1), ("ur5e_wall", 16384, 0.1)):
             try:
                 per_config[cname] = config_row(torch, cache, cname, cB, sg, flush)
             except Exception as exc:
                 per_config[cname] = {"error": f"{type(exc).__name__}: {exc}"}
+        try:
+            per_config["ur5e_single_instance"] = latency_row(torch, cache, "ur5e", flush)
+        except Exception as exc:
+            per_config["ur5e_single_instance"] = {"error": f"{type(exc).__name__}: {exc}"}
         try:
             per_config["g1_few_active_bounds"] = config_row(torch, cache, "g1", 65536, 0.01, flush)   # delta ~ N(0, 0.01^2)
         except Exception as exc:
