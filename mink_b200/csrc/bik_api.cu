@@ -217,6 +217,7 @@ extern "C" int bik_problem_create(const bik_model* model, const bik_task_desc* t
   p->k2_general = path && (std::string(path) == "dense" || std::string(path) == "general");
   p->k2_group = env_int("BIK_K2_GROUP", p->h.nu > 8 ? 8 : 4) == 8 ? 8 : 4;
   p->k2_warps = env_int("BIK_K2_WARPS", 8);
+  p->k2_lanes = env_int("BIK_K2_LANES", 0);
   p->k2_dynamic = env_int("BIK_K2_DYNAMIC", 1) != 0;
   if (p->k2_warps != 1 && p->k2_warps != 2 && p->k2_warps != 4 && p->k2_warps != 8) p->k2_warps = 8;
   const char* k1p = getenv("BIK_K1_PRECISION");

@@ -116,28 +116,55 @@ template <> BIK_HD double bik_rsqrt<double>(double x) {
 #endif
 }
 
+// The lanes of one problem are W consecutive lanes of a warp (W = 32: the whole warp; W = 1 on the host).  Sub-warp groups
+// synchronise and shuffle among themselves only, so the groups of one warp may run different iteration counts.
+template <int W> BIK_HD unsigned k2_gmask() {
+#if defined(__CUDA_ARCH__)
+  if (W >= 32) return 0xffffffffu;
+  unsigned lane32;
+  asm("mov.u32 %0, %%laneid;" : "=r"(lane32));
+  return (W >= 32 ? 0u : ((1u << (W & 31)) - 1u)) << (lane32 & ~(unsigned)(W - 1));
+#else
+  return 0u;
+#endif
+}
+template <int W> BIK_HD void k2_sync() {
+#if defined(__CUDA_ARCH__)
+  __syncwarp(k2_gmask<W>());
+#endif
+}
 template <int W> BIK_HD int warp_sum_i(int v) {
 #if defined(__CUDA_ARCH__)
-  for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const unsigned m = k2_gmask<W>();
+  for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
 #endif
   return v;
 }
 template <int W> BIK_HD int warp_max_i(int v) {
 #if defined(__CUDA_ARCH__)
-  for (int o = W / 2; o > 0; o >>= 1) { int t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+  const unsigned m = k2_gmask<W>();
+  for (int o = W / 2; o > 0; o >>= 1) { int t = __shfl_xor_sync(m, v, o); v = t > v ? t : v; }
 #endif
   return v;
 }
 template <int W> BIK_HD int warp_min_i(int v) { return -warp_max_i<W>(-v); }
 template <int W, typename T> BIK_HD T warp_min_t(T v) {
 #if defined(__CUDA_ARCH__)
-  for (int o = W / 2; o > 0; o >>= 1) { T t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
+  const unsigned m = k2_gmask<W>();
+  for (int o = W / 2; o > 0; o >>= 1) { T t = __shfl_xor_sync(m, v, o); v = t < v ? t : v; }
 #endif
   return v;
 }
-template <typename T> BIK_HD T warp_bcast(T v, int src) {
+template <int W, typename T> BIK_HD T warp_sum_t(T v) {
 #if defined(__CUDA_ARCH__)
-  return __shfl_sync(0xffffffffu, v, src);
+  const unsigned m = k2_gmask<W>();
+  for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
+#endif
+  return v;
+}
+template <typename T, int W> BIK_HD T warp_bcast(T v, int src) {   // src: lane within the group
+#if defined(__CUDA_ARCH__)
+  return __shfl_sync(k2_gmask<W>(), v, src, W);
 #else
   (void)src;
   return v;
@@ -219,7 +246,7 @@ BIK_HD int k2_assemble(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int l
       w.wpk[tk.pk_off + k] = k < nj ? T(tk.cost[r]) * v : T(tk.cost[r]) * (T(-tk.gain) * v);
     }
   }
-  BIK_SYNCWARP();
+  k2_sync<W>();
   // block contributions (W J)^T (W J) and the linear term, lower triangle of the COUPLED block, per task over its non-zero columns
   for (int t = 0; t < h.F + h.C; ++t) {
     const K2Task tk = k2_task(P, t);
@@ -239,7 +266,7 @@ BIK_HD int k2_assemble(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int l
       for (int r = 0; r < tk.nr; ++r) cs += we[r] * blk[ia * tk.nr + r];
       w.c[umap[cols[tk.coff + ia] & 0xffff]] -= cs;
     }
-    BIK_SYNCWARP();
+    k2_sync<W>();
   }
   // Levenberg-Marquardt terms mu_t = lm_t ||W(-gain e)||^2 (task.py:131) -- every lane, same order
   T mu = T(a.damping);
@@ -257,9 +284,7 @@ BIK_HD int k2_assemble(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int l
     if (pr[1] != 0.f) {
       T s = T(0);
       for (int d = lane; d < n; d += W) { T v = T(pr[2 + d]) * T(pr[0]) * eperr(p, d); s += v * v; }
-#if defined(__CUDA_ARCH__)
-      for (int o = W / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-#endif
+      s = warp_sum_t<W, T>(s);
       mu += T(pr[1]) * s;
     }
   }
@@ -288,7 +313,7 @@ BIK_HD int k2_assemble(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int l
       if (a.Hout) { a.Hout[((long long)b * n + d) * n + d] = double(hd); a.cout[(long long)b * n + d] = double(cd); }
     }
   }
-  BIK_SYNCWARP();
+  k2_sync<W>();
   return status;
 }
 
@@ -310,7 +335,7 @@ BIK_NOINLINE int k2_factor(T* __restrict__ Lp, T* __restrict__ dinv, int nf, int
     if (!(d > T(0))) { bad = 1; d = T(1e-30); }
     dinv[0] = bik_rsqrt<T>(d);
   }
-  BIK_SYNCWARP();
+  k2_sync<W>();
 #pragma unroll 1
   for (int j = 0; j < nf; ++j) {
     const T* Lj = Lp + tri(j);
@@ -335,7 +360,7 @@ BIK_NOINLINE int k2_factor(T* __restrict__ Lp, T* __restrict__ dinv, int nf, int
         }
       }
     }
-    BIK_SYNCWARP();
+    k2_sync<W>();
   }
   return bad;
 }
@@ -353,13 +378,13 @@ BIK_NOINLINE void k2_backsub(const T* __restrict__ Lp, const T* __restrict__ din
     T cand = y[0];
 #pragma unroll
     for (int s = 1; s < SLOTS; ++s) if (ks == s) cand = y[s];
-    T xk = warp_bcast<T>(cand, kl) * dinv[k];
+    T xk = warp_bcast<T, W>(cand, kl) * dinv[k];
     if (lane == kl) out[k] = xk;
     const T* Lk = Lp + tri(k);
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) { int i = lane + s * W; if (i < k) y[s] -= Lk[i] * xk; }
   }
-  BIK_SYNCWARP();
+  k2_sync<W>();
 }
 // y <- L^-1 y for a separate vector (general-row path only)
 template <typename T, int W>
@@ -367,11 +392,11 @@ BIK_NOINLINE void k2_forward(const T* Lp, const T* dinv, T* y, int nf, int lane)
   BIK_IN_SHARED(Lp); BIK_IN_SHARED(dinv); BIK_IN_SHARED(y);
   for (int k = 0; k < nf; ++k) {
     if (k % W == lane) y[k] = y[k] * dinv[k];
-    BIK_SYNCWARP();
+    k2_sync<W>();
     T yk = y[k];
     for (int i = lane; i < nf; i += W) if (i > k) y[i] -= Lp[tri(i) + k] * yk;
   }
-  BIK_SYNCWARP();
+  k2_sync<W>();
 }
 
 // element j of collision row r of instance b
@@ -394,7 +419,7 @@ BIK_NOINLINE int k2_general_rows(const K2Ws<T> w, const K2Args& a, long long gba
     if (nf < n) {   // some dofs sit on their bounds: move their part of the row to the right-hand side
       if (lane == 0) { T sv = hg[gidx[r]]; for (int j = 0; j < n; ++j) if (st[j]) sv -= k2_grow<T>(a, gbase, gidx[r], n, j) * x[j]; rg[r] = sv; }
     } else if (lane == 0) rg[r] = hg[gidx[r]];
-    BIK_SYNCWARP();
+    k2_sync<W>();
     k2_forward<T, W>(w.Lp, w.dinv, Yr, nf, lane);
   }
   // S = Y Y^T and the right-hand side Y (L^-1 y) - rhs: one (r, q) entry per lane
@@ -407,7 +432,7 @@ BIK_NOINLINE int k2_general_rows(const K2Ws<T> w, const K2Args& a, long long gba
     for (int i = 0; i < nf; ++i) v += Yr[i] * Yq[i];
     if (q2 >= 0) { S[r * mg + q2] = v; S[q2 * mg + r] = v; } else lam[r] = v - rg[r];
   }
-  BIK_SYNCWARP();
+  k2_sync<W>();
   if (lane == 0) {  // tiny dense solve, serial
     for (int j = 0; j < ng; ++j) {  // Cholesky of S in place + solve
       const T sjj = S[j * mg + j];
@@ -419,9 +444,9 @@ BIK_NOINLINE int k2_general_rows(const K2Ws<T> w, const K2Args& a, long long gba
     for (int i = 0; i < ng; ++i) { T v = lam[i]; for (int k = 0; k < i; ++k) v -= S[i * mg + k] * lam[k]; lam[i] = v / S[i * mg + i]; }
     for (int i = ng - 1; i >= 0; --i) { T v = lam[i]; for (int k = i + 1; k < ng; ++k) v -= S[k * mg + i] * lam[k]; lam[i] = v / S[i * mg + i]; }
   }
-  BIK_SYNCWARP();
+  k2_sync<W>();
   for (int i = lane; i < nf; i += W) { T v = rhs[i]; for (int r = 0; r < ng; ++r) v -= Y[r * n + i] * lam[r]; rhs[i] = v; }
-  BIK_SYNCWARP();
+  k2_sync<W>();
   return warp_max_i<W>(bad);
 }
 
@@ -446,10 +471,10 @@ BIK_HD int k2_solve_working_set(const PHeader& h, const K2Args& a, long long gba
   for (int i = 0; i < n; ++i) if (w.st[i] == 0) { w.idx[nf] = i; ++nf; if (i < 63) key |= 1ull << i; }
   const bool reuse = key != 0ull && key == *fkey;
   for (int r = 0; r < np; ++r) if (w.gst[r]) { if (ng < mg) { w.gidx[ng] = r; ++ng; } else status |= 2; }
-  BIK_SYNCWARP();
+  k2_sync<W>();
   // x on the bounds, rhs of the reduced system, copy of H_FF
   for (int i = lane; i < n; i += W) w.x[i] = w.st[i] == 1 ? w.lo[i] : (w.st[i] == 2 ? w.hi[i] : T(0));
-  BIK_SYNCWARP();
+  k2_sync<W>();
   T* rhs = w.Lp + tri(nf);
   for (int i = lane; i < nf; i += W) {
     int ii = w.idx[i];
@@ -463,7 +488,7 @@ BIK_HD int k2_solve_working_set(const PHeader& h, const K2Args& a, long long gba
       for (int j = 0; j <= i; ++j) Li[j] = Hrow[w.idx[j]];
     }
   }
-  BIK_SYNCWARP();
+  k2_sync<W>();
   if (reuse) k2_forward<T, W>(w.Lp, w.dinv, rhs, nf, lane);
   else if (k2_factor<T, W, SLOTS>(w.Lp, w.dinv, nf, lane)) status |= 4;
   *fkey = key;
@@ -472,7 +497,7 @@ BIK_HD int k2_solve_working_set(const PHeader& h, const K2Args& a, long long gba
   // x_F = L^-T (.), overwriting the rhs row in place
   k2_backsub<T, W, SLOTS>(w.Lp, w.dinv, nf, rhs, lane);
   for (int i = lane; i < nf; i += W) w.x[w.idx[i]] = rhs[i];
-  BIK_SYNCWARP();
+  k2_sync<W>();
   *ng_out = ng;
   return status;
 }
@@ -501,7 +526,7 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
     w.st[i] = s0;
   }
   for (int r = lane; r < np; r += W) { w.gst[r] = 0; w.hg[r] = ldin<T>(a.hc, (long long)b * np + r, a.gc64); }
-  BIK_SYNCWARP();
+  k2_sync<W>();
   int status = 0, best = n + np + 1, patience = PATIENCE, it = 0, ng = 0;
   unsigned long long fkey = 0ull;
   bool done = n == 0;
@@ -510,7 +535,7 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
   int mode = 0;
   while (!done && it < MAXIT) {
     if (mode == 1) {
-      BIK_SYNCWARP();
+      k2_sync<W>();
       for (int i = lane; i < n; i += W) {   // clip(0, lo, hi); a bound that holds the iterate is in the working set
         T v = T(0);
         int s0 = 0;
@@ -518,7 +543,7 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
         if (w.hi[i] < v) { v = w.hi[i]; s0 = 2; }
         w.xf[i] = v; w.st[i] = s0;
       }
-      BIK_SYNCWARP();
+      k2_sync<W>();
       int infeas = 0;
       for (int r = lane; r < np; r += W) {
         w.gst[r] = 0;
@@ -530,7 +555,7 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
         }
       }
       if (warp_max_i<W>(infeas)) status |= 8;   // no feasible starting point: limits inconsistent with the collision rows
-      BIK_SYNCWARP();
+      k2_sync<W>();
       mode = 2;
       if (status & 8) break;
     }
@@ -577,10 +602,10 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
       if (ninf < best) { best = ninf; patience = PATIENCE; }
       else if (patience > 0) --patience;
       else { mode = 1; continue; }
-      BIK_SYNCWARP();
+      k2_sync<W>();
       for (int i = lane; i < n; i += W) w.st[i] = w.idx[i];
       for (int r = lane; r < np; r += W) w.gst[r] = w.gnew[r];
-      BIK_SYNCWARP();
+      k2_sync<W>();
       continue;
     }
     // mode 2 -- ratio test: how far can xf move towards x before a bound of a free dof or an inactive general row stops it
@@ -612,15 +637,15 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
     }
     const T amin = warp_min_t<W, T>(alpha);
     blk = warp_min_i<W>(alpha == amin ? blk : 0x7fffffff);   // ties: smallest index
-    BIK_SYNCWARP();   // every lane has read xf (the shuffles above already gather the lanes; this orders the memory accesses too)
+    k2_sync<W>();   // every lane has read xf (the shuffles above already gather the lanes; this orders the memory accesses too)
     if (amin < T(1.5)) {   // blocked: partial step, the blocking constraint joins the working set
       const T al = amin > T(1) ? T(1) : amin;
       for (int i = lane; i < n; i += W) if (w.st[i] == 0) w.xf[i] += al * (w.x[i] - w.xf[i]);
-      BIK_SYNCWARP();
+      k2_sync<W>();
       if (blk < n) {
         if (lane == 0) { const bool lower = w.x[blk] < w.lo[blk]; w.st[blk] = lower ? 1 : 2; w.xf[blk] = lower ? w.lo[blk] : w.hi[blk]; }
       } else if (lane == 0) w.gst[blk - n] = 1;
-      BIK_SYNCWARP();
+      k2_sync<W>();
       continue;
     }
     // feasible subspace minimiser: it becomes the iterate; let go of the constraint with the most negative multiplier
@@ -638,9 +663,9 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
     const T wmin = warp_min_t<W, T>(worst);
     rel = warp_min_i<W>(worst == wmin ? rel : 0x7fffffff);
     if (rel == 0x7fffffff) { done = true; break; }
-    BIK_SYNCWARP();
+    k2_sync<W>();
     if (lane == 0) { if (rel < n) w.st[rel] = 0; else w.gst[rel - n] = 0; }
-    BIK_SYNCWARP();
+    k2_sync<W>();
   }
   if (!done) status |= 2;
   if (a.warm) for (int i = lane; i < n; i += W) a.warm[(long long)b * n + i] = (signed char)w.st[i];
@@ -680,7 +705,7 @@ BIK_HD void k2_warp(const PView& P, const K2Args& a, int b, void* wsm, int lane)
     if (a.status) a.status[b] |= st;
     if (a.iters) a.iters[b] = iters;
   }
-  BIK_SYNCWARP();
+  k2_sync<W>();
   if (a.integrate) {   // q <- q (+) dq, node by node (mj_integratePos); fp32 callers: the sum is rounded once
     for (int nn = lane; nn < h.nnode; nn += W) {
       const NodeRec& r = P.node(nn);
@@ -690,7 +715,7 @@ BIK_HD void k2_warp(const PView& P, const K2Args& a, int b, void* wsm, int lane)
       integrate_node<T>(r, qn - r.qadr, w.xfull);
       for (int k = 0; k < nqn; ++k) stout<T>(const_cast<void*>(a.q), (long long)b * nq + r.qadr + k, a.io64, qn[k]);
     }
-    BIK_SYNCWARP();
+    k2_sync<W>();
   }
 }
 
