@@ -260,6 +260,7 @@ extern "C" void bik_problem_destroy(bik_problem* p) {
   if (p->conv_host) cudaFreeHost(p->conv_host);
   for (int i = 0; i < 4; ++i) if (p->hs[i]) cudaStreamDestroy(p->hs[i]);
   for (cudaEvent_t e : p->hev) cudaEventDestroy(e);
+  if (p->ws_event) cudaEventDestroy(p->ws_event);
   delete p;
 }
 extern "C" int bik_problem_dims(const bik_problem* p, bik_dims* out) {
@@ -403,6 +404,19 @@ extern "C" int bik_limits_box64(const bik_problem* p, int B, const double* q, do
   return box_common(p, B, q, dt, lo, hi, 1, stream);
 }
 
+// Cross-stream ordering of the per-problem workspace (callers hold p->mu).
+static int ws_acquire(bik_problem* p, cudaStream_t st) {
+  if (p->ws_pending && p->ws_stream != st) CUDA_OK(cudaStreamWaitEvent(st, p->ws_event, 0));
+  return BIK_OK;
+}
+static int ws_release(bik_problem* p, cudaStream_t st, int rc) {
+  if (rc) return rc;
+  if (!p->ws_event) CUDA_OK(cudaEventCreateWithFlags(&p->ws_event, cudaEventDisableTiming));
+  CUDA_OK(cudaEventRecord(p->ws_event, st));
+  p->ws_stream = st; p->ws_pending = 1;
+  return BIK_OK;
+}
+
 static int solve_common(const bik_problem* cp, int B, const void* q, const void* J, const void* e, const void* e_posture, const void* G_coll,
                         const void* h_coll, double dt, double damping, void* dq, int32_t* status, int32_t* iters, int f64, void* stream) {
   if (!cp || !q || !dq || B < 0) return bik_fail(BIK_ERR_INVALID, "null argument");
@@ -417,7 +431,10 @@ static int solve_common(const bik_problem* cp, int B, const void* q, const void*
   a.dt = dt; a.damping = damping; a.dq = dq; a.status = status; a.iters = iters;
   if (status) CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, static_cast<cudaStream_t>(stream)));
   std::lock_guard<std::mutex> lock(p->mu);
-  return dispatch_k2(p, a, static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = ws_acquire(p, st);   // the tile counters live in the problem
+  if (rc) return rc;
+  return ws_release(p, st, dispatch_k2(p, a, st));
 }
 extern "C" int bik_solve_ex(const bik_problem* p, int B, const float* q, const float* J, const float* e, const float* e_posture, const float* G_coll,
                             const float* h_coll, float dt, double damping, float* dq, int32_t* status, int32_t* iters, void* stream) {
@@ -529,8 +546,10 @@ static int step_common(const bik_problem* cp, int B, void* q, const bik_inputs* 
   rc = ensure_workspace(p, B, k1d ? 8 : 4);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = ws_acquire(p, st);
+  if (rc) return rc;
   // (status needs no clearing: K1's fused check_limits assigns it on the first step, everything later ORs into it)
-  return step_core(p, B, 0, q, in, dt, damping, nsteps, integrate, dq, status, f64, k1d, st);
+  return ws_release(p, st, step_core(p, B, 0, q, in, dt, damping, nsteps, integrate, dq, status, f64, k1d, st));
 }
 extern "C" int bik_step(const bik_problem* p, int B, float* q, const bik_inputs* in, float dt, double damping, int nsteps, int integrate, float* dq,
                         int32_t* status, void* stream) {
@@ -623,6 +642,8 @@ extern "C" int bik_converge(const bik_problem* cp, int B, float* q, const bik_in
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const PHeader& h = p->h;
+  rc = ws_acquire(p, st);
+  if (rc) return rc;
   if ((size_t)B > p->conv_B) {
     conv_graph_drop(p);   // the cached graph captured the old buffers
     cudaFree(p->conv_done); cudaFree(p->conv_dq);
@@ -708,7 +729,7 @@ extern "C" int bik_converge(const bik_problem* cp, int B, float* q, const bik_in
   // instances that never met the thresholds: iters = max_iters, status bit BIK_STATUS_NOT_CONVERGED
   converge_finish_kernel<<<blocks, 128, 0, st>>>(B, max_iters, p->conv_done, iters, status);
   CUDA_OK(cudaGetLastError());
-  return BIK_OK;
+  return ws_release(p, st, BIK_OK);
 }
 
 // Host-buffer variant: device staging lives in the problem (separate allocations).  The batch is cut into chunks that flow
@@ -728,6 +749,7 @@ extern "C" int bik_step_host(const bik_problem* cp, int B, float* q_host, const 
   size_t nq = h.nq, nv = h.nv, b = (size_t)B;
   size_t pt_elems = (in->posture_batched ? b : 1) * (size_t)h.P * nq;
   std::lock_guard<std::mutex> lock(p->mu);
+  if (p->ws_pending) { CUDA_OK(cudaEventSynchronize(p->ws_event)); p->ws_pending = 0; }   // this call runs on the problem's own streams
   if (b > p->host_B || pt_elems > p->host_pt_elems) {
     CUDA_OK(cudaDeviceSynchronize());
     cudaFree(p->hq); cudaFree(p->hft); cudaFree(p->hpt); cudaFree(p->hct); cudaFree(p->hdq); cudaFree(p->hst);

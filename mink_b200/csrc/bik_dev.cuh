@@ -88,6 +88,11 @@ struct bik_problem {
   int ws_elem = 0;        // element size the hand-off buffers were sized for (4 or 8)
   void *pk = nullptr, *Gc = nullptr, *hc = nullptr;
   signed char* warm = nullptr;          // [B][nu] active-set guess carried between the steps of one bik_step call
+  // the hand-off buffers, tile counters and the warm start belong to the problem, not to a stream: a call on another stream
+  // than the previous one first waits for that call's kernels (event recorded at the end of every call that uses them)
+  cudaEvent_t ws_event = nullptr;
+  cudaStream_t ws_stream = nullptr;
+  int ws_pending = 0;
   unsigned int* d_sched = nullptr;      // BIK_SCHED_SLOTS x 32 words: {next tile, finished CTAs} per launching stream (own 128-byte line each)
   cudaStream_t sched_stream[BIK_SCHED_SLOTS];
   int n_sched = 0;

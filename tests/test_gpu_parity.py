@@ -587,3 +587,33 @@ def test_converge_device_loop_matches_host_polled_loop():
         for a, b in zip(out[("1", thr)], out[("0", thr)]):
             np.testing.assert_array_equal(a, b)
     assert (out[("1", 5e-3)][0] <= out[("1", 2e-3)][0]).all() and (out[("1", 5e-3)][0] < out[("1", 2e-3)][0]).any()
+
+
+def test_one_problem_used_from_two_streams():
+    """The K1 -> K2 hand-off buffers, tile counters and warm start belong to the problem handle: calls issued on different
+    streams must not overlap on them (each call waits for the event the previous one recorded)."""
+    _need_gpu()
+    wl, fm, spec, g, model, prob = _engine("g1")
+    orc = _oracle(fm, spec)
+    frames = task_frames(wl, fm)
+    B = 20000
+    sets = [make_inputs(fm, wl, B, lambda qq: orc.fk(qq, frames), seed=s) for s in (21, 22)]
+    dev = [dict(q=torch.tensor(i["q"], dtype=torch.float32, device="cuda:0"),
+                ft=torch.tensor(i["frame_targets"], dtype=torch.float32, device="cuda:0")) for i in sets]
+    ref = []
+    for d, i in zip(dev, sets):
+        q = d["q"].clone()
+        dq, st = prob.step(q, d["ft"], i["posture_target"], None, dt=wl["dt"], damping=wl["damping"], nsteps=3, integrate=True)
+        ref.append((_np(dq), _np(q)))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for rep in range(4):
+        outs = []
+        for s, d, i in zip(streams, dev, sets):
+            with torch.cuda.stream(s):
+                q = d["q"].clone()
+                dq, st = prob.step(q, d["ft"], i["posture_target"], None, dt=wl["dt"], damping=wl["damping"], nsteps=3, integrate=True)
+                outs.append((dq, q))
+        torch.cuda.synchronize()
+        for (dq, q), (dq_ref, q_ref) in zip(outs, ref):
+            assert np.array_equal(_np(dq), dq_ref) and np.array_equal(_np(q), q_ref)
