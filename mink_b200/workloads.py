@@ -15,6 +15,9 @@ import numpy as np
 
 PI = float(np.pi)
 
+# Example robots of the reference beyond the BASELINE configs (goldens tests/golden/<name>.npz, models mink_b200/models/<name>.*)
+EXAMPLE_ROBOTS = ["iiwa", "h1", "go1", "stretch", "tidybot", "aloha"]
+
 WORKLOADS: Dict[str, dict] = {
     # BASELINE config 1: UR5e single instance, FrameTask + PostureTask + ConfigurationLimit
     # (examples/arm_ur5e.py:20-28,66,74: dt = 1/500, damping 1e-3, lm_damping 1).
@@ -125,6 +128,57 @@ WORKLOADS: Dict[str, dict] = {
                 dict(kind="collision", pairs=[(["wrist_3_link"], ["floor", "wall"])],
                      gain=0.85, minimum_distance=0.005, detection_distance=0.5, bound_relaxation=0.0)],
         dt=2e-3, damping=1e-3, batch=1024,
+    ),
+    # ---- the reference's other example robots (not BASELINE configs): task sets as in examples/*.py, default limits -------
+    # examples/arm_iiwa.py:24-33,64 (7-dof arm).
+    "iiwa": dict(
+        robot="iiwa", scene="kuka_iiwa_14/scene.xml", key="home",
+        frames=[dict(name="attachment_site", type="site", position_cost=1.0, orientation_cost=1.0, lm_damping=1.0)],
+        posture=dict(cost=1e-2), com=None, limits=[dict(kind="configuration", gain=0.95)],
+        dt=5e-3, damping=1e-3, batch=4096,
+    ),
+    # examples/humanoid_h1.py:20-54,88 (floating base, CoM task, feet and wrists).
+    "h1": dict(
+        robot="h1", scene="unitree_h1/scene.xml", key="stand",
+        frames=[dict(name="pelvis", type="body", position_cost=0.0, orientation_cost=10.0, lm_damping=0.0),
+                dict(name="right_foot", type="site", position_cost=200.0, orientation_cost=10.0, lm_damping=1.0),
+                dict(name="left_foot", type="site", position_cost=200.0, orientation_cost=10.0, lm_damping=1.0),
+                dict(name="right_wrist", type="site", position_cost=200.0, orientation_cost=0.0, lm_damping=1.0),
+                dict(name="left_wrist", type="site", position_cost=200.0, orientation_cost=0.0, lm_damping=1.0)],
+        posture=dict(cost=1.0), com=dict(cost=200.0), limits=[dict(kind="configuration", gain=0.95)],
+        dt=5e-3, damping=1e-1, batch=4096,
+    ),
+    # examples/quadruped_go1.py:19-38,70 (floating base, trunk + four feet, posture cost 1e-5, damping 1e-5).
+    "go1": dict(
+        robot="go1", scene="unitree_go1/scene.xml", key="home",
+        frames=[dict(name="trunk", type="body", position_cost=1.0, orientation_cost=1.0, lm_damping=0.0)] +
+               [dict(name=f, type="site", position_cost=1.0, orientation_cost=0.0, lm_damping=0.0) for f in ("FL", "FR", "RR", "RL")],
+        posture=dict(cost=1e-5), com=None, limits=[dict(kind="configuration", gain=0.95)],
+        dt=5e-3, damping=1e-5, batch=4096,
+    ),
+    # examples/mobile_stretch.py:18-33,73 (mobile base + lift / telescoping SLIDE joints; no posture task).
+    "stretch": dict(
+        robot="stretch", scene="hello_robot_stretch_3/scene.xml", key="home",
+        frames=[dict(name="base_link", type="body", position_cost=0.1, orientation_cost=1.0, lm_damping=0.0),
+                dict(name="link_grasp_center", type="site", position_cost=1.0, orientation_cost=1e-4, lm_damping=0.0)],
+        posture=None, com=None, limits=[dict(kind="configuration", gain=0.95)],
+        dt=1e-2, damping=1e-3, batch=4096,
+    ),
+    # examples/mobile_tidybot.py:45-70,111 (planar base + 7-dof arm + gripper; per-dof posture cost: 0 on the base dofs).
+    "tidybot": dict(
+        robot="tidybot", scene="stanford_tidybot/scene.xml", key="home",
+        frames=[dict(name="pinch_site", type="site", position_cost=1.0, orientation_cost=1.0, lm_damping=1.0)],
+        posture=dict(cost=[0.0] * 3 + [1e-3] * 15), com=None, limits=[dict(kind="configuration", gain=0.95)],
+        dt=1e-2, damping=1e-3, batch=4096,
+    ),
+    # examples/arm_aloha.py:75-115,153 (two 6-dof arms + grippers; configuration + velocity limits; the example's collision
+    # pairs include mesh geoms and are left out).
+    "aloha": dict(
+        robot="aloha", scene="aloha/scene.xml", key="neutral_pose",
+        frames=[dict(name="left/gripper", type="site", position_cost=1.0, orientation_cost=1.0, lm_damping=1.0),
+                dict(name="right/gripper", type="site", position_cost=1.0, orientation_cost=1.0, lm_damping=1.0)],
+        posture=dict(cost=1e-4), com=None, limits=[dict(kind="configuration", gain=0.95), dict(kind="velocity", vmax=PI)],
+        dt=5e-3, damping=1e-5, batch=4096,
     ),
     # Not a BASELINE config: edge-case model authored for this repository (mink_b200/models/edge.xml):
     # ball joint with off-centre anchor, slide joint with ref, two joints on one body, a second floating

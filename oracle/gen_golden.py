@@ -26,7 +26,7 @@ from mink_b200.flatten import flatten  # noqa: E402
 from mink_b200.workloads import WORKLOADS, make_inputs  # noqa: E402
 
 OUT = os.path.join(REPO, "tests", "golden")
-GOLDEN_B = {"ur5e_wall": 24, "ur5e_damp": 12, "ur5e": 8, "ur5e_dls": 16, "g1": 32, "shadow": 24, "spot": 24, "g1_rel": 16, "edge": 48, "g1_full": 16, "g1_hands": 24}
+GOLDEN_B = {"iiwa": 8, "h1": 8, "go1": 8, "stretch": 8, "tidybot": 8, "aloha": 8, "ur5e_wall": 24, "ur5e_damp": 12, "ur5e": 8, "ur5e_dls": 16, "g1": 32, "shadow": 24, "spot": 24, "g1_rel": 16, "edge": 48, "g1_full": 16, "g1_hands": 24}
 ROLLOUT_T, ROLLOUT_B = 8, 4
 CONV_B, CONV_MAX_ITERS, CONV_POS, CONV_ORI = 8, 20, 2e-3, 2e-3
 
@@ -81,7 +81,7 @@ def main():
         scene = os.path.join(REPO, wl["scene"][1:]) if wl["scene"].startswith("@") else os.path.join(REF, "examples", wl["scene"])
         model = mujoco.MjModel.from_xml_path(scene)
         fm = flatten(model)
-        if wl["robot"] not in done_models and not only:
+        if wl["robot"] not in done_models and (not only or not os.path.exists(os.path.join(MODELS, wl["robot"] + ".bikm"))):
             with open(os.path.join(MODELS, wl["robot"] + ".bikm"), "wb") as f:
                 f.write(fm.to_blob())
             with open(os.path.join(MODELS, wl["robot"] + ".json"), "w") as f:
