@@ -14,6 +14,8 @@ from .exceptions import (InvalidDamping, InvalidFrame, InvalidGain, InvalidKeyfr
 from .lie import SE3, SO3, MatrixLieGroup
 from .mjcf import Model
 from .flatten import FlatModel, flatten
+from .utils import (custom_configuration_vector, get_body_body_ids, get_body_geom_ids, get_freejoint_dims,
+                    get_subtree_body_ids, get_subtree_geom_ids)
 
 
 def __getattr__(name):
