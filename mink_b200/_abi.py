@@ -219,6 +219,9 @@ def _collision_pairs(fm: FlatModel, groups, names: List[str]):
                 pb = fm.node_parent[nb] if nb >= 0 else -2
                 if pa == nb or pb == na:
                     continue
+                if fm.geom_contype is not None and not ((fm.geom_contype[a] & fm.geom_conaffinity[b]) or
+                                                        (fm.geom_contype[b] & fm.geom_conaffinity[a])):
+                    continue   # contype / conaffinity filter (collision_avoidance_limit.py:269-278)
                 out.append((min(a, b), max(a, b)))
     return out
 
@@ -260,7 +263,9 @@ def spec_from_workload(fm: FlatModel, wl: dict) -> ProblemSpec:
             limits.append(LimitSpec(LIMIT_VELOCITY, dof=dof, vmax=np.full(len(dof), float(l["vmax"]))))
         elif l["kind"] == "collision":
             names = fm.names["geom"]
-            id_pairs = _collision_pairs(fm, l["pairs"], names)
+            from .workloads import resolve_geom_groups
+
+            id_pairs = _collision_pairs(fm, resolve_geom_groups(fm, l["pairs"]), names)
             used = sorted({g for p in id_pairs for g in p})
             local = {g: i for i, g in enumerate(used)}
             geoms = [(int(fm.geom_type[g]), fm.geom_frames[g], fm.geom_size[g]) for g in used]

@@ -97,6 +97,10 @@ class FlatModel:
     key_qpos: np.ndarray = None
     com_missing: list = None   # bodies of subtree(body 1) whose mass the MJCF compiler could not derive (no <inertial>)
     geom_type: np.ndarray = None
+    body_parentid: np.ndarray = None      # MJCF body tree and geom -> body map: what mink_b200.utils walks; None: not recorded
+    geom_bodyid: np.ndarray = None
+    geom_contype: np.ndarray = None       # collision filter bits (collision_avoidance_limit.py:269-278); None: not recorded
+    geom_conaffinity: np.ndarray = None
     geom_size: np.ndarray = None
     jnt_limited: np.ndarray = None
     jnt_range: np.ndarray = None
@@ -155,7 +159,11 @@ class FlatModel:
             geom_frames=fr(self.geom_frames), key_qpos=self.key_qpos.tolist(),
             geom_type=self.geom_type.tolist(), geom_size=self.geom_size.tolist(),
             jnt_limited=[int(x) for x in self.jnt_limited], jnt_range=self.jnt_range.tolist(),
-            com_missing=list(self.com_missing or [])))
+            com_missing=list(self.com_missing or []),
+            body_parentid=None if self.body_parentid is None else [int(x) for x in self.body_parentid],
+            geom_bodyid=None if self.geom_bodyid is None else [int(x) for x in self.geom_bodyid],
+            geom_contype=None if self.geom_contype is None else [int(x) for x in self.geom_contype],
+            geom_conaffinity=None if self.geom_conaffinity is None else [int(x) for x in self.geom_conaffinity]))
 
     @classmethod
     def from_blob(cls, blob: bytes, meta_json: str = None) -> "FlatModel":
@@ -185,7 +193,30 @@ class FlatModel:
             fm.geom_size = np.array(meta["geom_size"]).reshape(-1, 3)
             fm.jnt_limited = np.array(meta["jnt_limited"], dtype=bool)
             fm.jnt_range = np.array(meta["jnt_range"]).reshape(-1, 2)
+            if meta.get("body_parentid") is not None:
+                fm.body_parentid = np.array(meta["body_parentid"], dtype=np.int32)
+                fm.geom_bodyid = np.array(meta["geom_bodyid"], dtype=np.int32)
+            if meta.get("geom_contype") is not None:
+                fm.geom_contype = np.array(meta["geom_contype"], dtype=np.int32)
+                fm.geom_conaffinity = np.array(meta["geom_conaffinity"], dtype=np.int32)
         return fm
+
+    # what mink_b200.utils needs of an MjModel (geoms of one body are contiguous in MuJoCo's tables)
+    @property
+    def nbody(self) -> int:
+        return len(self.body_parentid)
+
+    @property
+    def body_geomnum(self) -> np.ndarray:
+        return np.bincount(self.geom_bodyid, minlength=self.nbody).astype(np.int32)
+
+    @property
+    def body_geomadr(self) -> np.ndarray:
+        num = self.body_geomnum
+        first = np.full(self.nbody, -1, dtype=np.int32)
+        for g in range(len(self.geom_bodyid) - 1, -1, -1):
+            first[self.geom_bodyid[g]] = g
+        return np.where(num > 0, first, -1).astype(np.int32)
 
     def key(self, name: str) -> np.ndarray:
         return self.key_qpos[self.names["key"].index(name)].copy()
@@ -294,6 +325,11 @@ def flatten(model) -> FlatModel:
     fm.key_qpos = np.asarray(model.key_qpos, dtype=np.float64).reshape(-1, nq).copy()
     fm.com_missing = com_missing
     fm.geom_type = np.asarray(model.geom_type).astype(np.int32)
+    fm.body_parentid = np.asarray(model.body_parentid).astype(np.int32)
+    fm.geom_bodyid = np.asarray(model.geom_bodyid).astype(np.int32)
+    if getattr(model, "geom_contype", None) is not None:
+        fm.geom_contype = np.asarray(model.geom_contype).astype(np.int32)
+        fm.geom_conaffinity = np.asarray(model.geom_conaffinity).astype(np.int32)
     fm.geom_size = np.asarray(model.geom_size, dtype=np.float64).reshape(-1, 3).copy()
     fm.jnt_limited = limited.copy()
     fm.jnt_range = rng.copy()

@@ -180,6 +180,20 @@ WORKLOADS: Dict[str, dict] = {
         posture=dict(cost=1e-4), com=None, limits=[dict(kind="configuration", gain=0.95), dict(kind="velocity", vmax=PI)],
         dt=5e-3, damping=1e-5, batch=4096,
     ),
+    # examples/arm_aloha.py as written: the same tasks and limits PLUS its CollisionAvoidanceLimit (:95-110) -- wrist subtree
+    # against wrist subtree, both arm subtrees against the metal frame and the table: 1 104 geom pairs after the reference's
+    # filtering (capsule-capsule, sphere-capsule, sphere-sphere, box-capsule, box-sphere).
+    "aloha_coll": dict(
+        robot="aloha", scene="aloha/scene.xml", key="neutral_pose",
+        frames=[dict(name="left/gripper", type="site", position_cost=1.0, orientation_cost=1.0, lm_damping=1.0),
+                dict(name="right/gripper", type="site", position_cost=1.0, orientation_cost=1.0, lm_damping=1.0)],
+        posture=dict(cost=1e-4), com=None,
+        limits=[dict(kind="configuration", gain=0.95), dict(kind="velocity", vmax=PI),
+                dict(kind="collision", pairs=[(["subtree:left/wrist_link"], ["subtree:right/wrist_link"]),
+                                              (["subtree:left/upper_arm_link", "subtree:right/upper_arm_link"], ["body:metal_frame", "table"])],
+                     gain=0.85, minimum_distance=0.05, detection_distance=0.1, bound_relaxation=0.0)],
+        dt=5e-3, damping=1e-5, batch=1024,
+    ),
     # Not a BASELINE config: edge-case model authored for this repository (mink_b200/models/edge.xml):
     # ball joint with off-centre anchor, slide joint with ref, two joints on one body, a second floating
     # root, capsule/sphere/plane collision pairs, every task and limit kind at once.
@@ -196,6 +210,30 @@ WORKLOADS: Dict[str, dict] = {
         dt=1e-2, damping=1e-3, batch=1024,
     ),
 }
+
+
+def resolve_geom_groups(model, groups):
+    """Collision groups of a workload: plain geom names / ids, or "subtree:<body>" / "body:<body>" for what the reference's
+    examples build with get_subtree_geom_ids / get_body_geom_ids (examples/arm_aloha.py:95-102).  `model` is a FlatModel, a
+    mink_b200.Model or an MjModel-like object."""
+    from .utils import get_body_geom_ids, get_subtree_geom_ids
+
+    def body_id(name):
+        names = getattr(model, "names", None)
+        return names["body"].index(name) if isinstance(names, dict) else model.body(name).id
+
+    def expand(group):
+        out = []
+        for g in group:
+            if isinstance(g, str) and g.startswith("subtree:"):
+                out += get_subtree_geom_ids(model, body_id(g[8:]))
+            elif isinstance(g, str) and g.startswith("body:"):
+                out += get_body_geom_ids(model, body_id(g[5:]))
+            else:
+                out.append(g)
+        return out
+
+    return [(expand(a), expand(b)) for a, b in groups]
 
 
 def _quat_exp(w: np.ndarray) -> np.ndarray:
