@@ -203,6 +203,27 @@ def test_collision_limit_against_box_wall_ur5e():
             bad.compute_qp_inequalities(cfg, 0.01)
 
 
+def test_aloha_example_collision_limit_through_the_python_api():
+    """examples/arm_aloha.py:95-110 as a user would write it against this package: subtree / body geom groups from the utils
+    helpers, CollisionAvoidanceLimit over the resulting 1 104 pairs, rows against the reference's golden."""
+    wl, fm, spec, g = load_case("aloha_coll")
+    body = fm.names["body"].index
+    l_wrist = mink.get_subtree_geom_ids(fm, body("left/wrist_link"))
+    r_wrist = mink.get_subtree_geom_ids(fm, body("right/wrist_link"))
+    arms = mink.get_subtree_geom_ids(fm, body("left/upper_arm_link")) + mink.get_subtree_geom_ids(fm, body("right/upper_arm_link"))
+    frame = mink.get_body_geom_ids(fm, body("metal_frame"))
+    lim = mink.CollisionAvoidanceLimit(model=fm, geom_pairs=[(l_wrist, r_wrist), (arms, frame + ["table"])],
+                                       minimum_distance_from_collisions=0.05, collision_detection_distance=0.1)
+    assert lim.max_num_contacts == 1104
+    cfg = mink.Configuration(fm, g["q"])
+    con = lim.compute_qp_inequalities(cfg, float(g["dt"]))
+    Gr, hr = g["G"][:, -1104:], g["h"][:, -1104:]
+    fin = np.isfinite(hr)
+    assert fin.sum() >= 20 and np.array_equal(np.isfinite(_np(con.h)), fin)
+    np.testing.assert_allclose(_np(con.h)[fin], hr[fin], rtol=2e-4, atol=2e-3)
+    np.testing.assert_allclose(_np(con.G), Gr, atol=5e-5)
+
+
 def test_relative_frame_task_matches_reference_and_world_root_identity():
     """RelativeFrameTask vs the reference golden (g1_rel), and the reference's own cross-check
     (tests/test_relative_frame_task.py:128-154): with root = world it equals minus the FrameTask."""
