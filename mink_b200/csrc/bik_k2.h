@@ -517,7 +517,7 @@ template <typename T, int W, int SLOTS>
 BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane, int* iters_out) {
   const PHeader& h = P.h();
   const int n = h.nu, np = h.npairs;   // coupled dofs only (n == nv whenever there are general rows)
-  const int MAXIT = 60 + 2 * (n + np), PATIENCE = 2;
+  const int MAXIT = 60 + 2 * (n + k2_max_gen(h)), PATIENCE = 2;   // bounds + the general rows that may be active at once
   const T tolx = K2Tol<T>::x(), tolg = K2Tol<T>::g();
   const long long gbase = (long long)b * np * n;
   for (int i = lane; i < n; i += W) {
@@ -562,6 +562,7 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
     const int ws = k2_solve_working_set<T, W, SLOTS>(h, a, gbase, w, lane, &ng, &fkey);
     status |= ws & ~32;
     ++it;
+    if (ws & 2) break;   // more rows active than the working set holds: the answer is flagged, further iterations cannot repair it
     if (mode == 0) {
       if (ws & 32) { mode = 1; continue; }   // block flips activated dependent rows (the primal method never does)
       // gradient on the active bounds, feasibility of free variables and of general rows.

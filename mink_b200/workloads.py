@@ -192,7 +192,7 @@ WORKLOADS: Dict[str, dict] = {
                 dict(kind="collision", pairs=[(["subtree:left/wrist_link"], ["subtree:right/wrist_link"]),
                                               (["subtree:left/upper_arm_link", "subtree:right/upper_arm_link"], ["body:metal_frame", "table"])],
                      gain=0.85, minimum_distance=0.05, detection_distance=0.1, bound_relaxation=0.0)],
-        dt=5e-3, damping=1e-5, batch=1024,
+        q_spread=0.35, dt=5e-3, damping=1e-5, batch=1024,
     ),
     # Not a BASELINE config: edge-case model authored for this repository (mink_b200/models/edge.xml):
     # ball joint with off-centre anchor, slide joint with ref, two joints on one body, a second floating
@@ -307,7 +307,14 @@ def make_inputs(fm, wl: dict, B: int, fk: FkFn, seed: int = 0, sigma: float = 0.
     """
     rng = np.random.default_rng(seed)
     key_q = fm.key(wl["key"])
-    q = sample_q(fm, key_q, B, rng)
+    if wl.get("q_spread") is not None:   # configurations around the keyframe (an arm workspace, not the whole joint range)
+        q = perturb_q(fm, np.tile(key_q, (B, 1)).astype(np.float64), float(wl["q_spread"]), rng)
+        for d in range(fm.nv):
+            qa = int(fm.dof_qadr[d])
+            if qa >= 0 and fm.dof_limited[d]:
+                q[:, qa] = np.clip(q[:, qa], fm.dof_lo[d] + 1e-3, fm.dof_hi[d] - 1e-3)
+    else:
+        q = sample_q(fm, key_q, B, rng)
     qp = perturb_q(fm, q, sigma, rng)
     poses_now, _ = fk(q)
     poses_tgt, com_tgt = fk(qp)
