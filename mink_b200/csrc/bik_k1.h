@@ -649,7 +649,9 @@ BIK_HD void k1_warp_tile(const PView& P, const K1Args& a, int inst0, T* wsm, int
   // touches 12 of G1's 43 columns).  Zero-fill and scatter are ordered by the warp barrier; the partial sectors merge in L2.
   // (Measured alternatives, same box: zero-fill at the top of the tile -- by plain stores or by bulk async stores from a block
   //  of zeros -- 0.120 ms instead of 0.096: the zeros are written back to DRAM before the scatter reaches L2 and every line
-  //  goes out twice; bulk async zero-fill issued just before the frame algebra: 0.099 ms.)
+  //  goes out twice; bulk async zero-fill issued just before the frame algebra: 0.099 ms; "write once" -- non-zero columns parked
+  //  in a compact [6][max_cols] block per instance, then every element of the 6 x nv blocks produced from an inverse column
+  //  table and stored as contiguous runs, no zero-fill: 0.172 ms, the per-element expansion makes the kernel issue-bound.)
   if (direct && h.F > 0) zero_words<W, T>(Jg + (long long)inst0 * K * nv, nvalid * K * nv, lane);
   BIK_SYNCWARP();
   // ---- the tile's inputs are dead from here on: send the next tile's ahead (bulk async copies into the same buffers) ----
