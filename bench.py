@@ -617,7 +617,8 @@ def main():
     if extras and world == 1:
         cache = {wl["robot"]: model}
         per_config = {}
-        for cname, cB, sg in (("ur5e_dls", 4096, 0.1), ("shadow", 16384, 0.1), ("spot", 32768, 0.1), ("g1_full", 4096, 0.1), ("ur5e_wall", 16384, 0.1)):
+        for cname, cB, sg in (("ur5e_dls", 4096, 0.1), ("shadow", 16384, 0.1), ("spot", 32768, 0.1), ("g1_full", 4096, 0.1), ("ur5e_wall", 16384, 0.1),
+                               ("h1", 4096, 0.1), ("aloha", 16384, 0.1), ("aloha_coll", 1024, 0.1)):   # beyond BASELINE: more of the reference's examples
             try:
                 per_config[cname] = config_row(torch, cache, cname, cB, sg, flush)
             except Exception as exc:
