@@ -84,6 +84,11 @@ enum { K2_MAX_GEN = 24 };  // general (collision) rows that may be active at onc
 BIK_HD int tri(int i) { return (i * (i + 1)) >> 1; }
 
 BIK_HD int k2_max_gen(const PHeader& h) { return h.npairs < K2_MAX_GEN ? h.npairs : K2_MAX_GEN; }
+// General rows whose h is finite (pairs inside the detection distance) are gathered into a window of at most this many rows per
+// problem; everything the solver keeps per row is sized by the window, not by the number of pairs (ALOHA: 1 104 pairs, a
+// dozen inside the detection distance).  More finite rows than the window sets BIK_STATUS_QP_MAXITER.
+enum { K2_ROW_WINDOW = 64 };
+BIK_HD int k2_row_cap(const PHeader& h) { return h.npairs < K2_ROW_WINDOW ? h.npairs : K2_ROW_WINDOW; }
 // per-warp scratch, in bytes, for scalar type of size `ts`.
 // Layout: Hp | dinv c lo hi x xf xfull | [general-row block] | U | ints.   U is a union: during assembly it
 // holds the weighted task blocks (packed layout), afterwards the packed factor augmented by the rhs row.
@@ -94,9 +99,9 @@ BIK_HD int k2_union_bytes(const PHeader& h, int ts) {
   return ((lp > wj ? lp : wj) + 15) & ~15;
 }
 BIK_HD int k2_warp_bytes(const PHeader& h, int ts) {
-  int n = h.nu, np = h.npairs, mg = k2_max_gen(h);
-  int words_T = tri(n) + 6 * n + h.nv + (np > 0 ? (mg * n + mg * mg + 3 * mg + 2 * np) : 0);
-  int bytes = ((words_T * ts + 15) & ~15) + k2_union_bytes(h, ts) + 4 * (2 * n + 3 * np + 16);
+  int n = h.nu, np = h.npairs, mg = k2_max_gen(h), rc = k2_row_cap(h);
+  int words_T = tri(n) + 6 * n + h.nv + (np > 0 ? (mg * n + mg * mg + 2 * mg + rc) : 0);
+  int bytes = ((words_T * ts + 15) & ~15) + k2_union_bytes(h, ts) + 4 * (2 * n + 4 * rc + 20);
   return (bytes + 15) & ~15;
 }
 
@@ -173,26 +178,28 @@ template <typename T, int W> BIK_HD T warp_bcast(T v, int src) {   // src: lane 
 
 template <typename T> struct K2Ws {
   T *Hp, *Lp, *dinv, *c, *lo, *hi, *x, *xf, *xfull;
-  T *Y, *S, *lam, *rg, *sg, *hg, *gp;  // general rows: Y = L^-1 G_F^T (maxg x n), S Schur, lam, rhs, slack, h [np], scratch [np]
-  int *st, *idx, *gst, *gidx, *gnew;
+  T *Y, *S, *lam, *rg, *hg;            // general rows: Y = L^-1 G_F^T (maxg x n), S Schur, lam, rhs, h of the window rows
+  int *st, *idx, *gst, *gidx, *gnew, *frow;   // per window row: state, active list, proposed state, pair index of the row
+  int nrows;                           // rows in the window (set by k2_solve)
   T *wpk;                              // weighted task blocks in the packed layout (aliases Lp)
 };
 template <typename T> BIK_HD K2Ws<T> k2_carve(const PHeader& h, void* mem) {
   K2Ws<T> w;
-  int n = h.nu, np = h.npairs, mg = k2_max_gen(h);
+  int n = h.nu, np = h.npairs, mg = k2_max_gen(h), rc = k2_row_cap(h);
+  w.nrows = 0;
   char* base = reinterpret_cast<char*>(mem);
   BIK_IN_SHARED(base);
   T* p = reinterpret_cast<T*>(base);
   w.Hp = p; p += tri(n);
   w.dinv = p; p += n; w.c = p; p += n; w.lo = p; p += n; w.hi = p; p += n; w.x = p; p += n; w.xf = p; p += n; w.xfull = p; p += h.nv;
-  w.Y = w.S = w.lam = w.rg = w.hg = w.sg = w.gp = nullptr;
-  if (np > 0) { w.Y = p; p += mg * n; w.S = p; p += mg * mg; w.lam = p; p += mg; w.rg = p; p += mg; w.sg = p; p += mg; w.hg = p; p += np; w.gp = p; p += np; }
+  w.Y = w.S = w.lam = w.rg = w.hg = nullptr;
+  if (np > 0) { w.Y = p; p += mg * n; w.S = p; p += mg * mg; w.lam = p; p += mg; w.rg = p; p += mg; w.hg = p; p += rc; }
   int words_T = (int)(p - reinterpret_cast<T*>(base));
   char* u = base + ((words_T * (int)sizeof(T) + 15) & ~15);
   w.Lp = reinterpret_cast<T*>(u);
   w.wpk = reinterpret_cast<T*>(u);
   int* ip = reinterpret_cast<int*>(u + k2_union_bytes(h, sizeof(T)));
-  w.st = ip; ip += n; w.idx = ip; ip += n; w.gst = ip; ip += np + 4; w.gidx = ip; ip += np + 4; w.gnew = ip; ip += np + 4;
+  w.st = ip; ip += n; w.idx = ip; ip += n; w.gst = ip; ip += rc + 4; w.gidx = ip; ip += rc + 4; w.gnew = ip; ip += rc + 4; w.frow = ip; ip += rc + 4;
   return w;
 }
 
@@ -409,15 +416,16 @@ template <typename T, int W>
 BIK_NOINLINE int k2_general_rows(const K2Ws<T> w, const K2Args& a, long long gbase, T* rhs, int n, int nf, int ng, int mg, int lane) {
   // local copies: the assumption has to sit on the very pointer values the loops use
   T* const Y = w.Y; T* const S = w.S; T* const lam = w.lam; T* const rg = w.rg; const T* const hg = w.hg; const T* const x = w.x;
-  const int* const st = w.st; const int* const idx = w.idx; const int* const gidx = w.gidx;
+  const int* const st = w.st; const int* const idx = w.idx; const int* const gidx = w.gidx; const int* const frow = w.frow;
+  BIK_IN_SHARED(frow);
   BIK_IN_SHARED(Y); BIK_IN_SHARED(S); BIK_IN_SHARED(lam); BIK_IN_SHARED(rg); BIK_IN_SHARED(hg); BIK_IN_SHARED(x);
   BIK_IN_SHARED(st); BIK_IN_SHARED(idx); BIK_IN_SHARED(gidx); BIK_IN_SHARED(rhs);
   int bad = 0;
   for (int r = 0; r < ng; ++r) {
     T* Yr = Y + r * n;
-    for (int i = lane; i < nf; i += W) Yr[i] = k2_grow<T>(a, gbase, gidx[r], n, idx[i]);
+    for (int i = lane; i < nf; i += W) Yr[i] = k2_grow<T>(a, gbase, frow[gidx[r]], n, idx[i]);
     if (nf < n) {   // some dofs sit on their bounds: move their part of the row to the right-hand side
-      if (lane == 0) { T sv = hg[gidx[r]]; for (int j = 0; j < n; ++j) if (st[j]) sv -= k2_grow<T>(a, gbase, gidx[r], n, j) * x[j]; rg[r] = sv; }
+      if (lane == 0) { T sv = hg[gidx[r]]; for (int j = 0; j < n; ++j) if (st[j]) sv -= k2_grow<T>(a, gbase, frow[gidx[r]], n, j) * x[j]; rg[r] = sv; }
     } else if (lane == 0) rg[r] = hg[gidx[r]];
     k2_sync<W>();
     k2_forward<T, W>(w.Lp, w.dinv, Yr, nf, lane);
@@ -463,7 +471,7 @@ template <> struct K2Tol<float> { static BIK_HD float x() { return 1e-7f; } stat
 // right-hand side is forward-substituted.
 template <typename T, int W, int SLOTS>
 BIK_HD int k2_solve_working_set(const PHeader& h, const K2Args& a, long long gbase, K2Ws<T>& w, int lane, int* ng_out, unsigned long long* fkey) {
-  const int n = h.nu, np = h.npairs, mg = k2_max_gen(h);
+  const int n = h.nu, np = w.nrows, mg = k2_max_gen(h);   // np: rows in the window
   int status = 0;
   // compact free list / active general rows (every lane writes the same values)
   int nf = 0, ng = 0;
@@ -508,7 +516,7 @@ BIK_HD T k2_grad(const K2Args& a, long long gbase, const K2Ws<T>& w, int n, int 
   const T* Hrow = w.Hp + tri(i);
   for (int j = 0; j <= i; ++j) gi += Hrow[j] * w.x[j];
   for (int j = i + 1; j < n; ++j) gi += w.Hp[tri(j) + i] * w.x[j];
-  for (int r = 0; r < ng; ++r) gi += k2_grow<T>(a, gbase, w.gidx[r], n, i) * w.lam[r];
+  for (int r = 0; r < ng; ++r) gi += k2_grow<T>(a, gbase, w.frow[w.gidx[r]], n, i) * w.lam[r];
   return gi;
 }
 
@@ -516,18 +524,40 @@ BIK_HD T k2_grad(const K2Args& a, long long gbase, const K2Ws<T>& w, int n, int 
 template <typename T, int W, int SLOTS>
 BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane, int* iters_out) {
   const PHeader& h = P.h();
-  const int n = h.nu, np = h.npairs;   // coupled dofs only (n == nv whenever there are general rows)
+  const int n = h.nu, npair = h.npairs;   // coupled dofs only (n == nv whenever there are general rows)
   const int MAXIT = 60 + 2 * (n + k2_max_gen(h)), PATIENCE = 2;   // bounds + the general rows that may be active at once
   const T tolx = K2Tol<T>::x(), tolg = K2Tol<T>::g();
-  const long long gbase = (long long)b * np * n;
+  const long long gbase = (long long)b * npair * n;
   for (int i = lane; i < n; i += W) {
     int s0 = a.warm ? (a.warm[(long long)b * n + i] & 3) : 0;   // warm start: last step's active set (bit 2 is the small-group path's marker)
     if ((s0 == 1 && !(w.lo[i] > T(-1e30))) || (s0 == 2 && !(w.hi[i] < T(1e30)))) s0 = 0;
     w.st[i] = s0;
   }
-  for (int r = lane; r < np; r += W) { w.gst[r] = 0; w.hg[r] = ldin<T>(a.hc, (long long)b * np + r, a.gc64); }
+  // gather the finite rows (pairs inside the detection distance) into the window, in pair order
+  int np = 0, overflow = 0;
+  {
+    const int cap = k2_row_cap(h);
+    for (int r0 = 0; r0 < npair; r0 += W) {
+      const int r = r0 + lane;
+      T hv = T(BIK_INF_F);
+      if (r < npair) hv = ldin<T>(a.hc, (long long)b * npair + r, a.gc64);
+      const bool fin = r < npair && hv < T(1e30);
+#if defined(__CUDA_ARCH__)
+      unsigned lane32;
+      asm("mov.u32 %0, %%laneid;" : "=r"(lane32));
+      const unsigned bits = __ballot_sync(k2_gmask<W>(), fin);
+      const int pos = np + __popc(bits & ((1u << lane32) - 1u)), cnt = __popc(bits);
+#else
+      const int pos = np, cnt = fin ? 1 : 0;
+#endif
+      if (fin && pos < cap) { w.frow[pos] = r; w.hg[pos] = hv; w.gst[pos] = 0; }
+      np += cnt;
+    }
+    if (np > cap) { overflow = 1; np = cap; }
+    w.nrows = np;
+  }
   k2_sync<W>();
-  int status = 0, best = n + np + 1, patience = PATIENCE, it = 0, ng = 0;
+  int status = overflow ? 2 : 0, best = n + np + 1, patience = PATIENCE, it = 0, ng = 0;
   unsigned long long fkey = 0ull;
   bool done = n == 0;
   // One loop, one call site of the working-set solve (the kernel is instruction-cache bound):
@@ -550,7 +580,7 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
         T hr = w.hg[r];
         if (hr < T(1e30)) {
           T sv = -hr;
-          for (int j = 0; j < n; ++j) sv += k2_grow<T>(a, gbase, r, n, j) * w.xf[j];
+          for (int j = 0; j < n; ++j) sv += k2_grow<T>(a, gbase, w.frow[r], n, j) * w.xf[j];
           if (sv > tolx * (T(1) + (hr < 0 ? -hr : hr))) infeas = 1;
         }
       }
@@ -588,7 +618,7 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
         if (!(hr < T(1e30))) ns = 0;  // inactive row: h = +inf (collision_avoidance_limit.py:192-199)
         else if (cur == 0) {
           T sv = -hr;
-          for (int j = 0; j < n; ++j) sv += k2_grow<T>(a, gbase, r, n, j) * w.x[j];
+          for (int j = 0; j < n; ++j) sv += k2_grow<T>(a, gbase, w.frow[r], n, j) * w.x[j];
           if (sv > tolx * (T(1) + (hr < 0 ? -hr : hr))) ns = 1;
         } else {
           int k = 0;
@@ -628,7 +658,7 @@ BIK_HD int k2_solve(const PView& P, const K2Args& a, int b, K2Ws<T>& w, int lane
       const T hr = w.hg[r];
       if (w.gst[r] || !(hr < T(1e30))) continue;
       T gx = T(0), gf = T(0);
-      for (int j = 0; j < n; ++j) { const T gj = k2_grow<T>(a, gbase, r, n, j); gx += gj * w.x[j]; gf += gj * w.xf[j]; }
+      for (int j = 0; j < n; ++j) { const T gj = k2_grow<T>(a, gbase, w.frow[r], n, j); gx += gj * w.x[j]; gf += gj * w.xf[j]; }
       if (gx > hr + tolx * (T(1) + (hr < 0 ? -hr : hr))) {
         const T d = gx - gf;
         T al = d > T(0) ? (hr - gf) / d : T(0);
