@@ -124,10 +124,9 @@ def test_k2_objective_box_and_solve_from_reference_jacobians(name):
     assert np.all(np.isneginf(_np(lo)[~fin]))
     fin = np.isfinite(g["box_hi"])
     np.testing.assert_allclose(_np(hi)[fin], g["box_hi"][fin], atol=1e-6)
-    if name != "aloha_coll":   # its near-parallel collision rows, cast to fp32, make the active set degenerate (flagged); fp64 below
-        dq, st = prob.solve(g["q"], J, e, ep, Gc, hc, float(g["dt"]), float(g["damping"]))
-        assert int(st.max()) == 0
-        np.testing.assert_allclose(_np(dq), g["dq"], atol={"spot": 2e-3, "g1_rel": 5e-5}.get(name, 1e-5))   # spot: the fp32 cast of J alone
+    dq, st = prob.solve(g["q"], J, e, ep, Gc, hc, float(g["dt"]), float(g["damping"]))
+    assert int(st.max()) == 0
+    np.testing.assert_allclose(_np(dq), g["dq"], atol={"spot": 2e-3, "g1_rel": 5e-5, "aloha_coll": 1e-4}.get(name, 1e-5))   # spot: the fp32 cast of J alone
     # same through the fp64 entry points: the reference's own (J, e) in, the reference's dq out
     f64 = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda:0")
     J8 = f64(np.concatenate([g["J_frame"].reshape(B, 6 * F, fm.nv)] + ([g["J_com"]] if spec.ncom else []), axis=1))

@@ -60,9 +60,6 @@ def test_k1_errors_and_jacobians(name):
 @pytest.mark.parametrize("use_double", [True, False])
 def test_k2_from_golden_jacobians(name, use_double):
     """K2 alone: feed the reference's own (J, e) cast to fp32, compare H, c, box and dq."""
-    if name == "aloha_coll" and not use_double:
-        pytest.skip("rows of neighbouring geoms on one link are parallel to ~1e-6: their Schur complement is singular to fp32 "
-                    "working precision (status 4); the product solves in fp64, BIK_SOLVE_PRECISION=f32 is an experiment knob")
     wl, fm, spec, g, emu = _emu(name)
     B, F = g["q"].shape[0], spec.nframe
     J = np.concatenate([g["J_frame"].reshape(B, 6 * F, fm.nv)] + ([g["J_com"]] if spec.ncom else []), axis=1)
@@ -94,11 +91,8 @@ def test_full_step(name):
     """K1 -> K2 -> integrate in fp32 I/O against the reference's solve_ik + integrate."""
     wl, fm, spec, g, emu = _emu(name)
     dt, damping = float(g["dt"]), float(g["damping"])
-    # aloha_coll: rows of neighbouring geoms on one link are parallel to ~1e-6; rounded to fp32 they make the active set
-    # degenerate and the solve cycles.  bik_step runs K1 in fp64 whenever there are collision pairs -- do the same here.
-    prec = "f64" if name == "aloha_coll" else "f32"
-    J, e, ep, Gc, hc = emu.fk_jac(g["q"], g["frame_targets"], g["posture_target"], g.get("com_target"), dt=dt, prec=prec)
-    dq, st, it, *_ = emu.solve(g["q"], J, e, ep, Gc, hc, dt, damping, use_double=True, io64=prec == "f64")
+    J, e, ep, Gc, hc = emu.fk_jac(g["q"], g["frame_targets"], g["posture_target"], g.get("com_target"), dt=dt)
+    dq, st, it, *_ = emu.solve(g["q"], J, e, ep, Gc, hc, dt, damping, use_double=True)
     assert not st.any()
     tol = {"spot": 5e-3, "g1_rel": 1e-4 * max(1.0, np.abs(g["dq"]).max()),
            "edge": 2e-3}.get(name, 1e-4)   # edge: an active near-parallel capsule pair (ill-conditioned contact point)
@@ -232,9 +226,7 @@ def _k2_path(emu):
     return 8 if h["nu"] > 32 else 3
 
 
-# aloha_coll is left out: with fp32 collision rows its near-parallel active rows make the solve cycle (status 2); bik_step never
-# runs that combination (K1 and the hand-off are fp64 whenever there are pairs) -- test_fp64_path / test_mixed below cover it.
-@pytest.mark.parametrize("name", [c for c in CASES if c != "aloha_coll"])
+@pytest.mark.parametrize("name", CASES)
 def test_packed_handoff_matches_dense(name):
     """bik_step's K1 -> K2 hand-off (non-zero columns only, posture error recomputed by K2) gives the dq of the dense
     Task.compute_jacobian form; the fused check_limits reports the same bits as the stand-alone one."""
