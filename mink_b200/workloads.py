@@ -16,7 +16,7 @@ import numpy as np
 PI = float(np.pi)
 
 # Example robots of the reference beyond the BASELINE configs (goldens tests/golden/<name>.npz, models mink_b200/models/<name>.*)
-EXAMPLE_ROBOTS = ["iiwa", "h1", "go1", "stretch", "tidybot", "aloha"]
+EXAMPLE_ROBOTS = ["iiwa", "h1", "go1", "stretch", "tidybot", "aloha", "leap"]
 
 WORKLOADS: Dict[str, dict] = {
     # BASELINE config 1: UR5e single instance, FrameTask + PostureTask + ConfigurationLimit
@@ -180,6 +180,14 @@ WORKLOADS: Dict[str, dict] = {
         posture=dict(cost=1e-4), com=None, limits=[dict(kind="configuration", gain=0.95), dict(kind="velocity", vmax=PI)],
         dt=5e-3, damping=1e-5, batch=4096,
     ),
+    # examples/arm_hand_xarm_leap.py:75-85: the LEAP hand's four fingertip tasks (position only) + posture, on the hand alone (the
+    # example attaches it to an arm with MjSpec, which the MJCF subset here does not do).
+    "leap": dict(
+        robot="leap", scene="leap_hand/scene_right.xml", key=None,
+        frames=[dict(name=f, type="site", position_cost=1.0, orientation_cost=0.0, lm_damping=1.0) for f in ("tip_1", "tip_2", "tip_3", "th_tip")],
+        posture=dict(cost=5e-2), com=None, limits=[dict(kind="configuration", gain=0.95)],
+        q_spread=0.3, dt=5e-3, damping=1e-3, batch=16384,
+    ),
     # examples/arm_aloha.py as written: the same tasks and limits PLUS its CollisionAvoidanceLimit (:95-110) -- wrist subtree
     # against wrist subtree, both arm subtrees against the metal frame and the table: 1 104 geom pairs after the reference's
     # filtering (capsule-capsule, sphere-capsule, sphere-sphere, box-capsule, box-sphere).
@@ -306,7 +314,7 @@ def make_inputs(fm, wl: dict, B: int, fk: FkFn, seed: int = 0, sigma: float = 0.
     identity branch of SE3.ljacinv (mink/lie/se3.py:213).
     """
     rng = np.random.default_rng(seed)
-    key_q = fm.key(wl["key"])
+    key_q = fm.key(wl["key"]) if wl.get("key") else np.asarray(fm.qpos0, dtype=np.float64).copy()   # no keyframe: the model's qpos0
     if wl.get("q_spread") is not None:   # configurations around the keyframe (an arm workspace, not the whole joint range)
         q = perturb_q(fm, np.tile(key_q, (B, 1)).astype(np.float64), float(wl["q_spread"]), rng)
         for d in range(fm.nv):

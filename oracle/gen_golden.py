@@ -26,7 +26,7 @@ from mink_b200.flatten import flatten  # noqa: E402
 from mink_b200.workloads import WORKLOADS, make_inputs, resolve_geom_groups  # noqa: E402
 
 OUT = os.path.join(REPO, "tests", "golden")
-GOLDEN_B = {"aloha_coll": 6, "iiwa": 8, "h1": 8, "go1": 8, "stretch": 8, "tidybot": 8, "aloha": 8, "ur5e_wall": 24, "ur5e_damp": 12, "ur5e": 8, "ur5e_dls": 16, "g1": 32, "shadow": 24, "spot": 24, "g1_rel": 16, "edge": 48, "g1_full": 16, "g1_hands": 24}
+GOLDEN_B = {"leap": 8, "aloha_coll": 6, "iiwa": 8, "h1": 8, "go1": 8, "stretch": 8, "tidybot": 8, "aloha": 8, "ur5e_wall": 24, "ur5e_damp": 12, "ur5e": 8, "ur5e_dls": 16, "g1": 32, "shadow": 24, "spot": 24, "g1_rel": 16, "edge": 48, "g1_full": 16, "g1_hands": 24}
 ROLLOUT_T, ROLLOUT_B = 8, 4
 CONV_B, CONV_MAX_ITERS, CONV_POS, CONV_ORI = 8, 20, 2e-3, 2e-3
 

@@ -13,7 +13,7 @@ from mink_b200.workloads import make_inputs
 from tests.helpers import load_case, quat_align, task_frames
 
 CASES = ["ur5e", "ur5e_dls", "g1", "shadow", "spot", "g1_rel", "edge", "g1_full", "g1_hands", "ur5e_damp", "ur5e_wall",
-         "iiwa", "h1", "go1", "stretch", "tidybot", "aloha", "aloha_coll"]   # the last seven: the reference's other example robots
+         "iiwa", "h1", "go1", "stretch", "tidybot", "aloha", "aloha_coll", "leap"]   # the last eight: the reference's other example robots
 
 
 def _emu(name):

@@ -19,7 +19,7 @@ from tests.helpers import load_case
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
 from qpsolvers import goldfarb_idnani  # noqa: E402  (oracle shim; test infrastructure)
 
-BOX_CASES = ["ur5e", "g1", "shadow", "g1_hands", "g1_full", "g1_rel", "ur5e_damp", "iiwa", "h1", "go1", "stretch", "tidybot", "aloha"]
+BOX_CASES = ["ur5e", "g1", "shadow", "g1_hands", "g1_full", "g1_rel", "ur5e_damp", "iiwa", "h1", "go1", "stretch", "tidybot", "aloha", "leap"]
 ROW_CASES = ["spot", "edge"]
 
 
