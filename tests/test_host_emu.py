@@ -365,3 +365,22 @@ def test_degenerate_contact_sets_are_solved_not_flagged():
     err = np.abs(dq - dq_ref).max(axis=1)
     print("aloha_coll sample: max err %.2e, instances above 1e-6: %d of %d, iterations mean %.1f max %d" % (err.max(), (err > 1e-6).sum(), B, it.mean(), it.max()))
     assert (err > 1e-6).mean() < 0.01 and err.max() < 2e-3
+
+
+def test_more_finite_rows_than_the_row_window_are_flagged():
+    """The general path gathers the pairs inside the detection distance into a window of K2_ROW_WINDOW (64) rows per problem.
+    With the detection distance blown up to 10 m every one of ALOHA's 1 104 pairs is finite: the instance must come back
+    flagged (BIK_STATUS_QP_MAXITER), not solved on a truncated row set."""
+    from mink_b200._abi import spec_from_workload
+    from mink_b200.workloads import WORKLOADS
+
+    wl = dict(WORKLOADS["aloha_coll"])
+    wl["limits"] = [dict(l, detection_distance=10.0) if l["kind"] == "collision" else l for l in wl["limits"]]
+    _, fm, _, g = load_case("aloha_coll")
+    spec = spec_from_workload(fm, wl)
+    emu = Emu(fm.to_blob(), spec, fm.nq, fm.nv)
+    q = g["q"][:2]
+    J, e, ep, Gc, hc = emu.fk_jac(q, g["frame_targets"][:2], g["posture_target"], None, dt=wl["dt"], prec="f64")
+    assert (np.isfinite(hc).sum(axis=1) > 64).all()
+    dq, st, *_ = emu.solve(q, J, e, ep, Gc, hc, wl["dt"], wl["damping"], use_double=True, io64=True)
+    assert (st & 2).all(), st
