@@ -41,7 +41,8 @@ typedef enum bik_status {
  * replace the reference's exceptions (NotWithinConfigurationLimits, configuration.py:97-105;
  * `assert dq is not None`, solve_ik.py:103). */
 #define BIK_STATUS_OUT_OF_LIMITS 1u  /* q outside [range - tol, range + tol] */
-#define BIK_STATUS_QP_MAXITER    2u  /* active-set iteration cap reached; dq is the last iterate */
+#define BIK_STATUS_QP_MAXITER    2u  /* active-set iteration cap reached, or more general rows in play than the solver holds
+                                         (24 active at once, 64 inside the detection distance); dq is the last iterate */
 #define BIK_STATUS_NONFINITE     4u  /* NaN/Inf met in q, targets or the factorisation */
 #define BIK_STATUS_QP_INFEASIBLE 8u  /* inequality set inconsistent (lower > upper for a dof, or no feasible start): the
                                       * reference's solver returns None there and solve_ik asserts (solve_ik.py:103) */
