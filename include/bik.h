@@ -15,7 +15,9 @@
  *   - batch layout is row-major with the instance index outermost: q[B][nq], J[B][K][nv], ...
  *   - quaternions are (w,x,y,z); poses are (qw,qx,qy,qz,x,y,z) like mink.SE3.wxyz_xyz
  *     (reference mink/lie/se3.py:24-29); twists are (v, omega) (ibid.).
- *   - handles are immutable after creation and may be shared between streams.
+ *   - model handles are immutable after creation and may be shared between streams.  A problem handle owns the K1 -> K2
+ *     hand-off buffers of bik_step / bik_converge: calls on one problem handle are ordered (a call on another stream than
+ *     the previous one first waits, on the device, for that call's kernels); use one problem handle per stream for overlap.
  */
 #ifndef BIK_H
 #define BIK_H
