@@ -480,8 +480,24 @@ BIK_HD int k2_solve_working_set(const PHeader& h, const K2Args& a, long long gba
   // compact free list / active general rows (every lane writes the same values)
   int nf = 0, ng = 0;
   unsigned long long key = n <= 63 ? 1ull << 63 : 0ull;
+#if defined(__CUDA_ARCH__)
+  {   // one ballot per W dofs: lane i tests dof base + i, the free ones are numbered by the bits below them
+    unsigned lane32;
+    asm("mov.u32 %0, %%laneid;" : "=r"(lane32));
+    const unsigned gm = k2_gmask<W>(), gshift = lane32 & ~(unsigned)(W - 1);
+    for (int base = 0; base < n; base += W) {
+      const int i = base + lane;
+      const bool fr = i < n && w.st[i] == 0;
+      const unsigned bits = __ballot_sync(gm, fr) >> gshift;   // bit k: dof base + k is free
+      if (fr) w.idx[nf + __popc(bits & ((1u << lane) - 1u))] = i;
+      nf += __popc(bits);
+      if (base < 63) key |= ((unsigned long long)bits << base) & 0x7fffffffffffffffull;
+    }
+  }
+#else
   for (int i = 0; i < n; ++i) if (w.st[i] == 0) { w.idx[nf] = i; ++nf; if (i < 63) key |= 1ull << i; }
-  const bool reuse = key != 0ull && key == *fkey;
+#endif
+  const bool reuse = (key >> 63) != 0ull && key == *fkey;   // bit 63: the mask covers every coupled dof (n <= 63)
   for (int r = 0; r < np; ++r) if (w.gst[r]) { if (ng < mg) { w.gidx[ng] = r; ++ng; } else status |= 2; }
   k2_sync<W>();
   // x on the bounds, rhs of the reduced system, copy of H_FF
@@ -492,8 +508,10 @@ BIK_HD int k2_solve_working_set(const PHeader& h, const K2Args& a, long long gba
     int ii = w.idx[i];
     const T* Hrow = w.Hp + tri(ii);
     T r = -w.c[ii];
-    for (int j = 0; j < ii; ++j) if (w.st[j]) r -= Hrow[j] * w.x[j];
-    for (int j = ii + 1; j < n; ++j) if (w.st[j]) r -= w.Hp[tri(j) + ii] * w.x[j];
+    if (nf < n) {   // some dofs sit on their bounds: their columns move to the right-hand side
+      for (int j = 0; j < ii; ++j) if (w.st[j]) r -= Hrow[j] * w.x[j];
+      for (int j = ii + 1; j < n; ++j) if (w.st[j]) r -= w.Hp[tri(j) + ii] * w.x[j];
+    }
     rhs[i] = r;
     if (!reuse) {
       T* Li = w.Lp + tri(i);
