@@ -16,7 +16,7 @@ import numpy as np
 
 from . import exceptions
 from .flatten import FlatModel, flatten
-from .lie import SE3, SO3
+from .lie import SE3
 
 SUPPORTED_FRAMES = ("body", "geom", "site")
 

@@ -22,11 +22,11 @@ from __future__ import annotations
 import json
 import struct
 from dataclasses import dataclass, field
-from typing import Dict, List, Tuple
+from typing import Dict, List
 
 import numpy as np
 
-from .mjcf import DOF_WIDTH, JNT_BALL, JNT_FREE, JNT_HINGE, JNT_SLIDE, QPOS_WIDTH
+from .mjcf import DOF_WIDTH, JNT_BALL, JNT_FREE, JNT_HINGE, JNT_SLIDE, QPOS_WIDTH  # noqa: F401  (re-exported through __all__)
 
 BLOB_MAGIC = 0x4D4B4942  # 'BIKM'
 BLOB_VERSION = 1

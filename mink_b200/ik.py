@@ -8,16 +8,14 @@ the exact optimum of the same strictly convex QP that quadprog / daqp solve.
 
 from __future__ import annotations
 
-import logging
 from typing import NamedTuple, Optional, Sequence
 
 import numpy as np
 
 from ._abi import ProblemSpec
 from .configuration import Configuration
-from .exceptions import NotWithinConfigurationLimits
 from .limits import ConfigurationLimit, Limit
-from .tasks import ComTask, FrameTask, Objective, PostureTask, Task, problem_for
+from .tasks import ComTask, FrameTask, PostureTask, Task, problem_for
 
 
 class Problem(NamedTuple):

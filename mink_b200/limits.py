@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import abc
 import itertools
-from typing import Mapping, NamedTuple, Optional, Sequence
+from typing import Mapping, NamedTuple, Optional
 
 import numpy as np
 

@@ -13,8 +13,8 @@ from typing import NamedTuple, Optional
 
 import numpy as np
 
-from ._abi import LIMIT_CONFIGURATION, TASK_COM, TASK_FRAME, TASK_POSTURE, TASK_RELATIVE_FRAME, ProblemSpec, TaskSpec
-from .configuration import SUPPORTED_FRAMES, Configuration, as_flat, device_model
+from ._abi import TASK_COM, TASK_FRAME, TASK_POSTURE, TASK_RELATIVE_FRAME, ProblemSpec, TaskSpec
+from .configuration import SUPPORTED_FRAMES, Configuration, as_flat
 from .exceptions import (InvalidDamping, InvalidFrame, InvalidGain, InvalidTarget, TargetNotSet, TaskDefinitionError,
                          UnsupportedFrame)
 from .lie import SE3

@@ -8,7 +8,6 @@ Per spec it prints one JSON line: step (event-timed, L2 flushed, as bench.py), K
 K1 / K2 through the dense API (bik_fk_jac / bik_solve), iterations.
 """
 import concurrent.futures as cf
-import json
 import os
 import subprocess
 import sys
